@@ -1,0 +1,312 @@
+"""ctypes bindings for the two product libraries.
+
+* ``libptgpu.so``  — the C ABI of include/ptgpu.h (CUDA, sm_100a).  `Device` wraps one ``ptgpu_ctx``.
+* ``libpthost.so`` — the C++ host side (scene classes, reference kd-tree builder, flattener, Renderer), reached
+  through its ``pth_*`` C entry points.  `HostWorld` is a scene being authored on it.
+
+There is no CPU fallback anywhere in this module: if the CUDA library cannot be built/loaded, or no device is present,
+the calls raise `PtgpuError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import build as _build
+from .authoring import World, bind, c_double_p, c_float_p, c_int_p
+
+c_ll_p = C.POINTER(C.c_longlong)
+
+
+class PtgpuError(RuntimeError):
+    pass
+
+
+class Camera(C.Structure):
+    _fields_ = [("p", C.c_float * 3), ("u", C.c_float * 3), ("v", C.c_float * 3), ("w", C.c_float * 3),
+                ("m", C.c_double), ("focalDistance", C.c_double), ("apertureRadius", C.c_double)]
+
+
+class Pass(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("stratified", C.c_int32),
+                ("sampleBase", C.c_int32), ("sampleStride", C.c_int32), ("firstHitSamples", C.c_int32),
+                ("maxBounces", C.c_int32), ("directLighting", C.c_int32), ("softShadows", C.c_int32),
+                ("lightMode", C.c_int32), ("specularMode", C.c_int32), ("seed", C.c_uint32), ("passIndex", C.c_uint32),
+                ("camera", Camera)]
+
+
+class Params(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_int32), ("queueCapacity", C.c_uint64)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("cameraSamples", C.c_uint64), ("segments", C.c_uint64), ("shadowRays", C.c_uint64),
+                ("nanSamples", C.c_uint64), ("kernelLaunches", C.c_uint64), ("lastPassMs", C.c_double),
+                ("traceMs", C.c_double), ("shadeMs", C.c_double), ("shadowMs", C.c_double), ("raygenMs", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/ptgpu.h declares (tests check the library exports all of them)
+PTGPU_SYMBOLS = [
+    "ptgpu_abi_version", "ptgpu_create", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_upload_scene", "ptgpu_scene_bytes",
+    "ptgpu_render_pass", "ptgpu_accumulate_device", "ptgpu_add_sample_device", "ptgpu_read_buffer", "ptgpu_reset_buffer",
+    "ptgpu_intersect_batch", "ptgpu_cast_rays", "ptgpu_keyed_draw", "ptgpu_get_counters", "ptgpu_reset_counters",
+    "ptgpu_set_profiling",
+]
+
+_gpu = None
+_host = None
+
+
+def gpu_lib() -> C.CDLL:
+    global _gpu
+    if _gpu is None:
+        path = _build.build_gpu()
+        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        lib.ptgpu_abi_version.restype = C.c_int
+        lib.ptgpu_create.restype = C.c_int
+        lib.ptgpu_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+        lib.ptgpu_destroy.restype = None
+        lib.ptgpu_destroy.argtypes = [C.c_void_p]
+        lib.ptgpu_last_error.restype = C.c_char_p
+        lib.ptgpu_last_error.argtypes = [C.c_void_p]
+        lib.ptgpu_upload_scene.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ptgpu_scene_bytes.restype = C.c_uint64
+        lib.ptgpu_scene_bytes.argtypes = [C.c_void_p]
+        lib.ptgpu_render_pass.argtypes = [C.c_void_p, C.POINTER(Pass), c_float_p]
+        lib.ptgpu_accumulate_device.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_void_p, C.c_void_p]
+        lib.ptgpu_add_sample_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p]
+        lib.ptgpu_read_buffer.argtypes = [C.c_void_p, C.c_int32, c_float_p]
+        lib.ptgpu_reset_buffer.argtypes = [C.c_void_p]
+        lib.ptgpu_intersect_batch.argtypes = [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p,
+                                              c_float_p, c_float_p, c_int_p, c_int_p]
+        lib.ptgpu_cast_rays.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_int32, c_int_p, c_int_p, c_double_p, c_double_p,
+                                        c_int_p, c_float_p, c_float_p]
+        lib.ptgpu_keyed_draw.argtypes = [C.c_void_p] + [C.c_uint32] * 9 + [c_double_p]
+        lib.ptgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        lib.ptgpu_reset_counters.argtypes = [C.c_void_p]
+        lib.ptgpu_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        _gpu = lib
+    return _gpu
+
+
+_HOST_EXTRA = {
+    "last_error": (C.c_char_p, [C.c_void_p]),
+    "flatten": (C.c_void_p, [C.c_void_p]),
+    "flat_bytes": (C.c_uint64, [C.c_void_p]),
+    "make_pass": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.POINTER(Pass)]),
+    "tree_stats": (C.c_int, [C.c_void_p, C.c_int, c_ll_p, c_float_p]),
+    "tree_dump": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_double_p, c_int_p, c_int_p, c_int_p]),
+    "builder_friendly_order": (None, [C.c_int, c_float_p, C.c_double, C.c_int, C.c_int, c_int_p]),
+    "renderer_new": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "renderer_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "renderer_render": (C.c_int, [C.c_void_p, c_float_p]),
+    "renderer_iterative": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "renderer_image": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
+    "renderer_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "renderer_ctx": (C.c_void_p, [C.c_void_p]),
+}
+
+
+def host_lib() -> C.CDLL:
+    global _host
+    if _host is None:
+        gpu_lib()
+        lib = C.CDLL(_build.build_host())
+        bind(lib, "pth_", _HOST_EXTRA)
+        _host = lib
+    return _host
+
+
+def builder_friendly_order(V: np.ndarray, balance: float = 0.70, min_repair: int = 16, verbose: bool = False) -> np.ndarray:
+    """Permutation of triangles (ntri,3,3) for which the unmodified reference kd builder yields a balanced tree."""
+    V = np.ascontiguousarray(V, dtype=np.float32)
+    perm = np.empty(V.shape[0], np.int32)
+    host_lib().pth_builder_friendly_order(V.shape[0], V.ctypes.data_as(c_float_p), float(balance), min_repair, int(verbose),
+                                          perm.ctypes.data_as(c_int_p))
+    return perm
+
+
+class HostWorld(World):
+    """A scene authored on the C++ host library (the product path)."""
+
+    def __init__(self):
+        super().__init__(host_lib(), "pth_")
+        self._flat = None
+
+    def _err(self) -> str:
+        e = self.lib.pth_last_error(self.h)
+        return e.decode() if e else ""
+
+    def flatten(self) -> int:
+        """Scene.Compile() + flatten; returns the address of the ptgpu_flat_scene view."""
+        p = self.lib.pth_flatten(self.h)
+        if not p:
+            raise PtgpuError("flatten: " + self._err())
+        self._flat = p
+        return p
+
+    def flat_bytes(self) -> int:
+        return int(self.lib.pth_flat_bytes(self.h))
+
+    def make_pass(self, width, height, spp, stratified=False, seed=0x50545348, pass_index=0, sample_base=0,
+                  sample_stride=1) -> Pass:
+        p = Pass()
+        self.lib.pth_make_pass(self.h, width, height, spp, int(stratified), seed, pass_index, sample_base, sample_stride,
+                               C.byref(p))
+        return p
+
+    def tree_stats(self, which=-1):
+        out = (C.c_longlong * 4)()
+        box = (C.c_float * 6)()
+        if self.lib.pth_tree_stats(self.h, which, out, box) != 0:
+            raise ValueError("not a mesh")
+        return dict(nodes=out[0], leafItems=out[1], maxLeaf=out[2], maxDepth=out[3], box=np.array(list(box), np.float32))
+
+    def tree_dump(self, which=-1):
+        st = self.tree_stats(which)
+        n, m = st["nodes"], st["leafItems"]
+        axis = np.empty(n, np.int32); point = np.empty(n, np.float64)
+        a = np.empty(n, np.int32); b = np.empty(n, np.int32); items = np.empty(max(m, 1), np.int32)
+        self.lib.pth_tree_dump(self.h, which, axis.ctypes.data_as(c_int_p), point.ctypes.data_as(c_double_p),
+                               a.ctypes.data_as(c_int_p), b.ctypes.data_as(c_int_p), items.ctypes.data_as(c_int_p))
+        return dict(axis=axis, point=point, a=a, b=b, items=items[:m], box=st["box"])
+
+    # Renderer.cs mirror ------------------------------------------------------------------------------------------
+    def new_renderer(self, width, height, device=0):
+        if self.lib.pth_renderer_new(self.h, width, height, device) != 0:
+            raise PtgpuError(self._err())
+
+    def renderer_set(self, samples_per_pixel, stratified=False, seed=0x50545348):
+        if self.lib.pth_renderer_set(self.h, samples_per_pixel, int(stratified), seed) != 0:
+            raise PtgpuError(self._err())
+
+    def render_parallel(self, width, height) -> np.ndarray:
+        out = np.empty((height, width, 3), np.float32)
+        if self.lib.pth_renderer_render(self.h, out.ctypes.data_as(c_float_p)) != 0:
+            raise PtgpuError(self._err())
+        return out
+
+    def iterative_render(self, path_template: str, iterations: int):
+        if self.lib.pth_renderer_iterative(self.h, path_template.encode(), iterations) != 0:
+            raise PtgpuError(self._err())
+
+    def renderer_image(self, width, height, channel=0) -> np.ndarray:
+        out = np.empty((height, width, 3), np.float32)
+        if self.lib.pth_renderer_image(self.h, channel, out.ctypes.data_as(c_float_p)) != 0:
+            raise PtgpuError(self._err())
+        return out
+
+    def renderer_counters(self) -> dict:
+        c = Counters()
+        if self.lib.pth_renderer_counters(self.h, C.byref(c)) != 0:
+            raise PtgpuError(self._err())
+        return c.as_dict()
+
+
+class Device:
+    """One ptgpu_ctx: a CUDA device with an uploaded scene, its wavefront queues and its image Buffer."""
+
+    def __init__(self, device: int = 0, queue_capacity: int = 0):
+        self.lib = gpu_lib()
+        self.h = C.c_void_p()
+        p = Params(device, 0, queue_capacity)
+        rc = self.lib.ptgpu_create(C.byref(p), C.byref(self.h))
+        if rc != 0:
+            e = self.lib.ptgpu_last_error(None)
+            raise PtgpuError(f"ptgpu_create failed ({rc}): {e.decode() if e else ''}")
+
+    def close(self):
+        if self.h:
+            self.lib.ptgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            e = self.lib.ptgpu_last_error(self.h)
+            raise PtgpuError(f"{what} failed ({rc}): {e.decode() if e else ''}")
+
+    def upload(self, world: HostWorld):
+        self._ck(self.lib.ptgpu_upload_scene(self.h, world.flatten()), "ptgpu_upload_scene")
+
+    def upload_flat(self, flat_ptr: int):
+        self._ck(self.lib.ptgpu_upload_scene(self.h, flat_ptr), "ptgpu_upload_scene")
+
+    def scene_bytes(self) -> int:
+        return int(self.lib.ptgpu_scene_bytes(self.h))
+
+    def render_pass(self, p: Pass, want_mean=True, out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+        if want_mean and out is None:
+            out = np.empty((p.height, p.width, 3), np.float32)
+        ptr = out.ctypes.data_as(c_float_p) if out is not None else None
+        self._ck(self.lib.ptgpu_render_pass(self.h, C.byref(p), ptr), "ptgpu_render_pass")
+        return out
+
+    def accumulate_device(self, p: Pass, d_sum_ptr: int, stream: int = 0):
+        self._ck(self.lib.ptgpu_accumulate_device(self.h, C.byref(p), C.c_void_p(d_sum_ptr), C.c_void_p(stream)),
+                 "ptgpu_accumulate_device")
+
+    def add_sample_device(self, width, height, d_sum_ptr: int, divisor: float, stream: int = 0):
+        self._ck(self.lib.ptgpu_add_sample_device(self.h, width, height, C.c_void_p(d_sum_ptr), float(divisor),
+                                                  C.c_void_p(stream)), "ptgpu_add_sample_device")
+
+    def read_buffer(self, width, height, channel=0) -> np.ndarray:
+        out = np.empty((height, width, 3), np.float32)
+        self._ck(self.lib.ptgpu_read_buffer(self.h, channel, out.ctypes.data_as(c_float_p)), "ptgpu_read_buffer")
+        return out
+
+    def reset_buffer(self):
+        self._ck(self.lib.ptgpu_reset_buffer(self.h), "ptgpu_reset_buffer")
+
+    def intersect_batch(self, o: np.ndarray, d: np.ndarray) -> dict:
+        o = np.ascontiguousarray(o, dtype=np.float32); d = np.ascontiguousarray(d, dtype=np.float32)
+        n = o.shape[0]
+        out = dict(shape=np.empty(n, np.int32), prim=np.empty(n, np.int32), t=np.empty(n, np.float64),
+                   normal=np.empty((n, 3), np.float32), position=np.empty((n, 3), np.float32),
+                   inside=np.empty(n, np.int32), material=np.empty(n, np.int32))
+        self._ck(self.lib.ptgpu_intersect_batch(
+            self.h, n, o.ctypes.data_as(c_float_p), d.ctypes.data_as(c_float_p), out["shape"].ctypes.data_as(c_int_p),
+            out["prim"].ctypes.data_as(c_int_p), out["t"].ctypes.data_as(c_double_p),
+            out["normal"].ctypes.data_as(c_float_p), out["position"].ctypes.data_as(c_float_p),
+            out["inside"].ctypes.data_as(c_int_p), out["material"].ctypes.data_as(c_int_p)), "ptgpu_intersect_batch")
+        return out
+
+    def cast_rays(self, p: Pass, x, y, fu, fv, sample):
+        x = np.ascontiguousarray(x, np.int32); y = np.ascontiguousarray(y, np.int32)
+        fu = np.ascontiguousarray(fu, np.float64); fv = np.ascontiguousarray(fv, np.float64)
+        sample = np.ascontiguousarray(sample, np.int32)
+        n = x.shape[0]
+        o = np.empty((n, 3), np.float32); d = np.empty((n, 3), np.float32)
+        self._ck(self.lib.ptgpu_cast_rays(self.h, C.byref(p), n, x.ctypes.data_as(c_int_p), y.ctypes.data_as(c_int_p),
+                                          fu.ctypes.data_as(c_double_p), fv.ctypes.data_as(c_double_p),
+                                          sample.ctypes.data_as(c_int_p), o.ctypes.data_as(c_float_p),
+                                          d.ctypes.data_as(c_float_p)), "ptgpu_cast_rays")
+        return o, d
+
+    def keyed_draw(self, seed, pass_index, pixel, sample, bits, first, depth, sub, draw_index) -> float:
+        out = C.c_double()
+        self._ck(self.lib.ptgpu_keyed_draw(self.h, seed, pass_index, pixel, sample, bits, first, depth, sub, draw_index,
+                                           C.byref(out)), "ptgpu_keyed_draw")
+        return out.value
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(self.lib.ptgpu_get_counters(self.h, C.byref(c)), "ptgpu_get_counters")
+        return c.as_dict()
+
+    def reset_counters(self):
+        self._ck(self.lib.ptgpu_reset_counters(self.h), "ptgpu_reset_counters")
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.ptgpu_set_profiling(self.h, int(on)), "ptgpu_set_profiling")

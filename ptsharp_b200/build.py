@@ -1,0 +1,60 @@
+"""Build the two in-tree shared libraries.
+
+* ``ptsharp_b200/_lib/libptgpu.so``  — csrc/ptgpu.cu, nvcc, sm_100a only (``-gencode arch=compute_100a,code=sm_100a``),
+  ``-fmad=false`` because the numeric model forbids a*b+c contraction (see csrc/pt_device.cuh), ``-lineinfo`` so ncu's
+  source page maps to our code.  cudart is linked statically, so the library loads (and exports every symbol of
+  include/ptgpu.h) on a box without a GPU; compute entry points then fail with PTGPU_E_CUDA.
+* ``ptsharp_b200/_lib/libpthost.so`` — host/*.cpp, g++, ``-ffp-contract=off``; links libptgpu.so by $ORIGIN rpath.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIBDIR = os.path.join(PKG, "_lib")
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra",
+             "-Wno-unused-parameter"]
+
+
+def _newer(srcs, out) -> bool:
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build_gpu(force=False, verbose=False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libptgpu.so")
+    srcs = [os.path.join(PKG, "csrc", "ptgpu.cu"), os.path.join(PKG, "csrc", "pt_device.cuh"),
+            os.path.join(ROOT, "include", "ptgpu.h")]
+    if force or _newer(srcs, out):
+        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0]]
+        subprocess.check_call(cmd)
+    return out
+
+
+def build_host(force=False) -> str:
+    gpu = build_gpu()
+    out = os.path.join(LIBDIR, "libpthost.so")
+    srcs = [os.path.join(PKG, "host", f) for f in ("host.cpp", "capi.cpp", "ptsharp.hpp")] + [os.path.join(ROOT, "include", "ptgpu.h")]
+    if force or _newer(srcs + [gpu], out):
+        cmd = ["g++"] + CXX_FLAGS + ["-o", out, srcs[0], srcs[1], "-L" + LIBDIR, "-lptgpu", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return build_gpu(force, verbose), build_host(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

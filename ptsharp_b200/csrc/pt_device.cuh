@@ -1,0 +1,805 @@
+// pt_device.cuh — device-side numeric model, shape intersection, kd-tree traversal and surface evaluation.
+//
+// Numeric model: PTSharp's Vector stores three FP32 lanes; Add/Sub/Mul/Div/Min/Max/MulScalar
+// compute in FP64 on widened lanes and round once to FP32 (Vector.cs:408-444); Dot/Cross/Normalize/Length are FP32
+// System.Numerics.Vector3 calls (Vector.cs:356-393); scalars (t, tsplit, Fresnel terms) are FP64.  Because FP64 has
+// >= 2*24+2 significand bits, fl32(fl64(a op b)) == fl32(a op b) for + - * / on FP32 inputs, so lane-wise ops on two
+// Vectors are plain FP32 instructions here; only Vector x double-scalar products need the FP64 multiply.
+// The file is compiled with -fmad=false: no a*b+c contraction anywhere, like the .NET JIT.
+//
+// Self-intersection: bounce and shadow rays start exactly on the surface (EPS = 1e-9 with FP32-stored
+// positions), so the rate at which a ray re-hits the surface it left is set by these roundings and is part of the
+// reference's converged image.  That is why this code mirrors the reference's arithmetic instead of using a
+// conventional FP32 tracer with an origin offset.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ptgpu.h"
+
+#define PT_D __device__ __forceinline__
+#define PT_DN __device__ __noinline__
+
+namespace pt {
+
+static constexpr double kEPS = 1e-9;            // Util.cs:11
+static constexpr double kINF = 1e9;             // Util.cs:10
+static constexpr double kHitInf = 1000000000.0; // Hit.cs:6 (1e9F is exact)
+static constexpr double kPi = 3.14159265358979323846;
+static constexpr int kSceneStack = 32;          // scene-level kd stack entries
+static constexpr int kMeshStack = 64;           // mesh-level kd stack entries
+static constexpr int kSdfValueStack = 16;
+static constexpr int kSdfPointStack = 8;
+
+// ---------------------------------------------------------------------------------------------------- vectors
+struct V3 { float x, y, z; };
+PT_D V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+PT_D V3 v3d(double x, double y, double z) { V3 r; r.x = (float)x; r.y = (float)y; r.z = (float)z; return r; }  // new Vector(double,double,double)
+PT_D V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+PT_D V3 vadd(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PT_D V3 vsub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PT_D V3 vmul(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+PT_D V3 vdiv(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+PT_D V3 vneg(V3 a) { return v3(-a.x, -a.y, -a.z); }
+PT_D V3 vmuls(V3 a, double s) { return v3d((double)a.x * s, (double)a.y * s, (double)a.z * s); }  // MulScalar
+PT_D V3 vdivs(V3 a, double s) { return v3d((double)a.x / s, (double)a.y / s, (double)a.z / s); }  // DivScalar
+PT_D float vdotf(V3 a, V3 b) { float s = a.x * b.x + a.y * b.y; return s + a.z * b.z; }           // (xx+yy)+zz, unfused
+PT_D double vdot(V3 a, V3 b) { return (double)vdotf(a, b); }
+PT_D V3 vcross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+PT_D float vlenf(V3 a) { return sqrtf(vdotf(a, a)); }
+PT_D V3 vnorm(V3 a) { float l = vlenf(a); return v3(a.x / l, a.y / l, a.z / l); }
+PT_D bool veq(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+PT_D bool vzero(V3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+PT_D float vaxis(V3 a, uint32_t axis) { return axis == 1 ? a.x : (axis == 2 ? a.y : a.z); }
+
+// System.Math.Min/Max (.NET Core 3.0+): NaN-propagating, -0 < +0.  CUDA fmin/fmax drop NaNs, so hand-written.
+PT_D double netmax(double a, double b) {
+    if (a != b) return (a != a) ? a : (b < a ? a : b);
+    return (__double2hiint(b) < 0) ? a : b;
+}
+PT_D double netmin(double a, double b) {
+    if (a != b) return (a != a) ? a : (a < b ? a : b);
+    return (__double2hiint(a) < 0) ? a : b;
+}
+PT_D float netmaxf(float a, float b) {
+    if (a != b) return (a != a) ? a : (b < a ? a : b);
+    return (__float_as_int(b) < 0) ? a : b;
+}
+PT_D float netminf(float a, float b) {
+    if (a != b) return (a != a) ? a : (a < b ? a : b);
+    return (__float_as_int(a) < 0) ? a : b;
+}
+PT_D V3 vmin(V3 a, V3 b) { return v3(netminf(a.x, b.x), netminf(a.y, b.y), netminf(a.z, b.z)); }
+PT_D V3 vmax(V3 a, V3 b) { return v3(netmaxf(a.x, b.x), netmaxf(a.y, b.y), netmaxf(a.z, b.z)); }
+
+// Ray.Position (Ray.cs:19)
+PT_D V3 ray_at(V3 o, V3 d, double t) { return vadd(o, vmuls(d, t)); }
+
+// Matrix.MulPosition / MulDirection (Matrix.cs:134-150), m row-major
+PT_D V3 mat_pos(const double* __restrict__ m, V3 b) {
+    double X = m[0] * (double)b.x + m[1] * (double)b.y + m[2] * (double)b.z + m[3];
+    double Y = m[4] * (double)b.x + m[5] * (double)b.y + m[6] * (double)b.z + m[7];
+    double Z = m[8] * (double)b.x + m[9] * (double)b.y + m[10] * (double)b.z + m[11];
+    return v3d(X, Y, Z);
+}
+PT_D V3 mat_dir(const double* __restrict__ m, V3 b) {
+    double X = m[0] * (double)b.x + m[1] * (double)b.y + m[2] * (double)b.z;
+    double Y = m[4] * (double)b.x + m[5] * (double)b.y + m[6] * (double)b.z;
+    double Z = m[8] * (double)b.x + m[9] * (double)b.y + m[10] * (double)b.z;
+    return vnorm(v3d(X, Y, Z));
+}
+// Matrix.Transpose().MulDirection (TransformedShape.cs:57): read m column-wise
+PT_D V3 mat_dir_transposed(const double* __restrict__ m, V3 b) {
+    double X = m[0] * (double)b.x + m[4] * (double)b.y + m[8] * (double)b.z;
+    double Y = m[1] * (double)b.x + m[5] * (double)b.y + m[9] * (double)b.z;
+    double Z = m[2] * (double)b.x + m[6] * (double)b.y + m[10] * (double)b.z;
+    return vnorm(v3d(X, Y, Z));
+}
+
+// ---------------------------------------------------------------------------------------------------- device scene
+struct DScene {
+    const ptgpu_shape* shapes;
+    const uint32_t* lights;
+    const ptgpu_tree* trees;
+    const ptgpu_node* nodes;
+    const uint32_t* leafItems;
+    const ptgpu_sphere* spheres;
+    const ptgpu_cube* cubes;
+    const ptgpu_plane* planes;
+    const ptgpu_cylinder* cylinders;
+    const ptgpu_mesh* meshes;
+    const float4* triGeom;          // 3 x float4 per triangle
+    const ptgpu_tri_shade* triShade;
+    const ptgpu_instance* instances;
+    const ptgpu_sdf_shape* sdfShapes;
+    const ptgpu_sdf_op* sdfOps;
+    const ptgpu_volume* volumes;
+    const ptgpu_volume_window* volumeWindows;
+    const double* volumeData;
+    const ptgpu_material* materials;
+    const ptgpu_texture* textures;
+    const float4* texels;
+    uint32_t sceneTree, numSceneShapes, numLights, numShapes;
+    double envColor[3];
+    int32_t envTexture;
+    double envTextureAngle;
+};
+
+struct HitRec {
+    double t;       // Hit.T
+    double tInner;  // object-space T of the inner hit when shape is a TransformedShape
+    int32_t shape;  // index in Scene.Shapes (top level), -1 = miss
+    int32_t prim;   // global triangle index, -1 if the hit shape is not a triangle
+};
+
+// ---------------------------------------------------------------------------------------------------- Box.Intersect
+// Box.cs:72-94
+PT_D void box_intersect(const float* __restrict__ bmin, const float* __restrict__ bmax, V3 o, V3 d, double& tmin, double& tmax) {
+    double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
+    double x1 = ((double)bmin[0] - ox) / dx, y1 = ((double)bmin[1] - oy) / dy, z1 = ((double)bmin[2] - oz) / dz;
+    double x2 = ((double)bmax[0] - ox) / dx, y2 = ((double)bmax[1] - oy) / dy, z2 = ((double)bmax[2] - oz) / dz;
+    if (x1 > x2) { double t = x1; x1 = x2; x2 = t; }
+    if (y1 > y2) { double t = y1; y1 = y2; y2 = t; }
+    if (z1 > z2) { double t = z1; z1 = z2; z2 = t; }
+    tmin = netmax(netmax(x1, y1), z1);
+    tmax = netmin(netmin(x2, y2), z2);
+}
+
+// ---------------------------------------------------------------------------------------------------- primitives
+// Sphere.cs:40-60
+PT_D double sphere_intersect(const ptgpu_sphere& s, V3 o, V3 d) {
+    V3 to = vsub(o, ld3(s.center));
+    double b = vdot(to, d);
+    double c = vdot(to, to) - s.radius * s.radius;
+    double disc = b * b - c;
+    if (disc > 0) {
+        disc = sqrt(disc);
+        double t1 = -b - disc;
+        if (t1 > kEPS) return t1;
+        double t2 = -b + disc;
+        if (t2 > kEPS) return t2;
+    }
+    return kHitInf;
+}
+// Cube.cs:35-47
+PT_D double cube_intersect(const ptgpu_cube& c, V3 o, V3 d) {
+    V3 n = vdiv(vsub(ld3(c.min), o), d);
+    V3 f = vdiv(vsub(ld3(c.max), o), d);
+    V3 n2 = vmin(n, f), f2 = vmax(n, f);
+    double t0 = netmax(netmax((double)n2.x, (double)n2.y), (double)n2.z);
+    double t1 = netmin(netmin((double)f2.x, (double)f2.y), (double)f2.z);
+    if (t0 > 0 && t0 < t1) return t0;
+    return kHitInf;
+}
+// Plane.cs:38-52
+PT_D double plane_intersect(const ptgpu_plane& p, V3 o, V3 d) {
+    V3 N = ld3(p.normal);
+    double dd = vdot(N, d);
+    if (fabs(dd) < kEPS) return kHitInf;
+    V3 a = vsub(ld3(p.point), o);
+    double t = vdot(a, N) / dd;
+    if (t < kEPS) return kHitInf;
+    return t;
+}
+// Cylinder.cs:43-111 — first test that passes wins, in the reference's order (caps, then far root, then near root).
+PT_D double cylinder_intersect(const ptgpu_cylinder& cy, V3 o, V3 d) {
+    double r = cy.radius;
+    double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
+    double tTop = (cy.z1 - oz) / dz;
+    double tBottom = (cy.z0 - oz) / dz;
+    double a = dx * dx + dy * dy;
+    double b = 2 * (ox * dx + oy * dy);
+    double c = ox * ox + oy * oy - r * r;
+    double discriminant = b * b - 4 * a * c;
+    if (tTop > kEPS && tTop > 0) {
+        V3 p = vadd(o, vmuls(d, tTop));
+        double dist = sqrt((double)p.x * (double)p.x + (double)p.y * (double)p.y);
+        if (dist <= r) return tTop;
+    }
+    if (tBottom > kEPS && tBottom > 0) {
+        V3 p = vadd(o, vmuls(d, tBottom));
+        double dist = sqrt((double)p.x * (double)p.x + (double)p.y * (double)p.y);
+        if (dist <= r) return tBottom;
+    }
+    if (discriminant >= 0) {
+        double sq = sqrt(discriminant);
+        double t1 = (-b + sq) / (2 * a);
+        double t2 = (-b - sq) / (2 * a);
+        double tl = 0;
+        bool have = false;
+        if (t1 > kEPS && t1 > 0) { tl = t1; have = true; }
+        else if (t2 > kEPS && t2 > 0) { tl = t2; have = true; }
+        if (have) {
+            V3 p = vadd(o, vmuls(d, tl));
+            double z = p.z;
+            if (z >= cy.z0 && z <= cy.z1) return tl;
+        }
+    }
+    return kHitInf;
+}
+// Triangle.cs:95-124 (e1, e2 precomputed by the host exactly as V2.Sub(V1), V3.Sub(V1))
+PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) {
+    float4 a = __ldg(g), b4 = __ldg(g + 1), c4 = __ldg(g + 2);
+    V3 v1 = v3(a.x, a.y, a.z), e1 = v3(b4.x, b4.y, b4.z), e2 = v3(c4.x, c4.y, c4.z);
+    V3 h = vcross(d, e2);
+    double det = vdot(e1, h);
+    if (det > -kEPS && det < kEPS) return kHitInf;
+    double invDet = 1.0 / det;
+    V3 s = vsub(o, v1);
+    double u = vdot(s, h) * invDet;
+    if (u < 0 || u > 1) return kHitInf;
+    V3 q = vcross(s, e1);
+    double v = vdot(d, q) * invDet;
+    if (v < 0 || (u + v) > 1) return kHitInf;
+    double t = vdot(e2, q) * invDet;
+    if (t < kEPS) return kHitInf;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------- SDF
+// Vector.LengthN (Vector.cs:359-367)
+PT_D double length_n(V3 p, double n) {
+    if (n == 2) return (double)vlenf(p);
+    double ax = fabs((double)p.x), ay = fabs((double)p.y), az = fabs((double)p.z);
+    return pow(pow(ax, n) + pow(ay, n) + pow(az, n), 1 / n);
+}
+// Evaluate the SDF program of one SDFShape at p (SDF.cs Evaluate methods, see ptgpu.h for the op encoding).
+PT_DN double sdf_evaluate(const ptgpu_sdf_op* __restrict__ prog, uint32_t count, V3 p) {
+    double vs[kSdfValueStack];
+    V3 ps[kSdfPointStack];
+    int nv = 0, np = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        const ptgpu_sdf_op& op = prog[i];
+        switch (op.op) {
+            case PTGPU_SDF_SPHERE: vs[nv++] = length_n(p, op.p[1]) - op.p[0]; break;  // SDF.cs:130-133
+            case PTGPU_SDF_CUBE: {                                                     // SDF.cs:156-188
+                double x = p.x, y = p.y, z = p.z;
+                if (x < 0) x = -x;
+                if (y < 0) y = -y;
+                if (z < 0) z = -z;
+                // Size components are Vector lanes (FP32) widened
+                x -= (double)(float)op.p[0] / 2; y -= (double)(float)op.p[1] / 2; z -= (double)(float)op.p[2] / 2;
+                double a = x;
+                if (y > a) a = y;
+                if (z > a) a = z;
+                if (a > 0) a = 0;
+                if (x < 0) x = 0;
+                if (y < 0) y = 0;
+                if (z < 0) z = 0;
+                vs[nv++] = a + sqrt(x * x + y * y + z * z);
+                break;
+            }
+            case PTGPU_SDF_CYLINDER: {  // SDF.cs:226-251
+                double x = sqrt((double)p.x * (double)p.x + (double)p.z * (double)p.z);
+                double y = p.y;
+                if (x < 0) x = -x;
+                if (y < 0) y = -y;
+                x -= op.p[0];
+                y -= op.p[1] / 2;
+                double a = x;
+                if (y > a) a = y;
+                if (a > 0) a = 0;
+                if (x < 0) x = 0;
+                if (y < 0) y = 0;
+                vs[nv++] = a + sqrt(x * x + y * y);
+                break;
+            }
+            case PTGPU_SDF_CAPSULE: {  // SDF.cs:272-278
+                V3 A = v3d(op.p[0], op.p[1], op.p[2]), B = v3d(op.p[3], op.p[4], op.p[5]);
+                V3 pa = vsub(p, A), ba = vsub(B, A);
+                double h = netmax(0, netmin(1, vdot(pa, ba) / vdot(ba, ba)));
+                vs[nv++] = length_n(vsub(pa, vmuls(ba, h)), op.p[7]) - op.p[6];
+                break;
+            }
+            case PTGPU_SDF_TORUS: {  // SDF.cs:307-311
+                V3 q = v3d(length_n(v3(p.x, p.y, 0.f), op.p[2]) - op.p[0], (double)p.z, 0.0);
+                vs[nv++] = length_n(q, op.p[3]) - op.p[1];
+                break;
+            }
+            case PTGPU_SDF_PUSH_TRANSFORM: ps[np++] = p; p = mat_pos(op.p, p); break;          // SDF.cs:340-344
+            case PTGPU_SDF_PUSH_SCALE: ps[np++] = p; p = vdivs(p, op.p[0]); break;             // SDF.cs:371-374
+            case PTGPU_SDF_PUSH_REPEAT: {                                                      // SDF.cs:549-553, Vector.cs:420-426
+                ps[np++] = p;
+                V3 st = v3d(op.p[0], op.p[1], op.p[2]);
+                double mx = (double)p.x - (double)st.x * floor((double)p.x / (double)st.x);
+                double my = (double)p.y - (double)st.y * floor((double)p.y / (double)st.y);
+                double mz = (double)p.z - (double)st.z * floor((double)p.z / (double)st.z);
+                p = vsub(v3d(mx, my, mz), vdivs(st, 2));
+                break;
+            }
+            case PTGPU_SDF_POP:
+                p = ps[--np];
+                if (op.n == 1) vs[nv - 1] = vs[nv - 1] * op.p[0];
+                break;
+            case PTGPU_SDF_UNION: {  // SDF.cs:398-412
+                int base = nv - (int)op.n;
+                double result = vs[base];
+                for (int k = 1; k < (int)op.n; k++) if (vs[base + k] < result) result = vs[base + k];
+                nv = base; vs[nv++] = result;
+                break;
+            }
+            case PTGPU_SDF_DIFFERENCE: {  // SDF.cs:452-471
+                int base = nv - (int)op.n;
+                double result = vs[base];
+                for (int k = 1; k < (int)op.n; k++) if (-vs[base + k] > result) result = -vs[base + k];
+                nv = base; vs[nv++] = result;
+                break;
+            }
+            case PTGPU_SDF_INTERSECTION: {  // SDF.cs:493-509
+                int base = nv - (int)op.n;
+                double result = vs[base];
+                for (int k = 1; k < (int)op.n; k++) if (vs[base + k] > result) result = vs[base + k];
+                nv = base; vs[nv++] = result;
+                break;
+            }
+            default: break;
+        }
+    }
+    return nv > 0 ? vs[nv - 1] : 0.0;
+}
+// SDFShape.Intersect (SDF.cs:32-76)
+PT_D double sdf_intersect(const DScene& S, const ptgpu_sdf_shape& sh, V3 o, V3 d) {
+    const double epsilon = (double)0.00001f, start = (double)0.0001f, jumpSize = (double)0.001f;
+    double t1, t2;
+    box_intersect(sh.bmin, sh.bmax, o, d, t1, t2);
+    if (t2 < t1 || t2 < 0) return kHitInf;
+    double t = netmax(start, t1);
+    bool jump = true;
+    const ptgpu_sdf_op* prog = S.sdfOps + sh.progFirst;
+    for (int i = 0; i < 1000; i++) {
+        double dist = sdf_evaluate(prog, sh.progCount, ray_at(o, d, t));
+        if (jump && dist < 0) { t -= jumpSize; jump = false; continue; }
+        if (dist < epsilon) return t;
+        if (jump && dist < jumpSize) dist = jumpSize;
+        t += dist;
+        if (t > t2) return kHitInf;
+    }
+    return kHitInf;
+}
+// SDFShape.NormalAt (SDF.cs:83-92)
+PT_D V3 sdf_normal(const DScene& S, const ptgpu_sdf_shape& sh, V3 p) {
+    const double e = 0.0001;
+    double x = p.x, y = p.y, z = p.z;
+    const ptgpu_sdf_op* prog = S.sdfOps + sh.progFirst;
+    uint32_t n = sh.progCount;
+    double nx = sdf_evaluate(prog, n, v3d(x - e, y, z)) - sdf_evaluate(prog, n, v3d(x + e, y, z));
+    double ny = sdf_evaluate(prog, n, v3d(x, y - e, z)) - sdf_evaluate(prog, n, v3d(x, y + e, z));
+    double nz = sdf_evaluate(prog, n, v3d(x, y, z - e)) - sdf_evaluate(prog, n, v3d(x, y, z + e));
+    return vnorm(v3d(nx, ny, nz));
+}
+
+// ---------------------------------------------------------------------------------------------------- Volume
+PT_D double vol_get(const ptgpu_volume& v, const double* __restrict__ data, int x, int y, int z) {  // Volume.cs:40-46
+    if (x < 0 || y < 0 || z < 0 || x >= v.w || y >= v.h || z >= v.d) return 0;
+    return __ldg(data + v.dataOffset + (size_t)x + (size_t)y * v.w + (size_t)z * v.w * v.h);
+}
+PT_DN double vol_sample(const ptgpu_volume& v, const double* __restrict__ data, double x, double y, double z) {  // Volume.cs:73-104 (index quirks kept)
+    z /= v.zscale;
+    x = ((x + 1) / 2) * (double)v.w;
+    y = ((z + 1) / 2) * (double)v.h;
+    z = ((z + 2) / 2) * (double)v.d;
+    int x0 = (int)floor(x), y0 = (int)floor(y), z0 = (int)floor(z);
+    int x1 = x0 + 1, y1 = y0 + 1, z1 = z0 + 1;
+    double v000 = vol_get(v, data, x0, y0, z0), v001 = vol_get(v, data, x0, y0, z1), v010 = vol_get(v, data, x0, y1, z0), v011 = vol_get(v, data, x0, y1, z1);
+    double v100 = vol_get(v, data, x1, y0, z0), v101 = vol_get(v, data, x1, y0, z1), v110 = vol_get(v, data, x1, y1, z0), v111 = vol_get(v, data, x1, y1, z1);
+    x -= (double)x0; y -= (double)y0; z -= (double)z0;
+    double c00 = v000 * (1 - x) + v100 * x;
+    double c01 = v001 * (1 - x) + v101 * x;
+    double c10 = v010 * (1 - x) + v110 * x;
+    double c11 = v011 * (1 - x) + v111 * x;
+    double c0 = c00 * (1 - y) + c10 * y;
+    double c1 = c01 * (1 - y) + c11 * y;
+    return c0 * (1 - z) + c1 * z;
+}
+PT_D int vol_sign(const DScene& S, const ptgpu_volume& v, V3 a) {  // Volume.cs:113-131 (`i` never advances)
+    double s = vol_sample(v, S.volumeData, (double)a.x, (double)a.y, (double)a.z);
+    for (uint32_t k = 0; k < v.windowCount; k++) {
+        const ptgpu_volume_window& w = S.volumeWindows[v.windowFirst + k];
+        if (s < w.lo) return 1;
+        if (s > w.hi) continue;
+        return 0;
+    }
+    return (int)v.windowCount + 1;
+}
+PT_D double volume_intersect(const DScene& S, const ptgpu_volume& v, V3 o, V3 d) {  // Volume.cs:169-197
+    double tmin, tmax;
+    box_intersect(v.bmin, v.bmax, o, d, tmin, tmax);
+    double step = (double)(1.0f / 512.0f);
+    double start = netmax(step, tmin);
+    int sign = -1;
+    for (double t = start; t <= tmax; t += step) {
+        int s = vol_sign(S, v, ray_at(o, d, t));
+        if (s == 0 || (sign >= 0 && s != sign)) {
+            t -= step;
+            step /= 64;
+            t += step;
+            for (int i = 0; i < 64; i++) {
+                if (vol_sign(S, v, ray_at(o, d, t)) == 0) return t - step;
+                t += step;
+            }
+        }
+        sign = s;
+    }
+    return kHitInf;
+}
+PT_D V3 volume_normal(const DScene& S, const ptgpu_volume& v, V3 p) {  // Volume.cs:138-145
+    const double eps = (double)0.001f;
+    double x = p.x, y = p.y, z = p.z;
+    const double* D = S.volumeData;
+    double nx = vol_sample(v, D, x - eps, y, z) - vol_sample(v, D, x + eps, y, z);
+    double ny = vol_sample(v, D, x, y - eps, z) - vol_sample(v, D, x, y + eps, z);
+    double nz = vol_sample(v, D, x, y, z - eps) - vol_sample(v, D, x, y, z + eps);
+    return vnorm(v3d(nx, ny, nz));
+}
+PT_D int32_t volume_material(const DScene& S, const ptgpu_volume& v, V3 p) {  // Volume.cs:147-167; -1 = `new Material()`
+    double be = (double)1e9f;
+    int32_t bm = -1;
+    double s = vol_sample(v, S.volumeData, (double)p.x, (double)p.y, (double)p.z);
+    for (uint32_t k = 0; k < v.windowCount; k++) {
+        const ptgpu_volume_window& w = S.volumeWindows[v.windowFirst + k];
+        if (s >= w.lo && s <= w.hi) return w.material;
+        double e = netmin(fabs(s - w.lo), fabs(s - w.hi));
+        if (e < be) { be = e; bm = w.material; }
+    }
+    return bm;
+}
+
+// ---------------------------------------------------------------------------------------------------- kd traversal
+// Tree.Intersect / Node.Intersect (Tree.cs:31-113) in stack form: running best with strict `<`
+// updates; on "both children" push (second, tsplit, tmax); on pop skip when best.T <= tsplit, otherwise continue with
+// tmax = Math.Min(tmax, best.T).  Comparisons are written exactly as in the reference so NaNs take the same branches.
+// `leaf(first, count)` intersects leafItems[first, first+count) in array order and updates the caller's best hit.
+template <int STACK, class LeafFn>
+PT_D void kd_traverse(const ptgpu_node* __restrict__ nodes, const ptgpu_tree& tree, V3 o, V3 d, const double& bestT, LeafFn leaf) {
+    double tmin, tmax;
+    box_intersect(tree.bmin, tree.bmax, o, d, tmin, tmax);
+    if (tmax < tmin || tmax <= 0) return;
+    uint32_t stNode[STACK];
+    double stMin[STACK], stMax[STACK];
+    int sp = 0;
+    uint32_t node = tree.root;
+    for (;;) {
+        // one 128-bit load per node
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + node));
+        const double split = __hiloint2double(raw.y, raw.x);
+        const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
+        const uint32_t axis = a & 3u;
+        if (axis == 0) {
+            leaf(a >> 2, b);
+            bool resumed = false;
+            while (sp > 0) {
+                --sp;
+                double ts = stMin[sp];
+                if (bestT <= ts) continue;  // `if (h1.T <= tsplit) return h1`
+                node = stNode[sp];
+                tmin = ts;
+                tmax = netmin(stMax[sp], bestT);
+                resumed = true;
+                break;
+            }
+            if (!resumed) return;
+            continue;
+        }
+        const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+        const double tsplit = (split - oa) / da;
+        const bool leftFirst = (oa < split) || (oa == split && da <= 0);
+        const uint32_t first = leftFirst ? (a >> 2) : b;
+        const uint32_t second = leftFirst ? b : (a >> 2);
+        if (tsplit > tmax || tsplit <= 0) node = first;
+        else if (tsplit < tmin) node = second;
+        else {
+            if (sp < STACK) { stNode[sp] = second; stMin[sp] = tsplit; stMax[sp] = tmax; sp++; }
+            node = first;
+            tmax = tsplit;
+        }
+    }
+}
+
+// Mesh.Intersect (Mesh.cs:122-125): closest triangle of the mesh's own tree, starting from NoHit.
+PT_D void mesh_intersect(const DScene& S, const ptgpu_mesh& m, V3 o, V3 d, double& tOut, int32_t& primOut) {
+    double best = kHitInf;
+    int32_t prim = -1;
+    const ptgpu_tree tree = S.trees[m.tree];
+    kd_traverse<kMeshStack>(S.nodes, tree, o, d, best, [&](uint32_t first, uint32_t count) {
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t tri = __ldg(S.leafItems + first + i);
+            double t = triangle_intersect(S.triGeom + (size_t)tri * 3, o, d);
+            if (t < best) { best = t; prim = (int32_t)tri; }  // Tree.cs:122 strict <
+        }
+    });
+    tOut = best;
+    primOut = prim;
+}
+
+// IShape.Intersect for everything except TransformedShape.
+PT_D void simple_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3 d, double& t, int32_t& prim) {
+    prim = -1;
+    switch (sh.type) {
+        case PTGPU_SPHERE: t = sphere_intersect(S.spheres[sh.data], o, d); break;
+        case PTGPU_CUBE: t = cube_intersect(S.cubes[sh.data], o, d); break;
+        case PTGPU_PLANE: t = plane_intersect(S.planes[sh.data], o, d); break;
+        case PTGPU_CYLINDER: t = cylinder_intersect(S.cylinders[sh.data], o, d); break;
+        case PTGPU_MESH: mesh_intersect(S, S.meshes[sh.data], o, d, t, prim); break;
+        case PTGPU_SDF: t = sdf_intersect(S, S.sdfShapes[sh.data], o, d); break;
+        case PTGPU_VOLUME: t = volume_intersect(S, S.volumes[sh.data], o, d); break;
+        default: t = kHitInf; break;
+    }
+}
+
+// One entry of Scene.Shapes against the ray; updates best with strict `<` (Tree.cs:122).
+PT_D void shape_intersect(const DScene& S, uint32_t si, V3 o, V3 d, HitRec& best) {
+    const ptgpu_shape sh = S.shapes[si];
+    double t, tInner = 0;
+    int32_t prim;
+    if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:43-72
+        const ptgpu_instance& inst = S.instances[sh.data];
+        V3 so = mat_pos(inst.inv, o), sd = mat_dir(inst.inv, d);  // Matrix.MulRay (Matrix.cs:153)
+        const ptgpu_shape inner = S.shapes[inst.shape];
+        simple_intersect(S, inner, so, sd, tInner, prim);
+        if (!(tInner < kHitInf)) { t = tInner; }  // `if (!hit.Ok) return hit`
+        else {
+            V3 shapePosition = ray_at(so, sd, tInner);
+            V3 position = mat_pos(inst.m, shapePosition);
+            t = (double)vlenf(vsub(position, o));  // hit.T = position.Sub(r.Origin).Length()
+        }
+    } else {
+        simple_intersect(S, sh, o, d, t, prim);
+    }
+    if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)si; best.prim = prim; }
+}
+
+// Scene.Intersect (Scene.cs:75-79) -> Tree.Intersect over Scene.Shapes.
+PT_D HitRec scene_intersect(const DScene& S, V3 o, V3 d) {
+    HitRec best;
+    best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
+    const ptgpu_tree tree = S.trees[S.sceneTree];
+    kd_traverse<kSceneStack>(S.nodes, tree, o, d, best.t, [&](uint32_t first, uint32_t count) {
+        for (uint32_t i = 0; i < count; i++) shape_intersect(S, __ldg(S.leafItems + first + i), o, d, best);
+    });
+    if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------------- textures
+struct Col { double r, g, b; };
+PT_D void modf_net(double in, int& dec, double& frac) { double tr = trunc(in); dec = (int)tr; frac = in - tr; }  // Util.cs:108-113
+PT_D double fract_net(double x) { int d; double f; modf_net(x, d, f); return f; }                                 // Texture.cs:218-222
+PT_D Col tex_bilinear(const DScene& S, const ptgpu_texture& tx, double u, double v) {  // Texture.cs:188-216
+    if (u == 1) u -= kEPS;
+    if (v == 1) v -= kEPS;
+    double w = (double)tx.width - 1, h = (double)tx.height - 1;
+    int X, Y; double x, y;
+    modf_net(u * w, X, x);
+    modf_net(v * h, Y, y);
+    int x0 = X, y0 = Y, x1 = x0 + 1, y1 = y0 + 1;
+    const float4* T = S.texels + tx.texelOffset;
+    float4 c00 = __ldg(T + (size_t)y0 * tx.width + x0), c01 = __ldg(T + (size_t)y1 * tx.width + x0);
+    float4 c10 = __ldg(T + (size_t)y0 * tx.width + x1), c11 = __ldg(T + (size_t)y1 * tx.width + x1);
+    double w00 = (1 - x) * (1 - y), w10 = x * (1 - y), w01 = (1 - x) * y, w11 = x * y;
+    Col c = {0, 0, 0};
+    c.r = c.r + (double)c00.x * w00; c.g = c.g + (double)c00.y * w00; c.b = c.b + (double)c00.z * w00;
+    c.r = c.r + (double)c10.x * w10; c.g = c.g + (double)c10.y * w10; c.b = c.b + (double)c10.z * w10;
+    c.r = c.r + (double)c01.x * w01; c.g = c.g + (double)c01.y * w01; c.b = c.b + (double)c01.z * w01;
+    c.r = c.r + (double)c11.x * w11; c.g = c.g + (double)c11.y * w11; c.b = c.b + (double)c11.z * w11;
+    return c;
+}
+PT_D Col tex_sample(const DScene& S, int32_t id, double u, double v) {  // Texture.cs:224-229
+    const ptgpu_texture tx = S.textures[id];
+    u = fract_net(fract_net(u) + 1);
+    v = fract_net(fract_net(v) + 1);
+    return tex_bilinear(S, tx, u, 1 - v);
+}
+PT_D V3 tex_normal_sample(const DScene& S, int32_t id, double u, double v) {  // Texture.cs:231-237
+    Col c = tex_sample(S, id, u, v);
+    return vnorm(v3d(c.r * 2 - 1, c.g * 2 - 1, c.b * 2 - 1));
+}
+PT_D int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+PT_D V3 tex_bump_sample(const DScene& S, int32_t id, double u, double v) {  // Texture.cs:239-251 (row read clamped)
+    const ptgpu_texture tx = S.textures[id];
+    u = fract_net(fract_net(u) + 1);
+    v = fract_net(fract_net(v) + 1);
+    v = 1 - v;
+    int x = (int)(u * tx.width), y = (int)(v * tx.height);
+    int x1 = clampi(x - 1, 0, tx.width - 1), x2 = clampi(x + 1, 0, tx.width - 1);
+    int y1 = clampi(y - 1, 0, tx.height - 1), y2 = clampi(y + 1, 0, tx.height - 1);
+    int yr = clampi(y, 0, tx.height - 1), xr = clampi(x, 0, tx.width - 1);
+    const float4* T = S.texels + tx.texelOffset;
+    double cx = (double)__ldg(T + (size_t)yr * tx.width + x1).x - (double)__ldg(T + (size_t)yr * tx.width + x2).x;
+    double cy = (double)__ldg(T + (size_t)y1 * tx.width + xr).x - (double)__ldg(T + (size_t)y2 * tx.width + xr).x;
+    return v3d(cx, cy, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------- surfaces
+struct Mat {  // Material.cs after MaterialAt
+    double cr, cg, cb;
+    double emittance, index, gloss, tint, reflectivity;
+    int32_t transparent;
+    int32_t id;
+};
+PT_D Mat mat_load(const DScene& S, int32_t id) {
+    Mat m;
+    if (id < 0) {  // `new Material()` (Mesh.cs:132-135, Volume.cs:150)
+        m.cr = m.cg = m.cb = 0; m.emittance = m.index = m.gloss = m.tint = m.reflectivity = 0; m.transparent = 0; m.id = -1;
+        return m;
+    }
+    const ptgpu_material& pm = S.materials[id];
+    m.cr = pm.color[0]; m.cg = pm.color[1]; m.cb = pm.color[2];
+    m.emittance = pm.emittance; m.index = pm.index; m.gloss = pm.gloss; m.tint = pm.tint; m.reflectivity = pm.reflectivity;
+    m.transparent = pm.transparent; m.id = id;
+    return m;
+}
+
+// Triangle.Barycentric (Triangle.cs:208-223)
+PT_D void tri_barycentric(V3 v1, V3 e1, V3 e2, V3 p, double& u, double& v, double& w) {
+    V3 v2 = vsub(p, v1);
+    double d00 = vdot(e1, e1), d01 = vdot(e1, e2), d11 = vdot(e2, e2), d20 = vdot(v2, e1), d21 = vdot(v2, e2);
+    double d = d00 * d11 - d01 * d01;
+    v = (d11 * d20 - d01 * d21) / d;
+    w = (d00 * d21 - d01 * d20) / d;
+    u = 1 - v - w;
+}
+PT_D V3 tri_blend_uv(const ptgpu_tri_shade& s, double u, double v, double w) {  // T1*u + T2*v + T3*w with Vector rounding
+    V3 t1 = v3(s.t1[0], s.t1[1], 0.f), t2 = v3(s.t2[0], s.t2[1], 0.f), t3 = v3(s.t3[0], s.t3[1], 0.f);
+    return vadd(vadd(vmuls(t1, u), vmuls(t2, v)), vmuls(t3, w));
+}
+// Triangle.NormalAt (Triangle.cs:142-189)
+PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
+    const float4* g = S.triGeom + (size_t)tri * 3;
+    float4 a = __ldg(g), b4 = __ldg(g + 1), c4 = __ldg(g + 2);
+    V3 v1 = v3(a.x, a.y, a.z), e1 = v3(b4.x, b4.y, b4.z), e2 = v3(c4.x, c4.y, c4.z);
+    const ptgpu_tri_shade& s = S.triShade[tri];
+    double u, v, w;
+    tri_barycentric(v1, e1, e2, p, u, v, w);
+    V3 n = vadd(vadd(vmuls(ld3(s.n1), u), vmuls(ld3(s.n2), v)), vmuls(ld3(s.n3), w));
+    const ptgpu_material& pm = S.materials[s.material];
+    if (pm.normalTexture >= 0) {
+        V3 b = tri_blend_uv(s, u, v, w);
+        V3 ns = tex_normal_sample(S, pm.normalTexture, (double)b.x, (double)b.y);
+        if (!vzero(ns)) {
+            V3 dt1 = v3(s.t2[0] - s.t1[0], s.t2[1] - s.t1[1], 0.f), dt2 = v3(s.t3[0] - s.t1[0], s.t3[1] - s.t1[1], 0.f);
+            V3 T = vnorm(vsub(vmuls(e1, (double)dt2.y), vmuls(e2, (double)dt1.y)));
+            V3 B = vnorm(vsub(vmuls(e2, (double)dt1.x), vmuls(e1, (double)dt2.x)));
+            V3 N = vcross(T, B);
+            double X = (double)T.x * (double)ns.x + (double)B.x * (double)ns.y + (double)N.x * (double)ns.z;
+            double Y = (double)T.y * (double)ns.x + (double)B.y * (double)ns.y + (double)N.y * (double)ns.z;
+            double Z = (double)T.z * (double)ns.x + (double)B.z * (double)ns.y + (double)N.z * (double)ns.z;
+            n = vnorm(v3d(X, Y, Z));  // Matrix.MulDirection
+        }
+    }
+    if (pm.bumpTexture >= 0) {
+        V3 b = tri_blend_uv(s, u, v, w);
+        V3 bump = tex_bump_sample(S, pm.bumpTexture, (double)b.x, (double)b.y);
+        if (!vzero(bump)) {
+            V3 dt1 = v3(s.t2[0] - s.t1[0], s.t2[1] - s.t1[1], 0.f), dt2 = v3(s.t3[0] - s.t1[0], s.t3[1] - s.t1[1], 0.f);
+            V3 tangent = vnorm(vsub(vmuls(e1, (double)dt2.y), vmuls(e2, (double)dt1.y)));
+            V3 bitangent = vnorm(vsub(vmuls(e2, (double)dt1.x), vmuls(e1, (double)dt2.x)));
+            n = vadd(n, vmuls(tangent, (double)bump.x * pm.bumpMultiplier));
+            n = vadd(n, vmuls(bitangent, (double)bump.y * pm.bumpMultiplier));
+        }
+    }
+    return vnorm(n);
+}
+
+// IShape.NormalAt for a non-transformed shape entry (prim = global triangle index for meshes).
+PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p) {
+    switch (sh.type) {
+        case PTGPU_SPHERE: return vnorm(vsub(p, ld3(S.spheres[sh.data].center)));  // Sphere.cs:78-81
+        case PTGPU_CUBE: {                                                          // Cube.cs:57-69
+            const ptgpu_cube& c = S.cubes[sh.data];
+            if (fabs((double)p.x - (double)c.min[0]) < kEPS) return v3(-1, 0, 0);
+            if (fabs((double)p.x - (double)c.max[0]) < kEPS) return v3(1, 0, 0);
+            if (fabs((double)p.y - (double)c.min[1]) < kEPS) return v3(0, -1, 0);
+            if (fabs((double)p.y - (double)c.max[1]) < kEPS) return v3(0, 1, 0);
+            if (fabs((double)p.z - (double)c.min[2]) < kEPS) return v3(0, 0, -1);
+            if (fabs((double)p.z - (double)c.max[2]) < kEPS) return v3(0, 0, 1);
+            return v3(0, 1, 0);
+        }
+        case PTGPU_PLANE: return ld3(S.planes[sh.data].normal);
+        case PTGPU_CYLINDER: {  // Cylinder.cs:122-163
+            const ptgpu_cylinder& c = S.cylinders[sh.data];
+            const double epsilon = 0.0001;
+            if (fabs((double)p.z - c.z0) > epsilon && fabs((double)p.z - c.z1) > epsilon) {
+                V3 center = v3d(0, 0, (c.z0 + c.z1) / 2);
+                V3 normal = vnorm(vsub(p, center));
+                if (vdot(normal, vsub(p, v3d(0, 0, c.z0))) < 0) normal = vneg(normal);
+                return normal;
+            }
+            if (fabs((double)p.z - c.z0) < epsilon) return v3(0, 0, -1);
+            if (fabs((double)p.z - c.z1) < epsilon) return v3(0, 0, 1);
+            return v3(0, 0, 0);
+        }
+        case PTGPU_MESH: return tri_normal(S, (uint32_t)prim, p);  // hit.Shape is the Triangle
+        case PTGPU_SDF: return sdf_normal(S, S.sdfShapes[sh.data], p);
+        case PTGPU_VOLUME: return volume_normal(S, S.volumes[sh.data], p);
+        default: return v3(0, 0, 0);
+    }
+}
+
+// Material.MaterialAt(shape, point) (Material.cs:124-138).  UVector is only evaluated when a texture needs it
+// (it has no side effects in the reference).
+PT_D Mat shape_material(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p) {
+    int32_t id = sh.material;
+    if (sh.type == PTGPU_MESH) id = S.triShade[prim].material;
+    else if (sh.type == PTGPU_VOLUME) id = volume_material(S, S.volumes[sh.data], p);
+    Mat m = mat_load(S, id);
+    if (id < 0) return m;
+    const ptgpu_material& pm = S.materials[id];
+    if (pm.texture >= 0 || pm.glossTexture >= 0) {
+        V3 uv = v3(0, 0, 0);
+        switch (sh.type) {
+            case PTGPU_SPHERE: {  // Sphere.cs:62-69 (sic: (p.X, 0, p.Y))
+                V3 q = vsub(p, ld3(S.spheres[sh.data].center));
+                double u = atan2((double)q.z, (double)q.x);
+                double v = atan2((double)q.y, (double)vlenf(v3(q.x, 0.f, q.y)));
+                u = 1 - (u + kPi) / (2 * kPi);
+                v = (v + kPi / 2) / kPi;
+                uv = v3d(u, v, 0);
+                break;
+            }
+            case PTGPU_CUBE: {  // Cube.cs:49-53
+                const ptgpu_cube& c = S.cubes[sh.data];
+                V3 q = vdiv(vsub(p, ld3(c.min)), vsub(ld3(c.max), ld3(c.min)));
+                uv = v3(q.x, q.z, 0.f);
+                break;
+            }
+            case PTGPU_CYLINDER: uv = vnorm(v3d(-(double)p.y, (double)p.x, 0)); break;  // Cylinder.cs:114-118
+            case PTGPU_MESH: {                                                           // Triangle.cs:128-136
+                const float4* g = S.triGeom + (size_t)prim * 3;
+                float4 a = __ldg(g), b4 = __ldg(g + 1), c4 = __ldg(g + 2);
+                double u, v, w;
+                tri_barycentric(v3(a.x, a.y, a.z), v3(b4.x, b4.y, b4.z), v3(c4.x, c4.y, c4.z), p, u, v, w);
+                const ptgpu_tri_shade& s = S.triShade[prim];
+                V3 n = v3(0, 0, 0);
+                n = vadd(n, vmuls(v3(s.t1[0], s.t1[1], 0.f), u));
+                n = vadd(n, vmuls(v3(s.t2[0], s.t2[1], 0.f), v));
+                n = vadd(n, vmuls(v3(s.t3[0], s.t3[1], 0.f), w));
+                uv = v3(n.x, n.y, 0.f);
+                break;
+            }
+            default: break;  // Plane / SDFShape / Volume: new Vector()
+        }
+        if (pm.texture >= 0) { Col c = tex_sample(S, pm.texture, (double)uv.x, (double)uv.y); m.cr = c.r; m.cg = c.g; m.cb = c.b; }
+        if (pm.glossTexture >= 0) { Col c = tex_sample(S, pm.glossTexture, (double)uv.x, (double)uv.y); m.gloss = (c.r + c.g + c.b) / 3; }
+    }
+    return m;
+}
+
+struct Surface {  // HitInfo (Hit.cs:58-75)
+    V3 position, normal;
+    Mat mat;
+    bool inside;
+};
+
+// Hit.Info (Hit.cs:26-55) / the HitInfo TransformedShape.Intersect pre-fills (TransformedShape.cs:52-70).
+PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
+    Surface sf;
+    const ptgpu_shape sh = S.shapes[h.shape];
+    if (sh.type == PTGPU_TRANSFORMED) {
+        const ptgpu_instance& inst = S.instances[sh.data];
+        V3 so = mat_pos(inst.inv, o), sd = mat_dir(inst.inv, d);
+        const ptgpu_shape inner = S.shapes[inst.shape];
+        V3 shapePosition = ray_at(so, sd, h.tInner);
+        V3 shapeNormal = shape_normal(S, inner, h.prim, shapePosition);
+        sf.position = mat_pos(inst.m, shapePosition);
+        V3 normal = mat_dir_transposed(inst.inv, shapeNormal);
+        sf.mat = shape_material(S, inner, h.prim, shapePosition);
+        sf.inside = false;
+        if (vdot(shapeNormal, sd) > 0) { normal = vneg(normal); sf.inside = true; }
+        sf.normal = normal;
+        return sf;
+    }
+    V3 position = ray_at(o, d, h.t);
+    V3 normal = shape_normal(S, sh, h.prim, position);
+    sf.mat = shape_material(S, sh, h.prim, position);
+    sf.inside = false;
+    if (vdot(normal, d) > 0) {
+        normal = vneg(normal);
+        sf.inside = true;
+        if (sh.type == PTGPU_VOLUME || sh.type == PTGPU_SDF) sf.inside = false;  // Hit.cs:41-47
+    }
+    sf.position = position;
+    sf.normal = normal;
+    return sf;
+}
+
+}  // namespace pt

@@ -1,0 +1,1111 @@
+// ptgpu.cu — libptgpu: the wavefront path-tracing pipeline and its C ABI (include/ptgpu.h), sm_100a only.
+//
+// Pipeline per batch of camera samples (replaces Renderer.RenderParallel's pixel/spp loops, Renderer.cs:287-311,
+// and DefaultSampler.sample's recursion, Sampler.cs:55-145, with an iterative throughput-weighted form):
+//
+//   k_raygen   Camera.CastRay (Camera.cs:98-119) + the fu/fv jitter of Renderer.cs:297-304      -> ray queue
+//   for depth = 0 .. MaxBounces:
+//     k_trace  Scene.Intersect (closest hit, kd-tree short stack)                               -> hit records
+//     k_shade  Hit.Info, emission/termination, Ray.Bounce, sampleLights ray generation          -> next ray queue,
+//              (queue appends are warp-aggregated: one atomic per coalesced group)                 shadow queue, sum
+//     k_shadow sampleLight's closest-hit identity test (Sampler.cs:262-265)                      -> sum buffer
+//   k_add_sample  c /= spp; Buffer.AddSample (Welford, Buffer.cs:33-44)
+//
+// All kernels are persistent grid-stride loops sized to the SM count and read their item counts from device memory,
+// so a pass is issued without any host synchronisation.  Random numbers: Philox4x32-10 keyed on
+// (seed, pass | pixel, sample, path node, sub-stream, draw) — see rng_enter().
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pt_device.cuh"
+
+namespace cg = cooperative_groups;
+using namespace pt;
+
+// ====================================================================================================== RNG
+struct Rng {
+    uint32_t k0, k1, c0, c1, c2, c3;
+    uint32_t draw;
+    uint32_t cache[4];
+    uint32_t cachedBlock;
+};
+PT_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+PT_D void rng_set_sample(Rng& r, uint32_t seed, uint32_t pass, uint32_t pixel, uint32_t sample) { r.k0 = seed; r.k1 = pass; r.c0 = pixel; r.c1 = sample; }
+// Counter word 3: [31:20] first-hit index+1 | [19:14] depth | [13:6] sub-stream | [5:0] block of two draws.
+// Word 2: one bit per depth >= 2 telling which BounceType branch the path took under SpecularModeAll.
+PT_D void rng_enter(Rng& r, uint32_t pathBits, uint32_t first, uint32_t depth, uint32_t sub) {
+    r.c2 = pathBits;
+    r.c3 = ((first & 0xFFFu) << 20) | ((depth & 0x3Fu) << 14) | ((sub & 0xFFu) << 6);
+    r.draw = 0;
+    r.cachedBlock = 0xFFFFFFFFu;
+}
+PT_D double rng_next(Rng& r) {  // Random.Shared.NextDouble(): 53 random bits / 2^53
+    uint32_t block = r.draw >> 1;
+    if (block != r.cachedBlock) {
+        philox4x32_10(r.c0, r.c1, r.c2, r.c3 | (block & 0x3Fu), r.k0, r.k1, r.cache);
+        r.cachedBlock = block;
+    }
+    uint32_t hi = (r.draw & 1) ? r.cache[2] : r.cache[0], lo = (r.draw & 1) ? r.cache[3] : r.cache[1];
+    r.draw++;
+    unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ====================================================================================================== sampling
+// Vector.RandomUnitVector (Vector.cs:339-347)
+PT_D V3 random_unit_vector(Rng& rng) {
+    double z = rng_next(rng) * 2.0 - 1.0;
+    double a = rng_next(rng) * 2.0 * kPi;
+    double r = sqrt(1.0 - z * z);
+    double s, c;
+    sincos(a, &s, &c);
+    return v3d(r * s, r * c, z);
+}
+// Util.Cone (Util.cs:17-32)
+PT_D V3 cone(V3 direction, double theta, double u, double v, Rng& rng) {
+    if (theta < kEPS) return direction;
+    theta = theta * (1 - (2 * acos(u) / kPi));
+    double m1, m2;
+    sincos(theta, &m1, &m2);
+    double a = v * 2 * kPi;
+    V3 q = random_unit_vector(rng);
+    V3 s = vcross(direction, q);
+    V3 t = vcross(direction, s);
+    double sa, ca;
+    sincos(a, &sa, &ca);
+    V3 d = v3(0, 0, 0);
+    d = vadd(d, vmuls(s, m1 * ca));
+    d = vadd(d, vmuls(t, m1 * sa));
+    d = vadd(d, vmuls(direction, m2));
+    return vnorm(d);
+}
+// Vector.Reflect (Vector.cs:497): n.Reflect(i) = i - n * (2 * n.i)
+PT_D V3 reflect(V3 n, V3 i) { return vsub(i, vmuls(n, 2 * vdot(n, i))); }
+// Vector.Refract (Vector.cs:500-514)
+PT_D V3 refract(V3 n, V3 i, double n1, double n2) {
+    double nr = n1 / n2;
+    double cosI = -vdot(n, i);
+    double sinT2 = nr * nr * (1 - cosI * cosI);
+    if (sinT2 > 1) return v3(0, 0, 0);
+    double cosT = sqrt(1 - sinT2);
+    return vadd(vmuls(i, nr), vmuls(n, nr * cosI - cosT));
+}
+// Vector.Reflectance (Vector.cs:517-536)
+PT_D double reflectance(V3 n, V3 i, double n1, double n2) {
+    double nr2 = (n1 * n1) / (n2 * n2);
+    double cosI = -vdot(n, i);
+    double sinT2 = nr2 * (1 - cosI * cosI);
+    if (sinT2 > 1) return 1;
+    double cosT = sqrt(1 - sinT2);
+    double a = n1 * cosI, b = n2 * cosT;
+    double rOrth = (a - b) / (a + b);
+    double rPar = (b - a) / (b + a);
+    return (rOrth * rOrth + rPar * rPar) / 2;
+}
+// Ray.Bounce (Ray.cs:44-85).  mode: BounceType (0 Any, 1 Diffuse, 2 Specular).
+PT_D void bounce(V3 rayDir, const Surface& sf, double u, double v, int mode, Rng& rng, V3& outO, V3& outD, bool& reflected, double& pOut) {
+    V3 n = sf.normal;
+    double n1 = 1.0, n2 = sf.mat.index;
+    if (sf.inside) { double t = n1; n1 = n2; n2 = t; }
+    double p = sf.mat.reflectivity >= 0 ? sf.mat.reflectivity : reflectance(n, rayDir, n1, n2);
+    bool refl = false;
+    if (mode == 0) refl = rng_next(rng) < p;
+    else if (mode == 2) refl = true;
+    if (refl) {
+        outO = sf.position;
+        outD = cone(reflect(n, rayDir), sf.mat.gloss, u, v, rng);
+        reflected = true;
+        pOut = p;
+    } else if (sf.mat.transparent) {
+        V3 rd = refract(n, rayDir, n1, n2);
+        outO = vadd(sf.position, vmuls(rd, 1e-4));  // Ray.cs:78, the only epsilon offset in the code base
+        outD = cone(rd, sf.mat.gloss, u, v, rng);
+        reflected = true;
+        pOut = 1 - p;
+    } else {  // Ray.WeightedBounce (Ray.cs:28-35)
+        double radius = sqrt(u);
+        double theta = 2 * kPi * v;
+        V3 s = vnorm(vcross(n, random_unit_vector(rng)));
+        V3 t = vcross(n, s);
+        double st, ct;
+        sincos(theta, &st, &ct);
+        V3 d = v3(0, 0, 0);
+        d = vadd(d, vmuls(s, radius * ct));
+        d = vadd(d, vmuls(t, radius * st));
+        d = vadd(d, vmuls(n, sqrt(1 - u)));
+        outO = sf.position;
+        outD = d;
+        reflected = false;
+        pOut = 1 - p;
+    }
+}
+
+// ====================================================================================================== pipeline state
+struct PassD {  // ptgpu_pass plus derived values, passed by value to kernels
+    int32_t width, height, spp, stratified, sppRoot;
+    int32_t sampleBase, sampleStride;
+    int32_t firstHitSamples, maxBounces, directLighting, softShadows, lightMode, specularMode;
+    uint32_t seed, passIndex;
+    ptgpu_camera cam;
+};
+
+struct DeviceCounters { unsigned long long cameraSamples, segments, shadowRays, nanSamples; };
+
+// Ray record: 52 bytes in three float4 streams + one u32 stream (SoA so each stream coalesces).
+//   od0 = (o.x, o.y, o.z, bits(pixel))   od1 = (d.x, d.y, d.z, bits(meta))   bt = (beta.r, beta.g, beta.b, bits(pathBits))
+//   meta = depth[5:0] | emission[6] | first[18:7]      smp = global sample index
+struct RayQueue { float4* od0; float4* od1; float4* bt; uint32_t* smp; };
+struct HitQueue { double* t; double* tInner; int32_t* shape; int32_t* prim; };
+// Shadow record: 48 bytes.  so = (o.xyz, bits(pixel))  sd = (d.xyz, bits(light shape index))  sc = (contribution rgb, 0)
+struct ShadowQueue { float4* so; float4* sd; float4* sc; };
+
+PT_D uint32_t f2u(float f) { return __float_as_uint(f); }
+PT_D float u2f(uint32_t u) { return __uint_as_float(u); }
+
+PT_D void accumulate(float* __restrict__ sum, DeviceCounters* cnt, uint32_t pixel, float r, float g, float b) {
+    if (!(isfinite(r) && isfinite(g) && isfinite(b))) { atomicAdd(&cnt->nanSamples, 1ull); return; }
+    if (r != 0.f) atomicAdd(sum + (size_t)pixel * 3 + 0, r);
+    if (g != 0.f) atomicAdd(sum + (size_t)pixel * 3 + 1, g);
+    if (b != 0.f) atomicAdd(sum + (size_t)pixel * 3 + 2, b);
+}
+
+// Camera.CastRay (Camera.cs:98-119)
+PT_D void cast_ray(const ptgpu_camera& cam, int x, int y, int w, int h, double u, double v, Rng& rng, V3& o, V3& d) {
+    double aspect = (double)w / (double)h;
+    double px = (((double)x + u - 0.5) / ((double)w - 1.0)) * 2 - 1;
+    double py = (((double)y + v - 0.5) / ((double)h - 1.0)) * 2 - 1;
+    V3 cu = ld3(cam.u), cv = ld3(cam.v), cw = ld3(cam.w), cp = ld3(cam.p);
+    V3 dir = v3(0, 0, 0);
+    dir = vadd(dir, vmuls(cu, -px * aspect));
+    dir = vadd(dir, vmuls(cv, -py));
+    dir = vadd(dir, vmuls(cw, cam.m));
+    dir = vnorm(dir);
+    V3 p = cp;
+    if (cam.apertureRadius > 0) {
+        V3 focalPoint = vadd(cp, vmuls(dir, cam.focalDistance));
+        double angle = rng_next(rng) * 2 * kPi;
+        double radius = rng_next(rng) * cam.apertureRadius;
+        double sa, ca;
+        sincos(angle, &sa, &ca);
+        p = vadd(p, vmuls(cu, ca * radius));
+        p = vadd(p, vmuls(cv, sa * radius));
+        dir = vnorm(vsub(focalPoint, p));
+    }
+    o = p;
+    d = dir;
+}
+
+// ====================================================================================================== kernels
+// K1.  Camera samples [g0, g0+n) of the pass: g -> (pixel = g % npix, slot k = g / npix), global sample index
+// sampleBase + k*sampleStride.  Non-stratified: fu = (x+xi1)/w, fv = (y+xi2)/h are passed where CastRay expects a
+// sub-pixel offset — the reference's behaviour (Renderer.cs:297-304), reproduced on purpose.
+__global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, uint32_t n, RayQueue q, uint32_t* __restrict__ count,
+                                                 DeviceCounters* cnt) {
+    const uint32_t npix = (uint32_t)P.width * (uint32_t)P.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long g = g0 + i;
+        uint32_t pixel = (uint32_t)(g % npix), k = (uint32_t)(g / npix);
+        int x = (int)(pixel % (uint32_t)P.width), y = (int)(pixel / (uint32_t)P.width);
+        uint32_t sample = (uint32_t)(P.sampleBase + (int)k * P.sampleStride);
+        Rng rng;
+        rng_set_sample(rng, P.seed, P.passIndex, pixel, sample);
+        rng_enter(rng, 0, 0, 0, 0);
+        double fu, fv;
+        if (P.stratified) {  // Renderer.cs:231-246: strata centres, no jitter; slot k -> (u, v) = (k / root, k % root)
+            uint32_t s = sample % (uint32_t)(P.sppRoot * P.sppRoot);
+            fu = ((double)(s / (uint32_t)P.sppRoot) + 0.5) / (double)P.sppRoot;
+            fv = ((double)(s % (uint32_t)P.sppRoot) + 0.5) / (double)P.sppRoot;
+        } else {
+            double xo = rng_next(rng), yo = rng_next(rng);
+            fu = ((double)x + xo) / (double)P.width;
+            fv = ((double)y + yo) / (double)P.height;
+        }
+        V3 o, d;
+        cast_ray(P.cam, x, y, P.width, P.height, fu, fv, rng, o, d);
+        q.od0[i] = make_float4(o.x, o.y, o.z, u2f(pixel));
+        q.od1[i] = make_float4(d.x, d.y, d.z, u2f(0u | (1u << 6)));  // depth 0, emission = true (Sampler.cs:42)
+        q.bt[i] = make_float4(1.f, 1.f, 1.f, u2f(0u));
+        q.smp[i] = sample;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *count = n; atomicAdd(&cnt->cameraSamples, (unsigned long long)n); }
+}
+
+// K2.  Closest hit for every queued ray.
+__global__ void __launch_bounds__(128) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, HitQueue hq, DeviceCounters* cnt) {
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = q.od0[i], b = q.od1[i];
+        HitRec h = scene_intersect(S, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z));
+        hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
+}
+
+// Light geometry used by sampleLight (Sampler.cs:215-236): Sphere -> its centre/radius; Cylinder -> (0,0,(Z0+Z1)/2),
+// Radius; anything else -> bounding box centre / outer radius.  Precomputed at upload into DLight.
+struct DLight { float center[3]; uint32_t shape; double radius; uint32_t classTyped; uint32_t isCylinder; };
+
+// K3.  One thread per hit record: Hit.Info, emission, then the (u, v, mode) loop of Sampler.cs:97-131.
+__global__ void __launch_bounds__(128) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
+                                                HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
+                                                float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow) {
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = q.od0[i], b = q.od1[i], c = q.bt[i];
+        const V3 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z);
+        const uint32_t pixel = f2u(a.w), meta = f2u(b.w), pathBits = f2u(c.w), sample = q.smp[i];
+        const uint32_t depth = meta & 63u, first = (meta >> 7) & 0xFFFu;
+        const bool emission = (meta >> 6) & 1u;
+        const float br = c.x, bg = c.y, bb = c.z;
+        HitRec h;
+        h.t = hq.t[i]; h.tInner = hq.tInner[i]; h.shape = hq.shape[i]; h.prim = hq.prim[i];
+        if (h.shape < 0) {  // sampleEnvironment (Sampler.cs:177-189)
+            double er = S.envColor[0], eg = S.envColor[1], eb = S.envColor[2];
+            if (S.envTexture >= 0) {
+                double u = atan2((double)d.z, (double)d.x) + S.envTextureAngle;
+                double v = atan2((double)d.y, (double)vlenf(v3(d.x, 0.f, d.z)));
+                u = (u + kPi) / (2 * kPi);
+                v = (v + kPi / 2) / kPi;
+                Col e = tex_sample(S, S.envTexture, u, v);
+                er = e.r; eg = e.g; eb = e.b;
+            }
+            accumulate(sum, cnt, pixel, br * (float)er, bg * (float)eg, bb * (float)eb);
+            continue;
+        }
+        const Surface sf = hit_info(S, o, d, h);
+        const int samples = depth == 0 ? P.firstHitSamples : 1;
+        const int nroot = (int)sqrt((double)samples);
+        const float invnn = 1.0f / (float)(nroot * nroot);
+        if (sf.mat.emittance > 0) {
+            if (P.directLighting && !emission) continue;  // Sampler.cs:75-78
+            float e = (float)(sf.mat.emittance * (double)samples) * invnn;  // Sampler.cs:79 then :144
+            accumulate(sum, cnt, pixel, br * (float)sf.mat.cr * e, bg * (float)sf.mat.cg * e, bb * (float)sf.mat.cb * e);
+        }
+        int ma, mb;
+        if (P.specularMode == PTGPU_SPECULAR_ALL || (depth == 0 && P.specularMode == PTGPU_SPECULAR_FIRST)) { ma = 1; mb = 2; }
+        else { ma = 0; mb = 0; }
+        Rng rng;
+        rng_set_sample(rng, P.seed, P.passIndex, pixel, sample);
+        uint32_t k = 0;
+        for (int u = 0; u < nroot; u++) {
+            for (int v = 0; v < nroot; v++) {
+                for (int mode = ma; mode <= mb; mode++, k++) {
+                    const uint32_t cFirst = depth == 0 ? (k + 1) : first;
+                    const uint32_t cBits = depth == 0 ? 0u : (pathBits | ((uint32_t)(mode - ma) << ((depth - 1) & 31u)));
+                    rng_enter(rng, cBits, cFirst, depth + 1, 0);
+                    double fu = ((double)u + rng_next(rng)) / (double)nroot;
+                    double fv = ((double)v + rng_next(rng)) / (double)nroot;
+                    V3 no, nd;
+                    bool reflected;
+                    double p;
+                    bounce(d, sf, fu, fv, mode, rng, no, nd, reflected, p);
+                    if (mode == 0) p = 1;
+                    if (!(p > 0)) continue;
+                    float wr, wg, wb;
+                    if (reflected) {  // indirect.Mix(Color.Mul(indirect), Tint) (Sampler.cs:113-114)
+                        double tint = sf.mat.tint;
+                        wr = (float)((1 - tint) + sf.mat.cr * tint); wg = (float)((1 - tint) + sf.mat.cg * tint); wb = (float)((1 - tint) + sf.mat.cb * tint);
+                    } else { wr = (float)sf.mat.cr; wg = (float)sf.mat.cg; wb = (float)sf.mat.cb; }
+                    const float pf = (float)p * invnn;
+                    const float cr = br * wr * pf, cgn = bg * wg * pf, cb = bb * wb * pf;
+                    // child path segment (traced only while depth+1 <= MaxBounces, Sampler.cs:57)
+                    const bool pushRay = (int)depth + 1 <= P.maxBounces;
+                    if (pushRay) {
+                        auto g2 = cg::coalesced_threads();
+                        uint32_t base = 0;
+                        if (g2.thread_rank() == 0) base = atomicAdd(ncount, g2.size());
+                        base = g2.shfl(base, 0);
+                        uint32_t slot = base + g2.thread_rank();
+                        if (slot < capRays) {
+                            nq.od0[slot] = make_float4(no.x, no.y, no.z, u2f(pixel));
+                            nq.od1[slot] = make_float4(nd.x, nd.y, nd.z, u2f((depth + 1) | ((reflected ? 1u : 0u) << 6) | (cFirst << 7)));
+                            nq.bt[slot] = make_float4(cr, cgn, cb, u2f(cBits));
+                            nq.smp[slot] = sample;
+                        }
+                    }
+                    // next-event estimation for diffuse bounces (Sampler.cs:122-128, 191-296)
+                    if (!reflected && P.directLighting && S.numLights > 0) {
+                        const uint32_t nL = S.numLights;
+                        const uint32_t loops = P.lightMode == PTGPU_LIGHT_ALL ? nL : 1u;
+                        const float lscale = P.lightMode == PTGPU_LIGHT_ALL ? 1.0f / (float)nL : (float)nL;
+                        for (uint32_t li = 0; li < loops; li++) {
+                            uint32_t lightIndex = li;
+                            if (P.lightMode == PTGPU_LIGHT_ALL) rng_enter(rng, cBits, cFirst, depth + 1, 1 + (li % 255u));
+                            else {
+                                rng_enter(rng, cBits, cFirst, depth + 1, 1);
+                                int idx = (int)(rng_next(rng) * (double)nL);  // Random.Shared.Next(nLights)
+                                lightIndex = (uint32_t)(idx >= (int)nL ? (int)nL - 1 : idx);
+                            }
+                            const DLight L = lights[lightIndex];
+                            const V3 center = ld3(L.center);
+                            const double radius = L.radius;
+                            V3 point = center;
+                            if (P.softShadows) {  // Sampler.cs:240-255
+                                for (;;) {
+                                    double x = rng_next(rng) * 2 - 1;
+                                    double y = rng_next(rng) * 2 - 1;
+                                    if (x * x + y * y <= 1) {
+                                        V3 l = vnorm(vsub(center, sf.position));
+                                        V3 uu = vnorm(vcross(l, random_unit_vector(rng)));
+                                        V3 vv = vcross(l, uu);
+                                        point = vadd(vadd(center, vmuls(uu, x * radius)), vmuls(vv, y * radius));
+                                        break;
+                                    }
+                                }
+                            }
+                            V3 rayDirection = vnorm(vsub(point, sf.position));
+                            double diffuse = vdot(rayDirection, sf.normal);
+                            if (diffuse <= 0) continue;
+                            if (!L.classTyped) continue;  // `hit.Shape != light` is always true for struct shapes
+                            double coverage;
+                            if (L.isCylinder) coverage = 1.0;
+                            else {  // Sampler.cs:277-288
+                                double hyp = (double)vlenf(vsub(center, sf.position));
+                                double theta = asin(radius / hyp);
+                                double adj = radius / tan(theta);
+                                double st, ct;
+                                sincos(theta, &st, &ct);
+                                double dd = ct * adj, rr = st * adj;
+                                coverage = (rr * rr) / (dd * dd);
+                                if (hyp < radius) coverage = 1;
+                                coverage = netmin(coverage, 1);
+                            }
+                            const ptgpu_shape lsh = S.shapes[L.shape];
+                            Mat lm = shape_material(S, lsh, -1, point);  // Material.MaterialAt(light, point)
+                            float m = (float)(lm.emittance * diffuse * coverage) * lscale;
+                            auto g3 = cg::coalesced_threads();
+                            uint32_t base = 0;
+                            if (g3.thread_rank() == 0) base = atomicAdd(scount, g3.size());
+                            base = g3.shfl(base, 0);
+                            uint32_t slot = base + g3.thread_rank();
+                            if (slot < capShadow) {
+                                sq.so[slot] = make_float4(sf.position.x, sf.position.y, sf.position.z, u2f(pixel));
+                                sq.sd[slot] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, u2f(L.shape));
+                                sq.sc[slot] = make_float4(cr * (float)lm.cr * m, cgn * (float)lm.cg * m, cb * (float)lm.cb * m, 0.f);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// K4.  sampleLight's visibility test: closest hit, then identity with the light (Sampler.cs:261-265).
+__global__ void __launch_bounds__(128) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, float* __restrict__ sum,
+                                                 DeviceCounters* cnt) {
+    uint32_t n = *scount;
+    if (n > capShadow) n = capShadow;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = sq.so[i], b = sq.sd[i];
+        HitRec h = scene_intersect(S, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z));
+        if (h.shape >= 0 && (uint32_t)h.shape == f2u(b.w)) {
+            float4 c = sq.sc[i];
+            accumulate(sum, cnt, f2u(a.w), c.x, c.y, c.z);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
+}
+
+__global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
+    if (*count > cap) { *overflow = 1; *count = cap; }
+}
+
+// K5.  c /= spp; Buffer.AddSample (Renderer.cs:307-309, Buffer.cs:33-44), Welford state in FP64 like Colour.
+struct PixelBuf { double* M; double* V; int32_t* samples; };
+__global__ void k_add_sample(const float* __restrict__ sum, double divisor, uint32_t npix, PixelBuf pb, float* __restrict__ meanOut) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        int32_t ns = pb.samples[i] + 1;
+        pb.samples[i] = ns;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double s = (double)sum[(size_t)i * 3 + c] / divisor;
+            if (meanOut) meanOut[(size_t)i * 3 + c] = (float)s;
+            if (ns == 1) { pb.M[(size_t)i * 3 + c] = s; continue; }
+            double m = pb.M[(size_t)i * 3 + c];
+            double M2 = m + (s - m) / (double)ns;
+            pb.M[(size_t)i * 3 + c] = M2;
+            pb.V[(size_t)i * 3 + c] = pb.V[(size_t)i * 3 + c] + (s - m) * (s - M2);
+        }
+    }
+}
+// Buffer.Color / Variance / StandardDeviation / Samples (Buffer.cs:46-57, 126-132)
+__global__ void k_read_buffer(PixelBuf pb, int channel, uint32_t npix, float* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        int32_t ns = pb.samples[i];
+        for (int c = 0; c < 3; c++) {
+            double v;
+            if (channel == 0) v = pb.M[(size_t)i * 3 + c];
+            else if (channel == 3) v = (double)ns;
+            else {
+                v = ns < 2 ? 0.0 : pb.V[(size_t)i * 3 + c] / (double)(ns - 1);
+                if (channel == 2) v = pow(v, (double)0.5f);
+            }
+            out[(size_t)i * 3 + c] = (float)v;
+        }
+    }
+}
+
+// K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays.
+__global__ void k_intersect_batch(DScene S, int n, const float* __restrict__ o3, const float* __restrict__ d3, int32_t* shape, int32_t* prim, double* t,
+                                  float* normal3, float* position3, int32_t* inside, int32_t* material, const uint32_t* __restrict__ triFirstOfMeshShape) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+        HitRec h = scene_intersect(S, o, d);
+        shape[i] = h.shape;
+        t[i] = h.t;
+        int32_t localPrim = -1;
+        V3 nn = v3(0, 0, 0), pp = v3(0, 0, 0);
+        int32_t ins = 0, mat = -1;
+        if (h.shape >= 0) {
+            if (h.prim >= 0) {  // report the triangle's index inside its mesh (Mesh.Triangles[])
+                ptgpu_shape sh = S.shapes[h.shape];
+                if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+                localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
+            }
+            Surface sf = hit_info(S, o, d, h);
+            nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+        }
+        prim[i] = localPrim;
+        if (normal3) { normal3[3 * i] = nn.x; normal3[3 * i + 1] = nn.y; normal3[3 * i + 2] = nn.z; }
+        if (position3) { position3[3 * i] = pp.x; position3[3 * i + 1] = pp.y; position3[3 * i + 2] = pp.z; }
+        if (inside) inside[i] = ins;
+        if (material) material[i] = mat;
+    }
+}
+__global__ void k_cast_rays(PassD P, int n, const int32_t* x, const int32_t* y, const double* fu, const double* fv, const int32_t* sample, float* o3, float* d3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Rng rng;
+        rng_set_sample(rng, P.seed, P.passIndex, (uint32_t)(y[i] * P.width + x[i]), (uint32_t)sample[i]);
+        rng_enter(rng, 0, 0, 0, 0);
+        rng_next(rng); rng_next(rng);  // the jitter draws come first in the stream
+        V3 o, d;
+        cast_ray(P.cam, x[i], y[i], P.width, P.height, fu[i], fv[i], rng, o, d);
+        o3[3 * i] = o.x; o3[3 * i + 1] = o.y; o3[3 * i + 2] = o.z;
+        d3[3 * i] = d.x; d3[3 * i + 1] = d.y; d3[3 * i + 2] = d.z;
+    }
+}
+__global__ void k_keyed_draw(uint32_t seed, uint32_t pass, uint32_t pixel, uint32_t sample, uint32_t bits, uint32_t first, uint32_t depth, uint32_t sub,
+                             uint32_t drawIndex, double* out) {
+    Rng rng;
+    rng_set_sample(rng, seed, pass, pixel, sample);
+    rng_enter(rng, bits, first, depth, sub);
+    double v = 0;
+    for (uint32_t i = 0; i <= drawIndex; i++) v = rng_next(rng);
+    *out = v;
+}
+
+// ====================================================================================================== host side
+struct ptgpu_ctx {
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    // scene
+    std::vector<void*> sceneAllocs;
+    DScene scene{};
+    DLight* dLights = nullptr;
+    bool haveScene = false;
+    uint64_t sceneBytes = 0;
+    // queues
+    uint64_t capRays = 0, capShadow = 0;
+    RayQueue rq[2]{};
+    HitQueue hq{};
+    ShadowQueue sq{};
+    uint32_t* dCounts = nullptr;  // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag
+    DeviceCounters* dCounters = nullptr;
+    // image state
+    int bufW = 0, bufH = 0;
+    float* dSum = nullptr;
+    float* dMean = nullptr;
+    PixelBuf pb{};
+    // stats
+    uint64_t launches = 0;
+    double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+};
+
+static std::string g_createError;
+static std::mutex g_mu;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            return PTGPU_E_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static int fail(ptgpu_ctx* ctx, int code, const std::string& msg) {
+    ctx->error = msg;
+    return code;
+}
+
+template <class T>
+static int upload(ptgpu_ctx* ctx, const T* host, uint64_t count, const T** dev) {
+    *dev = nullptr;
+    uint64_t bytes = (count ? count : 1) * sizeof(T);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    ctx->sceneAllocs.push_back(p);
+    ctx->sceneBytes += count * sizeof(T);
+    if (count) CK(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = reinterpret_cast<const T*>(p);
+    return PTGPU_OK;
+}
+
+static void free_scene(ptgpu_ctx* ctx) {
+    for (void* p : ctx->sceneAllocs) cudaFree(p);
+    ctx->sceneAllocs.clear();
+    ctx->haveScene = false;
+    ctx->sceneBytes = 0;
+    ctx->dLights = nullptr;
+}
+static void free_queues(ptgpu_ctx* ctx) {
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->rq[i].od0); cudaFree(ctx->rq[i].od1); cudaFree(ctx->rq[i].bt); cudaFree(ctx->rq[i].smp); ctx->rq[i] = RayQueue{}; }
+    cudaFree(ctx->hq.t); cudaFree(ctx->hq.tInner); cudaFree(ctx->hq.shape); cudaFree(ctx->hq.prim); ctx->hq = HitQueue{};
+    cudaFree(ctx->sq.so); cudaFree(ctx->sq.sd); cudaFree(ctx->sq.sc); ctx->sq = ShadowQueue{};
+    ctx->capShadow = 0;
+}
+static void free_image(ptgpu_ctx* ctx) {
+    cudaFree(ctx->dSum); cudaFree(ctx->dMean); cudaFree(ctx->pb.M); cudaFree(ctx->pb.V); cudaFree(ctx->pb.samples);
+    ctx->dSum = ctx->dMean = nullptr; ctx->pb = PixelBuf{}; ctx->bufW = ctx->bufH = 0;
+}
+
+static int grid_for(ptgpu_ctx* ctx, int blocksPerSM) { return ctx->numSMs * blocksPerSM; }
+
+extern "C" {
+
+int ptgpu_abi_version(void) { return PTGPU_ABI_VERSION; }
+
+const char* ptgpu_last_error(ptgpu_ctx* ctx) {
+    if (ctx) return ctx->error.c_str();
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_createError.c_str();
+}
+
+int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
+    if (!out) return PTGPU_E_ARG;
+    *out = nullptr;
+    int dev = params ? params->device : 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_createError = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (libptgpu has no CPU fallback)";
+        return PTGPU_E_CUDA;
+    }
+    if (dev < 0 || dev >= ndev) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_createError = "device ordinal out of range";
+        return PTGPU_E_ARG;
+    }
+    ptgpu_ctx* ctx = new ptgpu_ctx();
+    ctx->device = dev;
+    auto bail = [&](const char* what, cudaError_t err) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_createError = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return PTGPU_E_CUDA;
+    };
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    ctx->numSMs = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB);
+    ctx->capRays = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 24);
+    if (ctx->capRays > (1ull << 30)) ctx->capRays = 1ull << 30;
+    if ((e = cudaMalloc(&ctx->dCounts, 8 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->dCounters, sizeof(DeviceCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(ctx->dCounts, 0, 8 * sizeof(uint32_t));
+    cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters));
+    *out = ctx;
+    return PTGPU_OK;
+}
+
+void ptgpu_destroy(ptgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_queues(ctx);
+    free_image(ctx);
+    cudaFree(ctx->dCounts);
+    cudaFree(ctx->dCounters);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+uint64_t ptgpu_scene_bytes(ptgpu_ctx* ctx) { return ctx ? ctx->sceneBytes : 0; }
+
+int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
+    if (!ctx || !s) return PTGPU_E_ARG;
+    if (s->abiVersion != PTGPU_ABI_VERSION) return fail(ctx, PTGPU_E_ARG, "flat scene ABI version mismatch");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    // limits the kernels were compiled with
+    for (uint32_t i = 0; i < s->numTrees; i++) {
+        uint32_t lim = (i == s->sceneTree) ? (uint32_t)kSceneStack : (uint32_t)kMeshStack;
+        if (s->trees[i].maxDepth >= lim) return fail(ctx, PTGPU_E_LIMIT, "kd-tree deeper than the traversal stack (" + std::to_string(s->trees[i].maxDepth) + ")");
+    }
+    for (uint32_t i = 0; i < s->numInstances; i++)
+        if (s->shapes[s->instances[i].shape].type == PTGPU_TRANSFORMED) return fail(ctx, PTGPU_E_ARG, "nested TransformedShape is not supported");
+    for (uint32_t i = 0; i < s->numSdfShapes; i++) {  // validate SDF programs against the device stacks
+        int nv = 0, np = 0;
+        for (uint32_t k = 0; k < s->sdfShapes[i].progCount; k++) {
+            const ptgpu_sdf_op& op = s->sdfOps[s->sdfShapes[i].progFirst + k];
+            if (op.op >= PTGPU_SDF_SPHERE && op.op <= PTGPU_SDF_TORUS) nv++;
+            else if (op.op >= PTGPU_SDF_PUSH_TRANSFORM && op.op <= PTGPU_SDF_PUSH_REPEAT) np++;
+            else if (op.op == PTGPU_SDF_POP) np--;
+            else if (op.op >= PTGPU_SDF_UNION && op.op <= PTGPU_SDF_INTERSECTION) nv -= (int)op.n - 1;
+            else return fail(ctx, PTGPU_E_ARG, "unknown SDF op");
+            if (nv > kSdfValueStack || np > kSdfPointStack || nv < 0 || np < 0) return fail(ctx, PTGPU_E_LIMIT, "SDF program exceeds the evaluation stacks");
+        }
+        if (nv != 1) return fail(ctx, PTGPU_E_ARG, "SDF program does not reduce to one value");
+    }
+    DScene& D = ctx->scene;
+    std::memset(&D, 0, sizeof(D));
+    int rc;
+#define UP(field, src, cnt) if ((rc = upload(ctx, src, cnt, &D.field)) != PTGPU_OK) return rc
+    UP(shapes, s->shapes, s->numShapes);
+    UP(lights, s->lights, s->numLights);
+    UP(trees, s->trees, s->numTrees);
+    UP(nodes, s->nodes, s->numNodes);
+    UP(leafItems, s->leafItems, s->numLeafItems);
+    UP(spheres, s->spheres, s->numSpheres);
+    UP(cubes, s->cubes, s->numCubes);
+    UP(planes, s->planes, s->numPlanes);
+    UP(cylinders, s->cylinders, s->numCylinders);
+    UP(meshes, s->meshes, s->numMeshes);
+    {
+        const float4* g = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(s->triGeom), s->numTriangles * 3, &g)) != PTGPU_OK) return rc;
+        D.triGeom = g;
+    }
+    UP(triShade, s->triShade, s->numTriangles);
+    UP(instances, s->instances, s->numInstances);
+    UP(sdfShapes, s->sdfShapes, s->numSdfShapes);
+    UP(sdfOps, s->sdfOps, s->numSdfOps);
+    UP(volumes, s->volumes, s->numVolumes);
+    UP(volumeWindows, s->volumeWindows, s->numVolumeWindows);
+    UP(volumeData, s->volumeData, s->numVolumeData);
+    UP(materials, s->materials, s->numMaterials);
+    UP(textures, s->textures, s->numTextures);
+    {
+        const float4* t = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(s->texels), s->numTexels, &t)) != PTGPU_OK) return rc;
+        D.texels = t;
+    }
+#undef UP
+    D.sceneTree = s->sceneTree; D.numSceneShapes = s->numSceneShapes; D.numLights = s->numLights; D.numShapes = s->numShapes;
+    D.envColor[0] = s->envColor[0]; D.envColor[1] = s->envColor[1]; D.envColor[2] = s->envColor[2];
+    D.envTexture = s->envTexture; D.envTextureAngle = s->envTextureAngle;
+    // Light geometry (Sampler.cs:215-236), evaluated once with the reference's Vector rounding.
+    std::vector<DLight> lights(s->numLights);
+    for (uint32_t i = 0; i < s->numLights; i++) {
+        const ptgpu_shape& sh = s->shapes[s->lights[i]];
+        DLight L;
+        std::memset(&L, 0, sizeof(L));
+        L.shape = s->lights[i];
+        L.classTyped = sh.flags & 1u;
+        if (sh.type == PTGPU_SPHERE) {
+            const ptgpu_sphere& sp = s->spheres[sh.data];
+            L.center[0] = sp.center[0]; L.center[1] = sp.center[1]; L.center[2] = sp.center[2];
+            L.radius = sp.radius;
+        } else if (sh.type == PTGPU_CYLINDER) {
+            const ptgpu_cylinder& cy = s->cylinders[sh.data];
+            L.center[2] = (float)((cy.z0 + cy.z1) / 2); L.radius = cy.radius; L.isCylinder = 1;
+        } else {
+            float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+            if (sh.type == PTGPU_CUBE) { std::memcpy(mn, s->cubes[sh.data].min, 12); std::memcpy(mx, s->cubes[sh.data].max, 12); }
+            else if (sh.type == PTGPU_PLANE) { for (int k = 0; k < 3; k++) { mn[k] = -1e9f; mx[k] = 1e9f; } }
+            else if (sh.type == PTGPU_SDF) { std::memcpy(mn, s->sdfShapes[sh.data].bmin, 12); std::memcpy(mx, s->sdfShapes[sh.data].bmax, 12); }
+            else if (sh.type == PTGPU_VOLUME) { std::memcpy(mn, s->volumes[sh.data].bmin, 12); std::memcpy(mx, s->volumes[sh.data].bmax, 12); }
+            // struct-typed lights (Mesh, TransformedShape) never pass the identity test; geometry is irrelevant
+            // Box.Center / OuterRadius (Box.cs:46-50): Min + (Max-Min)*0.5 ; |Min - Center|
+            float c[3], dlt[3];
+            for (int k = 0; k < 3; k++) {
+                float size = mx[k] - mn[k];
+                float half = (float)((double)size * 0.5);
+                c[k] = mn[k] + half;
+                dlt[k] = mn[k] - c[k];
+            }
+            float s2 = dlt[0] * dlt[0] + dlt[1] * dlt[1];
+            s2 = s2 + dlt[2] * dlt[2];
+            L.center[0] = c[0]; L.center[1] = c[1]; L.center[2] = c[2];
+            L.radius = (double)std::sqrt(s2);
+        }
+        lights[i] = L;
+    }
+    {
+        const DLight* dl = nullptr;
+        if ((rc = upload(ctx, lights.data(), lights.size(), &dl)) != PTGPU_OK) return rc;
+        ctx->dLights = const_cast<DLight*>(dl);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->haveScene = true;
+    return PTGPU_OK;
+}
+
+static int ensure_queues(ptgpu_ctx* ctx, uint64_t capShadow) {
+    if (!ctx->rq[0].od0) {
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMalloc(&ctx->rq[i].od0, ctx->capRays * sizeof(float4)));
+            CK(cudaMalloc(&ctx->rq[i].od1, ctx->capRays * sizeof(float4)));
+            CK(cudaMalloc(&ctx->rq[i].bt, ctx->capRays * sizeof(float4)));
+            CK(cudaMalloc(&ctx->rq[i].smp, ctx->capRays * sizeof(uint32_t)));
+        }
+        CK(cudaMalloc(&ctx->hq.t, ctx->capRays * sizeof(double)));
+        CK(cudaMalloc(&ctx->hq.tInner, ctx->capRays * sizeof(double)));
+        CK(cudaMalloc(&ctx->hq.shape, ctx->capRays * sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->hq.prim, ctx->capRays * sizeof(int32_t)));
+    }
+    if (capShadow > ctx->capShadow) {
+        cudaFree(ctx->sq.so); cudaFree(ctx->sq.sd); cudaFree(ctx->sq.sc);
+        ctx->sq = ShadowQueue{};
+        CK(cudaMalloc(&ctx->sq.so, capShadow * sizeof(float4)));
+        CK(cudaMalloc(&ctx->sq.sd, capShadow * sizeof(float4)));
+        CK(cudaMalloc(&ctx->sq.sc, capShadow * sizeof(float4)));
+        ctx->capShadow = capShadow;
+    }
+    return PTGPU_OK;
+}
+
+static int ensure_image(ptgpu_ctx* ctx, int w, int h) {
+    if (ctx->bufW == w && ctx->bufH == h && ctx->dSum) return PTGPU_OK;
+    free_image(ctx);
+    size_t npix = (size_t)w * h;
+    CK(cudaMalloc(&ctx->dSum, npix * 3 * sizeof(float)));
+    CK(cudaMalloc(&ctx->dMean, npix * 3 * sizeof(float)));
+    CK(cudaMalloc(&ctx->pb.M, npix * 3 * sizeof(double)));
+    CK(cudaMalloc(&ctx->pb.V, npix * 3 * sizeof(double)));
+    CK(cudaMalloc(&ctx->pb.samples, npix * sizeof(int32_t)));
+    CK(cudaMemsetAsync(ctx->pb.M, 0, npix * 3 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->pb.V, 0, npix * 3 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->pb.samples, 0, npix * sizeof(int32_t), ctx->stream));
+    ctx->bufW = w; ctx->bufH = h;
+    return PTGPU_OK;
+}
+
+static int make_passd(ptgpu_ctx* ctx, const ptgpu_pass* p, PassD& P) {
+    if (p->width <= 1 || p->height <= 1 || p->spp <= 0) return fail(ctx, PTGPU_E_ARG, "width/height must be > 1 and spp > 0");
+    if (p->maxBounces < 0 || p->maxBounces > 62) return fail(ctx, PTGPU_E_LIMIT, "maxBounces must be in [0, 62]");
+    if (p->firstHitSamples < 1) return fail(ctx, PTGPU_E_ARG, "firstHitSamples must be >= 1");
+    int nroot = (int)std::sqrt((double)p->firstHitSamples);
+    int modes0 = (p->specularMode == PTGPU_SPECULAR_NAIVE) ? 1 : 2;
+    if (nroot * nroot * modes0 > 4094) return fail(ctx, PTGPU_E_LIMIT, "firstHitSamples too large for the 12-bit first-hit index");
+    P.width = p->width; P.height = p->height; P.spp = p->spp; P.stratified = p->stratified;
+    P.sppRoot = (int)std::sqrt((double)p->spp);
+    P.sampleBase = p->sampleBase; P.sampleStride = p->sampleStride ? p->sampleStride : 1;
+    P.firstHitSamples = p->firstHitSamples; P.maxBounces = p->maxBounces; P.directLighting = p->directLighting;
+    P.softShadows = p->softShadows; P.lightMode = p->lightMode; P.specularMode = p->specularMode;
+    P.seed = p->seed; P.passIndex = p->passIndex; P.cam = p->camera;
+    return PTGPU_OK;
+}
+
+// Issue every kernel of one pass on `stream`, adding radiance into d_sum.  nSlots = samples per pixel rendered.
+static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cudaStream_t stream) {
+    const uint64_t npix = (uint64_t)P.width * P.height;
+    const uint64_t total = npix * (uint64_t)nSlots;
+    // worst-case queue growth per camera sample: n^2 * modes at depth 0, x modes per later depth
+    const int nroot = (int)std::sqrt((double)P.firstHitSamples);
+    const uint64_t modes0 = (P.specularMode == PTGPU_SPECULAR_NAIVE) ? 1 : 2;
+    const uint64_t modesN = (P.specularMode == PTGPU_SPECULAR_ALL) ? 2 : 1;
+    uint64_t grow = 1, maxGrow = 1;
+    for (int depth = 0; depth < P.maxBounces; depth++) {
+        grow *= (depth == 0) ? (uint64_t)nroot * nroot * modes0 : modesN;
+        if (grow > maxGrow) maxGrow = grow;
+        if (maxGrow > ctx->capRays) break;
+    }
+    // shadow rays spawned by one shade pass <= children of that pass * lights sampled per child
+    const uint64_t lightsPer = (P.directLighting && ctx->scene.numLights) ? (P.lightMode == PTGPU_LIGHT_ALL ? ctx->scene.numLights : 1) : 0;
+    uint64_t childGrow = maxGrow;
+    {   // children of the deepest shade pass are not traced but still do NEE
+        uint64_t g = 1;
+        for (int depth = 0; depth <= P.maxBounces; depth++) { g *= (depth == 0) ? (uint64_t)nroot * nroot * modes0 : modesN; if (g > childGrow) childGrow = g; if (g > (1ull << 40)) break; }
+    }
+    uint64_t batch = ctx->capRays / maxGrow;
+    if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's branching factor");
+    if (batch > total) batch = total;
+    uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
+    const uint64_t shadowCeil = ctx->capRays * 4;
+    if (capShadow > shadowCeil) {  // shrink the batch so the shadow queue stays bounded
+        batch = shadowCeil / (childGrow * (lightsPer ? lightsPer : 1));
+        if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's light count");
+        capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
+    }
+    if (capShadow == 0) capShadow = 1;
+    int rc = ensure_queues(ctx, capShadow);
+    if (rc != PTGPU_OK) return rc;
+
+    const int gridTrace = grid_for(ctx, 8), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
+    uint32_t* counts = ctx->dCounts;
+    const bool prof = ctx->profiling;
+    float ms = 0;
+    if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; }
+    for (uint64_t g0 = 0; g0 < total; g0 += batch) {
+        uint32_t n = (uint32_t)std::min<uint64_t>(batch, total - g0);
+        int cur = 0;
+        if (prof) cudaEventRecord(ctx->evA, stream);
+        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, ctx->rq[0], counts + 0, ctx->dCounters);
+        ctx->launches++;
+        if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->raygenMs += ms; }
+        for (int depth = 0; depth <= P.maxBounces; depth++) {
+            CK(cudaMemsetAsync(counts + (cur ^ 1), 0, sizeof(uint32_t), stream));
+            CK(cudaMemsetAsync(counts + 2, 0, sizeof(uint32_t), stream));
+            if (prof) cudaEventRecord(ctx->evA, stream);
+            k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, ctx->hq, ctx->dCounters);
+            if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
+            k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, ctx->rq[cur], counts + cur, ctx->hq, ctx->rq[cur ^ 1], counts + (cur ^ 1),
+                                                   ctx->sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)ctx->capRays, (uint32_t)ctx->capShadow);
+            k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)ctx->capRays, counts + 3);
+            if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
+            ctx->launches += 3;
+            if (lightsPer) {
+                k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->sq, counts + 2, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters);
+                ctx->launches++;
+                if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
+            }
+            cur ^= 1;
+        }
+    }
+    CK(cudaGetLastError());
+    return PTGPU_OK;
+}
+
+int ptgpu_accumulate_device(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* d_sum_rgb, void* stream) {
+    if (!ctx || !pass || !d_sum_rgb) return PTGPU_E_ARG;
+    if (!ctx->haveScene) return fail(ctx, PTGPU_E_STATE, "no scene uploaded");
+    CK(cudaSetDevice(ctx->device));
+    PassD P;
+    int rc = make_passd(ctx, pass, P);
+    if (rc != PTGPU_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    CK(cudaEventRecord(ctx->ev0, st));
+    int nSlots = P.stratified ? P.sppRoot * P.sppRoot : P.spp;
+    rc = run_pass(ctx, P, nSlots, d_sum_rgb, st);
+    if (rc != PTGPU_OK) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    return PTGPU_OK;
+}
+
+int ptgpu_add_sample_device(ptgpu_ctx* ctx, int32_t width, int32_t height, const float* d_sum_rgb, double divisor, void* stream) {
+    if (!ctx || !d_sum_rgb) return PTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_image(ctx, width, height);
+    if (rc != PTGPU_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (st != ctx->stream) CK(cudaStreamSynchronize(ctx->stream));  // buffer allocation memsets
+    k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(d_sum_rgb, divisor, (uint32_t)((size_t)width * height), ctx->pb, ctx->dMean);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PTGPU_OK;
+}
+
+int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rgb) {
+    if (!ctx || !pass) return PTGPU_E_ARG;
+    if (!ctx->haveScene) return fail(ctx, PTGPU_E_STATE, "no scene uploaded");
+    CK(cudaSetDevice(ctx->device));
+    PassD P;
+    int rc = make_passd(ctx, pass, P);
+    if (rc != PTGPU_OK) return rc;
+    rc = ensure_image(ctx, P.width, P.height);
+    if (rc != PTGPU_OK) return rc;
+    const size_t npix = (size_t)P.width * P.height;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev0, st));
+    if (P.stratified) {
+        // Renderer.cs:231-246: every stratum sample is its own Buffer.AddSample
+        int nn = P.sppRoot * P.sppRoot;
+        for (int k = 0; k < nn; k++) {
+            PassD Q = P;
+            Q.sampleBase = P.sampleBase + k * P.sampleStride;
+            CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
+            rc = run_pass(ctx, Q, 1, ctx->dSum, st);
+            if (rc != PTGPU_OK) return rc;
+            k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, 1.0, (uint32_t)npix, ctx->pb, ctx->dMean);
+            ctx->launches++;
+        }
+    } else {
+        CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
+        rc = run_pass(ctx, P, P.spp, ctx->dSum, st);
+        if (rc != PTGPU_OK) return rc;
+        k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, (double)P.spp, (uint32_t)npix, ctx->pb, ctx->dMean);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    if (out_mean_rgb) CK(cudaMemcpyAsync(out_mean_rgb, ctx->dMean, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->lastPassMs = ms;
+    uint32_t overflow = 0;
+    CK(cudaMemcpy(&overflow, ctx->dCounts + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (overflow) return fail(ctx, PTGPU_E_LIMIT, "ray queue overflow (internal sizing error)");
+    return PTGPU_OK;
+}
+
+int ptgpu_read_buffer(ptgpu_ctx* ctx, int32_t channel, float* out_rgb) {
+    if (!ctx || !out_rgb || channel < 0 || channel > 3) return PTGPU_E_ARG;
+    if (!ctx->dSum) return fail(ctx, PTGPU_E_STATE, "no pass rendered yet");
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)ctx->bufW * ctx->bufH;
+    float* tmp = nullptr;
+    CK(cudaMalloc(&tmp, npix * 3 * sizeof(float)));
+    k_read_buffer<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pb, channel, (uint32_t)npix, tmp);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out_rgb, tmp, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    CK(e);
+    return PTGPU_OK;
+}
+
+int ptgpu_reset_buffer(ptgpu_ctx* ctx) {
+    if (!ctx) return PTGPU_E_ARG;
+    if (!ctx->dSum) return PTGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)ctx->bufW * ctx->bufH;
+    CK(cudaMemsetAsync(ctx->pb.M, 0, npix * 3 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->pb.V, 0, npix * 3 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->pb.samples, 0, npix * sizeof(int32_t), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PTGPU_OK;
+}
+
+int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const float* d3, int32_t* shape, int32_t* prim, double* t, float* normal3,
+                          float* position3, int32_t* inside, int32_t* material) {
+    if (!ctx || n < 0 || !o3 || !d3 || !shape || !prim || !t) return PTGPU_E_ARG;
+    if (!ctx->haveScene) return fail(ctx, PTGPU_E_STATE, "no scene uploaded");
+    if (n == 0) return PTGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    float *dO = nullptr, *dD = nullptr, *dN = nullptr, *dP = nullptr;
+    int32_t *dS = nullptr, *dPr = nullptr, *dI = nullptr, *dM = nullptr;
+    double* dT = nullptr;
+    size_t N = (size_t)n;
+    int rc = PTGPU_OK;
+    auto cleanup = [&]() { cudaFree(dO); cudaFree(dD); cudaFree(dN); cudaFree(dP); cudaFree(dS); cudaFree(dPr); cudaFree(dI); cudaFree(dM); cudaFree(dT); };
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return PTGPU_E_CUDA; } } while (0)
+    CKC(cudaMalloc(&dO, N * 12)); CKC(cudaMalloc(&dD, N * 12)); CKC(cudaMalloc(&dN, N * 12)); CKC(cudaMalloc(&dP, N * 12));
+    CKC(cudaMalloc(&dS, N * 4)); CKC(cudaMalloc(&dPr, N * 4)); CKC(cudaMalloc(&dI, N * 4)); CKC(cudaMalloc(&dM, N * 4)); CKC(cudaMalloc(&dT, N * 8));
+    CKC(cudaMemcpyAsync(dO, o3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
+    k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, dO, dD, dS, dPr, dT, dN, dP, dI, dM, nullptr);
+    ctx->launches++;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(shape, dS, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(prim, dPr, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(t, dT, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal3) CKC(cudaMemcpyAsync(normal3, dN, N * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (position3) CKC(cudaMemcpyAsync(position3, dP, N * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inside) CKC(cudaMemcpyAsync(inside, dI, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (material) CKC(cudaMemcpyAsync(material, dM, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+    cleanup();
+    return rc;
+}
+
+int ptgpu_cast_rays(ptgpu_ctx* ctx, const ptgpu_pass* pass, int32_t n, const int32_t* x, const int32_t* y, const double* fu, const double* fv,
+                    const int32_t* sample, float* o3, float* d3) {
+    if (!ctx || !pass || n < 0 || !x || !y || !fu || !fv || !sample || !o3 || !d3) return PTGPU_E_ARG;
+    if (n == 0) return PTGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    PassD P;
+    int rc = make_passd(ctx, pass, P);
+    if (rc != PTGPU_OK) return rc;
+    size_t N = (size_t)n;
+    int32_t *dx = nullptr, *dy = nullptr, *ds = nullptr;
+    double *du = nullptr, *dv = nullptr;
+    float *dO = nullptr, *dD = nullptr;
+    auto cleanup = [&]() { cudaFree(dx); cudaFree(dy); cudaFree(ds); cudaFree(du); cudaFree(dv); cudaFree(dO); cudaFree(dD); };
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return PTGPU_E_CUDA; } } while (0)
+    CKC(cudaMalloc(&dx, N * 4)); CKC(cudaMalloc(&dy, N * 4)); CKC(cudaMalloc(&ds, N * 4)); CKC(cudaMalloc(&du, N * 8)); CKC(cudaMalloc(&dv, N * 8));
+    CKC(cudaMalloc(&dO, N * 12)); CKC(cudaMalloc(&dD, N * 12));
+    CKC(cudaMemcpyAsync(dx, x, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(dy, y, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ds, sample, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(du, fu, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(dv, fv, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_cast_rays<<<grid_for(ctx, 2), 128, 0, ctx->stream>>>(P, n, dx, dy, du, dv, ds, dO, dD);
+    ctx->launches++;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(o3, dO, N * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(d3, dD, N * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+    cleanup();
+    return PTGPU_OK;
+}
+
+int ptgpu_keyed_draw(ptgpu_ctx* ctx, uint32_t seed, uint32_t pass, uint32_t pixel, uint32_t sample, uint32_t bits, uint32_t first, uint32_t depth,
+                     uint32_t sub, uint32_t drawIndex, double* out) {
+    if (!ctx || !out) return PTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    k_keyed_draw<<<1, 1, 0, ctx->stream>>>(seed, pass, pixel, sample, bits, first, depth, sub, drawIndex, d);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CK(e);
+    return PTGPU_OK;
+}
+
+int ptgpu_get_counters(ptgpu_ctx* ctx, ptgpu_counters* out) {
+    if (!ctx || !out) return PTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DeviceCounters dc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(&dc, ctx->dCounters, sizeof(dc), cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof(*out));
+    out->cameraSamples = dc.cameraSamples; out->segments = dc.segments; out->shadowRays = dc.shadowRays; out->nanSamples = dc.nanSamples;
+    out->kernelLaunches = ctx->launches;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->lastPassMs = ms;
+    out->lastPassMs = ctx->lastPassMs;
+    out->traceMs = ctx->traceMs; out->shadeMs = ctx->shadeMs; out->shadowMs = ctx->shadowMs; out->raygenMs = ctx->raygenMs;
+    return PTGPU_OK;
+}
+
+int ptgpu_reset_counters(ptgpu_ctx* ctx) {
+    if (!ctx) return PTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters)));
+    ctx->launches = 0;
+    return PTGPU_OK;
+}
+
+int ptgpu_set_profiling(ptgpu_ctx* ctx, int32_t on) {
+    if (!ctx) return PTGPU_E_ARG;
+    ctx->profiling = on != 0;
+    return PTGPU_OK;
+}
+
+}  // extern "C"

@@ -6,8 +6,9 @@ and volumes come from closed-form formulas so every back end sees identical floa
 
 Triangle order matters: the reference's kd-tree builder takes its split position from whichever shapes sit in the
 *middle of the array* (Tree.cs:130-148,208-226 — the "median" of an unsorted bag), so tree quality is a function
-of input order.  `spatial_order` arranges triangles along a Morton curve so that the reference
-builder, unmodified, produces a balanced tree; tests/test_tree_quality.py records the resulting leaf histogram.
+of input order.  `spatial_order` arranges triangles along a Morton curve and then applies the host
+library's `BuilderFriendlyOrder`, so that the reference builder, unmodified, produces a balanced tree;
+tests/test_tree.py records the resulting leaf statistics.
 """
 from __future__ import annotations
 
@@ -111,7 +112,13 @@ def kd_order(V: np.ndarray, leaf: int = 1) -> np.ndarray:
     return perm
 
 
-def spatial_order(V: np.ndarray, mode: str = "morton") -> np.ndarray:
+def spatial_order(V: np.ndarray, mode: str = "friendly") -> np.ndarray:
+    if mode == "friendly":
+        # Morton order for memory locality, then the host library's BuilderFriendlyOrder (host/host.cpp): the order for
+        # which the UNMODIFIED reference builder yields a balanced tree.  Both back ends receive the same triangles.
+        from .bindings import builder_friendly_order
+        V = V[morton_order(V)]
+        return V[builder_friendly_order(V)]
     if mode == "morton":
         return V[morton_order(V)]
     if mode == "kd":
@@ -166,7 +173,7 @@ def build_c2(w: World, width=1024, height=1024, spp=256) -> Config:
 # --------------------------------------------------------------------------------------------------------------------
 # C3 — 1 000 000-triangle displaced icospheres in kd-trees, Glossy + Clear
 # --------------------------------------------------------------------------------------------------------------------
-def build_c3(w: World, width=1920, height=1080, spp=512, freq_a=200, freq_b=100, order="morton") -> Config:
+def build_c3(w: World, width=1920, height=1080, spp=512, freq_a=200, freq_b=100, order="friendly") -> Config:
     glossy = w.GlossyMaterial(hm.hex_color(0xB7CA79), 1.5, hm.radians(20))
     clear = w.ClearMaterial(1.5, 0)
     floor = w.GlossyMaterial(hm.hex_color(0xD8CAA8), 1.2, hm.radians(5))

@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/ptgpu.h declares, and fails loudly (no CPU
+fallback) when asked to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ptgpu.h")).read()
+    return sorted(set(re.findall(r"\b(ptgpu_[a-z_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(bindings):
+    lib = bindings.gpu_lib()
+    declared = _declared_symbols()
+    assert set(declared) == set(bindings.PTGPU_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ptgpu_abi_version() == 1
+
+
+def test_struct_layouts_match_header(bindings):
+    # sizes the C compiler gives the ABI structs (see include/ptgpu.h)
+    assert C.sizeof(bindings.Camera) == 72
+    assert C.sizeof(bindings.Pass) == 56 + 72
+    assert C.sizeof(bindings.Params) == 16
+    assert C.sizeof(bindings.Counters) == 80
+
+
+def test_flatten_c1(bindings):
+    from ptsharp_b200 import scenes
+    w = bindings.HostWorld()
+    scenes.build_c1(w)
+    assert w.flatten() != 0
+    assert w.flat_bytes() > 0
+    p = w.make_pass(64, 48, 4)
+    assert (p.width, p.height, p.spp, p.firstHitSamples, p.maxBounces) == (64, 48, 4, 16, 4)
+    assert p.camera.m == pytest.approx(1 / __import__("math").tan(50 * __import__("math").pi / 360))
+
+
+def test_nested_transform_rejected(bindings):
+    import numpy as np
+    w = bindings.HostWorld()
+    m = w.DiffuseMaterial((1, 1, 1))
+    inner = w.transformed(w.sphere((0, 0, 0), 1, m), np.eye(4))
+    w.add(w.transformed(inner, np.eye(4)))
+    with pytest.raises(bindings.PtgpuError):
+        w.flatten()
+
+
+def test_no_cpu_fallback(bindings):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bindings.PtgpuError) as e:
+        bindings.Device()
+    assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
+    w = bindings.HostWorld()
+    from ptsharp_b200 import scenes
+    scenes.build_c1(w)
+    w.new_renderer(32, 32)
+    with pytest.raises(bindings.PtgpuError):
+        w.render_parallel(32, 32)
