@@ -217,10 +217,9 @@ PT_D double cylinder_intersect(const ptgpu_cylinder& cy, V3 o, V3 d) {
     }
     return kHitInf;
 }
-// Triangle.cs:95-124 (e1, e2 precomputed by the host exactly as V2.Sub(V1), V3.Sub(V1))
-PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) {
-    float4 a = __ldg(g), b4 = __ldg(g + 1), c4 = __ldg(g + 2);
-    V3 v1 = v3(a.x, a.y, a.z), e1 = v3(b4.x, b4.y, b4.z), e2 = v3(c4.x, c4.y, c4.z);
+// Triangle.cs:95-124 (e1, e2 precomputed by the host exactly as V2.Sub(V1), V3.Sub(V1)) — the reference sequence,
+// one FP64 division per call.  Kept as the arbiter for the borderline cases of the filtered version below.
+PT_D double triangle_intersect_exact(V3 v1, V3 e1, V3 e2, V3 o, V3 d) {
     V3 h = vcross(d, e2);
     double det = vdot(e1, h);
     if (det > -kEPS && det < kEPS) return kHitInf;
@@ -234,6 +233,41 @@ PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) {
     double t = vdot(e2, q) * invDet;
     if (t < kEPS) return kHitInf;
     return t;
+}
+// Same result, bit for bit, without the division on the (overwhelmingly common) miss path.  In the reference
+// det, a = s.h, b = d.q, c = e2.q are FP32 dot products and u = a*(1/det), v = b*(1/det), t = c*(1/det) are FP64, so
+//   u < 0        <=>  a and det have opposite signs           (1/det keeps det's sign, the product cannot underflow)
+//   u > 1        <=>  |a| > |det| with equal signs            (a, det are FP32: a != det implies |a/det - 1| >= 2^-24)
+//   v < 0        <=>  b and det have opposite signs
+//   u + v > 1    <=>  (a + b) / det > 1                       unless a + b is within 1e-13 relative of det
+//   t < EPS      <=>  c / det < 1e-9                          unless within 1e-13 relative of it
+// and the excluded borderline cases (a == det, near-equalities) are sent to the exact sequence above.
+PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) {
+    const float4 A = __ldg(g), B4 = __ldg(g + 1), C4 = __ldg(g + 2);
+    const V3 v1 = v3(A.x, A.y, A.z), e1 = v3(B4.x, B4.y, B4.z), e2 = v3(C4.x, C4.y, C4.z);
+    // all four FP32 dot products up front (a warp pays for its slowest lane anyway), then one decision
+    const V3 h = vcross(d, e2);
+    const float det = vdotf(e1, h);
+    const V3 s = vsub(o, v1);
+    const float a = vdotf(s, h);
+    const V3 q = vcross(s, e1);
+    const float b = vdotf(d, q);
+    const float c = vdotf(e2, q);
+    const bool pos = det > 0.f;
+    const float sa = pos ? a : -a, sb = pos ? b : -b, ad = fabsf(det);
+    // misses that need no FP64 at all: |det| <= 1e-9f (1e-9f is the largest float below 1e-9), u < 0, u > 1, v < 0
+    const bool quickMiss = (ad <= 1e-9f) | (sa < 0.f) | (sa > ad) | (sb < 0.f);
+    const bool odd = !(det == det) | !(a == a) | !(b == b) | !(c == c) | (a == det);  // NaNs and u == 1 +- ulp: ask the reference sequence
+    if (odd) return triangle_intersect_exact(v1, e1, e2, o, d);
+    if (quickMiss) return kHitInf;
+    const double detd = (double)det, adet = fabs(detd);
+    const double sum = (double)a + (double)b;                       // exact or within 2^-53
+    const double excess = pos ? (sum - detd) : (detd - sum);        // > 0  <=>  (a + b) / det > 1
+    const double cs = pos ? (double)c : -(double)c;                 // c / det = cs / |det|
+    const double lim = kEPS * adet;
+    if (fabs(excess) <= 1e-13 * adet || fabs(cs - lim) <= 1e-13 * lim) return triangle_intersect_exact(v1, e1, e2, o, d);
+    if (excess > 0 || cs < lim) return kHitInf;                     // u + v > 1, t < EPS
+    return (double)c * (1.0 / detd);                                // the reference's t = e2.q * invDet
 }
 
 // ---------------------------------------------------------------------------------------------------- SDF
@@ -448,116 +482,191 @@ PT_D int32_t volume_material(const DScene& S, const ptgpu_volume& v, V3 p) {  //
 // Tree.Intersect / Node.Intersect (Tree.cs:31-113) in stack form: running best with strict `<`
 // updates; on "both children" push (second, tsplit, tmax); on pop skip when best.T <= tsplit, otherwise continue with
 // tmax = Math.Min(tmax, best.T).  Comparisons are written exactly as in the reference so NaNs take the same branches.
-// `leaf(first, count)` intersects leafItems[first, first+count) in array order and updates the caller's best hit.
-template <int STACK, class LeafFn>
-PT_D void kd_traverse(const ptgpu_node* __restrict__ nodes, const ptgpu_tree& tree, V3 o, V3 d, const double& bestT, LeafFn leaf) {
+//
+// Execution model.  A naive "one thread walks one ray to completion" kernel measured 2.2 active lanes per warp
+// instruction on the 250k-triangle scene (ncu, profiles/r01_trace_naive.txt): per-ray cost is heavy-tailed (a few rays
+// cross leaves of hundreds of triangles) and a warp runs as long as its slowest lane.  The tracer is therefore a
+// persistent per-lane state machine with ray replacement: every lane owns one ray and advances it by one unit of work
+// per state block (a few kd node steps, one leaf triangle, one scene shape); a lane whose ray finishes immediately
+// pulls the next ray index from a global cursor (one atomic per coalesced group), so a long ray only ever occupies its
+// own lane.  The arithmetic of each unit is untouched, so hits are bit-identical to the recursive reference.
+struct KdCursor {  // one level of Tree.Intersect in flight
+    uint32_t node;
     double tmin, tmax;
-    box_intersect(tree.bmin, tree.bmax, o, d, tmin, tmax);
-    if (tmax < tmin || tmax <= 0) return;
-    uint32_t stNode[STACK];
-    double stMin[STACK], stMax[STACK];
-    int sp = 0;
-    uint32_t node = tree.root;
-    for (;;) {
-        // one 128-bit load per node
-        const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + node));
-        const double split = __hiloint2double(raw.y, raw.x);
-        const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
-        const uint32_t axis = a & 3u;
-        if (axis == 0) {
-            leaf(a >> 2, b);
-            bool resumed = false;
-            while (sp > 0) {
-                --sp;
-                double ts = stMin[sp];
-                if (bestT <= ts) continue;  // `if (h1.T <= tsplit) return h1`
-                node = stNode[sp];
-                tmin = ts;
-                tmax = netmin(stMax[sp], bestT);
-                resumed = true;
-                break;
-            }
-            if (!resumed) return;
-            continue;
-        }
-        const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-        const double tsplit = (split - oa) / da;
-        const bool leftFirst = (oa < split) || (oa == split && da <= 0);
-        const uint32_t first = leftFirst ? (a >> 2) : b;
-        const uint32_t second = leftFirst ? b : (a >> 2);
-        if (tsplit > tmax || tsplit <= 0) node = first;
-        else if (tsplit < tmin) node = second;
-        else {
-            if (sp < STACK) { stNode[sp] = second; stMin[sp] = tsplit; stMax[sp] = tmax; sp++; }
-            node = first;
-            tmax = tsplit;
-        }
+    int sp;
+};
+
+// One Node.Intersect step for an interior node.  Returns false when `node` is a leaf (first/count filled in).
+template <int STACK>
+PT_D bool kd_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d, uint32_t* stNode, double* stMin, double* stMax,
+                  uint32_t& leafFirst, uint32_t& leafCount) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));  // one 128-bit load per node
+    const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
+    const uint32_t axis = a & 3u;
+    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return false; }
+    const double split = __hiloint2double(raw.y, raw.x);
+    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+    const double tsplit = (split - oa) / da;
+    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
+    const uint32_t first = leftFirst ? (a >> 2) : b;
+    const uint32_t second = leftFirst ? b : (a >> 2);
+    if (tsplit > c.tmax || tsplit <= 0) c.node = first;
+    else if (tsplit < c.tmin) c.node = second;
+    else {
+        if (c.sp < STACK) { stNode[c.sp] = second; stMin[c.sp] = tsplit; stMax[c.sp] = c.tmax; c.sp++; }
+        c.node = first;
+        c.tmax = tsplit;
     }
+    return true;
+}
+// After a leaf: resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
+PT_D bool kd_pop(KdCursor& c, double bestT, const uint32_t* stNode, const double* stMin, const double* stMax) {
+    while (c.sp > 0) {
+        --c.sp;
+        const double ts = stMin[c.sp];
+        if (bestT <= ts) continue;  // `if (h1.T <= tsplit) return h1`
+        c.node = stNode[c.sp];
+        c.tmin = ts;
+        c.tmax = netmin(stMax[c.sp], bestT);
+        return true;
+    }
+    return false;
 }
 
-// Mesh.Intersect (Mesh.cs:122-125): closest triangle of the mesh's own tree, starting from NoHit.
-PT_D void mesh_intersect(const DScene& S, const ptgpu_mesh& m, V3 o, V3 d, double& tOut, int32_t& primOut) {
-    double best = kHitInf;
-    int32_t prim = -1;
-    const ptgpu_tree tree = S.trees[m.tree];
-    kd_traverse<kMeshStack>(S.nodes, tree, o, d, best, [&](uint32_t first, uint32_t count) {
-        for (uint32_t i = 0; i < count; i++) {
-            uint32_t tri = __ldg(S.leafItems + first + i);
-            double t = triangle_intersect(S.triGeom + (size_t)tri * 3, o, d);
-            if (t < best) { best = t; prim = (int32_t)tri; }  // Tree.cs:122 strict <
-        }
-    });
-    tOut = best;
-    primOut = prim;
-}
-
-// IShape.Intersect for everything except TransformedShape.
-PT_D void simple_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3 d, double& t, int32_t& prim) {
-    prim = -1;
+// IShape.Intersect for the analytic shapes (everything except Mesh and TransformedShape).
+PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3 d) {
     switch (sh.type) {
-        case PTGPU_SPHERE: t = sphere_intersect(S.spheres[sh.data], o, d); break;
-        case PTGPU_CUBE: t = cube_intersect(S.cubes[sh.data], o, d); break;
-        case PTGPU_PLANE: t = plane_intersect(S.planes[sh.data], o, d); break;
-        case PTGPU_CYLINDER: t = cylinder_intersect(S.cylinders[sh.data], o, d); break;
-        case PTGPU_MESH: mesh_intersect(S, S.meshes[sh.data], o, d, t, prim); break;
-        case PTGPU_SDF: t = sdf_intersect(S, S.sdfShapes[sh.data], o, d); break;
-        case PTGPU_VOLUME: t = volume_intersect(S, S.volumes[sh.data], o, d); break;
-        default: t = kHitInf; break;
+        case PTGPU_SPHERE: return sphere_intersect(S.spheres[sh.data], o, d);
+        case PTGPU_CUBE: return cube_intersect(S.cubes[sh.data], o, d);
+        case PTGPU_PLANE: return plane_intersect(S.planes[sh.data], o, d);
+        case PTGPU_CYLINDER: return cylinder_intersect(S.cylinders[sh.data], o, d);
+        case PTGPU_SDF: return sdf_intersect(S, S.sdfShapes[sh.data], o, d);
+        case PTGPU_VOLUME: return volume_intersect(S, S.volumes[sh.data], o, d);
+        default: return kHitInf;
     }
 }
 
-// One entry of Scene.Shapes against the ray; updates best with strict `<` (Tree.cs:122).
-PT_D void shape_intersect(const DScene& S, uint32_t si, V3 o, V3 d, HitRec& best) {
-    const ptgpu_shape sh = S.shapes[si];
-    double t, tInner = 0;
-    int32_t prim;
-    if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:43-72
-        const ptgpu_instance& inst = S.instances[sh.data];
-        V3 so = mat_pos(inst.inv, o), sd = mat_dir(inst.inv, d);  // Matrix.MulRay (Matrix.cs:153)
-        const ptgpu_shape inner = S.shapes[inst.shape];
-        simple_intersect(S, inner, so, sd, tInner, prim);
-        if (!(tInner < kHitInf)) { t = tInner; }  // `if (!hit.Ok) return hit`
-        else {
-            V3 shapePosition = ray_at(so, sd, tInner);
-            V3 position = mat_pos(inst.m, shapePosition);
-            t = (double)vlenf(vsub(position, o));  // hit.T = position.Sub(r.Origin).Length()
-        }
-    } else {
-        simple_intersect(S, sh, o, d, t, prim);
-    }
-    if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)si; best.prim = prim; }
-}
+enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT };
 
-// Scene.Intersect (Scene.cs:75-79) -> Tree.Intersect over Scene.Shapes.
-PT_D HitRec scene_intersect(const DScene& S, V3 o, V3 d) {
+// Scene.Intersect (Scene.cs:75-79) for rays [0, n): `source(i, o, d)` loads ray i, `sink(i, hit)` consumes its closest
+// hit.  `cursor` is a zero-initialised global counter shared by every warp of the launch.
+template <class Source, class Sink>
+PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor, Source source, Sink sink) {
+    int st = ST_IDLE;
+    uint32_t rayIdx = 0;
+    V3 o = v3(0, 0, 0), d = v3(0, 0, 1);    // world-space ray
+    V3 co = o, cd = d;                       // ray in the space of the mesh being traversed (object space for instances)
     HitRec best;
     best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
-    const ptgpu_tree tree = S.trees[S.sceneTree];
-    kd_traverse<kSceneStack>(S.nodes, tree, o, d, best.t, [&](uint32_t first, uint32_t count) {
-        for (uint32_t i = 0; i < count; i++) shape_intersect(S, __ldg(S.leafItems + first + i), o, d, best);
-    });
-    if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
-    return best;
+    // Scene tree (Scene.tree)
+    KdCursor sc; sc.node = 0; sc.tmin = sc.tmax = 0; sc.sp = 0;
+    uint32_t sStNode[kSceneStack]; double sStMin[kSceneStack], sStMax[kSceneStack];
+    uint32_t sPos = 0, sEnd = 0;
+    // Mesh tree (Mesh.tree) of the shape being visited
+    KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
+    uint32_t mStNode[kMeshStack]; double mStMin[kMeshStack], mStMax[kMeshStack];
+    uint32_t mPos = 0, mEnd = 0;
+    double mBest = kHitInf; int32_t mPrim = -1;
+    uint32_t curShape = 0; int32_t curInst = -1;
+    const ptgpu_tree sceneTree = S.trees[S.sceneTree];
+
+    for (;;) {
+        if (st == ST_IDLE) {
+            auto g = cooperative_groups::coalesced_threads();
+            uint32_t base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
+            rayIdx = g.shfl(base, 0) + g.thread_rank();
+            if (rayIdx >= n) st = ST_EXIT;
+            else {
+                source(rayIdx, o, d);
+                best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
+                box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
+                if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
+                else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, st == ST_EXIT)) break;
+
+        if (st == ST_SCENE_NODE) {
+#pragma unroll 1
+            for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
+                uint32_t first, count;
+                if (!kd_step<kSceneStack>(S.nodes, sc, o, d, sStNode, sStMin, sStMax, first, count)) { sPos = first; sEnd = first + count; st = ST_SCENE_LEAF; }
+            }
+        }
+        if (st == ST_SCENE_LEAF) {
+            if (sPos == sEnd) {
+                st = kd_pop(sc, best.t, sStNode, sStMin, sStMax) ? ST_SCENE_NODE : ST_FINISH;
+            } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
+                curShape = __ldg(S.leafItems + sPos);
+                sPos++;
+                ptgpu_shape sh = S.shapes[curShape];
+                curInst = -1; co = o; cd = d;
+                if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45: shapeRay = Matrix.Inverse().MulRay(r)
+                    curInst = (int32_t)sh.data;
+                    const ptgpu_instance& inst = S.instances[sh.data];
+                    co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
+                    sh = S.shapes[inst.shape];
+                }
+                if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
+                    const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
+                    mBest = kHitInf; mPrim = -1;
+                    box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
+                    if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
+                    else { mc.node = mt.root; mc.sp = 0; st = ST_MESH_NODE; }
+                } else {
+                    mBest = primitive_intersect(S, sh, co, cd);
+                    mPrim = -1;
+                    st = ST_MESH_DONE;
+                }
+            }
+        }
+        // The two heavy states.  Executing a block costs the same whatever the number of lanes in that state, so each
+        // iteration runs only the block the majority of lanes is waiting for; the minority accumulates until it wins.
+        const unsigned leafMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_LEAF);
+        const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE);
+        if (__popc(nodeMask) > __popc(leafMask)) {
+            if (st == ST_MESH_NODE) {
+#pragma unroll 1
+                for (int k = 0; k < 4 && st == ST_MESH_NODE; k++) {
+                    uint32_t first, count;
+                    if (!kd_step<kMeshStack>(S.nodes, mc, co, cd, mStNode, mStMin, mStMax, first, count)) {
+                        mPos = first; mEnd = first + count;
+                        st = ST_MESH_LEAF;
+                    }
+                }
+            }
+        } else if (leafMask) {
+            if (st == ST_MESH_LEAF) {
+#pragma unroll 1
+                for (int k = 0; k < 2 && mPos < mEnd; k++) {
+                    const uint32_t tri = __ldg(S.leafItems + mPos);
+                    mPos++;
+                    const double t = triangle_intersect(S.triGeom + (size_t)tri * 3, co, cd);
+                    if (t < mBest) { mBest = t; mPrim = (int32_t)tri; }  // Tree.cs:122 strict <
+                }
+                if (mPos >= mEnd) st = kd_pop(mc, mBest, mStNode, mStMin, mStMax) ? ST_MESH_NODE : ST_MESH_DONE;
+            }
+        }
+        if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
+            double t = mBest, tInner = 0;
+            if (curInst >= 0) {
+                tInner = mBest;
+                if (mBest < kHitInf) {  // TransformedShape.cs:47-69: hit.T = |Matrix.MulPosition(shapeRay.Position(T)) - r.Origin|
+                    const ptgpu_instance& inst = S.instances[curInst];
+                    V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
+                    t = (double)vlenf(vsub(position, o));
+                }
+            }
+            if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
+            st = ST_SCENE_LEAF;
+        }
+        if (st == ST_FINISH) {
+            if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
+            sink(rayIdx, best);
+            st = ST_IDLE;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- textures

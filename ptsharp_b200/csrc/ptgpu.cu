@@ -247,14 +247,13 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
     if (blockIdx.x == 0 && threadIdx.x == 0) { *count = n; atomicAdd(&cnt->cameraSamples, (unsigned long long)n); }
 }
 
-// K2.  Closest hit for every queued ray.
-__global__ void __launch_bounds__(128) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, HitQueue hq, DeviceCounters* cnt) {
+// K2.  Closest hit for every queued ray (persistent warps, per-lane ray replacement; see trace_rays).
+__global__ void __launch_bounds__(128) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursor, HitQueue hq,
+                                                DeviceCounters* cnt) {
     const uint32_t n = *count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 a = q.od0[i], b = q.od1[i];
-        HitRec h = scene_intersect(S, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z));
-        hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim;
-    }
+    trace_rays(S, n, cursor,
+               [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
+               [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
 
@@ -409,18 +408,19 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, PassD P, const DLight* 
 }
 
 // K4.  sampleLight's visibility test: closest hit, then identity with the light (Sampler.cs:261-265).
-__global__ void __launch_bounds__(128) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, float* __restrict__ sum,
-                                                 DeviceCounters* cnt) {
+__global__ void __launch_bounds__(128) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t* __restrict__ cursor,
+                                                 uint32_t capShadow, float* __restrict__ sum, DeviceCounters* cnt) {
     uint32_t n = *scount;
     if (n > capShadow) n = capShadow;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 a = sq.so[i], b = sq.sd[i];
-        HitRec h = scene_intersect(S, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z));
-        if (h.shape >= 0 && (uint32_t)h.shape == f2u(b.w)) {
-            float4 c = sq.sc[i];
-            accumulate(sum, cnt, f2u(a.w), c.x, c.y, c.z);
-        }
-    }
+    trace_rays(S, n, cursor,
+               [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
+               [&](uint32_t i, const HitRec& h) {
+                   const uint32_t light = f2u(sq.sd[i].w);
+                   if (h.shape >= 0 && (uint32_t)h.shape == light) {
+                       float4 c = sq.sc[i];
+                       accumulate(sum, cnt, f2u(sq.so[i].w), c.x, c.y, c.z);
+                   }
+               });
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
 }
 
@@ -463,32 +463,33 @@ __global__ void k_read_buffer(PixelBuf pb, int channel, uint32_t npix, float* __
     }
 }
 
-// K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays.
-__global__ void k_intersect_batch(DScene S, int n, const float* __restrict__ o3, const float* __restrict__ d3, int32_t* shape, int32_t* prim, double* t,
-                                  float* normal3, float* position3, int32_t* inside, int32_t* material, const uint32_t* __restrict__ triFirstOfMeshShape) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
-        HitRec h = scene_intersect(S, o, d);
-        shape[i] = h.shape;
-        t[i] = h.t;
-        int32_t localPrim = -1;
-        V3 nn = v3(0, 0, 0), pp = v3(0, 0, 0);
-        int32_t ins = 0, mat = -1;
-        if (h.shape >= 0) {
-            if (h.prim >= 0) {  // report the triangle's index inside its mesh (Mesh.Triangles[])
-                ptgpu_shape sh = S.shapes[h.shape];
-                if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
-                localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
-            }
-            Surface sf = hit_info(S, o, d, h);
-            nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
-        }
-        prim[i] = localPrim;
-        if (normal3) { normal3[3 * i] = nn.x; normal3[3 * i + 1] = nn.y; normal3[3 * i + 2] = nn.z; }
-        if (position3) { position3[3 * i] = pp.x; position3[3 * i + 1] = pp.y; position3[3 * i + 2] = pp.z; }
-        if (inside) inside[i] = ins;
-        if (material) material[i] = mat;
-    }
+// K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same trace_rays as the pipeline.
+__global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32_t* __restrict__ cursor, const float* __restrict__ o3, const float* __restrict__ d3,
+                                                          int32_t* shape, int32_t* prim, double* t, float* normal3, float* position3, int32_t* inside, int32_t* material) {
+    trace_rays(S, (uint32_t)n, cursor,
+               [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
+               [&](uint32_t i, const HitRec& h) {
+                   V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+                   shape[i] = h.shape;
+                   t[i] = h.t;
+                   int32_t localPrim = -1;
+                   V3 nn = v3(0, 0, 0), pp = v3(0, 0, 0);
+                   int32_t ins = 0, mat = -1;
+                   if (h.shape >= 0) {
+                       if (h.prim >= 0) {  // report the triangle's index inside its mesh (Mesh.Triangles[])
+                           ptgpu_shape sh = S.shapes[h.shape];
+                           if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+                           localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
+                       }
+                       Surface sf = hit_info(S, o, d, h);
+                       nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+                   }
+                   prim[i] = localPrim;
+                   if (normal3) { normal3[3 * i] = nn.x; normal3[3 * i + 1] = nn.y; normal3[3 * i + 2] = nn.z; }
+                   if (position3) { position3[3 * i] = pp.x; position3[3 * i + 1] = pp.y; position3[3 * i + 2] = pp.z; }
+                   if (inside) inside[i] = ins;
+                   if (material) material[i] = mat;
+               });
 }
 __global__ void k_cast_rays(PassD P, int n, const int32_t* x, const int32_t* y, const double* fu, const double* fv, const int32_t* sample, float* o3, float* d3) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -529,7 +530,7 @@ struct ptgpu_ctx {
     RayQueue rq[2]{};
     HitQueue hq{};
     ShadowQueue sq{};
-    uint32_t* dCounts = nullptr;  // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag
+    uint32_t* dCounts = nullptr;  // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag, [4] trace cursor, [5] shadow cursor, [6] batch cursor
     DeviceCounters* dCounters = nullptr;
     // image state
     int bufW = 0, bufH = 0;
@@ -876,8 +877,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         for (int depth = 0; depth <= P.maxBounces; depth++) {
             CK(cudaMemsetAsync(counts + (cur ^ 1), 0, sizeof(uint32_t), stream));
             CK(cudaMemsetAsync(counts + 2, 0, sizeof(uint32_t), stream));
+            CK(cudaMemsetAsync(counts + 4, 0, 2 * sizeof(uint32_t), stream));  // trace / shadow work cursors
             if (prof) cudaEventRecord(ctx->evA, stream);
-            k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, ctx->hq, ctx->dCounters);
+            k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, counts + 4, ctx->hq, ctx->dCounters);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, ctx->rq[cur], counts + cur, ctx->hq, ctx->rq[cur ^ 1], counts + (cur ^ 1),
                                                    ctx->sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)ctx->capRays, (uint32_t)ctx->capShadow);
@@ -885,7 +887,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 3;
             if (lightsPer) {
-                k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->sq, counts + 2, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters);
+                k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->sq, counts + 2, counts + 5, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters);
                 ctx->launches++;
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
             }
@@ -1014,7 +1016,8 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
     CKC(cudaMalloc(&dS, N * 4)); CKC(cudaMalloc(&dPr, N * 4)); CKC(cudaMalloc(&dI, N * 4)); CKC(cudaMalloc(&dM, N * 4)); CKC(cudaMalloc(&dT, N * 8));
     CKC(cudaMemcpyAsync(dO, o3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
-    k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, dO, dD, dS, dPr, dT, dN, dP, dI, dM, nullptr);
+    CKC(cudaMemsetAsync(ctx->dCounts + 6, 0, sizeof(uint32_t), ctx->stream));
+    k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM);
     ctx->launches++;
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(shape, dS, N * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -190,4 +190,95 @@ def build_c3(w: World, width=1920, height=1080, spp=512, freq_a=200, freq_b=100,
                   triangles=va.shape[0] + vb.shape[0], extra={"order": order})
 
 
-BUILDERS = {"c1": build_c1, "c2": build_c2, "c3": build_c3}
+# --------------------------------------------------------------------------------------------------------------------
+# C4 — 200 TransformedShape instances of one 50 000-triangle mesh, albedo + normal textures
+# --------------------------------------------------------------------------------------------------------------------
+def procedural_albedo(n: int = 1024) -> np.ndarray:
+    """(n, n, 3) linear colours: 0.2 + 0.8*checker(16), tinted by (u, v)."""
+    v, u = np.meshgrid((np.arange(n) + 0.5) / n, (np.arange(n) + 0.5) / n, indexing="ij")
+    checker = ((np.floor(u * 16) + np.floor(v * 16)) % 2)
+    base = 0.2 + 0.8 * checker
+    return np.stack([base * (0.5 + 0.5 * u), base * (0.5 + 0.5 * v), base * (1.0 - 0.5 * u)], axis=-1)
+
+
+def procedural_normal_map(n: int = 1024, strength: float = 0.15) -> np.ndarray:
+    """(n, n, 3) tangent-space normal map of h = 0.5 + 0.5 sin(40u) sin(40v), encoded (n + 1) / 2."""
+    v, u = np.meshgrid((np.arange(n) + 0.5) / n, (np.arange(n) + 0.5) / n, indexing="ij")
+    dhdu = 0.5 * 40 * np.cos(40 * u) * np.sin(40 * v)
+    dhdv = 0.5 * 40 * np.sin(40 * u) * np.cos(40 * v)
+    nrm = np.stack([-strength * dhdu / 40, -strength * dhdv / 40, np.ones_like(u)], axis=-1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    return (nrm + 1.0) / 2.0
+
+
+def build_c4(w: World, width=3840, height=2160, spp=1024, freq=50, nx=20, nz=10, tex=1024, order="friendly") -> Config:
+    albedo = w.texture(procedural_albedo(tex))
+    normal = w.texture(procedural_normal_map(tex))
+    mat = w.GlossyMaterial(hm.WHITE, 1.3, hm.radians(15), texture=albedo, normal_texture=normal)
+    V = spatial_order(displaced_icosphere(freq, 1.0, (0, 0, 0)), order)
+    T = spherical_uv(V, (0, 0, 0))
+    base = w.mesh(V, mat, T=T)
+    for i in range(nx * nz):
+        x = (i % nx - (nx - 1) / 2) * 2.2
+        z = (i // nx - (nz - 1) / 2) * 2.2
+        sy = 0.6 + 0.002 * i
+        # composed with .Mul as in Example.cs:1115-1117 (Translate/Rotate/Scale themselves ignore their receiver)
+        m = hm.mul(hm.mul(hm.translate(hm.vec((x, sy, z))), hm.rotate((0, 1, 0), 0.3 * i)), hm.scale(hm.vec((1, sy, 1))))
+        w.add(w.transformed(base, m))
+    w.add(w.cube((-60, -1, -60), (60, 0, 60), w.GlossyMaterial(hm.hex_color(0xD8CAA8), 1.2, hm.radians(5))))
+    w.add(w.sphere((-10, 25, -10), 3, w.LightMaterial(hm.WHITE, 60)))
+    w.add(w.sphere((15, 20, 10), 3, w.LightMaterial(hm.WHITE, 40)))
+    w.look_at((0, 18, -30), (0, 0, 0), (0, 1, 0), 45)
+    w.sampler(1, 4)
+    return Config("c4_instanced_10m", width, height, spp, "TransformedShape instances of one textured mesh, floor cube, two sphere lights",
+                  triangles=V.shape[0] * nx * nz, extra={"base_triangles": V.shape[0], "instances": nx * nz})
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# C5 — SDF solid (Example.sdf, Example.cs:1402-1418) + transformed cylinders + procedural Volume
+# --------------------------------------------------------------------------------------------------------------------
+def procedural_volume(n: int = 64) -> np.ndarray:
+    """(n, n, n) density rho(q) = exp(-4|q|^2) (0.75 + 0.25 sin(12qx) sin(12qy) sin(12qz)), q in [-1, 1]^3, index [z, y, x]."""
+    c = (np.arange(n) + 0.5) / n * 2 - 1
+    qz, qy, qx = np.meshgrid(c, c, c, indexing="ij")
+    return np.exp(-4 * (qx ** 2 + qy ** 2 + qz ** 2)) * (0.75 + 0.25 * np.sin(12 * qx) * np.sin(12 * qy) * np.sin(12 * qz))
+
+
+def build_c5(w: World, width=1920, height=1080, spp=256, volume_n=64, bars=8, with_sdf=True, with_volume=True) -> Config:
+    F = lambda x: float(np.float32(x))  # a C# `F` literal widened to double
+    light = w.LightMaterial(hm.WHITE, 180)
+    d = F(4.0)
+    for v in ((-1, -1, F(0.5)), (0, -1, F(0.25)), (-1, 1, 0)):
+        w.add(w.sphere(hm.vmuls(hm.vnormalize(hm.vec(v)), d), F(0.25), light))
+    if with_sdf:
+        material = w.GlossyMaterial(hm.hex_color(0x468966), F(1.2), hm.radians(20))
+        sphere = w.sdf_sphere(F(0.65))
+        cube = w.sdf_cube((1, 1, 1))
+        rounded = w.sdf_intersection([sphere, cube])
+        a = w.sdf_cylinder(F(0.25), F(1.1))
+        b = w.sdf_transform(a, hm.rotate((1, 0, 0), hm.radians(90)))
+        c = w.sdf_transform(a, hm.rotate((0, 0, 1), hm.radians(90)))
+        diff = w.sdf_difference([rounded, a, b, c])
+        sdf = w.sdf_transform(diff, hm.rotate((0, 0, 1), hm.radians(30)))
+        w.add(w.sdf_shape(sdf, material))
+    w.add(w.plane((0, 0, F(-0.5)), (0, 0, 1), w.GlossyMaterial(hm.hex_color(0xFFF0A5), F(1.2), hm.radians(20))))
+    colors = [0x730046, 0xBFBB11, 0xFFC200, 0xE88801, 0xC93C00]  # Example.cs:1288-1294
+    mats = [w.GlossyMaterial(hm.hex_color(c), F(1.6), hm.radians(45)) for c in colors]
+    for i in range(bars):
+        v0 = (-1.5 + 0.45 * i, 2.0 + 0.25 * i, -0.5)
+        v1 = (v0[0], v0[1], v0[2] + 1.0 + 0.1 * i)
+        w.add(w.transformed_cylinder(v0, v1, 0.2, mats[i % len(mats)]))
+    if with_volume:
+        vcolors = [0x004358, 0x1F8A70, 0xBEDB39, 0xFFE11A, 0xFD7400]  # Example.cs:1446-1453
+        windows = []
+        for i, c in enumerate(vcolors):
+            lo = F(0.2) + F(0.1) * i
+            windows.append((lo, lo + F(0.01), w.GlossyMaterial(hm.hex_color(c), F(1.3), hm.radians(0))))
+        vol = w.volume((-1, -1, F(-0.2)), (1, 1, 1), procedural_volume(volume_n), 1.0, windows)
+        w.add(w.transformed(vol, hm.translate(hm.vec((0, -2.5, 0)))))
+    w.look_at((-5, 0, 2), (0, 0, 0), (0, 0, 1), 45)
+    w.sampler(4, 4, light_mode=LightModeAll, specular_mode=SpecularModeAll)
+    return Config("c5_sdf_cylinder_volume", width, height, spp, "SDF solid + transformed cylinders + procedural Volume, three sphere lights")
+
+
+BUILDERS = {"c1": build_c1, "c2": build_c2, "c3": build_c3, "c4": build_c4, "c5": build_c5}
