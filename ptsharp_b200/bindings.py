@@ -66,7 +66,7 @@ _host = None
 def gpu_lib() -> C.CDLL:
     global _gpu
     if _gpu is None:
-        path = _build.build_gpu()
+        path = os.environ.get("PTGPU_LIB") or _build.build_gpu()  # PTGPU_LIB: development override (tuning variants)
         lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
         lib.ptgpu_abi_version.restype = C.c_int
         lib.ptgpu_create.restype = C.c_int

@@ -119,6 +119,8 @@ struct DScene {
     const ptgpu_material* materials;
     const ptgpu_texture* textures;
     const float4* texels;
+    const float4* nodeBounds;       // 2 x float4 per kd node: padded bounds of the triangles below it (mesh trees only)
+    const float4* leafGeom;         // 3 x float4 per leaf item of a mesh tree: the triangle's (V1, e1, e2) in leaf order
     uint32_t sceneTree, numSceneShapes, numLights, numShapes;
     double envColor[3];
     int32_t envTexture;
@@ -496,14 +498,42 @@ struct KdCursor {  // one level of Tree.Intersect in flight
     int sp;
 };
 
-// One Node.Intersect step for an interior node.  Returns false when `node` is a leaf (first/count filled in).
-template <int STACK>
-PT_D bool kd_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d, uint32_t* stNode, double* stMin, double* stMax,
-                  uint32_t& leafFirst, uint32_t& leafCount) {
+// Subtree culling.  The reference tree never splits off empty space (a split with an empty side scores N and is
+// rejected, Tree.cs:228-255), so a ray crossing a hollow mesh walks dozens of cells whose triangles it cannot touch
+// (measured: 229 triangle tests for rays that miss both meshes of C3).  Every node of a mesh tree therefore carries the
+// bounding box of the triangles below it, padded by far more than the FP32 error of the triangle test; a subtree whose
+// padded box the ray line misses for all t > 0 cannot change the running best, so skipping it (= returning NoHit from
+// Node.Intersect) leaves every later comparison of the reference's control flow unchanged.
+struct RayAux { float ix, iy, iz, pad; };  // 1/d per axis (inf where d == 0) and an origin-dependent extra padding
+PT_D RayAux ray_aux(V3 o, V3 d) {
+    RayAux a;
+    a.ix = 1.0f / d.x; a.iy = 1.0f / d.y; a.iz = 1.0f / d.z;
+    a.pad = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+    return a;
+}
+PT_D bool bounds_hit(const float4* __restrict__ nb, uint32_t node, V3 o, const RayAux& ra) {
+    const float4 lo = __ldg(nb + 2 * (size_t)node), hi = __ldg(nb + 2 * (size_t)node + 1);
+    // fminf/fmaxf ignore NaNs (0 * inf when the origin lies on a slab plane of a zero direction): conservative
+    const float x1 = (lo.x - ra.pad - o.x) * ra.ix, x2 = (hi.x + ra.pad - o.x) * ra.ix;
+    const float y1 = (lo.y - ra.pad - o.y) * ra.iy, y2 = (hi.y + ra.pad - o.y) * ra.iy;
+    const float z1 = (lo.z - ra.pad - o.z) * ra.iz, z2 = (hi.z + ra.pad - o.z) * ra.iz;
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float slack = 1e-5f * fabsf(tf) + 1e-30f;
+    return !(tn > tf + slack) && !(tf < -slack);  // NaN comparisons are false -> treated as a hit
+}
+
+enum { KD_INTERIOR = 0, KD_LEAF = 1, KD_CULLED = 2 };
+
+// One Node.Intersect step.  KD_LEAF: `node` is a leaf (first/count filled in); KD_CULLED: its subtree cannot be hit.
+template <int STACK, bool CULL>
+PT_D int kd_step(const ptgpu_node* __restrict__ nodes, const float4* __restrict__ nb, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint32_t* stNode,
+                 double* stMin, double* stMax, uint32_t& leafFirst, uint32_t& leafCount) {
+    if (CULL) { if (!bounds_hit(nb, c.node, o, ra)) return KD_CULLED; }
     const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));  // one 128-bit load per node
     const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
     const uint32_t axis = a & 3u;
-    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return false; }
+    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return KD_LEAF; }
     const double split = __hiloint2double(raw.y, raw.x);
     const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
     const double tsplit = (split - oa) / da;
@@ -517,7 +547,7 @@ PT_D bool kd_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d,
         c.node = first;
         c.tmax = tsplit;
     }
-    return true;
+    return KD_INTERIOR;
 }
 // After a leaf: resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
 PT_D bool kd_pop(KdCursor& c, double bestT, const uint32_t* stNode, const double* stMin, const double* stMax) {
@@ -568,103 +598,112 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
     uint32_t mPos = 0, mEnd = 0;
     double mBest = kHitInf; int32_t mPrim = -1;
     uint32_t curShape = 0; int32_t curInst = -1;
+    RayAux ra = ray_aux(co, cd);             // for the mesh being traversed
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
 
+    // Scheduling.  Lanes fall into three classes: LEAF (testing triangles of a mesh leaf), NODE (walking a mesh tree) and
+    // GLUE (everything else: fetching a ray, the scene tree, per-shape set-up, folding a shape's hit, writing the
+    // result).  Executing a block costs the same whatever the number of lanes in it, so each iteration runs only the
+    // class most lanes are waiting in; the others accumulate until they win.  (ncu on the two-block version showed
+    // the glue code running at 1-3 lanes and taking ~30 % of all issued instructions.)
     for (;;) {
-        if (st == ST_IDLE) {
-            auto g = cooperative_groups::coalesced_threads();
-            uint32_t base = 0;
-            if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
-            rayIdx = g.shfl(base, 0) + g.thread_rank();
-            if (rayIdx >= n) st = ST_EXIT;
-            else {
-                source(rayIdx, o, d);
-                best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
-                box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
-                if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-                else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }
-            }
-        }
-        if (__all_sync(0xFFFFFFFFu, st == ST_EXIT)) break;
-
-        if (st == ST_SCENE_NODE) {
-#pragma unroll 1
-            for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
-                uint32_t first, count;
-                if (!kd_step<kSceneStack>(S.nodes, sc, o, d, sStNode, sStMin, sStMax, first, count)) { sPos = first; sEnd = first + count; st = ST_SCENE_LEAF; }
-            }
-        }
-        if (st == ST_SCENE_LEAF) {
-            if (sPos == sEnd) {
-                st = kd_pop(sc, best.t, sStNode, sStMin, sStMax) ? ST_SCENE_NODE : ST_FINISH;
-            } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
-                curShape = __ldg(S.leafItems + sPos);
-                sPos++;
-                ptgpu_shape sh = S.shapes[curShape];
-                curInst = -1; co = o; cd = d;
-                if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45: shapeRay = Matrix.Inverse().MulRay(r)
-                    curInst = (int32_t)sh.data;
-                    const ptgpu_instance& inst = S.instances[sh.data];
-                    co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
-                    sh = S.shapes[inst.shape];
-                }
-                if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
-                    const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
-                    mBest = kHitInf; mPrim = -1;
-                    box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
-                    if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
-                    else { mc.node = mt.root; mc.sp = 0; st = ST_MESH_NODE; }
-                } else {
-                    mBest = primitive_intersect(S, sh, co, cd);
-                    mPrim = -1;
-                    st = ST_MESH_DONE;
-                }
-            }
-        }
-        // The two heavy states.  Executing a block costs the same whatever the number of lanes in that state, so each
-        // iteration runs only the block the majority of lanes is waiting for; the minority accumulates until it wins.
         const unsigned leafMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_LEAF);
         const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE);
-        if (__popc(nodeMask) > __popc(leafMask)) {
+        const unsigned exitMask = __ballot_sync(0xFFFFFFFFu, st == ST_EXIT);
+        if (exitMask == 0xFFFFFFFFu) break;
+        const int nLeaf = __popc(leafMask), nNode = __popc(nodeMask), nGlue = 32 - nLeaf - nNode - __popc(exitMask);
+
+        if (nGlue > 0 && nGlue >= nLeaf && nGlue >= nNode) {
+            if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
+                double t = mBest, tInner = 0;
+                if (curInst >= 0) {
+                    tInner = mBest;
+                    if (mBest < kHitInf) {  // TransformedShape.cs:47-69: hit.T = |Matrix.MulPosition(shapeRay.Position(T)) - r.Origin|
+                        const ptgpu_instance& inst = S.instances[curInst];
+                        V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
+                        t = (double)vlenf(vsub(position, o));
+                    }
+                }
+                if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
+                st = ST_SCENE_LEAF;
+            }
+            if (st == ST_FINISH) {
+                if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
+                sink(rayIdx, best);
+                st = ST_IDLE;
+            }
+            if (st == ST_IDLE) {
+                auto g = cooperative_groups::coalesced_threads();
+                uint32_t base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
+                rayIdx = g.shfl(base, 0) + g.thread_rank();
+                if (rayIdx >= n) st = ST_EXIT;
+                else {
+                    source(rayIdx, o, d);
+                    best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
+                    box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
+                    if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
+                    else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }
+                }
+            }
+            if (st == ST_SCENE_NODE) {
+#pragma unroll 1
+                for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
+                    uint32_t first, count;
+                    if (kd_step<kSceneStack, false>(S.nodes, nullptr, ra, sc, o, d, sStNode, sStMin, sStMax, first, count) == KD_LEAF) {
+                        sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
+                    }
+                }
+            }
+            if (st == ST_SCENE_LEAF) {
+                if (sPos == sEnd) {
+                    st = kd_pop(sc, best.t, sStNode, sStMin, sStMax) ? ST_SCENE_NODE : ST_FINISH;
+                } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
+                    curShape = __ldg(S.leafItems + sPos);
+                    sPos++;
+                    ptgpu_shape sh = S.shapes[curShape];
+                    curInst = -1; co = o; cd = d;
+                    if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45: shapeRay = Matrix.Inverse().MulRay(r)
+                        curInst = (int32_t)sh.data;
+                        const ptgpu_instance& inst = S.instances[sh.data];
+                        co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
+                        sh = S.shapes[inst.shape];
+                    }
+                    if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
+                        const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
+                        mBest = kHitInf; mPrim = -1;
+                        ra = ray_aux(co, cd);
+                        box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
+                        if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
+                        else { mc.node = mt.root; mc.sp = 0; st = ST_MESH_NODE; }
+                    } else {
+                        mBest = primitive_intersect(S, sh, co, cd);
+                        mPrim = -1;
+                        st = ST_MESH_DONE;
+                    }
+                }
+            }
+        } else if (nNode > nLeaf) {
             if (st == ST_MESH_NODE) {
 #pragma unroll 1
                 for (int k = 0; k < 4 && st == ST_MESH_NODE; k++) {
                     uint32_t first, count;
-                    if (!kd_step<kMeshStack>(S.nodes, mc, co, cd, mStNode, mStMin, mStMax, first, count)) {
-                        mPos = first; mEnd = first + count;
-                        st = ST_MESH_LEAF;
-                    }
+                    const int r = kd_step<kMeshStack, true>(S.nodes, S.nodeBounds, ra, mc, co, cd, mStNode, mStMin, mStMax, first, count);
+                    if (r == KD_LEAF) { mPos = first; mEnd = first + count; st = ST_MESH_LEAF; }
+                    else if (r == KD_CULLED) st = kd_pop(mc, mBest, mStNode, mStMin, mStMax) ? ST_MESH_NODE : ST_MESH_DONE;
                 }
             }
-        } else if (leafMask) {
+        } else {
             if (st == ST_MESH_LEAF) {
 #pragma unroll 1
                 for (int k = 0; k < 2 && mPos < mEnd; k++) {
-                    const uint32_t tri = __ldg(S.leafItems + mPos);
+                    // geometry is stored in leaf order (no index indirection on the miss path)
+                    const double t = triangle_intersect(S.leafGeom + (size_t)mPos * 3, co, cd);
+                    if (t < mBest) { mBest = t; mPrim = (int32_t)__ldg(S.leafItems + mPos); }  // Tree.cs:122 strict <
                     mPos++;
-                    const double t = triangle_intersect(S.triGeom + (size_t)tri * 3, co, cd);
-                    if (t < mBest) { mBest = t; mPrim = (int32_t)tri; }  // Tree.cs:122 strict <
                 }
                 if (mPos >= mEnd) st = kd_pop(mc, mBest, mStNode, mStMin, mStMax) ? ST_MESH_NODE : ST_MESH_DONE;
             }
-        }
-        if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
-            double t = mBest, tInner = 0;
-            if (curInst >= 0) {
-                tInner = mBest;
-                if (mBest < kHitInf) {  // TransformedShape.cs:47-69: hit.T = |Matrix.MulPosition(shapeRay.Position(T)) - r.Origin|
-                    const ptgpu_instance& inst = S.instances[curInst];
-                    V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
-                    t = (double)vlenf(vsub(position, o));
-                }
-            }
-            if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
-            st = ST_SCENE_LEAF;
-        }
-        if (st == ST_FINISH) {
-            if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
-            sink(rayIdx, best);
-            st = ST_IDLE;
         }
     }
 }

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -248,7 +249,10 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
 }
 
 // K2.  Closest hit for every queued ray (persistent warps, per-lane ray replacement; see trace_rays).
-__global__ void __launch_bounds__(128) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursor, HitQueue hq,
+#ifndef PT_TRACE_MINBLOCKS
+#define PT_TRACE_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursor, HitQueue hq,
                                                 DeviceCounters* cnt) {
     const uint32_t n = *count;
     trace_rays(S, n, cursor,
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, PassD P, const DLight* 
 }
 
 // K4.  sampleLight's visibility test: closest hit, then identity with the light (Sampler.cs:261-265).
-__global__ void __launch_bounds__(128) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t* __restrict__ cursor,
                                                  uint32_t capShadow, float* __restrict__ sum, DeviceCounters* cnt) {
     uint32_t n = *scount;
     if (n > capShadow) n = capShadow;
@@ -721,6 +725,64 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
         D.texels = t;
     }
 #undef UP
+    {   // padded triangle bounds per kd node (see bounds_hit in pt_device.cuh).  Nodes are stored parent-before-child,
+        // so one reverse sweep folds children into parents.  Scene-tree nodes get an unbounded box (never culled).
+        const uint64_t nn = s->numNodes;
+        std::vector<float> nb(nn * 8);
+        std::vector<uint8_t> isMeshNode(nn, 0);
+        for (uint32_t m = 0; m < s->numMeshes; m++) {
+            const ptgpu_tree& t = s->trees[s->meshes[m].tree];
+            // nodes of a tree are contiguous from its root up to the next tree's root
+            uint64_t end = nn;
+            for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > t.root && s->trees[k].root < end) end = s->trees[k].root;
+            for (uint64_t i = t.root; i < end; i++) isMeshNode[i] = 1;
+        }
+        const float BIG = 3.0e38f;
+        for (uint64_t ii = nn; ii-- > 0;) {
+            float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
+            const ptgpu_node& n = s->nodes[ii];
+            if (!isMeshNode[ii]) { for (int k = 0; k < 3; k++) { lo[k] = -BIG; hi[k] = BIG; } }
+            else if ((n.a & 3u) == 0) {
+                for (uint32_t k = 0; k < n.b; k++) {
+                    const ptgpu_tri_geom& g = s->triGeom[s->leafItems[(n.a >> 2) + k]];
+                    for (int c = 0; c < 3; c++) {
+                        float p0 = g.v1[c], p1 = g.v1[c] + g.e1[c], p2 = g.v1[c] + g.e2[c];
+                        lo[c] = std::min(lo[c], std::min(p0, std::min(p1, p2)));
+                        hi[c] = std::max(hi[c], std::max(p0, std::max(p1, p2)));
+                    }
+                }
+                // padding: 1e-4 of the box size plus 1e-5 of the coordinate magnitude (the FP32 triangle test errs by
+                // ~1e-7 of |origin - vertex|; the origin-dependent part is added per ray)
+                float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+                for (int c = 0; c < 3; c++) {
+                    float padv = 1e-4f * ext + 1e-5f * std::max(std::fabs(lo[c]), std::fabs(hi[c])) + 1e-7f;
+                    lo[c] -= padv; hi[c] += padv;
+                }
+            } else {
+                const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
+                const float* r = &nb[(uint64_t)n.b * 8];
+                for (int c = 0; c < 3; c++) { lo[c] = std::min(l[c], r[c]); hi[c] = std::max(l[4 + c], r[4 + c]); }
+            }
+            float* o = &nb[ii * 8];
+            o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = 0; o[4] = hi[0]; o[5] = hi[1]; o[6] = hi[2]; o[7] = 0;
+        }
+        const float4* d = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(nb.data()), nn * 2, &d)) != PTGPU_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));  // nb is a local
+        D.nodeBounds = d;
+        // triangle geometry replicated in leaf order, so a leaf is one contiguous run of 48-byte records
+        std::vector<ptgpu_tri_geom> lg(s->numLeafItems);
+        std::memset(lg.data(), 0, lg.size() * sizeof(ptgpu_tri_geom));
+        for (uint64_t i = 0; i < nn; i++) {
+            const ptgpu_node& n = s->nodes[i];
+            if (!isMeshNode[i] || (n.a & 3u) != 0) continue;
+            for (uint32_t k = 0; k < n.b; k++) lg[(n.a >> 2) + k] = s->triGeom[s->leafItems[(n.a >> 2) + k]];
+        }
+        const float4* dl = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(lg.data()), (uint64_t)lg.size() * 3, &dl)) != PTGPU_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        D.leafGeom = dl;
+    }
     D.sceneTree = s->sceneTree; D.numSceneShapes = s->numSceneShapes; D.numLights = s->numLights; D.numShapes = s->numShapes;
     D.envColor[0] = s->envColor[0]; D.envColor[1] = s->envColor[1]; D.envColor[2] = s->envColor[2];
     D.envTexture = s->envTexture; D.envTextureAngle = s->envTextureAngle;
@@ -862,7 +924,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     int rc = ensure_queues(ctx, capShadow);
     if (rc != PTGPU_OK) return rc;
 
-    const int gridTrace = grid_for(ctx, 8), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
+    const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
     uint32_t* counts = ctx->dCounts;
     const bool prof = ctx->profiling;
     float ms = 0;

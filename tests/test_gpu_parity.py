@@ -77,6 +77,39 @@ def test_closest_hit_bit_exact(orc, bindings, device, name):
         np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
 
 
+def test_closest_hit_large_random_batch(orc, bindings, device):
+    """150k random rays against the mesh scene — near, inside, grazing and very far origins — to exercise the padded
+    subtree bounds (bounds_hit) and the division-free triangle filter against the reference sequence."""
+    hw, ow, _ = _worlds(orc, bindings, "c3")
+    device.upload(hw)
+    rng = np.random.default_rng(11)
+    n = 50000
+    def dirs(k):
+        v = rng.normal(size=(k, 3)); return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+    # (a) origins in a box around the meshes, random directions
+    oa = (rng.random((n, 3)) * [5.0, 3.0, 4.0] + [-1.5, -0.2, -2.0]).astype(np.float32); da = dirs(n)
+    # (b) far origins aimed at points near the big mesh (|o| ~ 1e3: the origin-dependent padding)
+    tgt = (rng.normal(size=(n, 3)) * 0.6 + [0, 1, 0])
+    ob = (dirs(n).astype(np.float64) * 1000.0 + [0, 1, 0]).astype(np.float32)
+    db = tgt - ob; db = (db / np.linalg.norm(db, axis=1, keepdims=True)).astype(np.float32)
+    # (c) rays starting on the surface, grazing along it
+    hit0 = ow.intersect_batch(oa, da)
+    ok = np.flatnonzero(hit0["shape"] >= 0)
+    idx = rng.choice(ok, n, replace=True)
+    nrm = hit0["normal"][idx].astype(np.float64)
+    tang = np.cross(nrm, dirs(n)); tang /= np.maximum(np.linalg.norm(tang, axis=1, keepdims=True), 1e-9)
+    oc = hit0["position"][idx]; dc = (tang + 0.02 * nrm * rng.normal(size=(n, 1))).astype(np.float32)
+    dc /= np.linalg.norm(dc, axis=1, keepdims=True)
+    o = np.concatenate([oa, ob, oc]); d = np.concatenate([da, db, dc.astype(np.float32)])
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    assert hit.sum() > 50000
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["prim"], c["prim"])
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+
+
 def test_closest_hit_degenerate_rays(orc, bindings, device):
     """Axis-parallel rays (0/0 and x/0 in the slab and split tests), rays starting on a split plane, zero direction."""
     hw, ow, _ = _worlds(orc, bindings, "c3")
