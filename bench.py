@@ -200,17 +200,12 @@ def main():
     stream = tstream.cuda_stream
     d_sum = torch.zeros(npix * 3, dtype=torch.float32, device="cuda")
 
-    def make_pass(step):
-        # weak scaling: rank r draws global samples [r*spp, (r+1)*spp) of every pixel
-        return hw.make_pass(W, H, spp, pass_index=step, sample_base=rank * spp, sample_stride=1)
+    from ptsharp_b200 import distributed as D
+    # weak scaling: rank r draws global samples [r*spp, (r+1)*spp) of every pixel; one NCCL reduce per pass
+    rs = D.blocked_split(spp, rank, world_size)
 
     def one_step(step):
-        d_sum.zero_()
-        dev.accumulate_device(make_pass(step), d_sum.data_ptr(), stream)
-        if world_size > 1:
-            dist.reduce(d_sum, dst=0)
-        if rank == 0:
-            dev.add_sample_device(W, H, d_sum.data_ptr(), float(spp * world_size), stream)
+        D.render_pass_distributed(dev, hw, W, H, rs, d_sum, stream, pass_index=step, rank=rank)
 
     def barrier():
         torch.cuda.synchronize()

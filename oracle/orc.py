@@ -29,7 +29,7 @@ _EXTRA = {
                                c_float_p, c_int_p, c_int_p]),
     "cast_rays": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_int_p,
                          C.c_uint, C.c_uint, c_float_p, c_float_p]),
-    "render": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int,
+    "render": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int,
                       c_int_p, c_double_p, c_double_p, c_ll_p]),
     "tree_stats": (C.c_int, [C.c_void_p, C.c_int, c_ll_p, c_float_p]),
     "tree_dump": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_double_p, c_int_p, c_int_p, c_int_p]),
@@ -95,12 +95,12 @@ class OracleWorld(World):
         return o, d
 
     def render(self, W, H, spp, passes=1, stratified=False, threads=1, rng_mode=RNG_SEQUENTIAL, seed=0x50545348,
-               sample_base=0, window=None):
+               sample_base=0, sample_stride=1, window=None):
         mean = np.zeros((H, W, 3), np.float64)
         var = np.zeros((H, W, 3), np.float64)
         cnt = (C.c_longlong * 3)()
         win = None if window is None else (C.c_int * 4)(*window)
-        self.lib.orc_render(self.h, W, H, spp, passes, int(stratified), threads, rng_mode, seed, sample_base, win,
+        self.lib.orc_render(self.h, W, H, spp, passes, int(stratified), threads, rng_mode, seed, sample_base, sample_stride, win,
                             mean.ctypes.data_as(c_double_p), var.ctypes.data_as(c_double_p), cnt)
         return mean, var, dict(cameraSamples=cnt[0], segments=cnt[1], shadowRays=cnt[2])
 

@@ -208,7 +208,7 @@ void orc_cast_rays(orc_world* w, int W, int H, int n, const int* x, const int* y
 // `passes` calls of RenderParallel on a fresh Buffer; mean = Pixel.M, var = Pixel.Variance() (Buffer.cs:46-55).
 // window = {x0,y0,x1,y1} or NULL.  counters = {cameraSamples, segments, shadowRays}.
 void orc_render(orc_world* w, int W, int H, int spp, int passes, int stratified, int threads, int rngMode, unsigned seed,
-                int sampleBase, const int* window, double* mean, double* var, long long* counters) {
+                int sampleBase, int sampleStride, const int* window, double* mean, double* var, long long* counters) {
     if (!w->compiled) orc_compile(w);
     Buffer buf(W, H);
     Counters total;
@@ -221,6 +221,7 @@ void orc_render(orc_world* w, int W, int H, int spp, int passes, int stratified,
         opt.seed = seed;
         opt.pass = (uint32_t)p;
         opt.sampleBase = sampleBase;
+        opt.sampleStride = sampleStride > 0 ? sampleStride : 1;
         if (window) { opt.x0 = window[0]; opt.y0 = window[1]; opt.x1 = window[2]; opt.y1 = window[3]; }
         Counters c = RenderPass(w->scene, w->camera, w->sampler, buf, opt);
         total.cameraSamples += c.cameraSamples;

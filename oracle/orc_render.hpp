@@ -365,6 +365,7 @@ struct RenderOptions {
     uint32_t seed = 0x50545348u;      // "PTSH"
     uint32_t pass = 0;
     int sampleBase = 0;               // global index of this pass's first sample (keyed RNG)
+    int sampleStride = 1;             // global index stride (a rank of a multi-process job draws every stride-th sample)
     // optional window (bounded CPU-baseline samples): pixels outside it are skipped
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
 };
@@ -433,7 +434,7 @@ static inline Counters RenderPass(Scene& scene, const Camera& camera, const Defa
                             for (int v = 0; v < sppRoot; v++, si++) {
                                 double fu = ((double)u + 0.5) / (double)sppRoot;
                                 double fv = ((double)v + 0.5) / (double)sppRoot;
-                                rng.SetSample(opt.seed, opt.pass, pixel, (uint32_t)(opt.sampleBase + si));
+                                rng.SetSample(opt.seed, opt.pass, pixel, (uint32_t)(opt.sampleBase + si * opt.sampleStride));
                                 rng.Enter(0, 0, 0, 0);
                                 Ray ray = camera.CastRay(x, y, w, h, fu, fv, rng);
                                 cn.cameraSamples++;
@@ -442,7 +443,7 @@ static inline Counters RenderPass(Scene& scene, const Camera& camera, const Defa
                     } else {  // Renderer.cs:287-311
                         Colour c(0, 0, 0);
                         for (int p = 0; p < spp; p++) {
-                            rng.SetSample(opt.seed, opt.pass, pixel, (uint32_t)(opt.sampleBase + p));
+                            rng.SetSample(opt.seed, opt.pass, pixel, (uint32_t)(opt.sampleBase + p * opt.sampleStride));
                             rng.Enter(0, 0, 0, 0);
                             c = c.Add(RenderOneSample(scene, camera, sampler, w, h, x, y, rng, cn));
                         }
