@@ -696,7 +696,7 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
         } else {
             if (st == ST_MESH_LEAF) {
 #pragma unroll 1
-                for (int k = 0; k < 2 && mPos < mEnd; k++) {
+                for (int k = 0; k < 4 && mPos < mEnd; k++) {
                     // geometry is stored in leaf order (no index indirection on the miss path)
                     const double t = triangle_intersect(S.leafGeom + (size_t)mPos * 3, co, cd);
                     if (t < mBest) { mBest = t; mPrim = (int32_t)__ldg(S.leafItems + mPos); }  // Tree.cs:122 strict <
