@@ -576,7 +576,7 @@ PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3
     }
 }
 
-enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT };
+enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT, ST_SDF, ST_VOLUME };
 
 // Scene.Intersect (Scene.cs:75-79) for rays [0, n): `source(i, o, d)` loads ray i, `sink(i, hit)` consumes its closest
 // hit.  `cursor` is a zero-initialised global counter shared by every warp of the launch.
@@ -598,6 +598,7 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
     uint32_t mPos = 0, mEnd = 0;
     double mBest = kHitInf; int32_t mPrim = -1;
     uint32_t curShape = 0; int32_t curInst = -1;
+    uint32_t marchData = 0;                  // sdfShapes[] / volumes[] index while in the MARCH class
     RayAux ra = ray_aux(co, cd);             // for the mesh being traversed
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
 
@@ -611,9 +612,53 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
         const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE);
         const unsigned exitMask = __ballot_sync(0xFFFFFFFFu, st == ST_EXIT);
         if (exitMask == 0xFFFFFFFFu) break;
-        const int nLeaf = __popc(leafMask), nNode = __popc(nodeMask), nGlue = 32 - nLeaf - nNode - __popc(exitMask);
+        const unsigned marchMask = __ballot_sync(0xFFFFFFFFu, st == ST_SDF || st == ST_VOLUME);
+        const int nLeaf = __popc(leafMask), nNode = __popc(nodeMask), nMarch = __popc(marchMask);
+        const int nGlue = 32 - nLeaf - nNode - nMarch - __popc(exitMask);
 
-        if (nGlue > 0 && nGlue >= nLeaf && nGlue >= nNode) {
+        if (nMarch > 0 && nMarch >= nGlue && nMarch >= nLeaf && nMarch >= nNode) {
+            // MARCH class: one SDF sphere-tracing step / a few Volume marching steps per turn.  The loop state lives in
+            // the (idle) mesh-traversal variables of the lane: mc.tmin = t, mc.tmax = t2 | tmax, mc.sp = iteration
+            // counter, mc.node = flags, mBest = Volume step.
+            if (st == ST_SDF) {  // SDFShape.Intersect loop body (SDF.cs:47-74); mc.node bit0 = `jump`
+                const ptgpu_sdf_shape& sh = S.sdfShapes[marchData];
+#pragma unroll 1
+                for (int k = 0; k < 2 && st == ST_SDF; k++) {
+                    if (mc.sp >= 1000) { mBest = kHitInf; st = ST_MESH_DONE; break; }
+                    mc.sp++;
+                    double dist = sdf_evaluate(S.sdfOps + sh.progFirst, sh.progCount, ray_at(co, cd, mc.tmin));
+                    const bool jump = mc.node & 1u;
+                    if (jump && dist < 0) { mc.tmin -= (double)0.001f; mc.node = 0; continue; }
+                    if (dist < (double)0.00001f) { mBest = mc.tmin; st = ST_MESH_DONE; break; }
+                    if (jump && dist < (double)0.001f) dist = (double)0.001f;
+                    mc.tmin += dist;
+                    if (mc.tmin > mc.tmax) { mBest = kHitInf; st = ST_MESH_DONE; }
+                }
+            } else if (st == ST_VOLUME) {  // Volume.Intersect (Volume.cs:169-197), one Sign() per step
+                // mc.node: bits 0-15 = sign + 1, bit 16 = refining, bits 17-31 = pending sign + 1; mc.sp = refine counter
+                const ptgpu_volume& v = S.volumes[marchData];
+#pragma unroll 1
+                for (int k = 0; k < 4 && st == ST_VOLUME; k++) {
+                    const bool refining = (mc.node >> 16) & 1u;
+                    if (!refining) {
+                        if (!(mc.tmin <= mc.tmax)) { mBest = kHitInf; st = ST_MESH_DONE; break; }  // `t <= tmax` loop test
+                        const int sign = (int)(mc.node & 0xFFFFu) - 1;
+                        const int sg = vol_sign(S, v, ray_at(co, cd, mc.tmin));
+                        if (sg == 0 || (sign >= 0 && sg != sign)) {
+                            mc.tmin -= mBest; mBest /= 64; mc.tmin += mBest;
+                            mc.node = (mc.node & 0xFFFFu) | (1u << 16) | ((uint32_t)(sg + 1) << 17);
+                            mc.sp = 0;
+                        } else { mc.node = (uint32_t)(sg + 1); mc.tmin += mBest; }
+                    } else if (mc.sp < 64) {
+                        if (vol_sign(S, v, ray_at(co, cd, mc.tmin)) == 0) { const double t = mc.tmin - mBest; mBest = t; st = ST_MESH_DONE; break; }
+                        mc.tmin += mBest; mc.sp++;
+                    } else {  // refinement found nothing: `sign = s`, then the outer loop's `t += step`
+                        mc.node = (mc.node >> 17);
+                        mc.tmin += mBest;
+                    }
+                }
+            }
+        } else if (nGlue > 0 && nGlue >= nLeaf && nGlue >= nNode) {
             if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
                 double t = mBest, tInner = 0;
                 if (curInst >= 0) {
@@ -676,6 +721,21 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
                         box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
                         if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
                         else { mc.node = mt.root; mc.sp = 0; st = ST_MESH_NODE; }
+                    } else if (sh.type == PTGPU_SDF) {  // SDFShape.Intersect prologue (SDF.cs:34-46), loop in the MARCH class
+                        const ptgpu_sdf_shape& q = S.sdfShapes[sh.data];
+                        mPrim = -1; marchData = sh.data;
+                        double t1, t2;
+                        box_intersect(q.bmin, q.bmax, co, cd, t1, t2);
+                        if (t2 < t1 || t2 < 0) { mBest = kHitInf; st = ST_MESH_DONE; }
+                        else { mc.tmin = netmax((double)0.0001f, t1); mc.tmax = t2; mc.sp = 0; mc.node = 1u; st = ST_SDF; }
+                    } else if (sh.type == PTGPU_VOLUME) {  // Volume.Intersect prologue (Volume.cs:171-175)
+                        const ptgpu_volume& q = S.volumes[sh.data];
+                        mPrim = -1; marchData = sh.data;
+                        double tmin, tmax;
+                        box_intersect(q.bmin, q.bmax, co, cd, tmin, tmax);
+                        mBest = (double)(1.0f / 512.0f);  // step
+                        mc.tmin = netmax(mBest, tmin); mc.tmax = tmax; mc.sp = 0; mc.node = 0u;  // sign = -1
+                        st = ST_VOLUME;
                     } else {
                         mBest = primitive_intersect(S, sh, co, cd);
                         mPrim = -1;
