@@ -153,6 +153,14 @@ typedef struct ptgpu_pass {
     int32_t firstHitSamples, maxBounces, directLighting, softShadows, lightMode, specularMode;  /* DefaultSampler */
     uint32_t seed, passIndex;    /* Philox key */
     ptgpu_camera camera;
+    /* Extra passes of RenderParallel (Renderer.cs:340-468), run by ptgpu_render_pass after the main pass; 0 = off.
+     * adaptiveSamples: that many more samples for EVERY pixel, uniform sub-pixel jitter, each its own Buffer.AddSample
+     *   (the parallel path is not adaptive, Renderer.cs:349-364; its second, variance-only loop :376-388 changes nothing
+     *   and is not rendered).
+     * fireflySamples: for pixels whose StandardDeviation().MaxComponent() > fireflyThreshold (Renderer.cs:426), up to
+     *   that many more samples, stopping at the first one IsFirefly() rejects (Renderer.cs:430-441, 474-497). */
+    int32_t adaptiveSamples, fireflySamples;
+    double fireflyThreshold;     /* Renderer.FireflyThreshold, 1 in NewRenderer (Renderer.cs:47) */
 } ptgpu_pass;
 
 typedef struct ptgpu_params {

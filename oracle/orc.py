@@ -24,6 +24,8 @@ c_uint_p = C.POINTER(C.c_uint)
 
 _EXTRA = {
     "num_lights": (C.c_int, [C.c_void_p]),
+    "set_extra": (None, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
+    "last_samples": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "camera_get": (None, [C.c_void_p, c_float_p, c_double_p]),
     "intersect_batch": (None, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p, c_float_p,
                                c_float_p, c_int_p, c_int_p]),
@@ -103,6 +105,16 @@ class OracleWorld(World):
         self.lib.orc_render(self.h, W, H, spp, passes, int(stratified), threads, rng_mode, seed, sample_base, sample_stride, win,
                             mean.ctypes.data_as(c_double_p), var.ctypes.data_as(c_double_p), cnt)
         return mean, var, dict(cameraSamples=cnt[0], segments=cnt[1], shadowRays=cnt[2])
+
+    def set_extra(self, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0):
+        self.lib.orc_set_extra(self.h, adaptive_samples, firefly_samples, float(firefly_threshold))
+
+    def last_samples(self, W, H):
+        """Pixel.Samples of the Buffer the last render() filled."""
+        out = np.empty(W * H, np.int32)
+        if self.lib.orc_last_samples(self.h, W * H, out.ctypes.data_as(c_int_p)) != 0:
+            raise ValueError("size mismatch")
+        return out.reshape(H, W)
 
     def tree_stats(self, which=-1):
         out = (C.c_longlong * 4)()

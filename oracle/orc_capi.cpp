@@ -20,6 +20,9 @@ struct orc_world {
     std::vector<std::unique_ptr<SDF>> sdfs;
     std::unique_ptr<Buffer> buffer;
     bool compiled = false;
+    int adaptiveSamples = 0, fireflySamples = 0;
+    double fireflyThreshold = 1;
+    std::vector<int> lastSamples;  // Pixel.Samples of the last orc_render
 };
 
 static Vector V3(const double* v) { return Vector(v[0], v[1], v[2]); }
@@ -150,6 +153,17 @@ void orc_sampler(orc_world* w, int firstHit, int maxBounces, int directLighting,
     w->sampler.specularMode = specularMode;
 }
 
+// Renderer.AdaptiveSamples / FireflySamples / FireflyThreshold for subsequent orc_render calls.
+void orc_set_extra(orc_world* w, int adaptiveSamples, int fireflySamples, double fireflyThreshold) {
+    w->adaptiveSamples = adaptiveSamples; w->fireflySamples = fireflySamples; w->fireflyThreshold = fireflyThreshold;
+}
+
+int orc_last_samples(orc_world* w, int n, int* out) {
+    if ((size_t)n != w->lastSamples.size()) return -1;
+    std::memcpy(out, w->lastSamples.data(), (size_t)n * sizeof(int));
+    return 0;
+}
+
 void orc_compile(orc_world* w) {
     w->scene.Compile();
     w->compiled = true;
@@ -222,14 +236,17 @@ void orc_render(orc_world* w, int W, int H, int spp, int passes, int stratified,
         opt.pass = (uint32_t)p;
         opt.sampleBase = sampleBase;
         opt.sampleStride = sampleStride > 0 ? sampleStride : 1;
+        opt.AdaptiveSamples = w->adaptiveSamples; opt.FireflySamples = w->fireflySamples; opt.FireflyThreshold = w->fireflyThreshold;
         if (window) { opt.x0 = window[0]; opt.y0 = window[1]; opt.x1 = window[2]; opt.y1 = window[3]; }
         Counters c = RenderPass(w->scene, w->camera, w->sampler, buf, opt);
         total.cameraSamples += c.cameraSamples;
         total.segments += c.segments;
         total.shadowRays += c.shadowRays;
     }
+    w->lastSamples.resize(buf.Pixels.size());
     for (size_t i = 0; i < buf.Pixels.size(); i++) {
         const Pixel& px = buf.Pixels[i];
+        w->lastSamples[i] = px.Samples;
         if (mean) { mean[3 * i] = px.M.r; mean[3 * i + 1] = px.M.g; mean[3 * i + 2] = px.M.b; }
         if (var) { Colour v = px.Variance(); var[3 * i] = v.r; var[3 * i + 1] = v.g; var[3 * i + 2] = v.b; }
     }

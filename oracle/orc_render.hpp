@@ -14,6 +14,7 @@
 //     (Enter/EnterLight); a sequential source ignores that.
 #pragma once
 #include <algorithm>
+#include <functional>
 #include <thread>
 
 #include "orc_scene.hpp"
@@ -366,6 +367,9 @@ struct RenderOptions {
     uint32_t pass = 0;
     int sampleBase = 0;               // global index of this pass's first sample (keyed RNG)
     int sampleStride = 1;             // global index stride (a rank of a multi-process job draws every stride-th sample)
+    int AdaptiveSamples = 0;          // Renderer.cs:23
+    int FireflySamples = 0;           // Renderer.cs:27
+    double FireflyThreshold = 1;      // Renderer.cs:47
     // optional window (bounded CPU-baseline samples): pixels outside it are skipped
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
 };
@@ -459,6 +463,85 @@ static inline Counters RenderPass(Scene& scene, const Camera& camera, const Defa
     for (int i = 1; i < nthreads; i++) pool.emplace_back(worker, i);
     worker(0);
     for (auto& th : pool) th.join();  // Renderer.cs:336 (Dispose joins the pool)
+
+    // Parallel.For over pixel indices (Renderer.cs:349, 423): contiguous chunks handed to the same thread count.
+    auto parallelFor = [&](size_t n, const std::function<void(size_t, size_t, int)>& body) {
+        std::vector<std::thread> ths;
+        size_t chunk = (n + (size_t)nthreads - 1) / (size_t)nthreads;
+        for (int t = 1; t < nthreads; t++) ths.emplace_back([&, t] { size_t a = std::min(n, chunk * t), b = std::min(n, chunk * (t + 1)); if (a < b) body(a, b, t); });
+        if (n > 0) body(0, std::min(n, chunk), 0);
+        for (auto& th : ths) th.join();
+    };
+    const uint32_t kAdaptiveBase = 1u << 20, kFireflyBase = 1u << 21;  // global sample index ranges of the extra samples
+    // One extra camera sample with uniform sub-pixel jitter: fu, fv = Random.Shared.NextDouble() (Renderer.cs:351-354, 432).
+    auto extraSample = [&](int x, int y, uint32_t sampleIndex, Rng& rng, Counters& cn) {
+        rng.SetSample(opt.seed, opt.pass, (uint32_t)(y * w + x), sampleIndex);
+        rng.Enter(0, 0, 0, 0);
+        double fu = rng.NextDouble(), fv = rng.NextDouble();
+        Ray ray = camera.CastRay(x, y, w, h, fu, fv, rng);
+        cn.cameraSamples++;
+        return sampler.Sample(scene, ray, rng, cn);
+    };
+    if (opt.AdaptiveSamples > 0) {
+        // Renderer.cs:340-364: AdaptiveSamples more samples for EVERY pixel, each its own Buffer.AddSample.  (The second loop,
+        // :376-388, re-renders as many samples only to fill a dictionary nothing reads: no effect on the Buffer, omitted.)
+        parallelFor((size_t)w * h, [&](size_t a, size_t b, int tid) {
+            Rng rng; rng.mode = opt.rngMode;
+            if (opt.rngMode == RNG_SEQUENTIAL) rng.SeedSequential(((uint64_t)opt.seed << 32) ^ ((uint64_t)opt.pass << 20) ^ 0xA0000 ^ (uint64_t)tid);
+            Counters cn;
+            for (size_t i = a; i < b; i++) {
+                int y = (int)(i / (size_t)w), x = (int)(i % (size_t)w);
+                if (x < wx0 || x >= wx1 || y < wy0 || y >= wy1) continue;
+                for (int j = 0; j < opt.AdaptiveSamples; j++) buf.AddSample(x, y, extraSample(x, y, kAdaptiveBase + (uint32_t)j, rng, cn));
+            }
+            perThread[(size_t)tid].segments += cn.segments; perThread[(size_t)tid].shadowRays += cn.shadowRays; perThread[(size_t)tid].cameraSamples += cn.cameraSamples;
+        });
+    }
+    if (opt.FireflySamples > 0) {
+        // Renderer.cs:418-468.  Every pixel whose StandardDeviation().MaxComponent() > FireflyThreshold takes up to
+        // FireflySamples more samples and stops at the first one IsFirefly() rejects.  The reference lets every pixel's loop
+        // read its neighbours' running means while other threads update them; here the iterations are synchronous (all
+        // pixels draw sample j, decide against the buffer as it stood before sample j, then apply) so that a run is
+        // reproducible.  `skippedPixels` is local to the pass, so its else-branch (:448-463) is unreachable.
+        std::vector<uint32_t> list;
+        for (size_t i = 0; i < buf.Pixels.size(); i++) {
+            Colour sd = buf.Pixels[i].Variance().Pow((double)0.5f);  // Pixel.StandardDeviation (Buffer.cs:57)
+            if (sd.MaxComponent() > opt.FireflyThreshold) list.push_back((uint32_t)i);
+        }
+        std::vector<Colour> fresh;
+        std::vector<uint8_t> reject;
+        for (int j = 0; j < opt.FireflySamples && !list.empty(); j++) {
+            fresh.assign(list.size(), Colour());
+            parallelFor(list.size(), [&](size_t a, size_t b, int tid) {
+                Rng rng; rng.mode = opt.rngMode;
+                if (opt.rngMode == RNG_SEQUENTIAL) rng.SeedSequential(((uint64_t)opt.seed << 32) ^ ((uint64_t)opt.pass << 20) ^ 0xF0000 ^ ((uint64_t)j << 8) ^ (uint64_t)tid);
+                Counters cn;
+                for (size_t i = a; i < b; i++) {
+                    int y = (int)(list[i] / (uint32_t)w), x = (int)(list[i] % (uint32_t)w);
+                    fresh[i] = extraSample(x, y, kFireflyBase + (uint32_t)j, rng, cn);
+                }
+                perThread[(size_t)tid].segments += cn.segments; perThread[(size_t)tid].shadowRays += cn.shadowRays; perThread[(size_t)tid].cameraSamples += cn.cameraSamples;
+            });
+            reject.assign(list.size(), 0);
+            for (size_t i = 0; i < list.size(); i++) {  // IsFirefly + CalculateLocalDeviation (Renderer.cs:474-537)
+                const Colour& smp = fresh[i];
+                int y = (int)(list[i] / (uint32_t)w), x = (int)(list[i] % (uint32_t)w);
+                double brightness = smp.r * 0.2126 + smp.g * 0.7152 + smp.b * 0.0722;
+                if (brightness > 0.9) {
+                    int sx = std::max(0, x - 1), sy = std::max(0, y - 1), ex = std::min(w - 1, x + 1), ey = std::min(h - 1, y + 1);
+                    double tr = 0, tg = 0, tb = 0; int count = 0;
+                    for (int jj = sy; jj <= ey; jj++)
+                        for (int ii = sx; ii <= ex; ii++) { const Colour& c = buf.Pixels[(size_t)jj * w + ii].M; tr += c.r; tg += c.g; tb += c.b; count++; }
+                    double dr = std::fabs(smp.r - tr / count), dg = std::fabs(smp.g - tg / count), db = std::fabs(smp.b - tb / count);
+                    reject[i] = std::sqrt(dr * dr + dg * dg + db * db) > 0.2;
+                }
+            }
+            std::vector<uint32_t> next;
+            for (size_t i = 0; i < list.size(); i++)
+                if (!reject[i]) { buf.Pixels[list[i]].AddSample(fresh[i]); next.push_back(list[i]); }
+            list.swap(next);
+        }
+    }
     Counters total;
     for (const Counters& c : perThread) {
         total.segments += c.segments;

@@ -35,7 +35,8 @@ class Pass(C.Structure):
                 ("sampleBase", C.c_int32), ("sampleStride", C.c_int32), ("firstHitSamples", C.c_int32),
                 ("maxBounces", C.c_int32), ("directLighting", C.c_int32), ("softShadows", C.c_int32),
                 ("lightMode", C.c_int32), ("specularMode", C.c_int32), ("seed", C.c_uint32), ("passIndex", C.c_uint32),
-                ("camera", Camera)]
+                ("camera", Camera), ("adaptiveSamples", C.c_int32), ("fireflySamples", C.c_int32),
+                ("fireflyThreshold", C.c_double)]
 
 
 class Params(C.Structure):
@@ -105,6 +106,7 @@ _HOST_EXTRA = {
     "builder_friendly_order": (None, [C.c_int, c_float_p, C.c_double, C.c_int, C.c_int, c_int_p]),
     "renderer_new": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "renderer_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "renderer_set_extra": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "renderer_render": (C.c_int, [C.c_void_p, c_float_p]),
     "renderer_iterative": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "renderer_image": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
@@ -155,10 +157,11 @@ class HostWorld(World):
         return int(self.lib.pth_flat_bytes(self.h))
 
     def make_pass(self, width, height, spp, stratified=False, seed=0x50545348, pass_index=0, sample_base=0,
-                  sample_stride=1) -> Pass:
+                  sample_stride=1, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0) -> Pass:
         p = Pass()
         self.lib.pth_make_pass(self.h, width, height, spp, int(stratified), seed, pass_index, sample_base, sample_stride,
                                C.byref(p))
+        p.adaptiveSamples, p.fireflySamples, p.fireflyThreshold = adaptive_samples, firefly_samples, firefly_threshold
         return p
 
     def tree_stats(self, which=-1):
@@ -184,6 +187,10 @@ class HostWorld(World):
 
     def renderer_set(self, samples_per_pixel, stratified=False, seed=0x50545348):
         if self.lib.pth_renderer_set(self.h, samples_per_pixel, int(stratified), seed) != 0:
+            raise PtgpuError(self._err())
+
+    def renderer_set_extra(self, adaptive_samples=0, firefly_samples=0):
+        if self.lib.pth_renderer_set_extra(self.h, adaptive_samples, firefly_samples) != 0:
             raise PtgpuError(self._err())
 
     def render_parallel(self, width, height) -> np.ndarray:

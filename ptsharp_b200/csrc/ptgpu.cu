@@ -161,6 +161,7 @@ PT_D void bounce(V3 rayDir, const Surface& sf, double u, double v, int mode, Rng
 // ====================================================================================================== pipeline state
 struct PassD {  // ptgpu_pass plus derived values, passed by value to kernels
     int32_t width, height, spp, stratified, sppRoot;
+    int32_t subpixelJitter;  // 1: fu, fv = xi1, xi2 (adaptive / firefly passes, Renderer.cs:351-353, 432)
     int32_t sampleBase, sampleStride;
     int32_t firstHitSamples, maxBounces, directLighting, softShadows, lightMode, specularMode;
     uint32_t seed, passIndex;
@@ -218,11 +219,16 @@ PT_D void cast_ray(const ptgpu_camera& cam, int x, int y, int w, int h, double u
 // sampleBase + k*sampleStride.  Non-stratified: fu = (x+xi1)/w, fv = (y+xi2)/h are passed where CastRay expects a
 // sub-pixel offset — the reference's behaviour (Renderer.cs:297-304), reproduced on purpose.
 __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, uint32_t n, RayQueue q, uint32_t* __restrict__ count,
-                                                 DeviceCounters* cnt) {
+                                                 DeviceCounters* cnt, const uint32_t* __restrict__ pixelList, const uint32_t* __restrict__ listCount) {
     const uint32_t npix = (uint32_t)P.width * (uint32_t)P.height;
+    if (pixelList) {  // sparse pass: one sample for each listed pixel; this batch covers list[g0, g0+n)
+        const uint32_t lc = *listCount;
+        n = lc > (uint32_t)g0 ? min(n, lc - (uint32_t)g0) : 0u;
+    }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long g = g0 + i;
         uint32_t pixel = (uint32_t)(g % npix), k = (uint32_t)(g / npix);
+        if (pixelList) { pixel = pixelList[g0 + i]; k = 0; }
         int x = (int)(pixel % (uint32_t)P.width), y = (int)(pixel / (uint32_t)P.width);
         uint32_t sample = (uint32_t)(P.sampleBase + (int)k * P.sampleStride);
         Rng rng;
@@ -235,8 +241,8 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
             fv = ((double)(s % (uint32_t)P.sppRoot) + 0.5) / (double)P.sppRoot;
         } else {
             double xo = rng_next(rng), yo = rng_next(rng);
-            fu = ((double)x + xo) / (double)P.width;
-            fv = ((double)y + yo) / (double)P.height;
+            if (P.subpixelJitter) { fu = xo; fv = yo; }
+            else { fu = ((double)x + xo) / (double)P.width; fv = ((double)y + yo) / (double)P.height; }
         }
         V3 o, d;
         cast_ray(P.cam, x, y, P.width, P.height, fu, fv, rng, o, d);
@@ -467,6 +473,78 @@ __global__ void k_read_buffer(PixelBuf pb, int channel, uint32_t npix, float* __
     }
 }
 
+// Firefly pass (Renderer.cs:418-468).  Pixels whose StandardDeviation().MaxComponent() exceeds the threshold.
+__global__ void k_firefly_select(PixelBuf pb, double threshold, uint32_t npix, uint32_t* __restrict__ list, uint32_t* __restrict__ listCount) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        int32_t ns = pb.samples[i];
+        double mx = 0;
+        for (int c = 0; c < 3; c++) {
+            double v = ns < 2 ? 0.0 : pb.V[(size_t)i * 3 + c] / (double)(ns - 1);
+            double sd = pow(v, (double)0.5f);
+            mx = c == 0 ? sd : netmax(mx, sd);
+        }
+        if (mx > threshold) {
+            auto g = cg::coalesced_threads();
+            uint32_t base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(listCount, g.size());
+            list[g.shfl(base, 0) + g.thread_rank()] = i;
+        }
+    }
+}
+// IsFirefly (Renderer.cs:474-497) + CalculateLocalDeviation (:499-537) for the new sample of every listed pixel, against the
+// buffer as it stands at the start of this iteration (the reference reads its neighbours while other threads update them).
+__global__ void k_firefly_decide(const float* __restrict__ sum, const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount, PixelBuf pb,
+                                 int w, int h, uint8_t* __restrict__ reject) {
+    const uint32_t n = *listCount;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pixel = list[i];
+        const int x = (int)(pixel % (uint32_t)w), y = (int)(pixel / (uint32_t)w);
+        const double r = sum[(size_t)pixel * 3], g = sum[(size_t)pixel * 3 + 1], b = sum[(size_t)pixel * 3 + 2];
+        const double brightness = r * 0.2126 + g * 0.7152 + b * 0.0722;
+        bool rej = false;
+        if (brightness > 0.9) {
+            int x0 = max(0, x - 1), y0 = max(0, y - 1), x1 = min(w - 1, x + 1), y1 = min(h - 1, y + 1);
+            double tr = 0, tg = 0, tb = 0;
+            int count = 0;
+            for (int j = y0; j <= y1; j++)
+                for (int ii = x0; ii <= x1; ii++) {
+                    size_t q = ((size_t)j * w + ii) * 3;
+                    tr += pb.M[q]; tg += pb.M[q + 1]; tb += pb.M[q + 2];
+                    count++;
+                }
+            double dr = fabs(r - tr / count), dg = fabs(g - tg / count), db = fabs(b - tb / count);
+            rej = sqrt(dr * dr + dg * dg + db * db) > 0.2;
+        }
+        reject[i] = rej ? 1 : 0;
+    }
+}
+// Accepted samples go through Buffer.AddSample and the pixel stays listed; a rejected sample ends the pixel's loop (`break`).
+__global__ void k_firefly_apply(float* __restrict__ sum, const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount, const uint8_t* __restrict__ reject,
+                                PixelBuf pb, uint32_t* __restrict__ nextList, uint32_t* __restrict__ nextCount) {
+    const uint32_t n = *listCount;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pixel = list[i];
+        const bool rej = reject[i];
+        if (!rej) {
+            int32_t ns = pb.samples[pixel] + 1;
+            pb.samples[pixel] = ns;
+            for (int c = 0; c < 3; c++) {
+                double s = (double)sum[(size_t)pixel * 3 + c];
+                if (ns == 1) { pb.M[(size_t)pixel * 3 + c] = s; continue; }
+                double m = pb.M[(size_t)pixel * 3 + c];
+                double M2 = m + (s - m) / (double)ns;
+                pb.M[(size_t)pixel * 3 + c] = M2;
+                pb.V[(size_t)pixel * 3 + c] = pb.V[(size_t)pixel * 3 + c] + (s - m) * (s - M2);
+            }
+            auto g = cg::coalesced_threads();
+            uint32_t base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(nextCount, g.size());
+            nextList[g.shfl(base, 0) + g.thread_rank()] = pixel;
+        }
+        sum[(size_t)pixel * 3] = 0.f; sum[(size_t)pixel * 3 + 1] = 0.f; sum[(size_t)pixel * 3 + 2] = 0.f;
+    }
+}
+
 // K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same trace_rays as the pipeline.
 __global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32_t* __restrict__ cursor, const float* __restrict__ o3, const float* __restrict__ d3,
                                                           int32_t* shape, int32_t* prim, double* t, float* normal3, float* position3, int32_t* inside, int32_t* material) {
@@ -541,6 +619,8 @@ struct ptgpu_ctx {
     float* dSum = nullptr;
     float* dMean = nullptr;
     PixelBuf pb{};
+    uint32_t* dList[2] = {nullptr, nullptr};  // firefly pixel lists (ping-pong)
+    uint8_t* dReject = nullptr;
     // stats
     uint64_t launches = 0;
     double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0;
@@ -593,6 +673,8 @@ static void free_queues(ptgpu_ctx* ctx) {
 }
 static void free_image(ptgpu_ctx* ctx) {
     cudaFree(ctx->dSum); cudaFree(ctx->dMean); cudaFree(ctx->pb.M); cudaFree(ctx->pb.V); cudaFree(ctx->pb.samples);
+    cudaFree(ctx->dList[0]); cudaFree(ctx->dList[1]); cudaFree(ctx->dReject);
+    ctx->dList[0] = ctx->dList[1] = nullptr; ctx->dReject = nullptr;
     ctx->dSum = ctx->dMean = nullptr; ctx->pb = PixelBuf{}; ctx->bufW = ctx->bufH = 0;
 }
 
@@ -641,9 +723,9 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB);
     ctx->capRays = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 24);
     if (ctx->capRays > (1ull << 30)) ctx->capRays = 1ull << 30;
-    if ((e = cudaMalloc(&ctx->dCounts, 8 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->dCounts, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->dCounters, sizeof(DeviceCounters))) != cudaSuccess) return bail("cudaMalloc", e);
-    cudaMemset(ctx->dCounts, 0, 8 * sizeof(uint32_t));
+    cudaMemset(ctx->dCounts, 0, 16 * sizeof(uint32_t));
     cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters));
     *out = ctx;
     return PTGPU_OK;
@@ -866,6 +948,9 @@ static int ensure_image(ptgpu_ctx* ctx, int w, int h) {
     CK(cudaMalloc(&ctx->pb.M, npix * 3 * sizeof(double)));
     CK(cudaMalloc(&ctx->pb.V, npix * 3 * sizeof(double)));
     CK(cudaMalloc(&ctx->pb.samples, npix * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->dList[0], npix * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->dList[1], npix * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->dReject, npix));
     CK(cudaMemsetAsync(ctx->pb.M, 0, npix * 3 * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->pb.V, 0, npix * 3 * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->pb.samples, 0, npix * sizeof(int32_t), ctx->stream));
@@ -880,7 +965,7 @@ static int make_passd(ptgpu_ctx* ctx, const ptgpu_pass* p, PassD& P) {
     int nroot = (int)std::sqrt((double)p->firstHitSamples);
     int modes0 = (p->specularMode == PTGPU_SPECULAR_NAIVE) ? 1 : 2;
     if (nroot * nroot * modes0 > 4094) return fail(ctx, PTGPU_E_LIMIT, "firstHitSamples too large for the 12-bit first-hit index");
-    P.width = p->width; P.height = p->height; P.spp = p->spp; P.stratified = p->stratified;
+    P.width = p->width; P.height = p->height; P.spp = p->spp; P.stratified = p->stratified; P.subpixelJitter = 0;
     P.sppRoot = (int)std::sqrt((double)p->spp);
     P.sampleBase = p->sampleBase; P.sampleStride = p->sampleStride ? p->sampleStride : 1;
     P.firstHitSamples = p->firstHitSamples; P.maxBounces = p->maxBounces; P.directLighting = p->directLighting;
@@ -890,7 +975,8 @@ static int make_passd(ptgpu_ctx* ctx, const ptgpu_pass* p, PassD& P) {
 }
 
 // Issue every kernel of one pass on `stream`, adding radiance into d_sum.  nSlots = samples per pixel rendered.
-static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cudaStream_t stream) {
+static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cudaStream_t stream, const uint32_t* pixelList = nullptr,
+                    const uint32_t* listCount = nullptr) {
     const uint64_t npix = (uint64_t)P.width * P.height;
     const uint64_t total = npix * (uint64_t)nSlots;
     // worst-case queue growth per camera sample: n^2 * modes at depth 0, x modes per later depth
@@ -933,7 +1019,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         uint32_t n = (uint32_t)std::min<uint64_t>(batch, total - g0);
         int cur = 0;
         if (prof) cudaEventRecord(ctx->evA, stream);
-        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, ctx->rq[0], counts + 0, ctx->dCounters);
+        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, ctx->rq[0], counts + 0, ctx->dCounters, pixelList, listCount);
         ctx->launches++;
         if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->raygenMs += ms; }
         for (int depth = 0; depth <= P.maxBounces; depth++) {
@@ -1020,8 +1106,42 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
         k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, (double)P.spp, (uint32_t)npix, ctx->pb, ctx->dMean);
         ctx->launches++;
     }
-    CK(cudaEventRecord(ctx->ev1, st));
     if (out_mean_rgb) CK(cudaMemcpyAsync(out_mean_rgb, ctx->dMean, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // Extra samples use their own ranges of the global sample index so that no Philox stream is reused.
+    const int kAdaptiveBase = 1 << 20, kFireflyBase = 1 << 21;
+    if (pass->adaptiveSamples > 0) {  // Renderer.cs:340-364
+        PassD Q = P;
+        Q.stratified = 0; Q.subpixelJitter = 1; Q.sampleStride = 1;
+        for (int j = 0; j < pass->adaptiveSamples; j++) {
+            Q.sampleBase = kAdaptiveBase + j;
+            CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
+            rc = run_pass(ctx, Q, 1, ctx->dSum, st);
+            if (rc != PTGPU_OK) return rc;
+            k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, 1.0, (uint32_t)npix, ctx->pb, nullptr);
+            ctx->launches++;
+        }
+    }
+    if (pass->fireflySamples > 0) {  // Renderer.cs:418-468
+        PassD Q = P;
+        Q.stratified = 0; Q.subpixelJitter = 1; Q.sampleStride = 1;
+        uint32_t* lc = ctx->dCounts + 8;  // [8], [9]: list counts
+        CK(cudaMemsetAsync(lc, 0, 2 * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
+        k_firefly_select<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->pb, pass->fireflyThreshold, (uint32_t)npix, ctx->dList[0], lc);
+        ctx->launches++;
+        int cur = 0;
+        for (int j = 0; j < pass->fireflySamples; j++) {
+            Q.sampleBase = kFireflyBase + j;
+            rc = run_pass(ctx, Q, 1, ctx->dSum, st, ctx->dList[cur], lc + cur);
+            if (rc != PTGPU_OK) return rc;
+            CK(cudaMemsetAsync(lc + (cur ^ 1), 0, sizeof(uint32_t), st));
+            k_firefly_decide<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, ctx->dList[cur], lc + cur, ctx->pb, P.width, P.height, ctx->dReject);
+            k_firefly_apply<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, ctx->dList[cur], lc + cur, ctx->dReject, ctx->pb, ctx->dList[cur ^ 1], lc + (cur ^ 1));
+            ctx->launches += 2;
+            cur ^= 1;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     float ms = 0;

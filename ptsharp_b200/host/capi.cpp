@@ -120,6 +120,7 @@ void pth_make_pass(pth_world* w, int width, int height, int spp, int stratified,
     out->lightMode = w->sampler.LightMode; out->specularMode = w->sampler.SpecularMode;
     out->seed = seed; out->passIndex = passIndex;
     out->camera = FlattenCamera(w->camera);
+    out->adaptiveSamples = 0; out->fireflySamples = 0; out->fireflyThreshold = 1.0;
 }
 
 // kd-tree dump in the oracle's canonical pre-order form (builder parity tests).  which = -1: scene tree, else the
@@ -178,6 +179,11 @@ int pth_renderer_new(pth_world* w, int width, int height, int device) {
 int pth_renderer_set(pth_world* w, int samplesPerPixel, int stratified, unsigned seed) {
     if (!w->renderer) { w->error = "no renderer"; return -1; }
     w->renderer->SamplesPerPixel = samplesPerPixel; w->renderer->StratifiedSampling = stratified != 0; w->renderer->Seed = seed;
+    return 0;
+}
+int pth_renderer_set_extra(pth_world* w, int adaptiveSamples, int fireflySamples) {
+    if (!w->renderer) { w->error = "no renderer"; return -1; }
+    w->renderer->AdaptiveSamples = adaptiveSamples; w->renderer->FireflySamples = fireflySamples;
     return 0;
 }
 int pth_renderer_render(pth_world* w, float* outMeanRgb) {

@@ -850,7 +850,7 @@ Renderer Renderer::NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sam
 }
 Renderer::Renderer(Renderer&& o) noexcept
     : SamplesPerPixel(o.SamplesPerPixel), StratifiedSampling(o.StratifiedSampling), AdaptiveSamples(o.AdaptiveSamples),
-      FireflySamples(o.FireflySamples), Device(o.Device), Seed(o.Seed), scene_(o.scene_), camera_(o.camera_),
+      FireflySamples(o.FireflySamples), FireflyThreshold(o.FireflyThreshold), Device(o.Device), Seed(o.Seed), scene_(o.scene_), camera_(o.camera_),
       sampler_(o.sampler_), w_(o.w_), h_(o.h_), passIndex_(o.passIndex_), ctx_(o.ctx_), flat_(std::move(o.flat_)) {
     o.ctx_ = nullptr;
 }
@@ -877,6 +877,7 @@ ptgpu_pass Renderer::MakePass() const {
     p.lightMode = sampler_->LightMode; p.specularMode = sampler_->SpecularMode;
     p.seed = Seed; p.passIndex = passIndex_;
     p.camera = FlattenCamera(*camera_);
+    p.adaptiveSamples = AdaptiveSamples; p.fireflySamples = FireflySamples; p.fireflyThreshold = FireflyThreshold;
     return p;
 }
 void Renderer::RenderParallel(float* out) {

@@ -297,7 +297,8 @@ class Renderer {  // Renderer.cs:15-56, 199-338, 702-765
 public:
     int SamplesPerPixel = 2;
     bool StratifiedSampling = false;
-    int AdaptiveSamples = 0, FireflySamples = 0;  // accepted, not yet rendered on the device
+    int AdaptiveSamples = 0, FireflySamples = 0;  // Renderer.cs:340-468, run on the device after the main pass
+    double FireflyThreshold = 1;                  // Renderer.cs:47
     int Device = 0;
     uint32_t Seed = 0x50545348u;
     static Renderer NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sampler, int w, int h, bool multithreaded);

@@ -227,6 +227,34 @@ def test_stratified_branch(orc, bindings, device):
     device.reset_buffer()
 
 
+def test_adaptive_and_firefly_passes(orc, bindings, device):
+    """Renderer.cs:340-468 after the main pass: AdaptiveSamples extra samples for every pixel, then up to FireflySamples
+    more for pixels above the standard-deviation threshold, stopping at the first sample IsFirefly() rejects."""
+    hw, ow, _ = _worlds(orc, bindings, "c1")
+    device.upload(hw)
+    W, H, spp, A, F, thr = 64, 48, 2, 3, 5, 0.05
+    device.reset_buffer()
+    device.reset_counters()
+    device.render_pass(hw.make_pass(W, H, spp, pass_index=0, adaptive_samples=A, firefly_samples=F, firefly_threshold=thr), want_mean=False)
+    cnt = device.counters()
+    mean = device.read_buffer(W, H, 0).astype(np.float64)
+    var = device.read_buffer(W, H, 1).astype(np.float64)
+    ns = device.read_buffer(W, H, 3)[..., 0].astype(np.int64)
+    device.reset_buffer()
+    ow.set_extra(A, F, thr)
+    ref, rvar, ocnt = ow.render(W, H, spp, passes=1, threads=os.cpu_count() or 1, rng_mode=orc.RNG_KEYED)
+    rns = ow.last_samples(W, H)
+    ow.set_extra(0, 0, 1.0)
+    assert ns.min() == 1 + A and ns.max() <= 1 + A + F and ns.max() > 1 + A  # some pixels took firefly samples
+    assert (ns != rns).mean() < 0.01                                          # same pixels, same stopping points
+    same = ns == rns
+    rel = np.abs(mean - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert (rel.max(axis=2)[same] > 1e-4).mean() < 5e-3
+    relv = np.abs(var - rvar) / np.maximum(np.abs(rvar), 1e-3)
+    assert (relv.max(axis=2)[same] > 1e-3).mean() < 1e-2
+    assert abs(cnt["cameraSamples"] - ocnt["cameraSamples"]) <= 0.01 * ocnt["cameraSamples"]
+
+
 def test_buffer_welford_matches_reference_formula(orc, bindings, device):
     """Buffer.AddSample over several passes (Buffer.cs:33-57) against numpy on the per-pass means."""
     hw, _, _ = _worlds(orc, bindings, "c1")
