@@ -576,6 +576,16 @@ PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3
     }
 }
 
+#ifndef PT_LEAF_BURST
+#define PT_LEAF_BURST 4
+#endif
+#ifndef PT_NODE_BURST
+#define PT_NODE_BURST 4
+#endif
+#ifndef PT_LEAF_UNROLL
+#define PT_LEAF_UNROLL 1
+#endif
+static constexpr int kLeafUnroll = PT_LEAF_UNROLL;
 enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT, ST_SDF, ST_VOLUME };
 
 // Scene.Intersect (Scene.cs:75-79) for rays [0, n): `source(i, o, d)` loads ray i, `sink(i, hit)` consumes its closest
@@ -746,7 +756,7 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
         } else if (nNode > nLeaf) {
             if (st == ST_MESH_NODE) {
 #pragma unroll 1
-                for (int k = 0; k < 4 && st == ST_MESH_NODE; k++) {
+                for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
                     uint32_t first, count;
                     const int r = kd_step<kMeshStack, true>(S.nodes, S.nodeBounds, ra, mc, co, cd, mStNode, mStMin, mStMax, first, count);
                     if (r == KD_LEAF) { mPos = first; mEnd = first + count; st = ST_MESH_LEAF; }
@@ -755,8 +765,8 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
             }
         } else {
             if (st == ST_MESH_LEAF) {
-#pragma unroll 1
-                for (int k = 0; k < 4 && mPos < mEnd; k++) {
+#pragma unroll kLeafUnroll
+                for (int k = 0; k < PT_LEAF_BURST && mPos < mEnd; k++) {
                     // geometry is stored in leaf order (no index indirection on the miss path)
                     const double t = triangle_intersect(S.leafGeom + (size_t)mPos * 3, co, cd);
                     if (t < mBest) { mBest = t; mPrim = (int32_t)__ldg(S.leafItems + mPos); }  // Tree.cs:122 strict <
