@@ -609,6 +609,15 @@ PT_D bool box_line_hit(float lox, float loy, float loz, float hix, float hiy, fl
     return !(tn > tf + slack) && !(tf < -slack);  // NaN comparisons are false -> treated as a hit
 }
 
+// FP32 pre-test of Tree.Intersect's box test (Tree.cs:36-41): false only when the ray misses the mesh box by far more
+// than any rounding, in which case the FP64 Box.Intersect gives tmax < tmin or tmax <= 0 as well (NoHit).
+PT_D bool tree_box_maybe_hit(const ptgpu_tree& t, V3 o, const RayAux& ra) {
+    const float ext = fmaxf(fmaxf(t.bmax[0] - t.bmin[0], t.bmax[1] - t.bmin[1]), t.bmax[2] - t.bmin[2]);
+    const float mag = fmaxf(fmaxf(fmaxf(fabsf(t.bmin[0]), fabsf(t.bmax[0])), fmaxf(fabsf(t.bmin[1]), fabsf(t.bmax[1]))), fmaxf(fabsf(t.bmin[2]), fabsf(t.bmax[2])));
+    const float p = 1e-4f * ext + 1e-5f * mag + 1e-7f;
+    return box_line_hit(t.bmin[0] - p, t.bmin[1] - p, t.bmin[2] - p, t.bmax[0] + p, t.bmax[1] + p, t.bmax[2] + p, o, ra);
+}
+
 // Resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
 PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
     while (c.sp > 0) {
@@ -691,10 +700,16 @@ PT_D bool leaf_work(const DScene& S, const RayAux& ra, V3 o, V3 d, uint32_t& gPo
 }
 
 #ifndef PT_LEAF_BURST
-#define PT_LEAF_BURST 4
+#define PT_LEAF_BURST 8
 #endif
 #ifndef PT_NODE_BURST
-#define PT_NODE_BURST 4
+#define PT_NODE_BURST 8
+#endif
+#ifndef PT_GLUE_PRIO
+#define PT_GLUE_PRIO 33   // run the GLUE class as soon as this many lanes wait in it (33 = only when it is the plurality)
+#endif
+#ifndef PT_GLUE_CHAIN
+#define PT_GLUE_CHAIN 1
 #endif
 #ifndef PT_LEAF_UNROLL
 #define PT_LEAF_UNROLL 1
@@ -783,88 +798,97 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
                     }
                 }
             }
-        } else if (nGlue > 0 && nGlue >= nLeaf && nGlue >= nNode) {
-            if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
-                double t = mBest, tInner = 0;
-                if (curInst >= 0) {
-                    tInner = mBest;
-                    if (mBest < kHitInf) {  // TransformedShape.cs:47-69: hit.T = |Matrix.MulPosition(shapeRay.Position(T)) - r.Origin|
-                        const ptgpu_instance& inst = S.instances[curInst];
-                        V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
-                        t = (double)vlenf(vsub(position, o));
-                    }
-                }
-                if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
-                st = ST_SCENE_LEAF;
-            }
-            if (st == ST_FINISH) {
-                if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
-                sink(rayIdx, best);
-                st = ST_IDLE;
-            }
-            if (st == ST_IDLE) {
-                auto g = cooperative_groups::coalesced_threads();
-                uint32_t base = 0;
-                if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
-                rayIdx = g.shfl(base, 0) + g.thread_rank();
-                if (rayIdx >= n) st = ST_EXIT;
-                else {
-                    source(rayIdx, o, d);
-                    best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
-                    box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
-                    if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-                    else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }
-                }
-            }
-            if (st == ST_SCENE_NODE) {
+        } else if (nGlue > 0 && ((nGlue >= nLeaf && nGlue >= nNode) || nGlue >= PT_GLUE_PRIO)) {
+            // one GLUE turn carries a lane through consecutive glue states (fold a hit, analytic shapes, the next ray ...)
+            // until it needs a mesh walk or a march, so a ray costs ~one GLUE turn per mesh it enters
 #pragma unroll 1
-                for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
-                    uint32_t first, count;
-                    if (kd_step<kSceneStack, false>(S.nodes, nullptr, ra, sc, o, d, sStNode, sStMin, sStMax, first, count) == KD_LEAF) {
-                        sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
+            for (int it = 0; it < PT_GLUE_CHAIN; it++) {
+                if (st == ST_MESH_NODE || st == ST_MESH_LEAF || st == ST_SDF || st == ST_VOLUME || st == ST_EXIT) break;
+                if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
+                    double t = mBest, tInner = 0;
+                    if (curInst >= 0) {
+                        tInner = mBest;
+                        if (mBest < kHitInf) {  // TransformedShape.cs:47-69: hit.T = |Matrix.MulPosition(shapeRay.Position(T)) - r.Origin|
+                            const ptgpu_instance& inst = S.instances[curInst];
+                            V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
+                            t = (double)vlenf(vsub(position, o));
+                        }
+                    }
+                    if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
+                    st = ST_SCENE_LEAF;
+                }
+                if (st == ST_FINISH) {
+                    if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
+                    sink(rayIdx, best);
+                    st = ST_IDLE;
+                }
+                if (st == ST_IDLE) {
+                    auto g = cooperative_groups::coalesced_threads();
+                    uint32_t base = 0;
+                    if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
+                    rayIdx = g.shfl(base, 0) + g.thread_rank();
+                    if (rayIdx >= n) st = ST_EXIT;
+                    else {
+                        source(rayIdx, o, d);
+                        best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
+                        box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
+                        if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
+                        else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }
                     }
                 }
-            }
-            if (st == ST_SCENE_LEAF) {
-                if (sPos == sEnd) {
-                    st = kd_pop(sc, best.t, sStNode, sStMin, sStMax) ? ST_SCENE_NODE : ST_FINISH;
-                } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
-                    curShape = __ldg(S.leafItems + sPos);
-                    sPos++;
-                    ptgpu_shape sh = S.shapes[curShape];
-                    curInst = -1; co = o; cd = d;
-                    if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45: shapeRay = Matrix.Inverse().MulRay(r)
-                        curInst = (int32_t)sh.data;
-                        const ptgpu_instance& inst = S.instances[sh.data];
-                        co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
-                        sh = S.shapes[inst.shape];
+                if (st == ST_SCENE_NODE) {
+    #pragma unroll 1
+                    for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
+                        uint32_t first, count;
+                        if (kd_step<kSceneStack, false>(S.nodes, nullptr, ra, sc, o, d, sStNode, sStMin, sStMax, first, count) == KD_LEAF) {
+                            sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
+                        }
                     }
-                    if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
-                        const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
-                        mBest = kHitInf; mPrim = -1;
-                        ra = ray_aux(co, cd);
-                        box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
-                        if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
-                        else { mc.node = mt.root; mc.sp = 0; stk_put(mStk, mc.tmax, 0u, 0u); st = ST_MESH_NODE; }
-                    } else if (sh.type == PTGPU_SDF) {  // SDFShape.Intersect prologue (SDF.cs:34-46), loop in the MARCH class
-                        const ptgpu_sdf_shape& q = S.sdfShapes[sh.data];
-                        mPrim = -1; marchData = sh.data;
-                        double t1, t2;
-                        box_intersect(q.bmin, q.bmax, co, cd, t1, t2);
-                        if (t2 < t1 || t2 < 0) { mBest = kHitInf; st = ST_MESH_DONE; }
-                        else { mc.tmin = netmax((double)0.0001f, t1); mc.tmax = t2; mc.sp = 0; mc.node = 1u; st = ST_SDF; }
-                    } else if (sh.type == PTGPU_VOLUME) {  // Volume.Intersect prologue (Volume.cs:171-175)
-                        const ptgpu_volume& q = S.volumes[sh.data];
-                        mPrim = -1; marchData = sh.data;
-                        double tmin, tmax;
-                        box_intersect(q.bmin, q.bmax, co, cd, tmin, tmax);
-                        mBest = (double)(1.0f / 512.0f);  // step
-                        mc.tmin = netmax(mBest, tmin); mc.tmax = tmax; mc.sp = 0; mc.node = 0u;  // sign = -1
-                        st = ST_VOLUME;
-                    } else {
-                        mBest = primitive_intersect(S, sh, co, cd);
-                        mPrim = -1;
-                        st = ST_MESH_DONE;
+                }
+                if (st == ST_SCENE_LEAF) {
+                    if (sPos == sEnd) {
+                        st = kd_pop(sc, best.t, sStNode, sStMin, sStMax) ? ST_SCENE_NODE : ST_FINISH;
+                    } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
+                        curShape = __ldg(S.leafItems + sPos);
+                        sPos++;
+                        ptgpu_shape sh = S.shapes[curShape];
+                        curInst = -1; co = o; cd = d;
+                        if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45: shapeRay = Matrix.Inverse().MulRay(r)
+                            curInst = (int32_t)sh.data;
+                            const ptgpu_instance& inst = S.instances[sh.data];
+                            co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
+                            sh = S.shapes[inst.shape];
+                        }
+                        if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
+                            const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
+                            mBest = kHitInf; mPrim = -1;
+                            ra = ray_aux(co, cd);
+                            if (!tree_box_maybe_hit(mt, co, ra)) st = ST_MESH_DONE;  // clear miss: Box.Intersect would say so too
+                            else {
+                                box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
+                                if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
+                                else { mc.node = mt.root; mc.sp = 0; stk_put(mStk, mc.tmax, 0u, 0u); st = ST_MESH_NODE; }
+                            }
+                        } else if (sh.type == PTGPU_SDF) {  // SDFShape.Intersect prologue (SDF.cs:34-46), loop in the MARCH class
+                            const ptgpu_sdf_shape& q = S.sdfShapes[sh.data];
+                            mPrim = -1; marchData = sh.data;
+                            double t1, t2;
+                            box_intersect(q.bmin, q.bmax, co, cd, t1, t2);
+                            if (t2 < t1 || t2 < 0) { mBest = kHitInf; st = ST_MESH_DONE; }
+                            else { mc.tmin = netmax((double)0.0001f, t1); mc.tmax = t2; mc.sp = 0; mc.node = 1u; st = ST_SDF; }
+                        } else if (sh.type == PTGPU_VOLUME) {  // Volume.Intersect prologue (Volume.cs:171-175)
+                            const ptgpu_volume& q = S.volumes[sh.data];
+                            mPrim = -1; marchData = sh.data;
+                            double tmin, tmax;
+                            box_intersect(q.bmin, q.bmax, co, cd, tmin, tmax);
+                            mBest = (double)(1.0f / 512.0f);  // step
+                            mc.tmin = netmax(mBest, tmin); mc.tmax = tmax; mc.sp = 0; mc.node = 0u;  // sign = -1
+                            st = ST_VOLUME;
+                        } else {
+                            mBest = primitive_intersect(S, sh, co, cd);
+                            mPrim = -1;
+                            st = ST_MESH_DONE;
+                        }
                     }
                 }
             }
@@ -1195,11 +1219,11 @@ PT_D void trace_rays_pool(const DScene& S, uint32_t n, uint32_t* __restrict__ cu
                             if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
                                 const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
                                 mBest = kHitInf; mPrim = -1;
-                                double tmin, tmax;
-                                box_intersect(mt.bmin, mt.bmax, co, cd, tmin, tmax);
+                                double tmin = 0, tmax = -1;
+                                const RayAux ra = ray_aux(co, cd);
+                                if (tree_box_maybe_hit(mt, co, ra)) box_intersect(mt.bmin, mt.bmax, co, cd, tmin, tmax);
                                 if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
                                 else {
-                                    const RayAux ra = ray_aux(co, cd);
                                     H_F(6, slot) = ra.ix; H_F(7, slot) = ra.iy; H_F(8, slot) = ra.iz; H_F(9, slot) = ra.pad;
                                     H_NODE(slot) = mt.root; H_TMIN(slot) = tmin; H_TMAX(slot) = tmax; H_SP(slot) = 0u;
                                     stk_put(wMeshStk + (size_t)slot * kMeshStackEnt, tmax, 0u, 0u);
