@@ -120,9 +120,8 @@ struct DScene {
     const ptgpu_texture* textures;
     const float4* texels;
     // Derived at upload for mesh trees (see "mesh traversal" below):
-    const uint4* meshNodes;         // 4 x uint4 per kd node: the reference node + padded triangle bounds of both children
-    const float4* leafGroups;       // 2 x float4 per group of <= 4 leaf triangles: (lo.xyz, first triangle) (hi.xyz, count)
-    const float4* leafGeom;         // 3 x float4 per leaf triangle in group order: (V1, triangle id) (e1, position in the leaf) (e2, -)
+    const uint4* meshNodes;         // 4 x uint4 per node: reference kd nodes, bounds-only nodes and micro leaves (see mesh_step)
+    const float4* leafGeom;         // 3 x float4 per leaf triangle in sorted order: (V1, triangle id) (e1, position in the leaf) (e2, -)
     uint32_t sceneTree, numSceneShapes, numLights, numShapes;
     double envColor[3];
     int32_t envTexture;
@@ -589,12 +588,13 @@ PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3
 //    (= its Node.Intersect returns NoHit, see bounds_hit) is known before descending, so a culled near child costs no
 //    memory round trip and a culled far child is skipped when it is popped.  It is still pushed: its tsplit is the
 //    `tmax` of the entries above it.
-//  * Leaf groups.  Rays mostly cross LARGE leaves (the builder stops at 85 % overlap; a C3 camera ray meets ~60
-//    triangles in ~2 leaves).  Every leaf is stored as groups of <= 4 spatially sorted triangles with padded bounds; a
-//    group the ray line misses is skipped (each of its triangles would return NoHit).  Groups reorder the leaf, and the
-//    reference keeps the FIRST shape in array order among equal T (strict <, Tree.cs:122), so every triangle carries
-//    its position in the reference leaf and a tie inside the leaf goes to the lower position; a tie with a hit from an
-//    earlier leaf never replaces it (bestPos = 0 at leaf entry).
+//  * Bounds-only nodes below the reference leaves.  Rays mostly cross LARGE leaves (the builder stops at 85 % overlap;
+//    a C3 camera ray meets ~60 triangles in ~2 leaves).  The triangles of a leaf are sorted spatially and hung under a
+//    small binary hierarchy of padded bounds ending in micro leaves of <= 4 triangles; a subtree the ray line misses is
+//    skipped (each of its triangles would return NoHit).  This reorders the leaf, and the reference keeps the FIRST
+//    shape in array order among equal T (strict <, Tree.cs:122), so every triangle carries its position in the
+//    reference leaf and a tie inside the leaf goes to the lower position; a tie with a hit from an earlier leaf never
+//    replaces it (bestPos = 0 at leaf entry).
 PT_D void stk_put(uint4* e, double ts, uint32_t node, uint32_t culled) { *e = make_uint4((uint32_t)__double2loint(ts), (uint32_t)__double2hiint(ts), node, culled); }
 PT_D double stk_t(const uint4& e) { return __hiloint2double((int)e.y, (int)e.x); }
 
@@ -635,68 +635,72 @@ PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
 }
 
 enum { MESH_INTERIOR = 0, MESH_LEAF = 1, MESH_DONE = 2 };
-// One Node.Intersect step at c.node (whose bounds are known to be hit).  MESH_LEAF: groups [gFirst, gFirst+gCount).
-PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& gFirst, uint32_t& gCount) {
+static constexpr uint32_t kNodeVirtual = 0x80000000u, kNodeRefLeaf = 0x40000000u, kNodeIndexMask = 0x3FFFFFFFu;
+static constexpr int kVirtualDepthMax = 12;  // levels of bounds-only nodes below a reference leaf (4 * 2^12 triangles)
+static constexpr int kMeshStackEnt = kMeshStack + kVirtualDepthMax + 1;
+
+// One step at c.node (whose bounds are known to be hit).  Node records (4 x uint4, q0 = {split, a, b}):
+//   reference interior  a = left << 2 | axis (1..3), b = right                  -> Node.Intersect (Tree.cs:67-113)
+//   bounds-only node    a = left << 2, b = kNodeVirtual | right [| kNodeRefLeaf]  -> both children hold triangles of ONE
+//                       reference leaf; every child whose padded bounds the ray line hits is visited, in any order
+//   micro leaf          a = first triangle << 2, b = count (<= 4) [| kNodeRefLeaf]
+// kNodeRefLeaf marks the root of a reference leaf (where the tie-break position restarts).
+// MESH_LEAF: triangles [tFirst, tFirst + tCount).
+PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
+                   uint32_t& tCount) {
     const uint4* np = nodes + (size_t)c.node * 4;
     const uint4 q0 = __ldg(np);
     const uint32_t a = q0.z, b = q0.w;
     const uint32_t axis = a & 3u;
-    if (axis == 0) { gFirst = a >> 2; gCount = b; return MESH_LEAF; }
+    if (axis == 0) {
+        if (b & kNodeRefLeaf) bestPos = 0;
+        if (!(b & kNodeVirtual)) { tFirst = a >> 2; tCount = b & 0xFFu; return MESH_LEAF; }
+    }
     const uint4 q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-    const double split = __hiloint2double((int)q0.y, (int)q0.x);
-    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-    const double tsplit = (split - oa) / da;
-    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
     const bool hitL = box_line_hit(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
                                    __uint_as_float(q2.y), o, ra);
     const bool hitR = box_line_hit(__uint_as_float(q2.z), __uint_as_float(q2.w), __uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z),
                                    __uint_as_float(q3.w), o, ra);
-    const uint32_t left = a >> 2;
-    const uint32_t first = leftFirst ? left : b, second = leftFirst ? b : left;
-    const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
+    const uint32_t left = a >> 2, right = b & kNodeIndexMask;
     bool go;
-    if (tsplit > c.tmax || tsplit <= 0) { c.node = first; go = hitFirst; }
-    else if (tsplit < c.tmin) { c.node = second; go = hitSecond; }
-    else {
-        c.sp++;
-        stk_put(stk + c.sp, tsplit, second, hitSecond ? 0u : 1u);
-        c.node = first;
-        c.tmax = tsplit;
-        go = hitFirst;
+    if (axis == 0) {  // bounds-only node: -inf keeps the pending child from being skipped by `best.T <= tsplit`
+        if (hitL && hitR) { c.sp++; stk_put(stk + c.sp, -INFINITY, right, 0u); }
+        c.node = hitL ? left : right;
+        go = hitL || hitR;
+    } else {
+        const double split = __hiloint2double((int)q0.y, (int)q0.x);
+        const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+        const double tsplit = (split - oa) / da;
+        const bool leftFirst = (oa < split) || (oa == split && da <= 0);
+        const uint32_t first = leftFirst ? left : right, second = leftFirst ? right : left;
+        const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
+        if (tsplit > c.tmax || tsplit <= 0) { c.node = first; go = hitFirst; }
+        else if (tsplit < c.tmin) { c.node = second; go = hitSecond; }
+        else {
+            c.sp++;
+            stk_put(stk + c.sp, tsplit, second, hitSecond ? 0u : 1u);
+            c.node = first;
+            c.tmax = tsplit;
+            go = hitFirst;
+        }
     }
     if (go) return MESH_INTERIOR;
     return mesh_pop(c, bestT, stk) ? MESH_INTERIOR : MESH_DONE;
 }
 
-// The triangles of one leaf: up to `budget` triangle tests, skipping groups the ray line misses.  Returns true when the
-// leaf is exhausted.  (gPos, gEnd) = remaining groups, (tPos, tEnd) = remaining triangles of the current group.
-PT_D bool leaf_work(const DScene& S, const RayAux& ra, V3 o, V3 d, uint32_t& gPos, uint32_t gEnd, uint32_t& tPos, uint32_t& tEnd, double& best, int32_t& prim,
-                    uint32_t& bestPos, int budget) {
+// The triangles [tPos, tEnd) of a micro leaf, at most `budget` of them.  Triangles are stored in sorted order, and the
+// reference keeps the FIRST shape in array order among equal T (Tree.cs:122), hence the position tie-break.
+PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, double& best, int32_t& prim, uint32_t& bestPos, int budget) {
 #pragma unroll 1
-    for (int k = 0; k < budget; k++) {
-        if (tPos >= tEnd) {
-            bool found = false;
-#pragma unroll 1
-            while (gPos < gEnd) {
-                const float4 lo = __ldg(S.leafGroups + 2 * (size_t)gPos), hi = __ldg(S.leafGroups + 2 * (size_t)gPos + 1);
-                gPos++;
-                if (box_line_hit(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, ra)) {
-                    tPos = __float_as_uint(lo.w); tEnd = tPos + __float_as_uint(hi.w);
-                    found = true;
-                    break;
-                }
-            }
-            if (!found) return true;
-        }
+    for (int k = 0; k < budget && tPos < tEnd; k++) {
         const float4* g = S.leafGeom + (size_t)tPos * 3;
         const double t = triangle_intersect(g, o, d);
         if (t <= best && t < kHitInf) {  // rare: fetch the ids only for candidates (a T of INF never replaces NoHit)
             const uint32_t pos = __float_as_uint(__ldg(g + 1).w);
-            if (t < best || pos < bestPos) { best = t; prim = (int32_t)__float_as_uint(__ldg(g).w); bestPos = pos; }  // Tree.cs:122
+            if (t < best || pos < bestPos) { best = t; prim = (int32_t)__float_as_uint(__ldg(g).w); bestPos = pos; }
         }
         tPos++;
     }
-    return tPos >= tEnd && gPos >= gEnd;
 }
 
 #ifndef PT_LEAF_BURST
@@ -733,9 +737,8 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
     uint32_t sPos = 0, sEnd = 0;
     // Mesh tree (Mesh.tree) of the shape being visited
     KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
-    uint4 mStk[kMeshStack + 1];              // entry 0 = sentinel (root tmax)
-    uint32_t mPos = 0, mEnd = 0;             // remaining groups of the current leaf (sdfShapes[] / volumes[] index while marching)
-    uint32_t tPos = 0, tEnd = 0;             // remaining triangles of the current group
+    uint4 mStk[kMeshStackEnt];               // entry 0 = sentinel (root tmax)
+    uint32_t tPos = 0, tEnd = 0;             // remaining triangles of the current micro leaf
     double mBest = kHitInf; int32_t mPrim = -1; uint32_t mBestPos = 0;
     uint32_t curShape = 0; int32_t curInst = -1;
     uint32_t marchData = 0;                  // sdfShapes[] / volumes[] index while in the MARCH class
@@ -897,395 +900,18 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
 #pragma unroll 1
                 for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
                     uint32_t first, count;
-                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, first, count);
-                    if (r == MESH_LEAF) { mPos = first; mEnd = first + count; tPos = tEnd = 0; mBestPos = 0; st = ST_MESH_LEAF; }
+                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
+                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
                     else if (r == MESH_DONE) st = ST_MESH_DONE;
                 }
             }
         } else {
             if (st == ST_MESH_LEAF) {
-                if (leaf_work(S, ra, co, cd, mPos, mEnd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST))
-                    st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
+                leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
+                if (tPos >= tEnd) st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
             }
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------------- pooled tracer
-// Same semantics as trace_rays, different execution model.  With one ray per lane the three work classes (LEAF, NODE,
-// GLUE) settle at about a third of the lanes each, whatever the ray coherence: running a class drains it into the
-// others, so no class ever gathers a full warp (ncu: ~10 active lanes per instruction, camera rays included).  Here a warp
-// owns a POOL of kPoolSlots rays whose traversal state lives in shared memory (hot part) and in a per-warp global scratch
-// (cold part and the kd stacks); lanes are stateless workers.  Every turn the warp counts its slots per class, picks the
-// class that fills most lanes, hands the first 32 slots of that class to lanes 0..31, and each lane loads its slot, runs a
-// burst of that class's work and stores the slot back.  With 2-3 slots per lane the chosen class almost always has >= 32
-// members, so bursts start with a full warp.  The arithmetic of every unit of work is unchanged.
-//
-// Stack entries are 16 bytes {tsplit, node}: the `tmax` the reference passes to the far child is recoverable as
-// netmin(tsplit of the entry below | root tmax, best.T) — at push time c.tmax is either the root tmax, the tsplit of the
-// push directly below, or a netmin(.., best.T) of one of those from an earlier pop, and best.T only decreases — so entry
-// 0 is a sentinel holding the root tmax and nothing else needs storing.
-#ifndef PT_POOL_SLOTS
-#define PT_POOL_SLOTS 64
-#endif
-#ifndef PT_POOL_LEAF_BURST
-#define PT_POOL_LEAF_BURST 8
-#endif
-#ifndef PT_POOL_NODE_BURST
-#define PT_POOL_NODE_BURST 6
-#endif
-static constexpr int kPoolSlots = PT_POOL_SLOTS;
-static constexpr int kPoolWords = kPoolSlots / 32;
-static constexpr int kPoolWarpsPerBlock = 4;
-static constexpr int kMeshStackEnt = kMeshStack + 1, kSceneStackEnt = kSceneStack + 1;
-// shared memory per warp: 9 u32 + 10 f32 + 3 f64 fields per slot, plus the 32-entry assignment list
-static constexpr int kPoolSmemPerWarp = kPoolSlots * (9 * 4 + 10 * 4 + 3 * 8) + 32 * 4;
-static constexpr int kPoolSmemPerBlock = kPoolSmemPerWarp * kPoolWarpsPerBlock;
-static constexpr int kColdU = 9, kColdD = 4;
-
-struct PoolScratch {     // global memory, sized for the launch grid (see pool_scratch_bytes)
-    uint4* meshStack;    // [warp][slot][kMeshStackEnt]
-    uint4* sceneStack;   // [warp][slot][kSceneStackEnt]
-    uint32_t* coldU;     // [warp][kColdU][slot]: rayIdx, best.shape, best.prim, sc.node, sc.sp, sPos, sEnd, curShape, curInst
-    double* coldD;       // [warp][kColdD][slot]: best.t, best.tInner, sc.tmin, sc.tmax
-};
-
-PT_D void stk_write(uint4* e, double ts, uint32_t node) { *e = make_uint4((uint32_t)__double2loint(ts), (uint32_t)__double2hiint(ts), node, 0u); }
-PT_D double stk_ts(const uint4& e) { return __hiloint2double((int)e.y, (int)e.x); }
-
-// Node.Intersect step on the 16-byte stack (entries 1..sp; entry 0 = sentinel with the root tmax).
-template <int STACK, bool CULL>
-PT_D int kd_step2(const ptgpu_node* __restrict__ nodes, const float4* __restrict__ nb, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint4* stk,
-                  uint32_t& leafFirst, uint32_t& leafCount) {
-    if (CULL) { if (!bounds_hit(nb, c.node, o, ra)) return KD_CULLED; }
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));
-    const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
-    const uint32_t axis = a & 3u;
-    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return KD_LEAF; }
-    const double split = __hiloint2double(raw.y, raw.x);
-    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-    const double tsplit = (split - oa) / da;
-    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
-    const uint32_t first = leftFirst ? (a >> 2) : b;
-    const uint32_t second = leftFirst ? b : (a >> 2);
-    if (tsplit > c.tmax || tsplit <= 0) c.node = first;
-    else if (tsplit < c.tmin) c.node = second;
-    else {
-        if (c.sp < STACK) { c.sp++; stk_write(stk + c.sp, tsplit, second); }
-        c.node = first;
-        c.tmax = tsplit;
-    }
-    return KD_INTERIOR;
-}
-PT_D bool kd_pop2(KdCursor& c, double bestT, const uint4* stk) {
-    while (c.sp > 0) {
-        const uint4 e = stk[c.sp];
-        --c.sp;
-        const double ts = stk_ts(e);
-        if (bestT <= ts) continue;  // `if (h1.T <= tsplit) return h1`
-        c.node = e.z;
-        c.tmin = ts;
-        c.tmax = netmin(stk_ts(stk[c.sp]), bestT);
-        return true;
-    }
-    return false;
-}
-
-template <class Source, class Sink>
-PT_D void trace_rays_pool(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor, Source source, Sink sink, const PoolScratch& scr) {
-    extern __shared__ __align__(16) unsigned char pool_smem[];
-    const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
-    const size_t warpGlobal = (size_t)blockIdx.x * (blockDim.x >> 5) + warpInBlock;
-    unsigned char* wbase = pool_smem + (size_t)warpInBlock * kPoolSmemPerWarp;
-    double* hD = reinterpret_cast<double*>(wbase);                       // [3][slots]: mtmin, mtmax, mBest
-    float* hF = reinterpret_cast<float*>(hD + 3 * kPoolSlots);           // [10][slots]: co, cd, ra
-    uint32_t* hU = reinterpret_cast<uint32_t*>(hF + 10 * kPoolSlots);    // [9][slots]: st, mnode, msp, mPos, mEnd, mPrim, tPos, tEnd, bestPos
-    uint32_t* list = hU + 9 * kPoolSlots;                                // [32]
-#define H_TMIN(s) hD[0 * kPoolSlots + (s)]
-#define H_TMAX(s) hD[1 * kPoolSlots + (s)]
-#define H_BEST(s) hD[2 * kPoolSlots + (s)]
-#define H_F(k, s) hF[(k) * kPoolSlots + (s)]
-#define H_ST(s) hU[0 * kPoolSlots + (s)]
-#define H_NODE(s) hU[1 * kPoolSlots + (s)]
-#define H_SP(s) hU[2 * kPoolSlots + (s)]
-#define H_POS(s) hU[3 * kPoolSlots + (s)]
-#define H_END(s) hU[4 * kPoolSlots + (s)]
-#define H_PRIM(s) hU[5 * kPoolSlots + (s)]
-#define H_TPOS(s) hU[6 * kPoolSlots + (s)]
-#define H_TEND(s) hU[7 * kPoolSlots + (s)]
-#define H_BPOS(s) hU[8 * kPoolSlots + (s)]
-    uint4* const wMeshStk = scr.meshStack + warpGlobal * kPoolSlots * kMeshStackEnt;
-    uint4* const wSceneStk = scr.sceneStack + warpGlobal * kPoolSlots * kSceneStackEnt;
-    uint32_t* const cU = scr.coldU + warpGlobal * kColdU * kPoolSlots;
-    double* const cD = scr.coldD + warpGlobal * kColdD * kPoolSlots;
-    const ptgpu_tree sceneTree = S.trees[S.sceneTree];
-
-    for (int s = (int)lane; s < kPoolSlots; s += 32) H_ST(s) = ST_IDLE;
-    __syncwarp();
-    const unsigned ltMask = (1u << lane) - 1u;
-
-    for (;;) {
-        // ---- count the pool per class
-        unsigned mLeaf[kPoolWords], mNode[kPoolWords], mGlue[kPoolWords], mMarch[kPoolWords];
-        int nLeaf = 0, nNode = 0, nGlue = 0, nMarch = 0;
-#pragma unroll
-        for (int w = 0; w < kPoolWords; w++) {
-            const uint32_t stv = H_ST(w * 32 + lane);
-            mLeaf[w] = __ballot_sync(0xFFFFFFFFu, stv == ST_MESH_LEAF);
-            mNode[w] = __ballot_sync(0xFFFFFFFFu, stv == ST_MESH_NODE);
-            mMarch[w] = __ballot_sync(0xFFFFFFFFu, stv == ST_SDF || stv == ST_VOLUME);
-            mGlue[w] = __ballot_sync(0xFFFFFFFFu, stv != ST_EXIT) & ~(mLeaf[w] | mNode[w] | mMarch[w]);
-            nLeaf += __popc(mLeaf[w]); nNode += __popc(mNode[w]); nGlue += __popc(mGlue[w]); nMarch += __popc(mMarch[w]);
-        }
-        if ((nLeaf | nNode | nGlue | nMarch) == 0) break;
-        // ---- pick the class that fills most lanes (ties: LEAF, NODE, GLUE, MARCH)
-        const int eLeaf = min(nLeaf, 32), eNode = min(nNode, 32), eGlue = min(nGlue, 32), eMarch = min(nMarch, 32);
-        int cls = 0, eBest = eLeaf;
-        if (eNode > eBest) { cls = 1; eBest = eNode; }
-        if (eGlue > eBest) { cls = 2; eBest = eGlue; }
-        if (eMarch > eBest) { cls = 3; eBest = eMarch; }
-        // ---- hand the first 32 slots of that class to lanes 0..31
-        int prefix = 0;
-#pragma unroll
-        for (int w = 0; w < kPoolWords; w++) {
-            const unsigned m = cls == 0 ? mLeaf[w] : (cls == 1 ? mNode[w] : (cls == 2 ? mGlue[w] : mMarch[w]));
-            if ((m >> lane) & 1u) {
-                const int r = prefix + __popc(m & ltMask);
-                if (r < 32) list[r] = (uint32_t)(w * 32) + lane;
-            }
-            prefix += __popc(m);
-        }
-        __syncwarp();
-        const bool have = (int)lane < eBest;
-        const uint32_t slot = have ? list[lane] : 0u;
-
-        if (cls == 0) {
-            if (have) {  // LEAF: the triangles of one mesh leaf (Tree.cs:119-126), see leaf_work
-                const V3 co = v3(H_F(0, slot), H_F(1, slot), H_F(2, slot)), cd = v3(H_F(3, slot), H_F(4, slot), H_F(5, slot));
-                RayAux ra; ra.ix = H_F(6, slot); ra.iy = H_F(7, slot); ra.iz = H_F(8, slot); ra.pad = H_F(9, slot);
-                uint32_t gPos = H_POS(slot), tPos = H_TPOS(slot), tEnd = H_TEND(slot), bestPos = H_BPOS(slot);
-                const uint32_t gEnd = H_END(slot);
-                double mBest = H_BEST(slot);
-                int32_t mPrim = (int32_t)H_PRIM(slot);
-                const bool done = leaf_work(S, ra, co, cd, gPos, gEnd, tPos, tEnd, mBest, mPrim, bestPos, PT_POOL_LEAF_BURST);
-                H_POS(slot) = gPos; H_TPOS(slot) = tPos; H_TEND(slot) = tEnd; H_BPOS(slot) = bestPos;
-                H_BEST(slot) = mBest; H_PRIM(slot) = (uint32_t)mPrim;
-                if (done) {
-                    KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = (int)H_SP(slot);
-                    if (mesh_pop(mc, mBest, wMeshStk + (size_t)slot * kMeshStackEnt)) {
-                        H_NODE(slot) = mc.node; H_TMIN(slot) = mc.tmin; H_TMAX(slot) = mc.tmax; H_SP(slot) = (uint32_t)mc.sp;
-                        H_ST(slot) = ST_MESH_NODE;
-                    } else H_ST(slot) = ST_MESH_DONE;
-                }
-            }
-        } else if (cls == 1) {
-            if (have) {  // NODE: walk the mesh tree down to the next leaf
-                const V3 co = v3(H_F(0, slot), H_F(1, slot), H_F(2, slot)), cd = v3(H_F(3, slot), H_F(4, slot), H_F(5, slot));
-                RayAux ra; ra.ix = H_F(6, slot); ra.iy = H_F(7, slot); ra.iz = H_F(8, slot); ra.pad = H_F(9, slot);
-                KdCursor mc; mc.node = H_NODE(slot); mc.tmin = H_TMIN(slot); mc.tmax = H_TMAX(slot); mc.sp = (int)H_SP(slot);
-                const double mBest = H_BEST(slot);
-                uint4* stk = wMeshStk + (size_t)slot * kMeshStackEnt;
-                int st = ST_MESH_NODE;
-#pragma unroll 1
-                for (int k = 0; k < PT_POOL_NODE_BURST && st == ST_MESH_NODE; k++) {
-                    uint32_t first, count;
-                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, stk, mBest, first, count);
-                    if (r == MESH_LEAF) { H_POS(slot) = first; H_END(slot) = first + count; H_TPOS(slot) = 0u; H_TEND(slot) = 0u; H_BPOS(slot) = 0u; st = ST_MESH_LEAF; }
-                    else if (r == MESH_DONE) st = ST_MESH_DONE;
-                }
-                H_NODE(slot) = mc.node; H_TMIN(slot) = mc.tmin; H_TMAX(slot) = mc.tmax; H_SP(slot) = (uint32_t)mc.sp;
-                H_ST(slot) = (uint32_t)st;
-            }
-        } else if (cls == 3) {
-            if (have) {  // MARCH: see trace_rays; loop state in the mesh-cursor fields, sdfShapes[] / volumes[] index in mPos
-                const V3 co = v3(H_F(0, slot), H_F(1, slot), H_F(2, slot)), cd = v3(H_F(3, slot), H_F(4, slot), H_F(5, slot));
-                KdCursor mc; mc.node = H_NODE(slot); mc.tmin = H_TMIN(slot); mc.tmax = H_TMAX(slot); mc.sp = (int)H_SP(slot);
-                double mBest = H_BEST(slot);
-                const uint32_t marchData = H_POS(slot);
-                int st = (int)H_ST(slot);
-                if (st == ST_SDF) {
-                    const ptgpu_sdf_shape& sh = S.sdfShapes[marchData];
-#pragma unroll 1
-                    for (int k = 0; k < 4 && st == ST_SDF; k++) {
-                        if (mc.sp >= 1000) { mBest = kHitInf; st = ST_MESH_DONE; break; }
-                        mc.sp++;
-                        double dist = sdf_evaluate(S.sdfOps + sh.progFirst, sh.progCount, ray_at(co, cd, mc.tmin));
-                        const bool jump = mc.node & 1u;
-                        if (jump && dist < 0) { mc.tmin -= (double)0.001f; mc.node = 0; continue; }
-                        if (dist < (double)0.00001f) { mBest = mc.tmin; st = ST_MESH_DONE; break; }
-                        if (jump && dist < (double)0.001f) dist = (double)0.001f;
-                        mc.tmin += dist;
-                        if (mc.tmin > mc.tmax) { mBest = kHitInf; st = ST_MESH_DONE; }
-                    }
-                } else {
-                    const ptgpu_volume& v = S.volumes[marchData];
-#pragma unroll 1
-                    for (int k = 0; k < 8 && st == ST_VOLUME; k++) {
-                        const bool refining = (mc.node >> 16) & 1u;
-                        if (!refining) {
-                            if (!(mc.tmin <= mc.tmax)) { mBest = kHitInf; st = ST_MESH_DONE; break; }
-                            const int sign = (int)(mc.node & 0xFFFFu) - 1;
-                            const int sg = vol_sign(S, v, ray_at(co, cd, mc.tmin));
-                            if (sg == 0 || (sign >= 0 && sg != sign)) {
-                                mc.tmin -= mBest; mBest /= 64; mc.tmin += mBest;
-                                mc.node = (mc.node & 0xFFFFu) | (1u << 16) | ((uint32_t)(sg + 1) << 17);
-                                mc.sp = 0;
-                            } else { mc.node = (uint32_t)(sg + 1); mc.tmin += mBest; }
-                        } else if (mc.sp < 64) {
-                            if (vol_sign(S, v, ray_at(co, cd, mc.tmin)) == 0) { const double t = mc.tmin - mBest; mBest = t; st = ST_MESH_DONE; break; }
-                            mc.tmin += mBest; mc.sp++;
-                        } else {
-                            mc.node = (mc.node >> 17);
-                            mc.tmin += mBest;
-                        }
-                    }
-                }
-                H_NODE(slot) = mc.node; H_TMIN(slot) = mc.tmin; H_TMAX(slot) = mc.tmax; H_SP(slot) = (uint32_t)mc.sp;
-                H_BEST(slot) = mBest; H_ST(slot) = (uint32_t)st;
-            }
-        } else {
-            if (have) {  // GLUE: fetch a ray, the scene tree, per-shape set-up, folding a shape's hit, writing the result
-                int st = (int)H_ST(slot);
-                uint32_t rayIdx = cU[0 * kPoolSlots + slot];
-                HitRec best;
-                best.shape = (int32_t)cU[1 * kPoolSlots + slot]; best.prim = (int32_t)cU[2 * kPoolSlots + slot];
-                best.t = cD[0 * kPoolSlots + slot]; best.tInner = cD[1 * kPoolSlots + slot];
-                KdCursor sc; sc.node = cU[3 * kPoolSlots + slot]; sc.sp = (int)cU[4 * kPoolSlots + slot];
-                sc.tmin = cD[2 * kPoolSlots + slot]; sc.tmax = cD[3 * kPoolSlots + slot];
-                uint32_t sPos = cU[5 * kPoolSlots + slot], sEnd = cU[6 * kPoolSlots + slot], curShape = cU[7 * kPoolSlots + slot];
-                int32_t curInst = (int32_t)cU[8 * kPoolSlots + slot];
-                V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
-                if (st != ST_IDLE) source(rayIdx, o, d);
-                V3 co = v3(H_F(0, slot), H_F(1, slot), H_F(2, slot)), cd = v3(H_F(3, slot), H_F(4, slot), H_F(5, slot));
-                double mBest = H_BEST(slot);
-                int32_t mPrim = (int32_t)H_PRIM(slot);
-                uint4* sstk = wSceneStk + (size_t)slot * kSceneStackEnt;
-                const RayAux noAux = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int it = 0; it < 6; it++) {
-                    if (st == ST_MESH_DONE) {  // fold the shape's Hit into the leaf's running best (Tree.cs:121-125)
-                        double t = mBest, tInner = 0;
-                        if (curInst >= 0) {
-                            tInner = mBest;
-                            if (mBest < kHitInf) {  // TransformedShape.cs:47-69
-                                const ptgpu_instance& inst = S.instances[curInst];
-                                V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
-                                t = (double)vlenf(vsub(position, o));
-                            }
-                        }
-                        if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
-                        st = ST_SCENE_LEAF;
-                    }
-                    if (st == ST_FINISH) {
-                        if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
-                        sink(rayIdx, best);
-                        st = ST_IDLE;
-                    }
-                    if (st == ST_IDLE) {
-                        auto g = cooperative_groups::coalesced_threads();
-                        uint32_t base = 0;
-                        if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
-                        rayIdx = g.shfl(base, 0) + g.thread_rank();
-                        if (rayIdx >= n) { st = ST_EXIT; break; }
-                        source(rayIdx, o, d);
-                        best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
-                        box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
-                        if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-                        else { sc.node = sceneTree.root; sc.sp = 0; stk_write(sstk, sc.tmax, 0u); st = ST_SCENE_NODE; }
-                    }
-                    if (st == ST_SCENE_NODE) {
-#pragma unroll 1
-                        for (int k = 0; k < 8 && st == ST_SCENE_NODE; k++) {
-                            uint32_t first, count;
-                            if (kd_step2<kSceneStack, false>(S.nodes, nullptr, noAux, sc, o, d, sstk, first, count) == KD_LEAF) {
-                                sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
-                            }
-                        }
-                    }
-                    if (st == ST_SCENE_LEAF) {
-                        if (sPos == sEnd) {
-                            st = kd_pop2(sc, best.t, sstk) ? ST_SCENE_NODE : ST_FINISH;
-                        } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
-                            curShape = __ldg(S.leafItems + sPos);
-                            sPos++;
-                            ptgpu_shape sh = S.shapes[curShape];
-                            curInst = -1; co = o; cd = d;
-                            if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45
-                                curInst = (int32_t)sh.data;
-                                const ptgpu_instance& inst = S.instances[sh.data];
-                                co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
-                                sh = S.shapes[inst.shape];
-                            }
-                            if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
-                                const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
-                                mBest = kHitInf; mPrim = -1;
-                                double tmin = 0, tmax = -1;
-                                const RayAux ra = ray_aux(co, cd);
-                                if (tree_box_maybe_hit(mt, co, ra)) box_intersect(mt.bmin, mt.bmax, co, cd, tmin, tmax);
-                                if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
-                                else {
-                                    H_F(6, slot) = ra.ix; H_F(7, slot) = ra.iy; H_F(8, slot) = ra.iz; H_F(9, slot) = ra.pad;
-                                    H_NODE(slot) = mt.root; H_TMIN(slot) = tmin; H_TMAX(slot) = tmax; H_SP(slot) = 0u;
-                                    stk_put(wMeshStk + (size_t)slot * kMeshStackEnt, tmax, 0u, 0u);
-                                    st = ST_MESH_NODE;
-                                }
-                            } else if (sh.type == PTGPU_SDF) {  // SDFShape.Intersect prologue (SDF.cs:34-46)
-                                const ptgpu_sdf_shape& q = S.sdfShapes[sh.data];
-                                mPrim = -1;
-                                double t1, t2;
-                                box_intersect(q.bmin, q.bmax, co, cd, t1, t2);
-                                if (t2 < t1 || t2 < 0) { mBest = kHitInf; st = ST_MESH_DONE; }
-                                else {
-                                    H_POS(slot) = sh.data;
-                                    H_TMIN(slot) = netmax((double)0.0001f, t1); H_TMAX(slot) = t2; H_SP(slot) = 0u; H_NODE(slot) = 1u;
-                                    st = ST_SDF;
-                                }
-                            } else if (sh.type == PTGPU_VOLUME) {  // Volume.Intersect prologue (Volume.cs:171-175)
-                                const ptgpu_volume& q = S.volumes[sh.data];
-                                mPrim = -1;
-                                double tmin, tmax;
-                                box_intersect(q.bmin, q.bmax, co, cd, tmin, tmax);
-                                mBest = (double)(1.0f / 512.0f);  // step
-                                H_POS(slot) = sh.data;
-                                H_TMIN(slot) = netmax(mBest, tmin); H_TMAX(slot) = tmax; H_SP(slot) = 0u; H_NODE(slot) = 0u;  // sign = -1
-                                st = ST_VOLUME;
-                            } else {
-                                mBest = primitive_intersect(S, sh, co, cd);
-                                mPrim = -1;
-                                st = ST_MESH_DONE;
-                            }
-                        }
-                    }
-                    if (st == ST_MESH_NODE || st == ST_SDF || st == ST_VOLUME) break;
-                }
-                H_ST(slot) = (uint32_t)st;
-                if (st != ST_EXIT) {
-                    H_F(0, slot) = co.x; H_F(1, slot) = co.y; H_F(2, slot) = co.z; H_F(3, slot) = cd.x; H_F(4, slot) = cd.y; H_F(5, slot) = cd.z;
-                    H_BEST(slot) = mBest; H_PRIM(slot) = (uint32_t)mPrim;
-                    cU[0 * kPoolSlots + slot] = rayIdx; cU[1 * kPoolSlots + slot] = (uint32_t)best.shape; cU[2 * kPoolSlots + slot] = (uint32_t)best.prim;
-                    cD[0 * kPoolSlots + slot] = best.t; cD[1 * kPoolSlots + slot] = best.tInner;
-                    cU[3 * kPoolSlots + slot] = sc.node; cU[4 * kPoolSlots + slot] = (uint32_t)sc.sp;
-                    cD[2 * kPoolSlots + slot] = sc.tmin; cD[3 * kPoolSlots + slot] = sc.tmax;
-                    cU[5 * kPoolSlots + slot] = sPos; cU[6 * kPoolSlots + slot] = sEnd; cU[7 * kPoolSlots + slot] = curShape;
-                    cU[8 * kPoolSlots + slot] = (uint32_t)curInst;
-                }
-            }
-        }
-        __syncwarp();
-    }
-#undef H_TMIN
-#undef H_TMAX
-#undef H_BEST
-#undef H_F
-#undef H_ST
-#undef H_NODE
-#undef H_SP
-#undef H_POS
-#undef H_END
-#undef H_PRIM
-#undef H_TPOS
-#undef H_TEND
-#undef H_BPOS
 }
 
 // ---------------------------------------------------------------------------------------------------- textures

@@ -258,20 +258,10 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
 #ifndef PT_TRACE_MINBLOCKS
 #define PT_TRACE_MINBLOCKS 8
 #endif
-#ifndef PT_TRACER_POOL
-#define PT_TRACER_POOL 0
-#endif
-#if PT_TRACER_POOL
-#define TRACE_RAYS(...) trace_rays_pool(__VA_ARGS__, scr)
-static constexpr int kTraceSmem = kPoolSmemPerBlock;
-#else
-#define TRACE_RAYS(...) trace_rays(__VA_ARGS__)
-static constexpr int kTraceSmem = 0;
-#endif
 __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursor, HitQueue hq,
-                                                DeviceCounters* cnt, PoolScratch scr) {
+                                                DeviceCounters* cnt) {
     const uint32_t n = *count;
-    TRACE_RAYS(S, n, cursor,
+    trace_rays(S, n, cursor,
                [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
@@ -429,10 +419,10 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, PassD P, const DLight* 
 
 // K4.  sampleLight's visibility test: closest hit, then identity with the light (Sampler.cs:261-265).
 __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t* __restrict__ cursor,
-                                                 uint32_t capShadow, float* __restrict__ sum, DeviceCounters* cnt, PoolScratch scr) {
+                                                 uint32_t capShadow, float* __restrict__ sum, DeviceCounters* cnt) {
     uint32_t n = *scount;
     if (n > capShadow) n = capShadow;
-    TRACE_RAYS(S, n, cursor,
+    trace_rays(S, n, cursor,
                [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                [&](uint32_t i, const HitRec& h) {
                    const uint32_t light = f2u(sq.sd[i].w);
@@ -557,9 +547,8 @@ __global__ void k_firefly_apply(float* __restrict__ sum, const uint32_t* __restr
 
 // K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same trace_rays as the pipeline.
 __global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32_t* __restrict__ cursor, const float* __restrict__ o3, const float* __restrict__ d3,
-                                                          int32_t* shape, int32_t* prim, double* t, float* normal3, float* position3, int32_t* inside, int32_t* material,
-                                                          PoolScratch scr) {
-    TRACE_RAYS(S, (uint32_t)n, cursor,
+                                                          int32_t* shape, int32_t* prim, double* t, float* normal3, float* position3, int32_t* inside, int32_t* material) {
+    trace_rays(S, (uint32_t)n, cursor,
                [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
                [&](uint32_t i, const HitRec& h) {
                    V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
@@ -623,7 +612,6 @@ struct ptgpu_ctx {
     RayQueue rq[2]{};
     HitQueue hq{};
     ShadowQueue sq{};
-    PoolScratch scratch{};        // pooled tracer: kd stacks + cold ray state for gridTrace blocks
     uint32_t* dCounts = nullptr;  // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag, [4] trace cursor, [5] shadow cursor, [6] batch cursor
     DeviceCounters* dCounters = nullptr;
     // image state
@@ -692,26 +680,6 @@ static void free_image(ptgpu_ctx* ctx) {
 
 static int grid_for(ptgpu_ctx* ctx, int blocksPerSM) { return ctx->numSMs * blocksPerSM; }
 
-// Global scratch of the pooled tracer, sized once for the trace grid (every tracing kernel is launched with that grid).
-static int ensure_scratch(ptgpu_ctx* ctx) {
-#if PT_TRACER_POOL
-    if (ctx->scratch.meshStack) return PTGPU_OK;
-    const size_t warps = (size_t)grid_for(ctx, PT_TRACE_MINBLOCKS) * kPoolWarpsPerBlock, slots = warps * kPoolSlots;
-    CK(cudaMalloc(&ctx->scratch.meshStack, slots * kMeshStackEnt * sizeof(uint4)));
-    CK(cudaMalloc(&ctx->scratch.sceneStack, slots * kSceneStackEnt * sizeof(uint4)));
-    CK(cudaMalloc(&ctx->scratch.coldU, slots * kColdU * sizeof(uint32_t)));
-    CK(cudaMalloc(&ctx->scratch.coldD, slots * kColdD * sizeof(double)));
-    CK(cudaMemsetAsync(ctx->scratch.coldU, 0, slots * kColdU * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(ctx->scratch.coldD, 0, slots * kColdD * sizeof(double), ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-#endif
-    return PTGPU_OK;
-}
-static void free_scratch(ptgpu_ctx* ctx) {
-    cudaFree(ctx->scratch.meshStack); cudaFree(ctx->scratch.sceneStack); cudaFree(ctx->scratch.coldU); cudaFree(ctx->scratch.coldD);
-    ctx->scratch = PoolScratch{};
-}
-
 extern "C" {
 
 int ptgpu_abi_version(void) { return PTGPU_ABI_VERSION; }
@@ -770,7 +738,6 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
     free_scene(ctx);
     free_queues(ctx);
     free_image(ctx);
-    free_scratch(ctx);
     cudaFree(ctx->dCounts);
     cudaFree(ctx->dCounters);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
@@ -881,22 +848,86 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
             float* o = &nb[ii * 8];
             o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = 0; o[4] = hi[0]; o[5] = hi[1]; o[6] = hi[2]; o[7] = 0;
         }
-        // Leaves of mesh trees as groups of <= 4 spatially sorted triangles (see "mesh traversal" in pt_device.cuh).
-        // Every triangle carries its global index and its position in the reference leaf (tie-break of Tree.cs:122).
+        // Mesh nodes (see mesh_step in pt_device.cuh): 64-byte records = the reference node + both children's padded
+        // bounds.  The triangles of every reference leaf are sorted along a Morton curve and hung under bounds-only
+        // binary nodes ending in micro leaves of <= 4 triangles; each triangle carries its global index and its
+        // position in the reference leaf (tie-break of Tree.cs:122).
         std::vector<ptgpu_tri_geom> lg;
-        std::vector<float> groups;                       // 8 floats per group
-        std::vector<uint32_t> leafGroupFirst(nn, 0), leafGroupCount(nn, 0);
         lg.reserve(s->numLeafItems);
+        std::vector<uint32_t> mn(nn * 16, 0u);           // grows with the bounds-only nodes
+        std::vector<float> xb(nn * 8);                   // padded bounds of the appended nodes' subtrees (index - nn)
+        xb.clear();
         std::vector<std::pair<uint32_t, uint32_t>> order;  // (morton, position in leaf)
+        std::vector<float> cen;
         auto bitsToFloat = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+        auto floatBits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
         auto spread = [](uint32_t x) { x &= 1023u; x = (x | (x << 16)) & 0x030000FFu; x = (x | (x << 8)) & 0x0300F00Fu; x = (x | (x << 4)) & 0x030C30C3u; return (x | (x << 2)) & 0x09249249u; };
-        for (uint64_t i = 0; i < nn; i++) {
-            const ptgpu_node& n = s->nodes[i];
-            if (!isMeshNode[i] || (n.a & 3u) != 0) continue;
-            const uint32_t first = n.a >> 2, count = n.b;
-            leafGroupFirst[i] = (uint32_t)(groups.size() / 8);
+        int virtualDepth = 0;
+        // padded bounds of triangles lg[t0, t1)
+        auto tri_bounds = [&](uint32_t t0, uint32_t t1, float* out8) {
             float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
-            std::vector<float> cen((size_t)count * 3);
+            for (uint32_t t = t0; t < t1; t++) {
+                const ptgpu_tri_geom& g = lg[t];
+                for (int c = 0; c < 3; c++) {
+                    float p0 = g.v1[c], p1 = g.v1[c] + g.e1[c], p2 = g.v1[c] + g.e2[c];
+                    lo[c] = std::min(lo[c], std::min(p0, std::min(p1, p2)));
+                    hi[c] = std::max(hi[c], std::max(p0, std::max(p1, p2)));
+                }
+            }
+            float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+            for (int c = 0; c < 3; c++) {  // same padding rule as the reference nodes' bounds
+                float padv = 1e-4f * ext + 1e-5f * std::max(std::fabs(lo[c]), std::fabs(hi[c])) + 1e-7f;
+                out8[c] = lo[c] - padv; out8[4 + c] = hi[c] + padv;
+            }
+            out8[3] = out8[7] = 0;
+        };
+        // fill node record `idx` for triangles lg[t0, t1); appends children as needed; bounds of the subtree -> out8
+        struct Build { uint64_t idx; uint32_t t0, t1; int depth; };
+        auto build_leaf_subtree = [&](uint64_t rootIdx, uint32_t t0, uint32_t t1) {
+            std::vector<Build> todo{{rootIdx, t0, t1, 0}};
+            std::vector<uint64_t> interior;  // visit order, parents before children
+            while (!todo.empty()) {
+                Build bld = todo.back(); todo.pop_back();
+                virtualDepth = std::max(virtualDepth, bld.depth);
+                const uint32_t n = bld.t1 - bld.t0;
+                if (n <= 4) {
+                    uint32_t* o = &mn[bld.idx * 16];
+                    o[2] = bld.t0 << 2; o[3] = n;
+                    continue;
+                }
+                const uint32_t mid = bld.t0 + (n + 1) / 2;
+                const uint64_t l = mn.size() / 16, r = l + 1;
+                mn.resize(mn.size() + 32, 0u);
+                xb.resize(xb.size() + 16, 0.f);
+                uint32_t* o = &mn[bld.idx * 16];
+                o[2] = (uint32_t)l << 2; o[3] = kNodeVirtual | (uint32_t)r;
+                float lb[8], rb[8];
+                tri_bounds(bld.t0, mid, lb); tri_bounds(mid, bld.t1, rb);
+                const float pk[12] = {lb[0], lb[1], lb[2], lb[4], lb[5], lb[6], rb[0], rb[1], rb[2], rb[4], rb[5], rb[6]};
+                for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
+                todo.push_back({l, bld.t0, mid, bld.depth + 1});
+                todo.push_back({r, mid, bld.t1, bld.depth + 1});
+            }
+        };
+        for (uint64_t i = 0; i < nn; i++) {
+            if (!isMeshNode[i]) continue;
+            const ptgpu_node& n = s->nodes[i];
+            {
+                uint32_t* o = &mn[i * 16];
+                std::memcpy(o, &n.split, 8);
+            }
+            if ((n.a & 3u) != 0) {  // reference interior node: children's bounds
+                uint32_t* o = &mn[i * 16];
+                o[2] = n.a; o[3] = n.b;
+                const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
+                const float* r = &nb[(uint64_t)n.b * 8];
+                const float pk[12] = {l[0], l[1], l[2], l[4], l[5], l[6], r[0], r[1], r[2], r[4], r[5], r[6]};
+                for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
+                continue;
+            }
+            const uint32_t first = n.a >> 2, count = n.b;
+            float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
+            cen.resize((size_t)count * 3);
             for (uint32_t k = 0; k < count; k++) {
                 const ptgpu_tri_geom& g = s->triGeom[s->leafItems[first + k]];
                 for (int c = 0; c < 3; c++) {
@@ -915,53 +946,21 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
                 order.push_back({spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), k});
             }
             std::sort(order.begin(), order.end());
-            for (uint32_t g0 = 0; g0 < count; g0 += 4) {
-                const uint32_t gc = std::min<uint32_t>(4, count - g0);
-                float glo[3] = {BIG, BIG, BIG}, ghi[3] = {-BIG, -BIG, -BIG};
-                const uint32_t triFirst = (uint32_t)lg.size();
-                for (uint32_t k = 0; k < gc; k++) {
-                    const uint32_t pos = order[g0 + k].second, tri = s->leafItems[first + pos];
-                    ptgpu_tri_geom g = s->triGeom[tri];
-                    for (int c = 0; c < 3; c++) {
-                        float p0 = g.v1[c], p1 = g.v1[c] + g.e1[c], p2 = g.v1[c] + g.e2[c];
-                        glo[c] = std::min(glo[c], std::min(p0, std::min(p1, p2)));
-                        ghi[c] = std::max(ghi[c], std::max(p0, std::max(p1, p2)));
-                    }
-                    g.pad0 = bitsToFloat(tri); g.pad1 = bitsToFloat(pos); g.pad2 = 0.f;
-                    lg.push_back(g);
-                }
-                float ext = std::max(ghi[0] - glo[0], std::max(ghi[1] - glo[1], ghi[2] - glo[2]));
-                for (int c = 0; c < 3; c++) {  // same padding rule as the node bounds
-                    float padv = 1e-4f * ext + 1e-5f * std::max(std::fabs(glo[c]), std::fabs(ghi[c])) + 1e-7f;
-                    glo[c] -= padv; ghi[c] += padv;
-                }
-                const float rec[8] = {glo[0], glo[1], glo[2], bitsToFloat(triFirst), ghi[0], ghi[1], ghi[2], bitsToFloat(gc)};
-                groups.insert(groups.end(), rec, rec + 8);
+            const uint32_t t0 = (uint32_t)lg.size();
+            for (uint32_t k = 0; k < count; k++) {
+                const uint32_t pos = order[k].second, tri = s->leafItems[first + pos];
+                ptgpu_tri_geom g = s->triGeom[tri];
+                g.pad0 = bitsToFloat(tri); g.pad1 = bitsToFloat(pos); g.pad2 = 0.f;
+                lg.push_back(g);
             }
-            leafGroupCount[i] = (uint32_t)(groups.size() / 8) - leafGroupFirst[i];
+            build_leaf_subtree(i, t0, t0 + count);
+            mn[i * 16 + 3] |= kNodeRefLeaf;
         }
-        // 64-byte mesh nodes: the reference node (leaves re-pointed at their groups) + both children's padded bounds
-        std::vector<uint32_t> mn(nn * 16, 0u);
-        auto floatBits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
-        for (uint64_t i = 0; i < nn; i++) {
-            if (!isMeshNode[i]) continue;
-            const ptgpu_node& n = s->nodes[i];
-            uint32_t* o = &mn[i * 16];
-            std::memcpy(o, &n.split, 8);
-            if ((n.a & 3u) == 0) { o[2] = leafGroupFirst[i] << 2; o[3] = leafGroupCount[i]; continue; }
-            o[2] = n.a; o[3] = n.b;
-            const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
-            const float* r = &nb[(uint64_t)n.b * 8];
-            const float pk[12] = {l[0], l[1], l[2], l[4], l[5], l[6], r[0], r[1], r[2], r[4], r[5], r[6]};
-            for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
-        }
-        if (groups.size() / 8 >= (1ull << 30)) return fail(ctx, PTGPU_E_LIMIT, "too many leaf groups");
+        if (mn.size() / 16 >= (uint64_t)kNodeIndexMask || lg.size() >= (1ull << 30)) return fail(ctx, PTGPU_E_LIMIT, "mesh too large for the 30-bit node / triangle indices");
+        if (virtualDepth > kVirtualDepthMax) return fail(ctx, PTGPU_E_LIMIT, "a kd leaf holds more triangles than the bounds-only hierarchy supports");
         const uint4* dmn = nullptr;
-        if ((rc = upload(ctx, reinterpret_cast<const uint4*>(mn.data()), nn * 4, &dmn)) != PTGPU_OK) return rc;
+        if ((rc = upload(ctx, reinterpret_cast<const uint4*>(mn.data()), (uint64_t)mn.size() / 4, &dmn)) != PTGPU_OK) return rc;
         D.meshNodes = dmn;
-        const float4* dg = nullptr;
-        if ((rc = upload(ctx, reinterpret_cast<const float4*>(groups.data()), (uint64_t)groups.size() / 4, &dg)) != PTGPU_OK) return rc;
-        D.leafGroups = dg;
         const float4* dl = nullptr;
         if ((rc = upload(ctx, reinterpret_cast<const float4*>(lg.data()), (uint64_t)lg.size() * 3, &dl)) != PTGPU_OK) return rc;
         CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors are locals
@@ -1111,7 +1110,6 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     if (capShadow == 0) capShadow = 1;
     int rc = ensure_queues(ctx, capShadow);
     if (rc != PTGPU_OK) return rc;
-    if ((rc = ensure_scratch(ctx)) != PTGPU_OK) return rc;
 
     const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
     uint32_t* counts = ctx->dCounts;
@@ -1130,7 +1128,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             CK(cudaMemsetAsync(counts + 2, 0, sizeof(uint32_t), stream));
             CK(cudaMemsetAsync(counts + 4, 0, 2 * sizeof(uint32_t), stream));  // trace / shadow work cursors
             if (prof) cudaEventRecord(ctx->evA, stream);
-            k_trace<<<gridTrace, 128, kTraceSmem, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, counts + 4, ctx->hq, ctx->dCounters, ctx->scratch);
+            k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, counts + 4, ctx->hq, ctx->dCounters);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, ctx->rq[cur], counts + cur, ctx->hq, ctx->rq[cur ^ 1], counts + (cur ^ 1),
                                                    ctx->sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)ctx->capRays, (uint32_t)ctx->capShadow);
@@ -1138,7 +1136,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 3;
             if (lightsPer) {
-                k_shadow<<<gridTrace, 128, kTraceSmem, stream>>>(ctx->scene, ctx->sq, counts + 2, counts + 5, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters, ctx->scratch);
+                k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->sq, counts + 2, counts + 5, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters);
                 ctx->launches++;
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
             }
@@ -1302,8 +1300,7 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
     CKC(cudaMemcpyAsync(dO, o3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemsetAsync(ctx->dCounts + 6, 0, sizeof(uint32_t), ctx->stream));
-    { int rcs = ensure_scratch(ctx); if (rcs != PTGPU_OK) { cleanup(); return rcs; } }
-    k_intersect_batch<<<grid_for(ctx, 4), 128, kTraceSmem, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM, ctx->scratch);
+    k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM);
     ctx->launches++;
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(shape, dS, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
