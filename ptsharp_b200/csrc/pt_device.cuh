@@ -715,6 +715,9 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
 #ifndef PT_GLUE_CHAIN
 #define PT_GLUE_CHAIN 1
 #endif
+#ifndef PT_SPLIT_FETCH_MIN
+#define PT_SPLIT_FETCH_MIN 8   // mesh_walk refills idle lanes once this many wait (or nothing else is left to do)
+#endif
 #ifndef PT_LEAF_UNROLL
 #define PT_LEAF_UNROLL 1
 #endif
@@ -911,6 +914,204 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
                 if (tPos >= tEnd) st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- split tracer
+// Scene.Intersect as two kinds of kernels (used when the scene has meshes and no SDF / Volume shapes).
+//
+// In trace_rays the three work classes settle at a third of the lanes each: GLUE lanes (ray fetch, Scene.tree, analytic
+// shapes, TransformedShape set-up, FP64 Box.Intersect) drop out of step with the lanes walking a mesh.  Here the scene
+// level runs as a streaming kernel (`scene_advance`, one thread per ray, every lane busy) that carries each ray up to
+// the next Mesh it has to enter and emits a 48-byte work item; `mesh_walk` is a persistent kernel that only knows NODE
+// and LEAF work, so a warp alternates between the two with most of its lanes (a NODE burst ends in leaves, a LEAF burst
+// ends in nodes); the mesh's Hit is written back into the ray's record and the next `scene_advance` round folds it in and
+// continues with the ray's remaining shapes.  A ray takes as many rounds as it enters meshes.  The per-ray arithmetic
+// and visiting order are those of Tree.Intersect (Tree.cs:31-128), so hits are bit-identical to trace_rays.
+struct SplitState {      // per ray of the launch, SoA
+    double* bestT; double* bestTInner; int32_t* bestShape; int32_t* bestPrim;   // running Hit of Scene.tree's traversal
+    uint32_t* scNode; int32_t* scSp; double* scTmin; double* scTmax;            // Scene.tree cursor
+    uint32_t* sPos; uint32_t* sEnd; uint32_t* curShape; int32_t* curInst;       // position in the current scene leaf
+    double* mBest; int32_t* mPrim;                                              // Hit of the pending Mesh.Intersect
+    uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
+};
+struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root node)  c = (tmin, tmax)
+    float4* a; float4* b; double2* c; uint32_t* count;
+};
+
+// Node.Intersect step on Scene.tree (16-byte reference nodes, no culling) with the 16-byte stack.
+PT_D int scene_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d, uint4* stk, int stackEnt, uint32_t& leafFirst, uint32_t& leafCount) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));
+    const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
+    const uint32_t axis = a & 3u;
+    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return KD_LEAF; }
+    const double split = __hiloint2double(raw.y, raw.x);
+    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+    const double tsplit = (split - oa) / da;
+    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
+    const uint32_t first = leftFirst ? (a >> 2) : b;
+    const uint32_t second = leftFirst ? b : (a >> 2);
+    if (tsplit > c.tmax || tsplit <= 0) c.node = first;
+    else if (tsplit < c.tmin) c.node = second;
+    else {
+        if (c.sp + 1 < stackEnt) { c.sp++; stk_put(stk + c.sp, tsplit, second, 0u); }
+        c.node = first;
+        c.tmax = tsplit;
+    }
+    return KD_INTERIOR;
+}
+
+// Advance rays through Scene.tree until each either finishes (sink) or has to enter a Mesh (work item to `out`).
+// RESUME = false: rays [0, n) start; RESUME = true: the n rays named by the items of `in` continue after their mesh walk.
+template <bool RESUME, class Source, class Sink>
+PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink) {
+    const ptgpu_tree sceneTree = S.trees[S.sceneTree];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t ray = RESUME ? __float_as_uint(in.a[k].w) : k;
+        V3 o, d;
+        source(ray, o, d);
+        HitRec best;
+        KdCursor sc;
+        uint32_t sPos = 0, sEnd = 0, curShape = 0;
+        int32_t curInst = -1, mPrim = -1;
+        double mBest = kHitInf;
+        V3 co = o, cd = d;
+        uint4* sstk = W.sceneStack + (size_t)ray * W.stackEnt;
+        int st;
+        if (RESUME) {
+            best.t = W.bestT[ray]; best.tInner = W.bestTInner[ray]; best.shape = W.bestShape[ray]; best.prim = W.bestPrim[ray];
+            sc.node = W.scNode[ray]; sc.sp = W.scSp[ray]; sc.tmin = W.scTmin[ray]; sc.tmax = W.scTmax[ray];
+            sPos = W.sPos[ray]; sEnd = W.sEnd[ray]; curShape = W.curShape[ray]; curInst = W.curInst[ray];
+            mBest = W.mBest[ray]; mPrim = W.mPrim[ray];
+            if (curInst >= 0) { const ptgpu_instance& inst = S.instances[curInst]; co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d); }
+            st = ST_MESH_DONE;
+        } else {
+            best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
+            box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
+            if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
+            else { sc.node = sceneTree.root; sc.sp = 0; stk_put(sstk, sc.tmax, 0u, 0u); st = ST_SCENE_NODE; }
+        }
+        for (;;) {
+            if (st == ST_MESH_DONE) {  // fold the shape's Hit into the leaf's running best (Tree.cs:121-125)
+                double t = mBest, tInner = 0;
+                if (curInst >= 0) {
+                    tInner = mBest;
+                    if (mBest < kHitInf) {  // TransformedShape.cs:47-69
+                        const ptgpu_instance& inst = S.instances[curInst];
+                        V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
+                        t = (double)vlenf(vsub(position, o));
+                    }
+                }
+                if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
+                st = ST_SCENE_LEAF;
+            }
+            if (st == ST_SCENE_NODE) {
+                uint32_t first, count;
+                while (scene_step(S.nodes, sc, o, d, sstk, W.stackEnt, first, count) != KD_LEAF) {}
+                sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
+            }
+            if (st == ST_SCENE_LEAF) {
+                if (sPos == sEnd) st = mesh_pop(sc, best.t, sstk) ? ST_SCENE_NODE : ST_FINISH;
+                else {  // next shape of the leaf, in array order (Tree.cs:119-126)
+                    curShape = __ldg(S.leafItems + sPos);
+                    sPos++;
+                    ptgpu_shape sh = S.shapes[curShape];
+                    curInst = -1; co = o; cd = d;
+                    if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45
+                        curInst = (int32_t)sh.data;
+                        const ptgpu_instance& inst = S.instances[sh.data];
+                        co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
+                        sh = S.shapes[inst.shape];
+                    }
+                    mPrim = -1;
+                    if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
+                        const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
+                        mBest = kHitInf;
+                        double tmin = 0, tmax = -1;
+                        const RayAux ra = ray_aux(co, cd);
+                        if (tree_box_maybe_hit(mt, co, ra)) box_intersect(mt.bmin, mt.bmax, co, cd, tmin, tmax);
+                        if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
+                        else {
+                            auto g = cooperative_groups::coalesced_threads();
+                            uint32_t base = 0;
+                            if (g.thread_rank() == 0) base = atomicAdd(out.count, g.size());
+                            const uint32_t slot = g.shfl(base, 0) + g.thread_rank();
+                            out.a[slot] = make_float4(co.x, co.y, co.z, __uint_as_float(ray));
+                            out.b[slot] = make_float4(cd.x, cd.y, cd.z, __uint_as_float(mt.root));
+                            out.c[slot] = make_double2(tmin, tmax);
+                            W.bestT[ray] = best.t; W.bestTInner[ray] = best.tInner; W.bestShape[ray] = best.shape; W.bestPrim[ray] = best.prim;
+                            W.scNode[ray] = sc.node; W.scSp[ray] = sc.sp; W.scTmin[ray] = sc.tmin; W.scTmax[ray] = sc.tmax;
+                            W.sPos[ray] = sPos; W.sEnd[ray] = sEnd; W.curShape[ray] = curShape; W.curInst[ray] = curInst;
+                            break;
+                        }
+                    } else {
+                        mBest = primitive_intersect(S, sh, co, cd);
+                        st = ST_MESH_DONE;
+                    }
+                }
+            }
+            if (st == ST_FINISH) {
+                if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
+                sink(ray, best);
+                break;
+            }
+        }
+    }
+}
+
+// Mesh.Intersect for every work item of `q`; the Hit goes to W.mBest / W.mPrim of the item's ray.
+PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
+    const uint32_t n = *q.count;
+    int st = ST_IDLE;
+    uint32_t ray = 0;
+    V3 co = v3(0, 0, 0), cd = v3(0, 0, 1);
+    RayAux ra = ray_aux(co, cd);
+    KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
+    uint4 mStk[kMeshStackEnt];
+    uint32_t tPos = 0, tEnd = 0, mBestPos = 0;
+    double mBest = kHitInf;
+    int32_t mPrim = -1;
+    for (;;) {
+        const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
+        const unsigned leafMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_LEAF);
+        const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE);
+        const int nIdle = __popc(idleMask), nLeaf = __popc(leafMask), nNode = __popc(nodeMask);
+        if (nIdle + nLeaf + nNode == 0) break;
+        if (nIdle >= PT_SPLIT_FETCH_MIN || nLeaf + nNode == 0) {
+            if (st == ST_IDLE) {
+                auto g = cooperative_groups::coalesced_threads();
+                uint32_t base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
+                const uint32_t i = g.shfl(base, 0) + g.thread_rank();
+                if (i >= n) st = ST_EXIT;
+                else {
+                    const float4 a = q.a[i], b = q.b[i];
+                    const double2 c = q.c[i];
+                    co = v3(a.x, a.y, a.z); cd = v3(b.x, b.y, b.z); ray = __float_as_uint(a.w);
+                    ra = ray_aux(co, cd);
+                    mc.node = __float_as_uint(b.w); mc.tmin = c.x; mc.tmax = c.y; mc.sp = 0;
+                    stk_put(mStk, mc.tmax, 0u, 0u);
+                    mBest = kHitInf; mPrim = -1; mBestPos = 0;
+                    st = ST_MESH_NODE;
+                }
+            }
+        } else if (nNode >= nLeaf) {
+            if (st == ST_MESH_NODE) {
+#pragma unroll 1
+                for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
+                    uint32_t first, count;
+                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
+                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
+                    else if (r == MESH_DONE) st = ST_MESH_DONE;
+                }
+            }
+        } else {
+            if (st == ST_MESH_LEAF) {
+                leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
+                if (tPos >= tEnd) st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
+            }
+        }
+        if (st == ST_MESH_DONE) { W.mBest[ray] = mBest; W.mPrim[ray] = mPrim; st = ST_IDLE; }
     }
 }
 

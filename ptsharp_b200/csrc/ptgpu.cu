@@ -25,6 +25,9 @@
 #include <string>
 #include <vector>
 
+#ifndef PT_SPLIT
+#define PT_SPLIT 1
+#endif
 #include "pt_device.cuh"
 
 namespace cg = cooperative_groups;
@@ -434,6 +437,34 @@ __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_shadow(DScene S, Sh
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
 }
 
+// K2/K4, split form (see "split tracer" in pt_device.cuh): scene level as streaming kernels, mesh walks as a persistent one.
+template <bool RESUME>
+__global__ void __launch_bounds__(128) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
+                                                      DeviceCounters* cnt) {
+    const uint32_t n = RESUME ? *in.count : *count;
+    scene_advance<RESUME>(S, W, n, in, out,
+                          [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
+                          [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
+    if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
+}
+template <bool RESUME>
+__global__ void __launch_bounds__(128) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, MeshQueue in,
+                                                       MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
+    uint32_t n = RESUME ? *in.count : *scount;
+    if (!RESUME && n > capShadow) n = capShadow;
+    scene_advance<RESUME>(S, W, n, in, out,
+                          [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
+                          [&](uint32_t i, const HitRec& h) {
+                              const uint32_t light = f2u(sq.sd[i].w);
+                              if (h.shape >= 0 && (uint32_t)h.shape == light) {
+                                  float4 c = sq.sc[i];
+                                  accumulate(sum, cnt, f2u(sq.so[i].w), c.x, c.y, c.z);
+                              }
+                          });
+    if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
+}
+__global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) { mesh_walk(S, W, q, cursor); }
+
 __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
     if (*count > cap) { *overflow = 1; *count = cap; }
 }
@@ -573,6 +604,36 @@ __global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32
                    if (material) material[i] = mat;
                });
 }
+struct BatchOut { int32_t* shape; int32_t* prim; double* t; float* normal3; float* position3; int32_t* inside; int32_t* material; };
+template <bool RESUME>
+__global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uint32_t nStart, MeshQueue in, MeshQueue out, const float* __restrict__ o3,
+                                                      const float* __restrict__ d3, BatchOut B) {
+    const uint32_t n = RESUME ? *in.count : nStart;
+    scene_advance<RESUME>(S, W, n, in, out,
+                          [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
+                          [&](uint32_t i, const HitRec& h) {
+                              V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+                              B.shape[i] = h.shape;
+                              B.t[i] = h.t;
+                              int32_t localPrim = -1;
+                              V3 nn = v3(0, 0, 0), pp = v3(0, 0, 0);
+                              int32_t ins = 0, mat = -1;
+                              if (h.shape >= 0) {
+                                  if (h.prim >= 0) {
+                                      ptgpu_shape sh = S.shapes[h.shape];
+                                      if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+                                      localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
+                                  }
+                                  Surface sf = hit_info(S, o, d, h);
+                                  nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+                              }
+                              B.prim[i] = localPrim;
+                              if (B.normal3) { B.normal3[3 * i] = nn.x; B.normal3[3 * i + 1] = nn.y; B.normal3[3 * i + 2] = nn.z; }
+                              if (B.position3) { B.position3[3 * i] = pp.x; B.position3[3 * i + 1] = pp.y; B.position3[3 * i + 2] = pp.z; }
+                              if (B.inside) B.inside[i] = ins;
+                              if (B.material) B.material[i] = mat;
+                          });
+}
 __global__ void k_cast_rays(PassD P, int n, const int32_t* x, const int32_t* y, const double* fu, const double* fv, const int32_t* sample, float* o3, float* d3) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Rng rng;
@@ -612,6 +673,13 @@ struct ptgpu_ctx {
     RayQueue rq[2]{};
     HitQueue hq{};
     ShadowQueue sq{};
+    // split tracer (scene_advance / mesh_walk): per-ray scene-level state and the two mesh work queues
+    SplitState split{};
+    MeshQueue mq[2]{};
+    uint64_t splitCap = 0;
+    bool useSplit = false;
+    int splitStackEnt = 2;
+    int splitRounds = 0;          // > 0: every ray enters at most this many meshes (fixed rounds, no host sync); 0: loop on the queue count
     uint32_t* dCounts = nullptr;  // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag, [4] trace cursor, [5] shadow cursor, [6] batch cursor
     DeviceCounters* dCounters = nullptr;
     // image state
@@ -680,6 +748,59 @@ static void free_image(ptgpu_ctx* ctx) {
 
 static int grid_for(ptgpu_ctx* ctx, int blocksPerSM) { return ctx->numSMs * blocksPerSM; }
 
+static void free_split(ptgpu_ctx* ctx) {
+    SplitState& W = ctx->split;
+    void* ps[] = {W.bestT, W.bestTInner, W.bestShape, W.bestPrim, W.scNode, W.scSp, W.scTmin, W.scTmax, W.sPos, W.sEnd, W.curShape, W.curInst, W.mBest, W.mPrim,
+                  W.sceneStack, ctx->mq[0].a, ctx->mq[0].b, ctx->mq[0].c, ctx->mq[1].a, ctx->mq[1].b, ctx->mq[1].c};
+    for (void* p : ps) cudaFree(p);
+    W = SplitState{};
+    ctx->mq[0] = ctx->mq[1] = MeshQueue{};
+    ctx->splitCap = 0;
+}
+// Per-ray state of the split tracer for launches of up to `cap` rays.
+static int ensure_split(ptgpu_ctx* ctx, uint64_t cap, int stackEnt) {
+    if (cap <= ctx->splitCap && stackEnt == ctx->split.stackEnt) return PTGPU_OK;
+    free_split(ctx);
+    SplitState& W = ctx->split;
+    CK(cudaMalloc(&W.bestT, cap * 8)); CK(cudaMalloc(&W.bestTInner, cap * 8)); CK(cudaMalloc(&W.bestShape, cap * 4)); CK(cudaMalloc(&W.bestPrim, cap * 4));
+    CK(cudaMalloc(&W.scNode, cap * 4)); CK(cudaMalloc(&W.scSp, cap * 4)); CK(cudaMalloc(&W.scTmin, cap * 8)); CK(cudaMalloc(&W.scTmax, cap * 8));
+    CK(cudaMalloc(&W.sPos, cap * 4)); CK(cudaMalloc(&W.sEnd, cap * 4)); CK(cudaMalloc(&W.curShape, cap * 4)); CK(cudaMalloc(&W.curInst, cap * 4));
+    CK(cudaMalloc(&W.mBest, cap * 8)); CK(cudaMalloc(&W.mPrim, cap * 4));
+    CK(cudaMalloc(&W.sceneStack, cap * (uint64_t)stackEnt * sizeof(uint4)));
+    W.stackEnt = stackEnt;
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc(&ctx->mq[i].a, cap * sizeof(float4))); CK(cudaMalloc(&ctx->mq[i].b, cap * sizeof(float4))); CK(cudaMalloc(&ctx->mq[i].c, cap * sizeof(double2)));
+        ctx->mq[i].count = ctx->dCounts + 10 + i;
+    }
+    ctx->splitCap = cap;
+    return PTGPU_OK;
+}
+// One Scene.Intersect wavefront in split form.  start(out) launches the scene kernel for the fresh rays; resume(in, out)
+// launches it for the rays named by `in`'s items.  Fixed number of rounds when the scene bounds it, else until empty.
+template <class StartFn, class ResumeFn>
+static int run_split(ptgpu_ctx* ctx, cudaStream_t st, StartFn start, ResumeFn resume) {
+    uint32_t* cursor = ctx->dCounts + 12;
+    CK(cudaMemsetAsync(ctx->dCounts + 10, 0, 3 * sizeof(uint32_t), st));
+    start(ctx->mq[0]);
+    ctx->launches++;
+    int cur = 0;
+    for (int round = 0; ctx->splitRounds == 0 || round < ctx->splitRounds; round++) {
+        if (ctx->splitRounds == 0) {
+            uint32_t pending = 0;
+            CK(cudaMemcpyAsync(&pending, ctx->mq[cur].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (pending == 0) break;
+        }
+        CK(cudaMemsetAsync(ctx->mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
+        k_mesh<<<grid_for(ctx, PT_TRACE_MINBLOCKS), 128, 0, st>>>(ctx->scene, ctx->split, ctx->mq[cur], cursor);
+        resume(ctx->mq[cur], ctx->mq[cur ^ 1]);
+        ctx->launches += 2;
+        cur ^= 1;
+    }
+    return PTGPU_OK;
+}
+
 extern "C" {
 
 int ptgpu_abi_version(void) { return PTGPU_ABI_VERSION; }
@@ -738,6 +859,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
     free_scene(ctx);
     free_queues(ctx);
     free_image(ctx);
+    free_split(ctx);
     cudaFree(ctx->dCounts);
     cudaFree(ctx->dCounters);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
@@ -1012,6 +1134,25 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
         ctx->dLights = const_cast<DLight*>(dl);
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    {   // split tracer: scenes with meshes and without marched shapes; bound on the meshes a ray can enter = mesh-like
+        // items over all leaves of Scene.tree (a ray visits a leaf, and a shape of a leaf, at most once)
+        const ptgpu_tree& stree = s->trees[s->sceneTree];
+        uint64_t end = s->numNodes;
+        for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > stree.root && s->trees[k].root < end) end = s->trees[k].root;
+        uint64_t meshItems = 0;
+        for (uint64_t i = stree.root; i < end; i++) {
+            const ptgpu_node& n = s->nodes[i];
+            if ((n.a & 3u) != 0) continue;
+            for (uint32_t k = 0; k < n.b; k++) {
+                ptgpu_shape sh = s->shapes[s->leafItems[(n.a >> 2) + k]];
+                if (sh.type == PTGPU_TRANSFORMED) sh = s->shapes[s->instances[sh.data].shape];
+                if (sh.type == PTGPU_MESH) meshItems++;
+            }
+        }
+        ctx->useSplit = PT_SPLIT && meshItems > 0 && s->numSdfShapes == 0 && s->numVolumes == 0;
+        ctx->splitRounds = meshItems <= 4 ? (int)meshItems : 0;
+        ctx->splitStackEnt = (int)stree.maxDepth + 2;
+    }
     ctx->haveScene = true;
     return PTGPU_OK;
 }
@@ -1110,6 +1251,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     if (capShadow == 0) capShadow = 1;
     int rc = ensure_queues(ctx, capShadow);
     if (rc != PTGPU_OK) return rc;
+    if (ctx->useSplit && (rc = ensure_split(ctx, std::max<uint64_t>(ctx->capRays, ctx->capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
 
     const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
     uint32_t* counts = ctx->dCounts;
@@ -1128,6 +1270,15 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             CK(cudaMemsetAsync(counts + 2, 0, sizeof(uint32_t), stream));
             CK(cudaMemsetAsync(counts + 4, 0, 2 * sizeof(uint32_t), stream));  // trace / shadow work cursors
             if (prof) cudaEventRecord(ctx->evA, stream);
+            if (ctx->useSplit) {
+                const RayQueue rqc = ctx->rq[cur];
+                uint32_t* cnt = counts + cur;
+                rc = run_split(ctx, stream,
+                               [&](const MeshQueue& out) { k_scene_trace<false><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, rqc, cnt, out, out, ctx->hq, ctx->dCounters); },
+                               [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<true><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, rqc, cnt, in, out, ctx->hq, ctx->dCounters); });
+                if (rc != PTGPU_OK) return rc;
+                ctx->launches--;  // run_split counts its own; the common += 3 below includes one for the tracer
+            } else
             k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, counts + 4, ctx->hq, ctx->dCounters);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, ctx->rq[cur], counts + cur, ctx->hq, ctx->rq[cur ^ 1], counts + (cur ^ 1),
@@ -1136,8 +1287,15 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 3;
             if (lightsPer) {
+                if (ctx->useSplit) {
+                    rc = run_split(ctx, stream,
+                                   [&](const MeshQueue& out) { k_scene_shadow<false><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, ctx->sq, counts + 2, (uint32_t)ctx->capShadow, out, out, d_sum, ctx->dCounters); },
+                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<true><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, ctx->sq, counts + 2, (uint32_t)ctx->capShadow, in, out, d_sum, ctx->dCounters); });
+                    if (rc != PTGPU_OK) return rc;
+                } else {
                 k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->sq, counts + 2, counts + 5, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters);
                 ctx->launches++;
+                }
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
             }
             cur ^= 1;
@@ -1300,8 +1458,18 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
     CKC(cudaMemcpyAsync(dO, o3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemsetAsync(ctx->dCounts + 6, 0, sizeof(uint32_t), ctx->stream));
+    if (ctx->useSplit) {
+        int rcs = ensure_split(ctx, std::max<uint64_t>(N, ctx->splitCap), ctx->splitStackEnt);
+        if (rcs != PTGPU_OK) { cleanup(); return rcs; }
+        const BatchOut B{dS, dPr, dT, dN, dP, dI, dM};
+        rcs = run_split(ctx, ctx->stream,
+                        [&](const MeshQueue& out) { k_scene_batch<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, ctx->split, (uint32_t)n, out, out, dO, dD, B); },
+                        [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, ctx->split, (uint32_t)n, in, out, dO, dD, B); });
+        if (rcs != PTGPU_OK) { cleanup(); return rcs; }
+    } else {
     k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM);
     ctx->launches++;
+    }
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(shape, dS, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaMemcpyAsync(prim, dPr, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
