@@ -20,6 +20,13 @@
 #define PT_D __device__ __forceinline__
 #define PT_DN __device__ __noinline__
 
+#ifndef PT_PREFETCH
+#define PT_PREFETCH 0
+#endif
+#ifndef PT_SHORTCUT
+#define PT_SHORTCUT 1
+#endif
+
 namespace pt {
 
 static constexpr double kEPS = 1e-9;            // Util.cs:11
@@ -618,6 +625,18 @@ PT_D bool tree_box_maybe_hit(const ptgpu_tree& t, V3 o, const RayAux& ra) {
     return box_line_hit(t.bmin[0] - p, t.bmin[1] - p, t.bmin[2] - p, t.bmax[0] + p, t.bmax[1] + p, t.bmax[2] + p, o, ra);
 }
 
+// Same test, also returning a lower bound of the entry distance (for near-first ordering / distance culling).
+PT_D bool box_line_hit_t(float lox, float loy, float loz, float hix, float hiy, float hiz, V3 o, const RayAux& ra, float& tnear) {
+    const float x1 = (lox - ra.pad - o.x) * ra.ix, x2 = (hix + ra.pad - o.x) * ra.ix;
+    const float y1 = (loy - ra.pad - o.y) * ra.iy, y2 = (hiy + ra.pad - o.y) * ra.iy;
+    const float z1 = (loz - ra.pad - o.z) * ra.iz, z2 = (hiz + ra.pad - o.z) * ra.iz;
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float slack = 1e-5f * fabsf(tf) + 1e-30f;
+    tnear = tn - slack - 1e-5f * fabsf(tn);
+    return !(tn > tf + slack) && !(tf < -slack);
+}
+
 // Resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
 PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
     while (c.sp > 0) {
@@ -657,16 +676,30 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& 
         if (!(b & kNodeVirtual)) { tFirst = a >> 2; tCount = b & 0xFFu; return MESH_LEAF; }
     }
     const uint4 q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-    const bool hitL = box_line_hit(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
-                                   __uint_as_float(q2.y), o, ra);
-    const bool hitR = box_line_hit(__uint_as_float(q2.z), __uint_as_float(q2.w), __uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z),
-                                   __uint_as_float(q3.w), o, ra);
+    float tnL, tnR;
+    bool hitL = box_line_hit_t(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
+                               __uint_as_float(q2.y), o, ra, tnL);
+    bool hitR = box_line_hit_t(__uint_as_float(q2.z), __uint_as_float(q2.w), __uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z),
+                               __uint_as_float(q3.w), o, ra, tnR);
     const uint32_t left = a >> 2, right = b & kNodeIndexMask;
+#if PT_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (size_t)left * 4));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (size_t)right * 4));
+#endif
     bool go;
-    if (axis == 0) {  // bounds-only node: -inf keeps the pending child from being skipped by `best.T <= tsplit`
-        if (hitL && hitR) { c.sp++; stk_put(stk + c.sp, -INFINITY, right, 0u); }
-        c.node = hitL ? left : right;
-        go = hitL || hitR;
+    if (axis == 0) {
+        // bounds-only node.  tn* are strict lower bounds of the T of any triangle below the child (the padded box contains
+        // the triangles with a margin far above the FP32 error of the triangle test), so a child with best.T <= tn cannot
+        // improve or tie the running best: it is dropped here, or when it is popped (its tn is stored as the entry's
+        // `tsplit`, and mesh_pop skips entries with best.T <= tsplit).  Near child first.
+        hitL = hitL && !(bestT <= (double)tnL);
+        hitR = hitR && !(bestT <= (double)tnR);
+        const bool leftNear = !(tnR < tnL);
+        const uint32_t nearC = leftNear ? left : right, farC = leftNear ? right : left;
+        const bool hitNear = leftNear ? hitL : hitR, hitFar = leftNear ? hitR : hitL;
+        if (hitNear && hitFar) { c.sp++; stk_put(stk + c.sp, (double)(leftNear ? tnR : tnL), farC, 0u); }
+        c.node = hitNear ? nearC : farC;
+        go = hitNear || hitFar;
     } else {
         const double split = __hiloint2double((int)q0.y, (int)q0.x);
         const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
@@ -676,7 +709,11 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& 
         const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
         if (tsplit > c.tmax || tsplit <= 0) { c.node = first; go = hitFirst; }
         else if (tsplit < c.tmin) { c.node = second; go = hitSecond; }
-        else {
+        else if (PT_SHORTCUT && !hitFirst) {
+            // the near child returns NoHit: what the pop of (second, tsplit) would do, without the stack round trip
+            if (bestT <= tsplit || !hitSecond) go = false;
+            else { c.node = second; c.tmin = tsplit; c.tmax = netmin(c.tmax, bestT); go = true; }
+        } else {
             c.sp++;
             stk_put(stk + c.sp, tsplit, second, hitSecond ? 0u : 1u);
             c.node = first;
@@ -717,6 +754,9 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
 #endif
 #ifndef PT_SPLIT_FETCH_MIN
 #define PT_SPLIT_FETCH_MIN 8   // mesh_walk refills idle lanes once this many wait (or nothing else is left to do)
+#endif
+#ifndef PT_BURST_VOTE
+#define PT_BURST_VOTE 0     // mesh_walk: leave a NODE burst once fewer than this many lanes are still walking (0 = off)
 #endif
 #ifndef PT_LEAF_UNROLL
 #define PT_LEAF_UNROLL 1
@@ -1071,6 +1111,9 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
     uint32_t tPos = 0, tEnd = 0, mBestPos = 0;
     double mBest = kHitInf;
     int32_t mPrim = -1;
+#ifdef PT_DEBUG_STEPS
+    int dbgSteps = 0, dbgLeaves = 0; uint32_t dbgRoot = 0;
+#endif
     for (;;) {
         const unsigned idleMask = __ballot_sync(0xFFFFFFFFu, st == ST_IDLE);
         const unsigned leafMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_LEAF);
@@ -1090,27 +1133,55 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     co = v3(a.x, a.y, a.z); cd = v3(b.x, b.y, b.z); ray = __float_as_uint(a.w);
                     ra = ray_aux(co, cd);
                     mc.node = __float_as_uint(b.w); mc.tmin = c.x; mc.tmax = c.y; mc.sp = 0;
+#ifdef PT_DEBUG_STEPS
+                    dbgRoot = mc.node;
+#endif
                     stk_put(mStk, mc.tmax, 0u, 0u);
                     mBest = kHitInf; mPrim = -1; mBestPos = 0;
                     st = ST_MESH_NODE;
                 }
             }
         } else if (nNode >= nLeaf) {
-            if (st == ST_MESH_NODE) {
+#if PT_BURST_VOTE
 #pragma unroll 1
-                for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
+            for (int k = 0; k < PT_NODE_BURST; k++) {
+                if (k > 0 && __popc(__ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE)) < PT_BURST_VOTE) break;
+                if (st == ST_MESH_NODE) {
                     uint32_t first, count;
                     const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
                     if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
                     else if (r == MESH_DONE) st = ST_MESH_DONE;
                 }
             }
+#else
+            if (st == ST_MESH_NODE) {
+#pragma unroll 1
+                for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
+                    uint32_t first, count;
+                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
+#ifdef PT_DEBUG_STEPS
+                    dbgSteps++;
+#endif
+                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
+                    else if (r == MESH_DONE) st = ST_MESH_DONE;
+                }
+            }
+#endif
         } else {
             if (st == ST_MESH_LEAF) {
+#ifdef PT_DEBUG_STEPS
+                dbgLeaves++;
+#endif
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
                 if (tPos >= tEnd) st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
             }
         }
+#ifdef PT_DEBUG_STEPS
+        if (st == ST_MESH_DONE) {
+            if (dbgSteps + dbgLeaves > 400) printf("long ray: %d node steps, %d leaves, o=(%g,%g,%g) d=(%g,%g,%g) best=%g root=%u\n", dbgSteps, dbgLeaves, co.x, co.y, co.z, cd.x, cd.y, cd.z, mBest, dbgRoot);
+            dbgSteps = dbgLeaves = 0;
+        }
+#endif
         if (st == ST_MESH_DONE) { W.mBest[ray] = mBest; W.mPrim[ray] = mPrim; st = ST_IDLE; }
     }
 }

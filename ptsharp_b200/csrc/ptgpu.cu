@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -463,7 +464,18 @@ __global__ void __launch_bounds__(128) k_scene_shadow(DScene S, SplitState W, Sh
                           });
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
 }
-__global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) { mesh_walk(S, W, q, cursor); }
+// One warp per block: the warps of a launch finish at very different times (a few grazing rays take ~1000 steps), and a
+// block's registers are only returned when its last warp exits; with single-warp blocks the next kernel (of this or
+// another lane) moves in as warps drain.
+#ifndef PT_MESH_BLOCK
+#define PT_MESH_BLOCK 32
+#endif
+#ifndef PT_MESH_WARPS_PER_SM
+#define PT_MESH_WARPS_PER_SM 32
+#endif
+__global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
+    mesh_walk(S, W, q, cursor);
+}
 
 __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
     if (*count > cap) { *overflow = 1; *count = cap; }
@@ -657,6 +669,23 @@ __global__ void k_keyed_draw(uint32_t seed, uint32_t pass, uint32_t pixel, uint3
 }
 
 // ====================================================================================================== host side
+static constexpr int kMaxLanes = 8;
+#ifndef PT_LANES
+#define PT_LANES 1
+#endif
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    RayQueue rq[2]{};
+    HitQueue hq{};
+    ShadowQueue sq{};
+    uint64_t capShadow = 0;
+    uint32_t* counts = nullptr;   // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag, [4] trace cursor, [5] shadow cursor,
+                                  // [10],[11] mesh queue counts, [12] mesh cursor
+    SplitState split{};           // split tracer (scene_advance / mesh_walk): per-ray scene-level state and the two mesh work queues
+    MeshQueue mq[2]{};
+    uint64_t splitCap = 0;
+};
 struct ptgpu_ctx {
     int device = 0;
     int numSMs = 148;
@@ -668,19 +697,16 @@ struct ptgpu_ctx {
     DLight* dLights = nullptr;
     bool haveScene = false;
     uint64_t sceneBytes = 0;
-    // queues
-    uint64_t capRays = 0, capShadow = 0;
-    RayQueue rq[2]{};
-    HitQueue hq{};
-    ShadowQueue sq{};
-    // split tracer (scene_advance / mesh_walk): per-ray scene-level state and the two mesh work queues
-    SplitState split{};
-    MeshQueue mq[2]{};
-    uint64_t splitCap = 0;
+    // queues: `numLanes` independent sets (own stream, queues, split-tracer state); the batches of a pass go round the
+    // lanes so that the tail of one batch's kernel (a handful of long rays) overlaps the bulk of another batch's
+    uint64_t capRays = 0;         // path records per lane
+    Lane lanes[kMaxLanes];
+    int numLanes = 1;
+    cudaEvent_t evFork = nullptr;
     bool useSplit = false;
     int splitStackEnt = 2;
     int splitRounds = 0;          // > 0: every ray enters at most this many meshes (fixed rounds, no host sync); 0: loop on the queue count
-    uint32_t* dCounts = nullptr;  // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag, [4] trace cursor, [5] shadow cursor, [6] batch cursor
+    uint32_t* dCounts = nullptr;  // [6] batch cursor, [8],[9] firefly list counts
     DeviceCounters* dCounters = nullptr;
     // image state
     int bufW = 0, bufH = 0;
@@ -733,11 +759,24 @@ static void free_scene(ptgpu_ctx* ctx) {
     ctx->sceneBytes = 0;
     ctx->dLights = nullptr;
 }
+static void free_split(Lane& L) {
+    SplitState& W = L.split;
+    void* ps[] = {W.bestT, W.bestTInner, W.bestShape, W.bestPrim, W.scNode, W.scSp, W.scTmin, W.scTmax, W.sPos, W.sEnd, W.curShape, W.curInst, W.mBest, W.mPrim,
+                  W.sceneStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c};
+    for (void* p : ps) cudaFree(p);
+    W = SplitState{};
+    L.mq[0] = L.mq[1] = MeshQueue{};
+    L.splitCap = 0;
+}
 static void free_queues(ptgpu_ctx* ctx) {
-    for (int i = 0; i < 2; i++) { cudaFree(ctx->rq[i].od0); cudaFree(ctx->rq[i].od1); cudaFree(ctx->rq[i].bt); cudaFree(ctx->rq[i].smp); ctx->rq[i] = RayQueue{}; }
-    cudaFree(ctx->hq.t); cudaFree(ctx->hq.tInner); cudaFree(ctx->hq.shape); cudaFree(ctx->hq.prim); ctx->hq = HitQueue{};
-    cudaFree(ctx->sq.so); cudaFree(ctx->sq.sd); cudaFree(ctx->sq.sc); ctx->sq = ShadowQueue{};
-    ctx->capShadow = 0;
+    for (int k = 0; k < kMaxLanes; k++) {
+        Lane& L = ctx->lanes[k];
+        for (int i = 0; i < 2; i++) { cudaFree(L.rq[i].od0); cudaFree(L.rq[i].od1); cudaFree(L.rq[i].bt); cudaFree(L.rq[i].smp); L.rq[i] = RayQueue{}; }
+        cudaFree(L.hq.t); cudaFree(L.hq.tInner); cudaFree(L.hq.shape); cudaFree(L.hq.prim); L.hq = HitQueue{};
+        cudaFree(L.sq.so); cudaFree(L.sq.sd); cudaFree(L.sq.sc); L.sq = ShadowQueue{};
+        L.capShadow = 0;
+        free_split(L);
+    }
 }
 static void free_image(ptgpu_ctx* ctx) {
     cudaFree(ctx->dSum); cudaFree(ctx->dMean); cudaFree(ctx->pb.M); cudaFree(ctx->pb.V); cudaFree(ctx->pb.samples);
@@ -748,20 +787,12 @@ static void free_image(ptgpu_ctx* ctx) {
 
 static int grid_for(ptgpu_ctx* ctx, int blocksPerSM) { return ctx->numSMs * blocksPerSM; }
 
-static void free_split(ptgpu_ctx* ctx) {
-    SplitState& W = ctx->split;
-    void* ps[] = {W.bestT, W.bestTInner, W.bestShape, W.bestPrim, W.scNode, W.scSp, W.scTmin, W.scTmax, W.sPos, W.sEnd, W.curShape, W.curInst, W.mBest, W.mPrim,
-                  W.sceneStack, ctx->mq[0].a, ctx->mq[0].b, ctx->mq[0].c, ctx->mq[1].a, ctx->mq[1].b, ctx->mq[1].c};
-    for (void* p : ps) cudaFree(p);
-    W = SplitState{};
-    ctx->mq[0] = ctx->mq[1] = MeshQueue{};
-    ctx->splitCap = 0;
-}
 // Per-ray state of the split tracer for launches of up to `cap` rays.
-static int ensure_split(ptgpu_ctx* ctx, uint64_t cap, int stackEnt) {
-    if (cap <= ctx->splitCap && stackEnt == ctx->split.stackEnt) return PTGPU_OK;
-    free_split(ctx);
-    SplitState& W = ctx->split;
+static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
+    if (cap <= L.splitCap && stackEnt == L.split.stackEnt) return PTGPU_OK;
+    CK(cudaStreamSynchronize(L.stream));
+    free_split(L);
+    SplitState& W = L.split;
     CK(cudaMalloc(&W.bestT, cap * 8)); CK(cudaMalloc(&W.bestTInner, cap * 8)); CK(cudaMalloc(&W.bestShape, cap * 4)); CK(cudaMalloc(&W.bestPrim, cap * 4));
     CK(cudaMalloc(&W.scNode, cap * 4)); CK(cudaMalloc(&W.scSp, cap * 4)); CK(cudaMalloc(&W.scTmin, cap * 8)); CK(cudaMalloc(&W.scTmax, cap * 8));
     CK(cudaMalloc(&W.sPos, cap * 4)); CK(cudaMalloc(&W.sEnd, cap * 4)); CK(cudaMalloc(&W.curShape, cap * 4)); CK(cudaMalloc(&W.curInst, cap * 4));
@@ -769,32 +800,42 @@ static int ensure_split(ptgpu_ctx* ctx, uint64_t cap, int stackEnt) {
     CK(cudaMalloc(&W.sceneStack, cap * (uint64_t)stackEnt * sizeof(uint4)));
     W.stackEnt = stackEnt;
     for (int i = 0; i < 2; i++) {
-        CK(cudaMalloc(&ctx->mq[i].a, cap * sizeof(float4))); CK(cudaMalloc(&ctx->mq[i].b, cap * sizeof(float4))); CK(cudaMalloc(&ctx->mq[i].c, cap * sizeof(double2)));
-        ctx->mq[i].count = ctx->dCounts + 10 + i;
+        CK(cudaMalloc(&L.mq[i].a, cap * sizeof(float4))); CK(cudaMalloc(&L.mq[i].b, cap * sizeof(float4))); CK(cudaMalloc(&L.mq[i].c, cap * sizeof(double2)));
+        L.mq[i].count = L.counts + 10 + i;
     }
-    ctx->splitCap = cap;
+    L.splitCap = cap;
     return PTGPU_OK;
 }
 // One Scene.Intersect wavefront in split form.  start(out) launches the scene kernel for the fresh rays; resume(in, out)
 // launches it for the rays named by `in`'s items.  Fixed number of rounds when the scene bounds it, else until empty.
 template <class StartFn, class ResumeFn>
-static int run_split(ptgpu_ctx* ctx, cudaStream_t st, StartFn start, ResumeFn resume) {
-    uint32_t* cursor = ctx->dCounts + 12;
-    CK(cudaMemsetAsync(ctx->dCounts + 10, 0, 3 * sizeof(uint32_t), st));
-    start(ctx->mq[0]);
+static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, ResumeFn resume) {
+    uint32_t* cursor = L.counts + 12;
+    CK(cudaMemsetAsync(L.counts + 10, 0, 3 * sizeof(uint32_t), st));
+    start(L.mq[0]);
     ctx->launches++;
     int cur = 0;
     for (int round = 0; ctx->splitRounds == 0 || round < ctx->splitRounds; round++) {
         if (ctx->splitRounds == 0) {
             uint32_t pending = 0;
-            CK(cudaMemcpyAsync(&pending, ctx->mq[cur].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&pending, L.mq[cur].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (pending == 0) break;
         }
-        CK(cudaMemsetAsync(ctx->mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(L.mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
         CK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
-        k_mesh<<<grid_for(ctx, PT_TRACE_MINBLOCKS), 128, 0, st>>>(ctx->scene, ctx->split, ctx->mq[cur], cursor);
-        resume(ctx->mq[cur], ctx->mq[cur ^ 1]);
+        static const bool detail = std::getenv("PTGPU_TRACE_DETAIL") != nullptr;
+        if (detail) {
+            uint32_t items = 0;
+            cudaMemcpyAsync(&items, L.mq[cur].count, 4, cudaMemcpyDeviceToHost, st);
+            cudaEventRecord(ctx->evA, st);
+            k_mesh<<<grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK), PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            cudaEventRecord(ctx->evB, st); cudaEventSynchronize(ctx->evB);
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
+            fprintf(stderr, "k_mesh round %d items %u  %.3f ms  (%.1f Mitems/s)\n", round, items, ms, items / ms / 1e3);
+        } else
+        k_mesh<<<grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK), PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+        resume(L.mq[cur], L.mq[cur ^ 1]);
         ctx->launches += 2;
         cur ^= 1;
     }
@@ -842,8 +883,27 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     ctx->numSMs = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB);
-    ctx->capRays = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 24);
-    if (ctx->capRays > (1ull << 30)) ctx->capRays = 1ull << 30;
+    // queueCapacity = path records in flight over all lanes (default 2^25); flags bits 0-3 = number of lanes (0 = default)
+    {
+        uint64_t total = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 25);
+        int lanes = (params && (params->flags & 15)) ? (params->flags & 15) : PT_LANES;
+        if (const char* ev = std::getenv("PTGPU_LANES")) { int v = std::atoi(ev); if (v >= 1) lanes = v; }            // development overrides
+        if (const char* ev = std::getenv("PTGPU_QUEUE_LOG2")) { int v = std::atoi(ev); if (v >= 16 && v <= 30) total = 1ull << v; }
+        if (lanes > kMaxLanes) lanes = kMaxLanes;
+        if (total < (1ull << 22)) lanes = 1;
+        ctx->numLanes = lanes;
+        ctx->capRays = total / (uint64_t)lanes;
+        if (ctx->capRays > (1ull << 30)) ctx->capRays = 1ull << 30;
+        if (ctx->capRays == 0) ctx->capRays = 1;
+    }
+    for (int k = 0; k < ctx->numLanes; k++) {
+        Lane& L = ctx->lanes[k];
+        if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaMalloc(&L.counts, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+        cudaMemset(L.counts, 0, 16 * sizeof(uint32_t));
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->dCounts, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->dCounters, sizeof(DeviceCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(ctx->dCounts, 0, 16 * sizeof(uint32_t));
@@ -859,7 +919,13 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
     free_scene(ctx);
     free_queues(ctx);
     free_image(ctx);
-    free_split(ctx);
+    for (int k = 0; k < kMaxLanes; k++) {
+        Lane& L = ctx->lanes[k];
+        if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.done) cudaEventDestroy(L.done);
+        cudaFree(L.counts);
+    }
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     cudaFree(ctx->dCounts);
     cudaFree(ctx->dCounters);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
@@ -1157,26 +1223,27 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
     return PTGPU_OK;
 }
 
-static int ensure_queues(ptgpu_ctx* ctx, uint64_t capShadow) {
-    if (!ctx->rq[0].od0) {
+static int ensure_queues(ptgpu_ctx* ctx, Lane& L, uint64_t capShadow) {
+    if (!L.rq[0].od0) {
         for (int i = 0; i < 2; i++) {
-            CK(cudaMalloc(&ctx->rq[i].od0, ctx->capRays * sizeof(float4)));
-            CK(cudaMalloc(&ctx->rq[i].od1, ctx->capRays * sizeof(float4)));
-            CK(cudaMalloc(&ctx->rq[i].bt, ctx->capRays * sizeof(float4)));
-            CK(cudaMalloc(&ctx->rq[i].smp, ctx->capRays * sizeof(uint32_t)));
+            CK(cudaMalloc(&L.rq[i].od0, ctx->capRays * sizeof(float4)));
+            CK(cudaMalloc(&L.rq[i].od1, ctx->capRays * sizeof(float4)));
+            CK(cudaMalloc(&L.rq[i].bt, ctx->capRays * sizeof(float4)));
+            CK(cudaMalloc(&L.rq[i].smp, ctx->capRays * sizeof(uint32_t)));
         }
-        CK(cudaMalloc(&ctx->hq.t, ctx->capRays * sizeof(double)));
-        CK(cudaMalloc(&ctx->hq.tInner, ctx->capRays * sizeof(double)));
-        CK(cudaMalloc(&ctx->hq.shape, ctx->capRays * sizeof(int32_t)));
-        CK(cudaMalloc(&ctx->hq.prim, ctx->capRays * sizeof(int32_t)));
+        CK(cudaMalloc(&L.hq.t, ctx->capRays * sizeof(double)));
+        CK(cudaMalloc(&L.hq.tInner, ctx->capRays * sizeof(double)));
+        CK(cudaMalloc(&L.hq.shape, ctx->capRays * sizeof(int32_t)));
+        CK(cudaMalloc(&L.hq.prim, ctx->capRays * sizeof(int32_t)));
     }
-    if (capShadow > ctx->capShadow) {
-        cudaFree(ctx->sq.so); cudaFree(ctx->sq.sd); cudaFree(ctx->sq.sc);
-        ctx->sq = ShadowQueue{};
-        CK(cudaMalloc(&ctx->sq.so, capShadow * sizeof(float4)));
-        CK(cudaMalloc(&ctx->sq.sd, capShadow * sizeof(float4)));
-        CK(cudaMalloc(&ctx->sq.sc, capShadow * sizeof(float4)));
-        ctx->capShadow = capShadow;
+    if (capShadow > L.capShadow) {
+        CK(cudaStreamSynchronize(L.stream));
+        cudaFree(L.sq.so); cudaFree(L.sq.sd); cudaFree(L.sq.sc);
+        L.sq = ShadowQueue{};
+        CK(cudaMalloc(&L.sq.so, capShadow * sizeof(float4)));
+        CK(cudaMalloc(&L.sq.sd, capShadow * sizeof(float4)));
+        CK(cudaMalloc(&L.sq.sc, capShadow * sizeof(float4)));
+        L.capShadow = capShadow;
     }
     return PTGPU_OK;
 }
@@ -1217,7 +1284,7 @@ static int make_passd(ptgpu_ctx* ctx, const ptgpu_pass* p, PassD& P) {
 }
 
 // Issue every kernel of one pass on `stream`, adding radiance into d_sum.  nSlots = samples per pixel rendered.
-static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cudaStream_t stream, const uint32_t* pixelList = nullptr,
+static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cudaStream_t callerStream, const uint32_t* pixelList = nullptr,
                     const uint32_t* listCount = nullptr) {
     const uint64_t npix = (uint64_t)P.width * P.height;
     const uint64_t total = npix * (uint64_t)nSlots;
@@ -1249,20 +1316,42 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
     }
     if (capShadow == 0) capShadow = 1;
-    int rc = ensure_queues(ctx, capShadow);
-    if (rc != PTGPU_OK) return rc;
-    if (ctx->useSplit && (rc = ensure_split(ctx, std::max<uint64_t>(ctx->capRays, ctx->capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
-
-    const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
-    uint32_t* counts = ctx->dCounts;
     const bool prof = ctx->profiling;
+    // spread the pass over the lanes: at least one batch per lane when the pass is large enough to be worth it
+    int lanesUsed = prof ? 1 : ctx->numLanes;
+    {
+        const uint64_t per = (total + (uint64_t)lanesUsed - 1) / (uint64_t)lanesUsed;
+        const uint64_t minBatch = 1ull << 18;
+        if (per < batch) {
+            batch = std::max<uint64_t>(per, std::min<uint64_t>(minBatch, batch));
+            capShadow = std::max<uint64_t>(1, batch * childGrow * (lightsPer ? lightsPer : 1));
+        }
+        const uint64_t nBatches = (total + batch - 1) / batch;
+        if (nBatches < (uint64_t)lanesUsed) lanesUsed = (int)nBatches;
+    }
+    int rc = PTGPU_OK;
+    for (int k = 0; k < lanesUsed; k++) {
+        Lane& L = ctx->lanes[k];
+        if ((rc = ensure_queues(ctx, L, capShadow)) != PTGPU_OK) return rc;
+        if (ctx->useSplit && (rc = ensure_split(ctx, L, std::max<uint64_t>(ctx->capRays, L.capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
+    }
+    const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
     float ms = 0;
     if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; }
-    for (uint64_t g0 = 0; g0 < total; g0 += batch) {
+    // fork: the lanes' streams continue from the caller's stream ...
+    if (!prof) {
+        CK(cudaEventRecord(ctx->evFork, callerStream));
+        for (int k = 0; k < lanesUsed; k++) CK(cudaStreamWaitEvent(ctx->lanes[k].stream, ctx->evFork, 0));
+    }
+    uint64_t batchIndex = 0;
+    for (uint64_t g0 = 0; g0 < total; g0 += batch, batchIndex++) {
+        Lane& L = ctx->lanes[prof ? 0 : (int)(batchIndex % (uint64_t)lanesUsed)];
+        cudaStream_t stream = prof ? callerStream : L.stream;
+        uint32_t* counts = L.counts;
         uint32_t n = (uint32_t)std::min<uint64_t>(batch, total - g0);
         int cur = 0;
         if (prof) cudaEventRecord(ctx->evA, stream);
-        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, ctx->rq[0], counts + 0, ctx->dCounters, pixelList, listCount);
+        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, L.rq[0], counts + 0, ctx->dCounters, pixelList, listCount);
         ctx->launches++;
         if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->raygenMs += ms; }
         for (int depth = 0; depth <= P.maxBounces; depth++) {
@@ -1271,34 +1360,42 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             CK(cudaMemsetAsync(counts + 4, 0, 2 * sizeof(uint32_t), stream));  // trace / shadow work cursors
             if (prof) cudaEventRecord(ctx->evA, stream);
             if (ctx->useSplit) {
-                const RayQueue rqc = ctx->rq[cur];
+                const RayQueue rqc = L.rq[cur];
                 uint32_t* cnt = counts + cur;
-                rc = run_split(ctx, stream,
-                               [&](const MeshQueue& out) { k_scene_trace<false><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, rqc, cnt, out, out, ctx->hq, ctx->dCounters); },
-                               [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<true><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, rqc, cnt, in, out, ctx->hq, ctx->dCounters); });
+                rc = run_split(ctx, L, stream,
+                               [&](const MeshQueue& out) { k_scene_trace<false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); },
+                               [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); });
                 if (rc != PTGPU_OK) return rc;
-                ctx->launches--;  // run_split counts its own; the common += 3 below includes one for the tracer
-            } else
-            k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->rq[cur], counts + cur, counts + 4, ctx->hq, ctx->dCounters);
+            } else {
+                k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.rq[cur], counts + cur, counts + 4, L.hq, ctx->dCounters);
+                ctx->launches++;
+            }
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
-            k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, ctx->rq[cur], counts + cur, ctx->hq, ctx->rq[cur ^ 1], counts + (cur ^ 1),
-                                                   ctx->sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)ctx->capRays, (uint32_t)ctx->capShadow);
+            k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
+                                                   L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)ctx->capRays, (uint32_t)L.capShadow);
             k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)ctx->capRays, counts + 3);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
-            ctx->launches += 3;
+            ctx->launches += 2;
             if (lightsPer) {
                 if (ctx->useSplit) {
-                    rc = run_split(ctx, stream,
-                                   [&](const MeshQueue& out) { k_scene_shadow<false><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, ctx->sq, counts + 2, (uint32_t)ctx->capShadow, out, out, d_sum, ctx->dCounters); },
-                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<true><<<gridShade, 128, 0, stream>>>(ctx->scene, ctx->split, ctx->sq, counts + 2, (uint32_t)ctx->capShadow, in, out, d_sum, ctx->dCounters); });
+                    rc = run_split(ctx, L, stream,
+                                   [&](const MeshQueue& out) { k_scene_shadow<false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, out, out, d_sum, ctx->dCounters); },
+                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, out, d_sum, ctx->dCounters); });
                     if (rc != PTGPU_OK) return rc;
                 } else {
-                k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, ctx->sq, counts + 2, counts + 5, (uint32_t)ctx->capShadow, d_sum, ctx->dCounters);
-                ctx->launches++;
+                    k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.sq, counts + 2, counts + 5, (uint32_t)L.capShadow, d_sum, ctx->dCounters);
+                    ctx->launches++;
                 }
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
             }
             cur ^= 1;
+        }
+    }
+    // ... and the caller's stream continues after all of them (join)
+    if (!prof) {
+        for (int k = 0; k < lanesUsed; k++) {
+            CK(cudaEventRecord(ctx->lanes[k].done, ctx->lanes[k].stream));
+            CK(cudaStreamWaitEvent(callerStream, ctx->lanes[k].done, 0));
         }
     }
     CK(cudaGetLastError());
@@ -1406,9 +1503,11 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->lastPassMs = ms;
-    uint32_t overflow = 0;
-    CK(cudaMemcpy(&overflow, ctx->dCounts + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (overflow) return fail(ctx, PTGPU_E_LIMIT, "ray queue overflow (internal sizing error)");
+    for (int k = 0; k < ctx->numLanes; k++) {
+        uint32_t overflow = 0;
+        CK(cudaMemcpy(&overflow, ctx->lanes[k].counts + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (overflow) return fail(ctx, PTGPU_E_LIMIT, "ray queue overflow (internal sizing error)");
+    }
     return PTGPU_OK;
 }
 
@@ -1459,12 +1558,13 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
     CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemsetAsync(ctx->dCounts + 6, 0, sizeof(uint32_t), ctx->stream));
     if (ctx->useSplit) {
-        int rcs = ensure_split(ctx, std::max<uint64_t>(N, ctx->splitCap), ctx->splitStackEnt);
+        Lane& L = ctx->lanes[0];
+        int rcs = ensure_split(ctx, L, std::max<uint64_t>(N, L.splitCap), ctx->splitStackEnt);
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
         const BatchOut B{dS, dPr, dT, dN, dP, dI, dM};
-        rcs = run_split(ctx, ctx->stream,
-                        [&](const MeshQueue& out) { k_scene_batch<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, ctx->split, (uint32_t)n, out, out, dO, dD, B); },
-                        [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, ctx->split, (uint32_t)n, in, out, dO, dD, B); });
+        rcs = run_split(ctx, L, ctx->stream,
+                        [&](const MeshQueue& out) { k_scene_batch<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); },
+                        [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); });
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
     } else {
     k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM);
