@@ -758,6 +758,9 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
 #ifndef PT_BURST_VOTE
 #define PT_BURST_VOTE 0     // mesh_walk: leave a NODE burst once fewer than this many lanes are still walking (0 = off)
 #endif
+#ifndef PT_SPLIT_FETCH_MIN2
+#define PT_SPLIT_FETCH_MIN2 16  // mesh_walk2 (64 rays per warp)
+#endif
 #ifndef PT_LEAF_UNROLL
 #define PT_LEAF_UNROLL 1
 #endif
@@ -1183,6 +1186,85 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
         }
 #endif
         if (st == ST_MESH_DONE) { W.mBest[ray] = mBest; W.mPrim[ray] = mPrim; st = ST_IDLE; }
+    }
+}
+
+// mesh_walk with TWO rays per lane.  A warp's NODE and LEAF populations are about equal whatever the rays are, so with
+// one ray per lane a burst starts with half the lanes.  Here a lane owns two rays; the warp votes over all 64, and a lane
+// takes part in the winning class if EITHER of its rays is in it (the active ray lives in registers, the parked one is
+// swapped in when needed), which lifts the expected share of busy lanes from 1/2 to 3/4.
+struct WalkRay {
+    V3 co, cd;
+    RayAux ra;
+    KdCursor mc;
+    uint32_t tPos, tEnd, bestPos, ray, stackOff;
+    double best;
+    int32_t prim;
+    int st;
+};
+PT_D void walk_swap(WalkRay& a, WalkRay& b, bool p) {
+#define SW(f) { auto t_ = a.f; a.f = p ? b.f : a.f; b.f = p ? t_ : b.f; }
+    SW(co.x) SW(co.y) SW(co.z) SW(cd.x) SW(cd.y) SW(cd.z) SW(ra.ix) SW(ra.iy) SW(ra.iz) SW(ra.pad)
+    SW(mc.node) SW(mc.sp) SW(mc.tmin) SW(mc.tmax) SW(tPos) SW(tEnd) SW(bestPos) SW(ray) SW(stackOff) SW(best) SW(prim) SW(st)
+#undef SW
+}
+PT_D void mesh_walk2(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
+    const uint32_t n = *q.count;
+    WalkRay A, B;
+    A.co = B.co = v3(0, 0, 0); A.cd = B.cd = v3(0, 0, 1);
+    A.ra = B.ra = ray_aux(A.co, A.cd);
+    A.mc.node = B.mc.node = 0; A.mc.sp = B.mc.sp = 0; A.mc.tmin = A.mc.tmax = B.mc.tmin = B.mc.tmax = 0;
+    A.tPos = A.tEnd = A.bestPos = A.ray = B.tPos = B.tEnd = B.bestPos = B.ray = 0;
+    A.best = B.best = kHitInf; A.prim = B.prim = -1;
+    A.st = B.st = ST_IDLE;
+    A.stackOff = 0; B.stackOff = kMeshStackEnt;
+    uint4 mStk[2 * kMeshStackEnt];
+    bool drained = false;  // the cursor ran past n: nothing left to fetch
+    for (;;) {
+        const int nIdle = drained ? 0 : __popc(__ballot_sync(0xFFFFFFFFu, A.st == ST_IDLE)) + __popc(__ballot_sync(0xFFFFFFFFu, B.st == ST_IDLE));
+        const int nLeaf = __popc(__ballot_sync(0xFFFFFFFFu, A.st == ST_MESH_LEAF)) + __popc(__ballot_sync(0xFFFFFFFFu, B.st == ST_MESH_LEAF));
+        const int nNode = __popc(__ballot_sync(0xFFFFFFFFu, A.st == ST_MESH_NODE)) + __popc(__ballot_sync(0xFFFFFFFFu, B.st == ST_MESH_NODE));
+        if (nIdle + nLeaf + nNode == 0) break;
+        const int cls = (nIdle >= PT_SPLIT_FETCH_MIN2 || nLeaf + nNode == 0) ? ST_IDLE : (nNode >= nLeaf ? ST_MESH_NODE : ST_MESH_LEAF);
+        walk_swap(A, B, A.st != cls && B.st == cls);
+        if (cls == ST_IDLE) {
+            if (A.st == ST_IDLE) {
+                auto g = cooperative_groups::coalesced_threads();
+                uint32_t base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
+                const uint32_t i = g.shfl(base, 0) + g.thread_rank();
+                if (i >= n) A.st = ST_EXIT;
+                else {
+                    const float4 a = q.a[i], b = q.b[i];
+                    const double2 c = q.c[i];
+                    A.co = v3(a.x, a.y, a.z); A.cd = v3(b.x, b.y, b.z); A.ray = __float_as_uint(a.w);
+                    A.ra = ray_aux(A.co, A.cd);
+                    A.mc.node = __float_as_uint(b.w); A.mc.tmin = c.x; A.mc.tmax = c.y; A.mc.sp = 0;
+                    stk_put(mStk + A.stackOff, A.mc.tmax, 0u, 0u);
+                    A.best = kHitInf; A.prim = -1; A.bestPos = 0;
+                    A.st = ST_MESH_NODE;
+                }
+            }
+            if (__any_sync(0xFFFFFFFFu, A.st == ST_EXIT)) drained = true;
+            if (drained) { if (A.st == ST_IDLE) A.st = ST_EXIT; if (B.st == ST_IDLE) B.st = ST_EXIT; }
+        } else if (cls == ST_MESH_NODE) {
+            if (A.st == ST_MESH_NODE) {
+                uint4* stk = mStk + A.stackOff;
+#pragma unroll 1
+                for (int k = 0; k < PT_NODE_BURST && A.st == ST_MESH_NODE; k++) {
+                    uint32_t first, count;
+                    const int r = mesh_step(S.meshNodes, A.ra, A.mc, A.co, A.cd, stk, A.best, A.bestPos, first, count);
+                    if (r == MESH_LEAF) { A.tPos = first; A.tEnd = first + count; A.st = ST_MESH_LEAF; }
+                    else if (r == MESH_DONE) A.st = ST_MESH_DONE;
+                }
+            }
+        } else {
+            if (A.st == ST_MESH_LEAF) {
+                leaf_work(S, A.co, A.cd, A.tPos, A.tEnd, A.best, A.prim, A.bestPos, PT_LEAF_BURST);
+                if (A.tPos >= A.tEnd) A.st = mesh_pop(A.mc, A.best, mStk + A.stackOff) ? ST_MESH_NODE : ST_MESH_DONE;
+            }
+        }
+        if (A.st == ST_MESH_DONE) { W.mBest[A.ray] = A.best; W.mPrim[A.ray] = A.prim; A.st = drained ? ST_EXIT : ST_IDLE; }
     }
 }
 

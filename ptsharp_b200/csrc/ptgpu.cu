@@ -467,6 +467,9 @@ __global__ void __launch_bounds__(128) k_scene_shadow(DScene S, SplitState W, Sh
 // One warp per block: the warps of a launch finish at very different times (a few grazing rays take ~1000 steps), and a
 // block's registers are only returned when its last warp exits; with single-warp blocks the next kernel (of this or
 // another lane) moves in as warps drain.
+#ifndef PT_MESH_RAYS
+#define PT_MESH_RAYS 1
+#endif
 #ifndef PT_MESH_BLOCK
 #define PT_MESH_BLOCK 32
 #endif
@@ -474,7 +477,11 @@ __global__ void __launch_bounds__(128) k_scene_shadow(DScene S, SplitState W, Sh
 #define PT_MESH_WARPS_PER_SM 32
 #endif
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
+#if PT_MESH_RAYS == 2
+    mesh_walk2(S, W, q, cursor);
+#else
     mesh_walk(S, W, q, cursor);
+#endif
 }
 
 __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
