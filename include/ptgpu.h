@@ -177,6 +177,9 @@ typedef struct ptgpu_counters {
     uint64_t kernelLaunches;     /* this library's kernels launched since create/reset */
     double lastPassMs;           /* device time of the last render_pass / accumulate_device (CUDA events) */
     double traceMs, shadeMs, shadowMs, raygenMs;  /* per-stage device time of the last pass when profiling is on */
+    double meshMs;               /* of traceMs + shadowMs: time in the mesh-walk kernel (k_mesh), 0 when the scene has no meshes */
+    uint64_t meshItems;          /* Mesh.Intersect calls (work items of k_mesh) in that time */
+    uint64_t meshLaunches;       /* k_mesh launches in that time */
 } ptgpu_counters;
 
 typedef struct ptgpu_ctx ptgpu_ctx;

@@ -46,7 +46,8 @@ class Params(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("cameraSamples", C.c_uint64), ("segments", C.c_uint64), ("shadowRays", C.c_uint64),
                 ("nanSamples", C.c_uint64), ("kernelLaunches", C.c_uint64), ("lastPassMs", C.c_double),
-                ("traceMs", C.c_double), ("shadeMs", C.c_double), ("shadowMs", C.c_double), ("raygenMs", C.c_double)]
+                ("traceMs", C.c_double), ("shadeMs", C.c_double), ("shadowMs", C.c_double), ("raygenMs", C.c_double),
+                ("meshMs", C.c_double), ("meshItems", C.c_uint64), ("meshLaunches", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -18,6 +18,7 @@
 #include "../../include/ptgpu.h"
 
 #define PT_D __device__ __forceinline__
+#define PT_HD __host__ __device__ __forceinline__
 #define PT_DN __device__ __noinline__
 
 #ifndef PT_PREFETCH
@@ -655,6 +656,11 @@ PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
 
 enum { MESH_INTERIOR = 0, MESH_LEAF = 1, MESH_DONE = 2 };
 static constexpr uint32_t kNodeVirtual = 0x80000000u, kNodeRefLeaf = 0x40000000u, kNodeIndexMask = 0x3FFFFFFFu;
+// A child reference (30 bits) is either a node index (< 2^29) or a micro leaf named in place, saving the round trip
+// to a record that would only hold (first, count):  bit 29 = 1 | bit 28 = root of a reference leaf | bits 27:26 = count - 1
+// | bits 25:0 = first triangle in leafGeom.
+static constexpr uint32_t kRefLeaf = 1u << 29, kRefLeafRoot = 1u << 28, kRefFirstMask = (1u << 26) - 1u;
+PT_HD uint32_t leaf_ref(uint32_t first, uint32_t count, bool root) { return kRefLeaf | (root ? kRefLeafRoot : 0u) | ((count - 1u) << 26) | first; }
 static constexpr int kVirtualDepthMax = 12;  // levels of bounds-only nodes below a reference leaf (4 * 2^12 triangles)
 static constexpr int kMeshStackEnt = kMeshStack + kVirtualDepthMax + 1;
 
@@ -662,20 +668,22 @@ static constexpr int kMeshStackEnt = kMeshStack + kVirtualDepthMax + 1;
 //   reference interior  a = left << 2 | axis (1..3), b = right                  -> Node.Intersect (Tree.cs:67-113)
 //   bounds-only node    a = left << 2, b = kNodeVirtual | right [| kNodeRefLeaf]  -> both children hold triangles of ONE
 //                       reference leaf; every child whose padded bounds the ray line hits is visited, in any order
-//   micro leaf          a = first triangle << 2, b = count (<= 4) [| kNodeRefLeaf]
-// kNodeRefLeaf marks the root of a reference leaf (where the tie-break position restarts).
+//   micro leaf          no record: named in the parent's child reference (leaf_ref)
+// kNodeRefLeaf / kRefLeafRoot mark the root of a reference leaf (where the tie-break position restarts).
 // MESH_LEAF: triangles [tFirst, tFirst + tCount).
 PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
                    uint32_t& tCount) {
+    if (c.node & kRefLeaf) {
+        if (c.node & kRefLeafRoot) bestPos = 0;
+        tFirst = c.node & kRefFirstMask; tCount = ((c.node >> 26) & 3u) + 1u;
+        return MESH_LEAF;
+    }
     const uint4* np = nodes + (size_t)c.node * 4;
-    const uint4 q0 = __ldg(np);
+    // all four quads up front: behind the leaf test the bounds would cost a second, serialised memory round trip
+    const uint4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     const uint32_t a = q0.z, b = q0.w;
     const uint32_t axis = a & 3u;
-    if (axis == 0) {
-        if (b & kNodeRefLeaf) bestPos = 0;
-        if (!(b & kNodeVirtual)) { tFirst = a >> 2; tCount = b & 0xFFu; return MESH_LEAF; }
-    }
-    const uint4 q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    if (axis == 0 && (b & kNodeRefLeaf)) bestPos = 0;
     float tnL, tnR;
     bool hitL = box_line_hit_t(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
                                __uint_as_float(q2.y), o, ra, tnL);
@@ -737,6 +745,17 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
             if (t < best || pos < bestPos) { best = t; prim = (int32_t)__float_as_uint(__ldg(g).w); bestPos = pos; }
         }
         tPos++;
+    }
+}
+
+// The analytic subset (the split tracer is only used for scenes without SDFShape / Volume).
+PT_D double primitive_intersect_analytic(const DScene& S, const ptgpu_shape& sh, V3 o, V3 d) {
+    switch (sh.type) {
+        case PTGPU_SPHERE: return sphere_intersect(S.spheres[sh.data], o, d);
+        case PTGPU_CUBE: return cube_intersect(S.cubes[sh.data], o, d);
+        case PTGPU_PLANE: return plane_intersect(S.planes[sh.data], o, d);
+        case PTGPU_CYLINDER: return cylinder_intersect(S.cylinders[sh.data], o, d);
+        default: return kHitInf;
     }
 }
 
@@ -1088,7 +1107,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             break;
                         }
                     } else {
-                        mBest = primitive_intersect(S, sh, co, cd);
+                        mBest = primitive_intersect_analytic(S, sh, co, cd);
                         st = ST_MESH_DONE;
                     }
                 }

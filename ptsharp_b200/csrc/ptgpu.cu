@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_trace(DScene S, Ray
 struct DLight { float center[3]; uint32_t shape; double radius; uint32_t classTyped; uint32_t isCylinder; };
 
 // K3.  One thread per hit record: Hit.Info, emission, then the (u, v, mode) loop of Sampler.cs:97-131.
-__global__ void __launch_bounds__(128) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
+#ifndef PT_SHADE_MINBLOCKS
+#define PT_SHADE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
                                                 HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
                                                 float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow) {
     const uint32_t n = *count;
@@ -390,14 +393,12 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, PassD P, const DLight* 
                             double coverage;
                             if (L.isCylinder) coverage = 1.0;
                             else {  // Sampler.cs:277-288
+                                // theta = asin(R/hyp); adj = R/tan(theta); d = cos(theta)*adj; r = sin(theta)*adj; coverage = r*r/(d*d)
+                                // is tan^2(theta) = R^2 / (hyp^2 - R^2): evaluated in that form (no asin/tan/sincos; differs from
+                                // the reference's rounding by a few FP64 ulps, on a continuous weight)
                                 double hyp = (double)vlenf(vsub(center, sf.position));
-                                double theta = asin(radius / hyp);
-                                double adj = radius / tan(theta);
-                                double st, ct;
-                                sincos(theta, &st, &ct);
-                                double dd = ct * adj, rr = st * adj;
-                                coverage = (rr * rr) / (dd * dd);
-                                if (hyp < radius) coverage = 1;
+                                coverage = (radius * radius) / (hyp * hyp - radius * radius);
+                                if (hyp < radius || hyp == radius) coverage = 1;  // asin(>1) is NaN -> 1; tan^2(pi/2) ~ 2.7e32 -> min(.., 1)
                                 coverage = netmin(coverage, 1);
                             }
                             const ptgpu_shape lsh = S.shapes[L.shape];
@@ -439,8 +440,11 @@ __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_shadow(DScene S, Sh
 }
 
 // K2/K4, split form (see "split tracer" in pt_device.cuh): scene level as streaming kernels, mesh walks as a persistent one.
+#ifndef PT_SCENE_MINBLOCKS
+#define PT_SCENE_MINBLOCKS 8
+#endif
 template <bool RESUME>
-__global__ void __launch_bounds__(128) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
+__global__ void __launch_bounds__(128, PT_SCENE_MINBLOCKS) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
                                                       DeviceCounters* cnt) {
     const uint32_t n = RESUME ? *in.count : *count;
     scene_advance<RESUME>(S, W, n, in, out,
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(128) k_scene_trace(DScene S, SplitState W, Ray
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
 template <bool RESUME>
-__global__ void __launch_bounds__(128) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, MeshQueue in,
+__global__ void __launch_bounds__(128, PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, MeshQueue in,
                                                        MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
     uint32_t n = RESUME ? *in.count : *scount;
     if (!RESUME && n > capShadow) n = capShadow;
@@ -724,9 +728,10 @@ struct ptgpu_ctx {
     uint8_t* dReject = nullptr;
     // stats
     uint64_t launches = 0;
-    double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0;
+    double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0, meshMs = 0;
+    uint64_t meshItems = 0, meshLaunches = 0;
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
 };
 
 static std::string g_createError;
@@ -832,16 +837,18 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
         CK(cudaMemsetAsync(L.mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
         CK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
         static const bool detail = std::getenv("PTGPU_TRACE_DETAIL") != nullptr;
-        if (detail) {
+        const int gridMesh = grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK);
+        if (ctx->profiling || detail) {  // per-launch device time of the dominant kernel (bench.py's roofline)
             uint32_t items = 0;
             cudaMemcpyAsync(&items, L.mq[cur].count, 4, cudaMemcpyDeviceToHost, st);
-            cudaEventRecord(ctx->evA, st);
-            k_mesh<<<grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK), PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
-            cudaEventRecord(ctx->evB, st); cudaEventSynchronize(ctx->evB);
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->evA, ctx->evB);
-            fprintf(stderr, "k_mesh round %d items %u  %.3f ms  (%.1f Mitems/s)\n", round, items, ms, items / ms / 1e3);
+            cudaEventRecord(ctx->evC, st);
+            k_mesh<<<gridMesh, PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            cudaEventRecord(ctx->evD, st); cudaEventSynchronize(ctx->evD);
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->evC, ctx->evD);
+            ctx->meshMs += ms; ctx->meshItems += items; ctx->meshLaunches++;
+            if (detail) fprintf(stderr, "k_mesh round %d items %u  %.3f ms  (%.1f Mitems/s)\n", round, items, ms, items / ms / 1e3);
         } else
-        k_mesh<<<grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK), PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            k_mesh<<<gridMesh, PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
         resume(L.mq[cur], L.mq[cur ^ 1]);
         ctx->launches += 2;
         cur ^= 1;
@@ -889,7 +896,7 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     ctx->numSMs = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
     // queueCapacity = path records in flight over all lanes (default 2^25); flags bits 0-3 = number of lanes (0 = default)
     {
         uint64_t total = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 25);
@@ -935,7 +942,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     cudaFree(ctx->dCounts);
     cudaFree(ctx->dCounters);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1076,50 +1083,40 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
             }
             out8[3] = out8[7] = 0;
         };
-        // fill node record `idx` for triangles lg[t0, t1); appends children as needed; bounds of the subtree -> out8
+        // child reference for triangles lg[t0, t1): a micro leaf named in place, or a new bounds-only node (appended)
         struct Build { uint64_t idx; uint32_t t0, t1; int depth; };
-        auto build_leaf_subtree = [&](uint64_t rootIdx, uint32_t t0, uint32_t t1) {
+        auto fill_virtual = [&](uint64_t rootIdx, uint32_t t0, uint32_t t1) {  // record rootIdx becomes a bounds-only node over lg[t0, t1), t1 - t0 > 4
             std::vector<Build> todo{{rootIdx, t0, t1, 0}};
-            std::vector<uint64_t> interior;  // visit order, parents before children
             while (!todo.empty()) {
                 Build bld = todo.back(); todo.pop_back();
-                virtualDepth = std::max(virtualDepth, bld.depth);
-                const uint32_t n = bld.t1 - bld.t0;
-                if (n <= 4) {
-                    uint32_t* o = &mn[bld.idx * 16];
-                    o[2] = bld.t0 << 2; o[3] = n;
-                    continue;
+                virtualDepth = std::max(virtualDepth, bld.depth + 1);
+                const uint32_t n = bld.t1 - bld.t0, mid = bld.t0 + (n + 1) / 2;
+                uint32_t refs[2];
+                const uint32_t lo2[2] = {bld.t0, mid}, hi2[2] = {mid, bld.t1};
+                for (int side = 0; side < 2; side++) {
+                    const uint32_t cn = hi2[side] - lo2[side];
+                    if (cn <= 4) refs[side] = leaf_ref(lo2[side], cn, false);
+                    else {
+                        refs[side] = (uint32_t)(mn.size() / 16);
+                        mn.resize(mn.size() + 16, 0u);
+                        todo.push_back({refs[side], lo2[side], hi2[side], bld.depth + 1});
+                    }
                 }
-                const uint32_t mid = bld.t0 + (n + 1) / 2;
-                const uint64_t l = mn.size() / 16, r = l + 1;
-                mn.resize(mn.size() + 32, 0u);
-                xb.resize(xb.size() + 16, 0.f);
                 uint32_t* o = &mn[bld.idx * 16];
-                o[2] = (uint32_t)l << 2; o[3] = kNodeVirtual | (uint32_t)r;
+                o[2] = refs[0] << 2; o[3] = (o[3] & kNodeRefLeaf) | kNodeVirtual | refs[1];
                 float lb[8], rb[8];
                 tri_bounds(bld.t0, mid, lb); tri_bounds(mid, bld.t1, rb);
                 const float pk[12] = {lb[0], lb[1], lb[2], lb[4], lb[5], lb[6], rb[0], rb[1], rb[2], rb[4], rb[5], rb[6]};
                 for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
-                todo.push_back({l, bld.t0, mid, bld.depth + 1});
-                todo.push_back({r, mid, bld.t1, bld.depth + 1});
             }
         };
+        std::vector<uint32_t> ref(nn);                   // how a parent (or the tree) refers to reference node i
+        for (uint64_t i = 0; i < nn; i++) ref[i] = (uint32_t)i;
+        // pass 1: reference leaves -> sorted triangles + (for > 4 triangles) a bounds-only subtree rooted at record i
         for (uint64_t i = 0; i < nn; i++) {
             if (!isMeshNode[i]) continue;
             const ptgpu_node& n = s->nodes[i];
-            {
-                uint32_t* o = &mn[i * 16];
-                std::memcpy(o, &n.split, 8);
-            }
-            if ((n.a & 3u) != 0) {  // reference interior node: children's bounds
-                uint32_t* o = &mn[i * 16];
-                o[2] = n.a; o[3] = n.b;
-                const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
-                const float* r = &nb[(uint64_t)n.b * 8];
-                const float pk[12] = {l[0], l[1], l[2], l[4], l[5], l[6], r[0], r[1], r[2], r[4], r[5], r[6]};
-                for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
-                continue;
-            }
+            if ((n.a & 3u) != 0) continue;
             const uint32_t first = n.a >> 2, count = n.b;
             float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
             cen.resize((size_t)count * 3);
@@ -1148,10 +1145,39 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
                 g.pad0 = bitsToFloat(tri); g.pad1 = bitsToFloat(pos); g.pad2 = 0.f;
                 lg.push_back(g);
             }
-            build_leaf_subtree(i, t0, t0 + count);
-            mn[i * 16 + 3] |= kNodeRefLeaf;
+            if (lg.size() > (size_t)kRefFirstMask) return fail(ctx, PTGPU_E_LIMIT, "mesh too large for the 26-bit leaf triangle index");
+            if (count == 0) {  // cannot come out of Node.Split (an empty side is rejected) except for an empty mesh: one degenerate triangle
+                ptgpu_tri_geom z; std::memset(&z, 0, sizeof(z));
+                lg.push_back(z);
+                ref[i] = leaf_ref(t0, 1, true);
+                continue;
+            }
+            if (count <= 4) ref[i] = leaf_ref(t0, count, true);
+            else { mn[i * 16 + 3] = kNodeRefLeaf; fill_virtual(i, t0, t0 + count); }
         }
-        if (mn.size() / 16 >= (uint64_t)kNodeIndexMask || lg.size() >= (1ull << 30)) return fail(ctx, PTGPU_E_LIMIT, "mesh too large for the 30-bit node / triangle indices");
+        // pass 2: reference interior nodes with both children's padded bounds
+        for (uint64_t i = 0; i < nn; i++) {
+            if (!isMeshNode[i]) continue;
+            const ptgpu_node& n = s->nodes[i];
+            if ((n.a & 3u) == 0) continue;
+            uint32_t* o = &mn[i * 16];
+            std::memcpy(o, &n.split, 8);
+            o[2] = (ref[n.a >> 2] << 2) | (n.a & 3u); o[3] = ref[n.b];
+            const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
+            const float* r = &nb[(uint64_t)n.b * 8];
+            const float pk[12] = {l[0], l[1], l[2], l[4], l[5], l[6], r[0], r[1], r[2], r[4], r[5], r[6]};
+            for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
+        }
+        // the roots the split tracer / trace_rays start from
+        std::vector<ptgpu_tree> treesPatched(s->trees, s->trees + s->numTrees);
+        for (uint32_t m = 0; m < s->numMeshes; m++) treesPatched[s->meshes[m].tree].root = ref[s->trees[s->meshes[m].tree].root];
+        {
+            const ptgpu_tree* dt = nullptr;
+            if ((rc = upload(ctx, treesPatched.data(), (uint64_t)treesPatched.size(), &dt)) != PTGPU_OK) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+            D.trees = dt;
+        }
+        if (mn.size() / 16 >= (uint64_t)kRefLeaf) return fail(ctx, PTGPU_E_LIMIT, "mesh too large for the 29-bit node index");
         if (virtualDepth > kVirtualDepthMax) return fail(ctx, PTGPU_E_LIMIT, "a kd leaf holds more triangles than the bounds-only hierarchy supports");
         const uint4* dmn = nullptr;
         if ((rc = upload(ctx, reinterpret_cast<const uint4*>(mn.data()), (uint64_t)mn.size() / 4, &dmn)) != PTGPU_OK) return rc;
@@ -1344,7 +1370,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     }
     const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
     float ms = 0;
-    if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; }
+    if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = ctx->meshMs = 0; ctx->meshItems = ctx->meshLaunches = 0; }
     // fork: the lanes' streams continue from the caller's stream ...
     if (!prof) {
         CK(cudaEventRecord(ctx->evFork, callerStream));
@@ -1651,6 +1677,7 @@ int ptgpu_get_counters(ptgpu_ctx* ctx, ptgpu_counters* out) {
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->lastPassMs = ms;
     out->lastPassMs = ctx->lastPassMs;
     out->traceMs = ctx->traceMs; out->shadeMs = ctx->shadeMs; out->shadowMs = ctx->shadowMs; out->raygenMs = ctx->raygenMs;
+    out->meshMs = ctx->meshMs; out->meshItems = ctx->meshItems; out->meshLaunches = ctx->meshLaunches;
     return PTGPU_OK;
 }
 

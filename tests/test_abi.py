@@ -28,7 +28,7 @@ def test_struct_layouts_match_header(bindings):
     assert C.sizeof(bindings.Camera) == 72
     assert C.sizeof(bindings.Pass) == 56 + 72 + 16
     assert C.sizeof(bindings.Params) == 16
-    assert C.sizeof(bindings.Counters) == 80
+    assert C.sizeof(bindings.Counters) == 104
 
 
 def test_flatten_c1(bindings):
