@@ -654,6 +654,20 @@ PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
     return false;
 }
 
+#ifndef PT_PREFETCH2
+#define PT_PREFETCH2 0
+#endif
+PT_D void prefetch_l1(const void* p) {
+#if PT_PREFETCH2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+// A lane usually waits a scheduling turn or two between learning what it will touch next and touching it: ask for it now.
+PT_D void prefetch_node(const uint4* __restrict__ nodes, uint32_t node) { if (!(node & (1u << 29))) prefetch_l1(nodes + (size_t)node * 4); }
+PT_D void prefetch_leaf(const float4* __restrict__ geom, uint32_t first, uint32_t count) {
+    prefetch_l1(geom + (size_t)first * 3);
+    if (count > 2) prefetch_l1(geom + (size_t)first * 3 + 6);
+}
 enum { MESH_INTERIOR = 0, MESH_LEAF = 1, MESH_DONE = 2 };
 static constexpr uint32_t kNodeVirtual = 0x80000000u, kNodeRefLeaf = 0x40000000u, kNodeIndexMask = 0x3FFFFFFFu;
 // A child reference (30 bits) is either a node index (< 2^29) or a micro leaf named in place, saving the round trip
@@ -1184,9 +1198,10 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 #ifdef PT_DEBUG_STEPS
                     dbgSteps++;
 #endif
-                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
+                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; prefetch_leaf(S.leafGeom, first, count); }
                     else if (r == MESH_DONE) st = ST_MESH_DONE;
                 }
+                if (st == ST_MESH_NODE) prefetch_node(S.meshNodes, mc.node);
             }
 #endif
         } else {
@@ -1195,7 +1210,10 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                 dbgLeaves++;
 #endif
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
-                if (tPos >= tEnd) st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
+                if (tPos >= tEnd) {
+                    st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
+                    if (st == ST_MESH_NODE) prefetch_node(S.meshNodes, mc.node);
+                }
             }
         }
 #ifdef PT_DEBUG_STEPS

@@ -1340,8 +1340,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     }
     uint64_t batch = ctx->capRays / maxGrow;
     if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's branching factor");
-    if (batch > total) batch = total;
-    uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
+    uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);  // sized for a full batch whatever this pass needs: allocated once
     const uint64_t shadowCeil = ctx->capRays * 4;
     if (capShadow > shadowCeil) {  // shrink the batch so the shadow queue stays bounded
         batch = shadowCeil / (childGrow * (lightsPer ? lightsPer : 1));
@@ -1349,16 +1348,14 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
     }
     if (capShadow == 0) capShadow = 1;
+    if (batch > total) batch = total;
     const bool prof = ctx->profiling;
     // spread the pass over the lanes: at least one batch per lane when the pass is large enough to be worth it
     int lanesUsed = prof ? 1 : ctx->numLanes;
     {
         const uint64_t per = (total + (uint64_t)lanesUsed - 1) / (uint64_t)lanesUsed;
         const uint64_t minBatch = 1ull << 18;
-        if (per < batch) {
-            batch = std::max<uint64_t>(per, std::min<uint64_t>(minBatch, batch));
-            capShadow = std::max<uint64_t>(1, batch * childGrow * (lightsPer ? lightsPer : 1));
-        }
+        if (per < batch) batch = std::max<uint64_t>(per, std::min<uint64_t>(minBatch, batch));  // queues stay sized for the full batch
         const uint64_t nBatches = (total + batch - 1) / batch;
         if (nBatches < (uint64_t)lanesUsed) lanesUsed = (int)nBatches;
     }
