@@ -272,10 +272,13 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r01_k_mesh_traffic.json")
         if kname == "k_mesh" and os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f)   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+                tj = json.load(f)        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+            # per launch like `achieved`: the captured launch's DRAM bytes per item x the items of an average launch here
+            traffic = tj["bytes_per_item"] * units / max(klaunches, 1)
         roofline = {
             "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+            "traffic": traffic, "traffic_source": "profiles/r01_k_mesh_traffic.json (ncu --set full, dram read+write per item x items per launch)" if traffic else None,
+            "algorithmic_bytes_per_launch": units * unit_bytes / max(klaunches, 1), "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
             "algorithmic_bytes_per_unit": unit_bytes, "units_in_profiled_pass": units, "launches_in_profiled_pass": klaunches,
             "avg_launch_ms": kms / max(klaunches, 1), "kernel_ms_in_profiled_pass": kms, "share_of_step": kms / total_stage,
             "pipeline": {"bytes_per_bounce": B_PER_BOUNCE_NEE, "bytes_per_sample": B_PER_SAMPLE,
