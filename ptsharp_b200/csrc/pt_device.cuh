@@ -520,6 +520,27 @@ PT_D RayAux ray_aux(V3 o, V3 d) {
     a.pad = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
     return a;
 }
+// The same slab test with fewer instructions for the mesh walk: t = lo * i - o * i by FMA, and the per-ray padding applied
+// once to the interval ends as P = pad * max|i| (>= pad * |i| on every axis: only more conservative).
+struct RayBox { float ix, iy, iz, cx, cy, cz, P; };
+PT_D RayBox ray_box(V3 o, V3 d) {
+    RayBox a;
+    a.ix = 1.0f / d.x; a.iy = 1.0f / d.y; a.iz = 1.0f / d.z;
+    a.cx = o.x * a.ix; a.cy = o.y * a.iy; a.cz = o.z * a.iz;  // NaN when o = 0 and d = 0 on an axis: the min/max below ignore NaNs
+    const float pad = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+    a.P = pad * fmaxf(fmaxf(fabsf(a.ix), fabsf(a.iy)), fabsf(a.iz)) * 1.0001f;
+    return a;
+}
+PT_D bool box_line_hit_fast(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayBox& r, float& tnear) {
+    const float x1 = __fmaf_rn(lox, r.ix, -r.cx), x2 = __fmaf_rn(hix, r.ix, -r.cx);
+    const float y1 = __fmaf_rn(loy, r.iy, -r.cy), y2 = __fmaf_rn(hiy, r.iy, -r.cy);
+    const float z1 = __fmaf_rn(loz, r.iz, -r.cz), z2 = __fmaf_rn(hiz, r.iz, -r.cz);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2)) - r.P;
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2)) + r.P;
+    const float slack = 2e-5f * (fabsf(tf) + fabsf(tn)) + 1e-30f;   // the FMA form rounds o * i and lo * i - that separately
+    tnear = tn - slack;
+    return !(tn > tf + slack) && !(tf < -slack);  // NaN comparisons are false -> treated as a hit
+}
 PT_D bool bounds_hit(const float4* __restrict__ nb, uint32_t node, V3 o, const RayAux& ra) {
     const float4 lo = __ldg(nb + 2 * (size_t)node), hi = __ldg(nb + 2 * (size_t)node + 1);
     // fminf/fmaxf ignore NaNs (0 * inf when the origin lies on a slab plane of a zero direction): conservative
@@ -668,6 +689,12 @@ PT_D void prefetch_leaf(const float4* __restrict__ geom, uint32_t first, uint32_
     prefetch_l1(geom + (size_t)first * 3);
     if (count > 2) prefetch_l1(geom + (size_t)first * 3 + 6);
 }
+#ifdef PT_DEBUG_STEPS
+__device__ unsigned long long g_dbg[8];  // 0 items, 1 real steps, 2 virtual steps, 3 leaf visits, 4 triangle tests, 5 pops, 6 pushes
+#define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
+#else
+#define DBG_ADD(i, v)
+#endif
 enum { MESH_INTERIOR = 0, MESH_LEAF = 1, MESH_DONE = 2 };
 static constexpr uint32_t kNodeVirtual = 0x80000000u, kNodeRefLeaf = 0x40000000u, kNodeIndexMask = 0x3FFFFFFFu;
 // A child reference (30 bits) is either a node index (< 2^29) or a micro leaf named in place, saving the round trip
@@ -685,7 +712,7 @@ static constexpr int kMeshStackEnt = kMeshStack + kVirtualDepthMax + 1;
 //   micro leaf          no record: named in the parent's child reference (leaf_ref)
 // kNodeRefLeaf / kRefLeafRoot mark the root of a reference leaf (where the tie-break position restarts).
 // MESH_LEAF: triangles [tFirst, tFirst + tCount).
-PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
+PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
                    uint32_t& tCount) {
     if (c.node & kRefLeaf) {
         if (c.node & kRefLeafRoot) bestPos = 0;
@@ -698,11 +725,12 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayAux& ra, KdCursor& 
     const uint32_t a = q0.z, b = q0.w;
     const uint32_t axis = a & 3u;
     if (axis == 0 && (b & kNodeRefLeaf)) bestPos = 0;
+    DBG_ADD(axis == 0 ? 2 : 1, 1);
     float tnL, tnR;
-    bool hitL = box_line_hit_t(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
-                               __uint_as_float(q2.y), o, ra, tnL);
-    bool hitR = box_line_hit_t(__uint_as_float(q2.z), __uint_as_float(q2.w), __uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z),
-                               __uint_as_float(q3.w), o, ra, tnR);
+    bool hitL = box_line_hit_fast(__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
+                                  __uint_as_float(q2.y), ra, tnL);
+    bool hitR = box_line_hit_fast(__uint_as_float(q2.z), __uint_as_float(q2.w), __uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z),
+                                  __uint_as_float(q3.w), ra, tnR);
     const uint32_t left = a >> 2, right = b & kNodeIndexMask;
 #if PT_PREFETCH
     asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (size_t)left * 4));
@@ -753,6 +781,7 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
 #pragma unroll 1
     for (int k = 0; k < budget && tPos < tEnd; k++) {
         const float4* g = S.leafGeom + (size_t)tPos * 3;
+        DBG_ADD(4, 1);
         const double t = triangle_intersect(g, o, d);
         if (t <= best && t < kHitInf) {  // rare: fetch the ids only for candidates (a T of INF never replaces NoHit)
             const uint32_t pos = __float_as_uint(__ldg(g + 1).w);
@@ -821,7 +850,7 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
     double mBest = kHitInf; int32_t mPrim = -1; uint32_t mBestPos = 0;
     uint32_t curShape = 0; int32_t curInst = -1;
     uint32_t marchData = 0;                  // sdfShapes[] / volumes[] index while in the MARCH class
-    RayAux ra = ray_aux(co, cd);             // for the mesh being traversed
+    RayBox ra = ray_box(co, cd);             // for the mesh being traversed
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
 
     // Scheduling.  Lanes fall into three classes: LEAF (testing triangles of a mesh leaf), NODE (walking a mesh tree) and
@@ -922,7 +951,7 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
     #pragma unroll 1
                     for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
                         uint32_t first, count;
-                        if (kd_step<kSceneStack, false>(S.nodes, nullptr, ra, sc, o, d, sStNode, sStMin, sStMax, first, count) == KD_LEAF) {
+                        if (kd_step<kSceneStack, false>(S.nodes, nullptr, RayAux{0.f, 0.f, 0.f, 0.f}, sc, o, d, sStNode, sStMin, sStMax, first, count) == KD_LEAF) {
                             sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
                         }
                     }
@@ -944,8 +973,8 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
                         if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
                             const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
                             mBest = kHitInf; mPrim = -1;
-                            ra = ray_aux(co, cd);
-                            if (!tree_box_maybe_hit(mt, co, ra)) st = ST_MESH_DONE;  // clear miss: Box.Intersect would say so too
+                            ra = ray_box(co, cd);
+                            if (!tree_box_maybe_hit(mt, co, ray_aux(co, cd))) st = ST_MESH_DONE;  // clear miss: Box.Intersect would say so too
                             else {
                                 box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
                                 if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
@@ -1141,7 +1170,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
     int st = ST_IDLE;
     uint32_t ray = 0;
     V3 co = v3(0, 0, 0), cd = v3(0, 0, 1);
-    RayAux ra = ray_aux(co, cd);
+    RayBox ra = ray_box(co, cd);
     KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
     uint4 mStk[kMeshStackEnt];
     uint32_t tPos = 0, tEnd = 0, mBestPos = 0;
@@ -1167,10 +1196,11 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     const float4 a = q.a[i], b = q.b[i];
                     const double2 c = q.c[i];
                     co = v3(a.x, a.y, a.z); cd = v3(b.x, b.y, b.z); ray = __float_as_uint(a.w);
-                    ra = ray_aux(co, cd);
+                    ra = ray_box(co, cd);
                     mc.node = __float_as_uint(b.w); mc.tmin = c.x; mc.tmax = c.y; mc.sp = 0;
 #ifdef PT_DEBUG_STEPS
                     dbgRoot = mc.node;
+                    DBG_ADD(0, 1);
 #endif
                     stk_put(mStk, mc.tmax, 0u, 0u);
                     mBest = kHitInf; mPrim = -1; mBestPos = 0;
@@ -1208,6 +1238,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
             if (st == ST_MESH_LEAF) {
 #ifdef PT_DEBUG_STEPS
                 dbgLeaves++;
+                DBG_ADD(3, 1);
 #endif
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
                 if (tPos >= tEnd) {
@@ -1218,7 +1249,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
         }
 #ifdef PT_DEBUG_STEPS
         if (st == ST_MESH_DONE) {
-            if (dbgSteps + dbgLeaves > 400) printf("long ray: %d node steps, %d leaves, o=(%g,%g,%g) d=(%g,%g,%g) best=%g root=%u\n", dbgSteps, dbgLeaves, co.x, co.y, co.z, cd.x, cd.y, cd.z, mBest, dbgRoot);
+            if (dbgSteps + dbgLeaves > 100000) printf("long ray: %d node steps, %d leaves, o=(%g,%g,%g) d=(%g,%g,%g) best=%g root=%u\n", dbgSteps, dbgLeaves, co.x, co.y, co.z, cd.x, cd.y, cd.z, mBest, dbgRoot);
             dbgSteps = dbgLeaves = 0;
         }
 #endif
@@ -1232,7 +1263,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 // swapped in when needed), which lifts the expected share of busy lanes from 1/2 to 3/4.
 struct WalkRay {
     V3 co, cd;
-    RayAux ra;
+    RayBox ra;
     KdCursor mc;
     uint32_t tPos, tEnd, bestPos, ray, stackOff;
     double best;
@@ -1241,7 +1272,7 @@ struct WalkRay {
 };
 PT_D void walk_swap(WalkRay& a, WalkRay& b, bool p) {
 #define SW(f) { auto t_ = a.f; a.f = p ? b.f : a.f; b.f = p ? t_ : b.f; }
-    SW(co.x) SW(co.y) SW(co.z) SW(cd.x) SW(cd.y) SW(cd.z) SW(ra.ix) SW(ra.iy) SW(ra.iz) SW(ra.pad)
+    SW(co.x) SW(co.y) SW(co.z) SW(cd.x) SW(cd.y) SW(cd.z) SW(ra.ix) SW(ra.iy) SW(ra.iz) SW(ra.cx) SW(ra.cy) SW(ra.cz) SW(ra.P)
     SW(mc.node) SW(mc.sp) SW(mc.tmin) SW(mc.tmax) SW(tPos) SW(tEnd) SW(bestPos) SW(ray) SW(stackOff) SW(best) SW(prim) SW(st)
 #undef SW
 }
@@ -1249,7 +1280,7 @@ PT_D void mesh_walk2(const DScene& S, const SplitState& W, const MeshQueue& q, u
     const uint32_t n = *q.count;
     WalkRay A, B;
     A.co = B.co = v3(0, 0, 0); A.cd = B.cd = v3(0, 0, 1);
-    A.ra = B.ra = ray_aux(A.co, A.cd);
+    A.ra = B.ra = ray_box(A.co, A.cd);
     A.mc.node = B.mc.node = 0; A.mc.sp = B.mc.sp = 0; A.mc.tmin = A.mc.tmax = B.mc.tmin = B.mc.tmax = 0;
     A.tPos = A.tEnd = A.bestPos = A.ray = B.tPos = B.tEnd = B.bestPos = B.ray = 0;
     A.best = B.best = kHitInf; A.prim = B.prim = -1;
@@ -1275,7 +1306,7 @@ PT_D void mesh_walk2(const DScene& S, const SplitState& W, const MeshQueue& q, u
                     const float4 a = q.a[i], b = q.b[i];
                     const double2 c = q.c[i];
                     A.co = v3(a.x, a.y, a.z); A.cd = v3(b.x, b.y, b.z); A.ray = __float_as_uint(a.w);
-                    A.ra = ray_aux(A.co, A.cd);
+                    A.ra = ray_box(A.co, A.cd);
                     A.mc.node = __float_as_uint(b.w); A.mc.tmin = c.x; A.mc.tmax = c.y; A.mc.sp = 0;
                     stk_put(mStk + A.stackOff, A.mc.tmax, 0u, 0u);
                     A.best = kHitInf; A.prim = -1; A.bestPos = 0;
