@@ -152,7 +152,9 @@ def run_reference(args):
         "impl": "reference", "metric": "Msamples/s", "value": base["value"], "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 vectors + f64 scalars", "data": "synthetic",
-        "config": {"workload": cfg.name, "width": cfg.width, "height": cfg.height, "spp": cfg.spp, "triangles": cfg.triangles},
+        "config": {"workload": cfg.name, "width": cfg.width, "height": cfg.height, "spp_per_gpu": cfg.spp, "triangles": cfg.triangles,
+                   "sampler": "DefaultSampler.NewSampler(1,4)" if args.workload.startswith("c3") else "see scenes.py",
+                   "parallelism": "host CPU threads (rank 0 only)", "l2": "n/a (CPU)"},
         "gpaths_bounce_per_s": base["gpaths_bounce_per_s"],
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -541,57 +541,7 @@ PT_D bool box_line_hit_fast(float lox, float loy, float loz, float hix, float hi
     tnear = tn - slack;
     return !(tn > tf + slack) && !(tf < -slack);  // NaN comparisons are false -> treated as a hit
 }
-PT_D bool bounds_hit(const float4* __restrict__ nb, uint32_t node, V3 o, const RayAux& ra) {
-    const float4 lo = __ldg(nb + 2 * (size_t)node), hi = __ldg(nb + 2 * (size_t)node + 1);
-    // fminf/fmaxf ignore NaNs (0 * inf when the origin lies on a slab plane of a zero direction): conservative
-    const float x1 = (lo.x - ra.pad - o.x) * ra.ix, x2 = (hi.x + ra.pad - o.x) * ra.ix;
-    const float y1 = (lo.y - ra.pad - o.y) * ra.iy, y2 = (hi.y + ra.pad - o.y) * ra.iy;
-    const float z1 = (lo.z - ra.pad - o.z) * ra.iz, z2 = (hi.z + ra.pad - o.z) * ra.iz;
-    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
-    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
-    const float slack = 1e-5f * fabsf(tf) + 1e-30f;
-    return !(tn > tf + slack) && !(tf < -slack);  // NaN comparisons are false -> treated as a hit
-}
-
-enum { KD_INTERIOR = 0, KD_LEAF = 1, KD_CULLED = 2 };
-
-// One Node.Intersect step.  KD_LEAF: `node` is a leaf (first/count filled in); KD_CULLED: its subtree cannot be hit.
-template <int STACK, bool CULL>
-PT_D int kd_step(const ptgpu_node* __restrict__ nodes, const float4* __restrict__ nb, const RayAux& ra, KdCursor& c, V3 o, V3 d, uint32_t* stNode,
-                 double* stMin, double* stMax, uint32_t& leafFirst, uint32_t& leafCount) {
-    if (CULL) { if (!bounds_hit(nb, c.node, o, ra)) return KD_CULLED; }
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));  // one 128-bit load per node
-    const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
-    const uint32_t axis = a & 3u;
-    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return KD_LEAF; }
-    const double split = __hiloint2double(raw.y, raw.x);
-    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-    const double tsplit = (split - oa) / da;
-    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
-    const uint32_t first = leftFirst ? (a >> 2) : b;
-    const uint32_t second = leftFirst ? b : (a >> 2);
-    if (tsplit > c.tmax || tsplit <= 0) c.node = first;
-    else if (tsplit < c.tmin) c.node = second;
-    else {
-        if (c.sp < STACK) { stNode[c.sp] = second; stMin[c.sp] = tsplit; stMax[c.sp] = c.tmax; c.sp++; }
-        c.node = first;
-        c.tmax = tsplit;
-    }
-    return KD_INTERIOR;
-}
-// After a leaf: resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
-PT_D bool kd_pop(KdCursor& c, double bestT, const uint32_t* stNode, const double* stMin, const double* stMax) {
-    while (c.sp > 0) {
-        --c.sp;
-        const double ts = stMin[c.sp];
-        if (bestT <= ts) continue;  // `if (h1.T <= tsplit) return h1`
-        c.node = stNode[c.sp];
-        c.tmin = ts;
-        c.tmax = netmin(stMax[c.sp], bestT);
-        return true;
-    }
-    return false;
-}
+enum { KD_INTERIOR = 0, KD_LEAF = 1 };
 
 // IShape.Intersect for the analytic shapes (everything except Mesh and TransformedShape).
 PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3 d) {
@@ -614,7 +564,7 @@ PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3
 //    push directly below, or a netmin(.., best.T) of one of those from an earlier pop, and best.T only decreases — so
 //    entry 0 is a sentinel holding the root tmax.
 //  * Child bounds in the parent (64-byte node): whether a child's padded triangle bounds are missed by the ray line
-//    (= its Node.Intersect returns NoHit, see bounds_hit) is known before descending, so a culled near child costs no
+//    (= its Node.Intersect returns NoHit, see box_line_hit) is known before descending, so a culled near child costs no
 //    memory round trip and a culled far child is skipped when it is popped.  It is still pushed: its tsplit is the
 //    `tmax` of the entries above it.
 //  * Bounds-only nodes below the reference leaves.  Rays mostly cross LARGE leaves (the builder stops at 85 % overlap;
@@ -647,18 +597,6 @@ PT_D bool tree_box_maybe_hit(const ptgpu_tree& t, V3 o, const RayAux& ra) {
     return box_line_hit(t.bmin[0] - p, t.bmin[1] - p, t.bmin[2] - p, t.bmax[0] + p, t.bmax[1] + p, t.bmax[2] + p, o, ra);
 }
 
-// Same test, also returning a lower bound of the entry distance (for near-first ordering / distance culling).
-PT_D bool box_line_hit_t(float lox, float loy, float loz, float hix, float hiy, float hiz, V3 o, const RayAux& ra, float& tnear) {
-    const float x1 = (lox - ra.pad - o.x) * ra.ix, x2 = (hix + ra.pad - o.x) * ra.ix;
-    const float y1 = (loy - ra.pad - o.y) * ra.iy, y2 = (hiy + ra.pad - o.y) * ra.iy;
-    const float z1 = (loz - ra.pad - o.z) * ra.iz, z2 = (hiz + ra.pad - o.z) * ra.iz;
-    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
-    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
-    const float slack = 1e-5f * fabsf(tf) + 1e-30f;
-    tnear = tn - slack - 1e-5f * fabsf(tn);
-    return !(tn > tf + slack) && !(tf < -slack);
-}
-
 // Resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
 PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
     while (c.sp > 0) {
@@ -673,6 +611,28 @@ PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
         return true;
     }
     return false;
+}
+
+// Node.Intersect step on Scene.tree (16-byte reference nodes, no culling) with the 16-byte stack.
+PT_D int scene_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d, uint4* stk, int stackEnt, uint32_t& leafFirst, uint32_t& leafCount) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));
+    const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
+    const uint32_t axis = a & 3u;
+    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return KD_LEAF; }
+    const double split = __hiloint2double(raw.y, raw.x);
+    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+    const double tsplit = (split - oa) / da;
+    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
+    const uint32_t first = leftFirst ? (a >> 2) : b;
+    const uint32_t second = leftFirst ? b : (a >> 2);
+    if (tsplit > c.tmax || tsplit <= 0) c.node = first;
+    else if (tsplit < c.tmin) c.node = second;
+    else {
+        if (c.sp + 1 < stackEnt) { c.sp++; stk_put(stk + c.sp, tsplit, second, 0u); }
+        c.node = first;
+        c.tmax = tsplit;
+    }
+    return KD_INTERIOR;
 }
 
 #ifndef PT_PREFETCH2
@@ -841,7 +801,7 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
     best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
     // Scene tree (Scene.tree)
     KdCursor sc; sc.node = 0; sc.tmin = sc.tmax = 0; sc.sp = 0;
-    uint32_t sStNode[kSceneStack]; double sStMin[kSceneStack], sStMax[kSceneStack];
+    uint4 sStk[kSceneStack + 1];             // entry 0 = sentinel (root tmax)
     uint32_t sPos = 0, sEnd = 0;
     // Mesh tree (Mesh.tree) of the shape being visited
     KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
@@ -944,21 +904,21 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
                         best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
                         box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
                         if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-                        else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }
+                        else { sc.node = sceneTree.root; sc.sp = 0; stk_put(sStk, sc.tmax, 0u, 0u); st = ST_SCENE_NODE; }
                     }
                 }
                 if (st == ST_SCENE_NODE) {
     #pragma unroll 1
                     for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
                         uint32_t first, count;
-                        if (kd_step<kSceneStack, false>(S.nodes, nullptr, RayAux{0.f, 0.f, 0.f, 0.f}, sc, o, d, sStNode, sStMin, sStMax, first, count) == KD_LEAF) {
+                        if (scene_step(S.nodes, sc, o, d, sStk, kSceneStack + 1, first, count) == KD_LEAF) {
                             sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
                         }
                     }
                 }
                 if (st == ST_SCENE_LEAF) {
                     if (sPos == sEnd) {
-                        st = kd_pop(sc, best.t, sStNode, sStMin, sStMax) ? ST_SCENE_NODE : ST_FINISH;
+                        st = mesh_pop(sc, best.t, sStk) ? ST_SCENE_NODE : ST_FINISH;
                     } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
                         curShape = __ldg(S.leafItems + sPos);
                         sPos++;
@@ -1043,28 +1003,6 @@ struct SplitState {      // per ray of the launch, SoA
 struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root node)  c = (tmin, tmax)
     float4* a; float4* b; double2* c; uint32_t* count;
 };
-
-// Node.Intersect step on Scene.tree (16-byte reference nodes, no culling) with the 16-byte stack.
-PT_D int scene_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d, uint4* stk, int stackEnt, uint32_t& leafFirst, uint32_t& leafCount) {
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(nodes + c.node));
-    const uint32_t a = (uint32_t)raw.z, b = (uint32_t)raw.w;
-    const uint32_t axis = a & 3u;
-    if (axis == 0) { leafFirst = a >> 2; leafCount = b; return KD_LEAF; }
-    const double split = __hiloint2double(raw.y, raw.x);
-    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-    const double tsplit = (split - oa) / da;
-    const bool leftFirst = (oa < split) || (oa == split && da <= 0);
-    const uint32_t first = leftFirst ? (a >> 2) : b;
-    const uint32_t second = leftFirst ? b : (a >> 2);
-    if (tsplit > c.tmax || tsplit <= 0) c.node = first;
-    else if (tsplit < c.tmin) c.node = second;
-    else {
-        if (c.sp + 1 < stackEnt) { c.sp++; stk_put(stk + c.sp, tsplit, second, 0u); }
-        c.node = first;
-        c.tmax = tsplit;
-    }
-    return KD_INTERIOR;
-}
 
 // Advance rays through Scene.tree until each either finishes (sink) or has to enter a Mesh (work item to `out`).
 // RESUME = false: rays [0, n) start; RESUME = true: the n rays named by the items of `in` continue after their mesh walk.

@@ -1010,7 +1010,7 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
         D.texels = t;
     }
 #undef UP
-    {   // padded triangle bounds per kd node (see bounds_hit in pt_device.cuh).  Nodes are stored parent-before-child,
+    {   // padded triangle bounds per kd node (see box_line_hit in pt_device.cuh).  Nodes are stored parent-before-child,
         // so one reverse sweep folds children into parents.  Scene-tree nodes get an unbounded box (never culled).
         const uint64_t nn = s->numNodes;
         std::vector<float> nb(nn * 8);
@@ -1058,8 +1058,6 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
         std::vector<ptgpu_tri_geom> lg;
         lg.reserve(s->numLeafItems);
         std::vector<uint32_t> mn(nn * 16, 0u);           // grows with the bounds-only nodes
-        std::vector<float> xb(nn * 8);                   // padded bounds of the appended nodes' subtrees (index - nn)
-        xb.clear();
         std::vector<std::pair<uint32_t, uint32_t>> order;  // (morton, position in leaf)
         std::vector<float> cen;
         auto bitsToFloat = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };

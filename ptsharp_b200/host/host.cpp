@@ -783,7 +783,7 @@ std::unique_ptr<FlatScene> Flatten(const Scene& scene) {
     if (!scene.tree) throw std::runtime_error("Scene not compiled");
     auto fs = std::make_unique<FlatScene>();
     FlatScene& f = *fs;
-    Flattener fl{f};
+    Flattener fl{f, {}, {}, 0, {}};
     size_t n = scene.Shapes.size();
     f.shapes.resize(n);  // Scene.Shapes first, nested inner shapes after
     for (size_t i = 0; i < n; i++) {
