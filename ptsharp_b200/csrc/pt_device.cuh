@@ -129,6 +129,7 @@ struct DScene {
     const float4* texels;
     // Derived at upload for mesh trees (see "mesh traversal" below):
     const uint4* meshNodes;         // 4 x uint4 per node: reference kd nodes, bounds-only nodes and micro leaves (see mesh_step)
+    const float4* instBounds;       // 2 x float4 per TransformedShape of a Mesh: padded WORLD-space bounds of the instance (FP32 pre-test)
     const float4* leafGeom;         // 3 x float4 per leaf triangle in sorted order: (V1, triangle id) (e1, position in the leaf) (e2, -)
     uint32_t sceneTree, numSceneShapes, numLights, numShapes;
     double envColor[3];
@@ -1004,12 +1005,36 @@ struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root nod
     float4* a; float4* b; double2* c; uint32_t* count;
 };
 
+// Mesh.Intersect by one thread, start to end (the tail rounds of scenes where rays enter many meshes: a few thousand rays,
+// latency-bound whatever the scheduling, not worth a k_mesh launch each).
+PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double tmin, double tmax, double& best, int32_t& prim) {
+    const RayBox ra = ray_box(co, cd);
+    KdCursor mc; mc.node = root; mc.tmin = tmin; mc.tmax = tmax; mc.sp = 0;
+    uint4 stk[kMeshStackEnt];
+    stk_put(stk, tmax, 0u, 0u);
+    best = kHitInf; prim = -1;
+    uint32_t bestPos = 0;
+    for (;;) {
+        uint32_t first, count;
+        const int r = mesh_step(S.meshNodes, ra, mc, co, cd, stk, best, bestPos, first, count);
+        if (r == MESH_DONE) break;
+        if (r == MESH_LEAF) {
+            uint32_t tPos = first;
+            leaf_work(S, co, cd, tPos, first + count, best, prim, bestPos, 4);
+            if (!mesh_pop(mc, best, stk)) break;
+        }
+    }
+}
+
 // Advance rays through Scene.tree until each either finishes (sink) or has to enter a Mesh (work item to `out`).
-// RESUME = false: rays [0, n) start; RESUME = true: the n rays named by the items of `in` continue after their mesh walk.
-template <bool RESUME, class Source, class Sink>
+// MODE 0: rays [0, n) start.  MODE 1: the n rays named by the items of `in` continue after their mesh walk.  MODE 2: the
+// same rays, whose mesh walks have NOT run yet, are carried to their end by this thread (mesh walks inline, no more items).
+enum { SCENE_START = 0, SCENE_RESUME = 1, SCENE_FINISH = 2 };
+template <int MODE, class Source, class Sink>
 PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink) {
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        constexpr bool RESUME = MODE != SCENE_START;
         const uint32_t ray = RESUME ? __float_as_uint(in.a[k].w) : k;
         V3 o, d;
         source(ray, o, d);
@@ -1020,12 +1045,17 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
         double mBest = kHitInf;
         V3 co = o, cd = d;
         uint4* sstk = W.sceneStack + (size_t)ray * W.stackEnt;
+        const RayAux worldAux = ray_aux(o, d);
         int st;
         if (RESUME) {
             best.t = W.bestT[ray]; best.tInner = W.bestTInner[ray]; best.shape = W.bestShape[ray]; best.prim = W.bestPrim[ray];
             sc.node = W.scNode[ray]; sc.sp = W.scSp[ray]; sc.tmin = W.scTmin[ray]; sc.tmax = W.scTmax[ray];
             sPos = W.sPos[ray]; sEnd = W.sEnd[ray]; curShape = W.curShape[ray]; curInst = W.curInst[ray];
-            mBest = W.mBest[ray]; mPrim = W.mPrim[ray];
+            if (MODE == SCENE_FINISH) {  // the pending mesh walk first (the item holds the ray in the mesh's space)
+                const float4 ia = in.a[k], ib = in.b[k];
+                const double2 ic = in.c[k];
+                mesh_walk_single(S, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z), __float_as_uint(ib.w), ic.x, ic.y, mBest, mPrim);
+            } else { mBest = W.mBest[ray]; mPrim = W.mPrim[ray]; }
             if (curInst >= 0) { const ptgpu_instance& inst = S.instances[curInst]; co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d); }
             st = ST_MESH_DONE;
         } else {
@@ -1060,13 +1090,17 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                     sPos++;
                     ptgpu_shape sh = S.shapes[curShape];
                     curInst = -1; co = o; cd = d;
+                    mPrim = -1;
                     if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45
                         curInst = (int32_t)sh.data;
+                        // FP32 pre-test in world space: a ray that misses the padded world bounds of the instanced mesh gives a
+                        // shapeRay that misses the mesh's Box (Tree.cs:36-41) -> NoHit, without the FP64 transform
+                        const float4 wlo = __ldg(S.instBounds + 2 * (size_t)sh.data), whi = __ldg(S.instBounds + 2 * (size_t)sh.data + 1);
+                        if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
                         const ptgpu_instance& inst = S.instances[sh.data];
                         co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
                         sh = S.shapes[inst.shape];
                     }
-                    mPrim = -1;
                     if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
                         const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
                         mBest = kHitInf;
@@ -1074,6 +1108,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         const RayAux ra = ray_aux(co, cd);
                         if (tree_box_maybe_hit(mt, co, ra)) box_intersect(mt.bmin, mt.bmax, co, cd, tmin, tmax);
                         if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
+                        else if (MODE == SCENE_FINISH) { mesh_walk_single(S, co, cd, mt.root, tmin, tmax, mBest, mPrim); st = ST_MESH_DONE; }
                         else {
                             auto g = cooperative_groups::coalesced_threads();
                             uint32_t base = 0;

@@ -443,21 +443,23 @@ __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_shadow(DScene S, Sh
 #ifndef PT_SCENE_MINBLOCKS
 #define PT_SCENE_MINBLOCKS 8
 #endif
-template <bool RESUME>
-__global__ void __launch_bounds__(128, PT_SCENE_MINBLOCKS) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
+template <int MODE>
+__global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
                                                       DeviceCounters* cnt) {
+    constexpr bool RESUME = MODE != SCENE_START;
     const uint32_t n = RESUME ? *in.count : *count;
-    scene_advance<RESUME>(S, W, n, in, out,
+    scene_advance<MODE>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
-template <bool RESUME>
-__global__ void __launch_bounds__(128, PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, MeshQueue in,
+template <int MODE>
+__global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, MeshQueue in,
                                                        MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
+    constexpr bool RESUME = MODE != SCENE_START;
     uint32_t n = RESUME ? *in.count : *scount;
     if (!RESUME && n > capShadow) n = capShadow;
-    scene_advance<RESUME>(S, W, n, in, out,
+    scene_advance<MODE>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) {
                               const uint32_t light = f2u(sq.sd[i].w);
@@ -628,11 +630,12 @@ __global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32
                });
 }
 struct BatchOut { int32_t* shape; int32_t* prim; double* t; float* normal3; float* position3; int32_t* inside; int32_t* material; };
-template <bool RESUME>
+template <int MODE>
 __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uint32_t nStart, MeshQueue in, MeshQueue out, const float* __restrict__ o3,
                                                       const float* __restrict__ d3, BatchOut B) {
+    constexpr bool RESUME = MODE != SCENE_START;
     const uint32_t n = RESUME ? *in.count : nStart;
-    scene_advance<RESUME>(S, W, n, in, out,
+    scene_advance<MODE>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
                           [&](uint32_t i, const HitRec& h) {
                               V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
@@ -821,8 +824,11 @@ static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
 }
 // One Scene.Intersect wavefront in split form.  start(out) launches the scene kernel for the fresh rays; resume(in, out)
 // launches it for the rays named by `in`'s items.  Fixed number of rounds when the scene bounds it, else until empty.
-template <class StartFn, class ResumeFn>
-static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, ResumeFn resume) {
+#ifndef PT_FINISH_MAX
+#define PT_FINISH_MAX 65536   // pending mesh walks at or below which the remaining rounds run as one SCENE_FINISH launch
+#endif
+template <class StartFn, class ResumeFn, class FinishFn>
+static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, ResumeFn resume, FinishFn finish) {
     uint32_t* cursor = L.counts + 12;
     CK(cudaMemsetAsync(L.counts + 10, 0, 3 * sizeof(uint32_t), st));
     start(L.mq[0]);
@@ -834,6 +840,7 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
             CK(cudaMemcpyAsync(&pending, L.mq[cur].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (pending == 0) break;
+            if (pending <= PT_FINISH_MAX && round > 0) { finish(L.mq[cur]); ctx->launches++; break; }
         }
         CK(cudaMemsetAsync(L.mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
         CK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
@@ -997,6 +1004,36 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
     }
     UP(triShade, s->triShade, s->numTriangles);
     UP(instances, s->instances, s->numInstances);
+    {   // padded world-space bounds of every instanced mesh (see scene_advance): the 8 corners of Mesh.tree's Box through Matrix
+        std::vector<float> ib((size_t)(s->numInstances ? s->numInstances : 1) * 8, 0.f);
+        for (uint32_t i = 0; i < s->numInstances; i++) {
+            const ptgpu_instance& in = s->instances[i];
+            const ptgpu_shape& inner = s->shapes[in.shape];
+            float* o8 = &ib[(size_t)i * 8];
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            if (inner.type == PTGPU_MESH) {
+                const ptgpu_tree& t = s->trees[s->meshes[inner.data].tree];
+                for (int c = 0; c < 8; c++) {
+                    const double p[3] = {(c & 1) ? t.bmax[0] : t.bmin[0], (c & 2) ? t.bmax[1] : t.bmin[1], (c & 4) ? t.bmax[2] : t.bmin[2]};
+                    for (int r = 0; r < 3; r++) {
+                        const double v = in.m[4 * r] * p[0] + in.m[4 * r + 1] * p[1] + in.m[4 * r + 2] * p[2] + in.m[4 * r + 3];
+                        lo[r] = std::min(lo[r], v); hi[r] = std::max(hi[r], v);
+                    }
+                }
+                const double ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+                for (int r = 0; r < 3; r++) {
+                    const double padv = 1e-4 * ext + 1e-5 * std::max(std::fabs(lo[r]), std::fabs(hi[r])) + 1e-6;
+                    o8[r] = std::nextafter((float)(lo[r] - padv), -INFINITY); o8[4 + r] = std::nextafter((float)(hi[r] + padv), INFINITY);
+                }
+            } else {
+                for (int r = 0; r < 3; r++) { o8[r] = -3.0e38f; o8[4 + r] = 3.0e38f; }  // no Box test in the reference: never skipped
+            }
+        }
+        const float4* dib = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(ib.data()), (uint64_t)ib.size() / 4, &dib)) != PTGPU_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        D.instBounds = dib;
+    }
     UP(sdfShapes, s->sdfShapes, s->numSdfShapes);
     UP(sdfOps, s->sdfOps, s->numSdfOps);
     UP(volumes, s->volumes, s->numVolumes);
@@ -1389,7 +1426,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         if ((rc = ensure_queues(ctx, L, capShadow)) != PTGPU_OK) return rc;
         if (ctx->useSplit && (rc = ensure_split(ctx, L, std::max<uint64_t>(ctx->capRays, L.capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
     }
-    const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8);
+    const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
     float ms = 0;
     if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = ctx->meshMs = 0; ctx->meshItems = ctx->meshLaunches = 0; }
     // fork: the lanes' streams continue from the caller's stream ...
@@ -1417,8 +1454,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 const RayQueue rqc = L.rq[cur];
                 uint32_t* cnt = counts + cur;
                 rc = run_split(ctx, L, stream,
-                               [&](const MeshQueue& out) { k_scene_trace<false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); },
-                               [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); });
+                               [&](const MeshQueue& out) { k_scene_trace<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); },
+                               [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); },
+                               [&](const MeshQueue& in) { k_scene_trace<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); });
                 if (rc != PTGPU_OK) return rc;
             } else {
                 k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.rq[cur], counts + cur, counts + 4, L.hq, ctx->dCounters);
@@ -1433,8 +1471,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             if (lightsPer) {
                 if (ctx->useSplit) {
                     rc = run_split(ctx, L, stream,
-                                   [&](const MeshQueue& out) { k_scene_shadow<false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, out, out, d_sum, ctx->dCounters); },
-                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, out, d_sum, ctx->dCounters); });
+                                   [&](const MeshQueue& out) { k_scene_shadow<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, out, out, d_sum, ctx->dCounters); },
+                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, out, d_sum, ctx->dCounters); },
+                                   [&](const MeshQueue& in) { k_scene_shadow<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, in, d_sum, ctx->dCounters); });
                     if (rc != PTGPU_OK) return rc;
                 } else {
                     k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.sq, counts + 2, counts + 5, (uint32_t)L.capShadow, d_sum, ctx->dCounters);
@@ -1617,8 +1656,9 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
         const BatchOut B{dS, dPr, dT, dN, dP, dI, dM};
         rcs = run_split(ctx, L, ctx->stream,
-                        [&](const MeshQueue& out) { k_scene_batch<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); },
-                        [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); });
+                        [&](const MeshQueue& out) { k_scene_batch<SCENE_START><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); },
+                        [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<SCENE_RESUME><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); },
+                        [&](const MeshQueue& in) { k_scene_batch<SCENE_FINISH><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); });
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
     } else {
     k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM);
