@@ -255,7 +255,7 @@ def main():
         peak, peak_kind = measured_peaks()
         dev.set_profiling(True)
         dev.reset_counters()
-        prof_spp = max(1, min(spp, 16))
+        prof_spp = max(1, min(spp, 64))
         dev.render_pass(hw.make_pass(W, H, prof_spp, pass_index=10_000), want_mean=False)
         pc = dev.counters()
         dev.set_profiling(False)

@@ -166,7 +166,7 @@ typedef struct ptgpu_pass {
 typedef struct ptgpu_params {
     int32_t device;              /* CUDA ordinal */
     int32_t flags;               /* bits 0-3: number of lanes (independent streams + queues the batches of a pass go round), 0 = default (1) */
-    uint64_t queueCapacity;      /* path records in flight over all lanes; 0 = default (2^25 ~ 16 spp of a 1920x1080 frame per batch, ~10 GB) */
+    uint64_t queueCapacity;      /* path records in flight over all lanes; 0 = default (2^27 ~ 64 spp of a 1920x1080 frame per batch; queues are allocated on demand, ~50 GB when full) */
 } ptgpu_params;
 
 typedef struct ptgpu_counters {

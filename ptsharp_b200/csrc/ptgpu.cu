@@ -693,7 +693,7 @@ struct Lane {
     RayQueue rq[2]{};
     HitQueue hq{};
     ShadowQueue sq{};
-    uint64_t capShadow = 0;
+    uint64_t capRays = 0, capShadow = 0;   // records the lane's queues are allocated for (grown on demand up to ctx->capRays)
     uint32_t* counts = nullptr;   // [0],[1] ray queue counts, [2] shadow count, [3] overflow flag, [4] trace cursor, [5] shadow cursor,
                                   // [10],[11] mesh queue counts, [12] mesh cursor
     SplitState split{};           // split tracer (scene_advance / mesh_walk): per-ray scene-level state and the two mesh work queues
@@ -790,7 +790,7 @@ static void free_queues(ptgpu_ctx* ctx) {
         for (int i = 0; i < 2; i++) { cudaFree(L.rq[i].od0); cudaFree(L.rq[i].od1); cudaFree(L.rq[i].bt); cudaFree(L.rq[i].smp); L.rq[i] = RayQueue{}; }
         cudaFree(L.hq.t); cudaFree(L.hq.tInner); cudaFree(L.hq.shape); cudaFree(L.hq.prim); L.hq = HitQueue{};
         cudaFree(L.sq.so); cudaFree(L.sq.sd); cudaFree(L.sq.sc); L.sq = ShadowQueue{};
-        L.capShadow = 0;
+        L.capRays = 0; L.capShadow = 0;
         free_split(L);
     }
 }
@@ -905,9 +905,9 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     ctx->numSMs = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
-    // queueCapacity = path records in flight over all lanes (default 2^25); flags bits 0-3 = number of lanes (0 = default)
+    // queueCapacity = path records in flight over all lanes (default 2^27, allocated on demand); flags bits 0-3 = number of lanes (0 = default)
     {
-        uint64_t total = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 25);
+        uint64_t total = (params && params->queueCapacity) ? params->queueCapacity : (1ull << 27);
         int lanes = (params && (params->flags & 15)) ? (params->flags & 15) : PT_LANES;
         if (const char* ev = std::getenv("PTGPU_LANES")) { int v = std::atoi(ev); if (v >= 1) lanes = v; }            // development overrides
         if (const char* ev = std::getenv("PTGPU_QUEUE_LOG2")) { int v = std::atoi(ev); if (v >= 16 && v <= 30) total = 1ull << v; }
@@ -1317,27 +1317,37 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
     return PTGPU_OK;
 }
 
-static int ensure_queues(ptgpu_ctx* ctx, Lane& L, uint64_t capShadow) {
-    if (!L.rq[0].od0) {
+static uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+// Queues of one lane for batches of up to `needRays` path records and `needShadow` shadow records (grown, never shrunk).
+static int ensure_queues(ptgpu_ctx* ctx, Lane& L, uint64_t needRays, uint64_t needShadow) {
+    if (needRays > L.capRays) {
+        const uint64_t cap = std::min<uint64_t>(pow2_at_least(needRays), std::max<uint64_t>(ctx->capRays, needRays));
+        CK(cudaStreamSynchronize(L.stream));
+        for (int i = 0; i < 2; i++) { cudaFree(L.rq[i].od0); cudaFree(L.rq[i].od1); cudaFree(L.rq[i].bt); cudaFree(L.rq[i].smp); L.rq[i] = RayQueue{}; }
+        cudaFree(L.hq.t); cudaFree(L.hq.tInner); cudaFree(L.hq.shape); cudaFree(L.hq.prim); L.hq = HitQueue{};
+        L.capRays = 0;
         for (int i = 0; i < 2; i++) {
-            CK(cudaMalloc(&L.rq[i].od0, ctx->capRays * sizeof(float4)));
-            CK(cudaMalloc(&L.rq[i].od1, ctx->capRays * sizeof(float4)));
-            CK(cudaMalloc(&L.rq[i].bt, ctx->capRays * sizeof(float4)));
-            CK(cudaMalloc(&L.rq[i].smp, ctx->capRays * sizeof(uint32_t)));
+            CK(cudaMalloc(&L.rq[i].od0, cap * sizeof(float4)));
+            CK(cudaMalloc(&L.rq[i].od1, cap * sizeof(float4)));
+            CK(cudaMalloc(&L.rq[i].bt, cap * sizeof(float4)));
+            CK(cudaMalloc(&L.rq[i].smp, cap * sizeof(uint32_t)));
         }
-        CK(cudaMalloc(&L.hq.t, ctx->capRays * sizeof(double)));
-        CK(cudaMalloc(&L.hq.tInner, ctx->capRays * sizeof(double)));
-        CK(cudaMalloc(&L.hq.shape, ctx->capRays * sizeof(int32_t)));
-        CK(cudaMalloc(&L.hq.prim, ctx->capRays * sizeof(int32_t)));
+        CK(cudaMalloc(&L.hq.t, cap * sizeof(double)));
+        CK(cudaMalloc(&L.hq.tInner, cap * sizeof(double)));
+        CK(cudaMalloc(&L.hq.shape, cap * sizeof(int32_t)));
+        CK(cudaMalloc(&L.hq.prim, cap * sizeof(int32_t)));
+        L.capRays = cap;
     }
-    if (capShadow > L.capShadow) {
+    if (needShadow > L.capShadow) {
+        const uint64_t cap = pow2_at_least(needShadow);
         CK(cudaStreamSynchronize(L.stream));
         cudaFree(L.sq.so); cudaFree(L.sq.sd); cudaFree(L.sq.sc);
         L.sq = ShadowQueue{};
-        CK(cudaMalloc(&L.sq.so, capShadow * sizeof(float4)));
-        CK(cudaMalloc(&L.sq.sd, capShadow * sizeof(float4)));
-        CK(cudaMalloc(&L.sq.sc, capShadow * sizeof(float4)));
-        L.capShadow = capShadow;
+        L.capShadow = 0;
+        CK(cudaMalloc(&L.sq.so, cap * sizeof(float4)));
+        CK(cudaMalloc(&L.sq.sd, cap * sizeof(float4)));
+        CK(cudaMalloc(&L.sq.sc, cap * sizeof(float4)));
+        L.capShadow = cap;
     }
     return PTGPU_OK;
 }
@@ -1401,7 +1411,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     }
     uint64_t batch = ctx->capRays / maxGrow;
     if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's branching factor");
-    uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);  // sized for a full batch whatever this pass needs: allocated once
+    uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
     const uint64_t shadowCeil = ctx->capRays * 4;
     if (capShadow > shadowCeil) {  // shrink the batch so the shadow queue stays bounded
         batch = shadowCeil / (childGrow * (lightsPer ? lightsPer : 1));
@@ -1416,15 +1426,17 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     {
         const uint64_t per = (total + (uint64_t)lanesUsed - 1) / (uint64_t)lanesUsed;
         const uint64_t minBatch = 1ull << 18;
-        if (per < batch) batch = std::max<uint64_t>(per, std::min<uint64_t>(minBatch, batch));  // queues stay sized for the full batch
+        if (per < batch) batch = std::max<uint64_t>(per, std::min<uint64_t>(minBatch, batch));
         const uint64_t nBatches = (total + batch - 1) / batch;
         if (nBatches < (uint64_t)lanesUsed) lanesUsed = (int)nBatches;
     }
     int rc = PTGPU_OK;
     for (int k = 0; k < lanesUsed; k++) {
         Lane& L = ctx->lanes[k];
-        if ((rc = ensure_queues(ctx, L, capShadow)) != PTGPU_OK) return rc;
-        if (ctx->useSplit && (rc = ensure_split(ctx, L, std::max<uint64_t>(ctx->capRays, L.capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
+        // queues grow with the largest batch seen so far (powers of two), so a small pass does not allocate the full capacity
+        const uint64_t needShadow = std::max<uint64_t>(1, batch * childGrow * (lightsPer ? lightsPer : 1));
+        if ((rc = ensure_queues(ctx, L, batch * maxGrow, needShadow)) != PTGPU_OK) return rc;
+        if (ctx->useSplit && (rc = ensure_split(ctx, L, std::max<uint64_t>(L.capRays, L.capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
     }
     const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
     float ms = 0;
@@ -1464,8 +1476,8 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             }
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
-                                                   L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)ctx->capRays, (uint32_t)L.capShadow);
-            k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)ctx->capRays, counts + 3);
+                                                   L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow);
+            k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)L.capRays, counts + 3);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 2;
             if (lightsPer) {
