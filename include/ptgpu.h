@@ -202,8 +202,14 @@ int ptgpu_accumulate_device(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* d_sum
 /* Buffer.AddSample(x, y, sum/divisor) for every pixel; d_sum_rgb is a DEVICE pointer. */
 int ptgpu_add_sample_device(ptgpu_ctx* ctx, int32_t width, int32_t height, const float* d_sum_rgb, double divisor, void* stream);
 
-/* channel: 0 Color (Pixel.M), 1 Variance, 2 StandardDeviation, 3 Samples (Buffer.cs:8-16).  out: w*h*3 floats. */
+/* channel: 0 Color (Pixel.M), 1 Variance, 2 StandardDeviation, 3 Samples, 4 Albedo (Buffer.cs:240-282), 5 Normal
+ * (Buffer.cs:99-124, 222-233) — the Channel enum of Buffer.cs:8-16.  out: w*h*3 floats. */
 int ptgpu_read_buffer(ptgpu_ctx* ctx, int32_t channel, float* out_rgb);
+/* Exact FP64 copy of the Welford state (Pixel.M, Pixel.V, Pixel.Samples; Buffer.cs:18-58) out of / into the device: a
+ * checkpoint of a long IterativeRender loop (Example.cs:1696 runs 1000 iterations) and its resume.  Host pointers; any
+ * of M_rgb / V_rgb / samples may be NULL on export. */
+int ptgpu_export_buffer(ptgpu_ctx* ctx, int32_t* width, int32_t* height, double* M_rgb, double* V_rgb, int32_t* samples);
+int ptgpu_import_buffer(ptgpu_ctx* ctx, int32_t width, int32_t height, const double* M_rgb, const double* V_rgb, const int32_t* samples);
 int ptgpu_reset_buffer(ptgpu_ctx* ctx);
 
 /* Test hooks (same device functions the pipeline uses). */

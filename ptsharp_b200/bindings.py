@@ -58,7 +58,7 @@ PTGPU_SYMBOLS = [
     "ptgpu_abi_version", "ptgpu_create", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_upload_scene", "ptgpu_scene_bytes",
     "ptgpu_render_pass", "ptgpu_accumulate_device", "ptgpu_add_sample_device", "ptgpu_read_buffer", "ptgpu_reset_buffer",
     "ptgpu_intersect_batch", "ptgpu_cast_rays", "ptgpu_keyed_draw", "ptgpu_get_counters", "ptgpu_reset_counters",
-    "ptgpu_set_profiling",
+    "ptgpu_set_profiling", "ptgpu_export_buffer", "ptgpu_import_buffer",
 ]
 
 _gpu = None
@@ -85,6 +85,8 @@ def gpu_lib() -> C.CDLL:
         lib.ptgpu_add_sample_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p]
         lib.ptgpu_read_buffer.argtypes = [C.c_void_p, C.c_int32, c_float_p]
         lib.ptgpu_reset_buffer.argtypes = [C.c_void_p]
+        lib.ptgpu_export_buffer.argtypes = [C.c_void_p, c_int_p, c_int_p, c_double_p, c_double_p, c_int_p]
+        lib.ptgpu_import_buffer.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int_p]
         lib.ptgpu_intersect_batch.argtypes = [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p,
                                               c_float_p, c_float_p, c_int_p, c_int_p]
         lib.ptgpu_cast_rays.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_int32, c_int_p, c_int_p, c_double_p, c_double_p,
@@ -273,6 +275,21 @@ class Device:
         out = np.empty((height, width, 3), np.float32)
         self._ck(self.lib.ptgpu_read_buffer(self.h, channel, out.ctypes.data_as(c_float_p)), "ptgpu_read_buffer")
         return out
+
+    def export_buffer(self):
+        """Exact Welford state (M, V as float64 HxWx3, samples as int32 HxW): the checkpoint of an IterativeRender loop."""
+        w, h = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.ptgpu_export_buffer(self.h, C.byref(w), C.byref(h), None, None, None), "ptgpu_export_buffer")
+        M = np.empty((h.value, w.value, 3), np.float64); V = np.empty_like(M); n = np.empty((h.value, w.value), np.int32)
+        self._ck(self.lib.ptgpu_export_buffer(self.h, C.byref(w), C.byref(h), M.ctypes.data_as(c_double_p), V.ctypes.data_as(c_double_p),
+                                              n.ctypes.data_as(c_int_p)), "ptgpu_export_buffer")
+        return M, V, n
+
+    def import_buffer(self, M: np.ndarray, V: np.ndarray, samples: np.ndarray):
+        M = np.ascontiguousarray(M, np.float64); V = np.ascontiguousarray(V, np.float64); samples = np.ascontiguousarray(samples, np.int32)
+        h, w = samples.shape
+        self._ck(self.lib.ptgpu_import_buffer(self.h, w, h, M.ctypes.data_as(c_double_p), V.ctypes.data_as(c_double_p),
+                                              samples.ctypes.data_as(c_int_p)), "ptgpu_import_buffer")
 
     def reset_buffer(self):
         self._ck(self.lib.ptgpu_reset_buffer(self.h), "ptgpu_reset_buffer")

@@ -512,10 +512,37 @@ __global__ void k_add_sample(const float* __restrict__ sum, double divisor, uint
         }
     }
 }
-// Buffer.Color / Variance / StandardDeviation / Samples (Buffer.cs:46-57, 126-132)
-__global__ void k_read_buffer(PixelBuf pb, int channel, uint32_t npix, float* __restrict__ out) {
+// Buffer.Color / Variance / StandardDeviation / Samples (Buffer.cs:46-57, 126-132) and the two derived channels of
+// Buffer.Image: Albedo (CalculateAlbedo, Buffer.cs:240-282) and Normal (GetNormalAt / CalculateNormal, Buffer.cs:99-124, 222-233).
+PT_D double clamp01_net(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }  // Math.Clamp(v, 0, 1): NaN passes through
+__global__ void k_read_buffer(PixelBuf pb, int channel, int w, int h, float* __restrict__ out) {
+    const uint32_t npix = (uint32_t)w * (uint32_t)h;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         int32_t ns = pb.samples[i];
+        if (channel == 4) {  // color / max(r, g, b), clamped; NaN colour or zero maximum -> black
+            const double r = pb.M[(size_t)i * 3], g = pb.M[(size_t)i * 3 + 1], b = pb.M[(size_t)i * 3 + 2];
+            double o3[3] = {0, 0, 0};
+            if (!(r != r || g != g || b != b)) {
+                const double mx = netmax(netmax(r, g), b);
+                if (mx != 0) { o3[0] = clamp01_net(r / mx); o3[1] = clamp01_net(g / mx); o3[2] = clamp01_net(b / mx); }
+            }
+            for (int c = 0; c < 3; c++) out[(size_t)i * 3 + c] = (float)o3[c];
+            continue;
+        }
+        if (channel == 5) {  // Sobel-style differences of the neighbours' means; pixels outside the frame are `new Pixel()` (zero)
+            const int x = (int)(i % (uint32_t)w), y = (int)(i / (uint32_t)w);
+            auto M = [&](int xx, int yy, int c) -> double { return (xx < 0 || yy < 0 || xx >= w || yy >= h) ? 0.0 : pb.M[((size_t)yy * w + xx) * 3 + c]; };
+            double nx = (M(x - 1, y - 1, 0) + 2 * M(x - 1, y, 0) + M(x - 1, y + 1, 0) - M(x + 1, y - 1, 0) - 2 * M(x + 1, y, 0) - M(x + 1, y + 1, 0)) / 8.0;
+            double ny = (M(x - 1, y - 1, 1) + 2 * M(x, y - 1, 1) + M(x + 1, y - 1, 1) - M(x - 1, y + 1, 1) - 2 * M(x, y + 1, 1) - M(x + 1, y + 1, 1)) / 8.0;
+            double nz = 1.0;
+            const double length = sqrt(nx * nx + ny * ny + nz * nz);
+            nx /= length; ny /= length; nz /= length;
+            const V3 n = v3d(nx, ny, nz);  // new Vector(nx, ny, nz): FP32 storage
+            out[(size_t)i * 3] = (float)(((double)n.x + 1.0) * 0.5);
+            out[(size_t)i * 3 + 1] = (float)(((double)n.y + 1.0) * 0.5);
+            out[(size_t)i * 3 + 2] = n.z;
+            continue;
+        }
         for (int c = 0; c < 3; c++) {
             double v;
             if (channel == 0) v = pb.M[(size_t)i * 3 + c];
@@ -1617,18 +1644,44 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
 }
 
 int ptgpu_read_buffer(ptgpu_ctx* ctx, int32_t channel, float* out_rgb) {
-    if (!ctx || !out_rgb || channel < 0 || channel > 3) return PTGPU_E_ARG;
+    if (!ctx || !out_rgb || channel < 0 || channel > 5) return PTGPU_E_ARG;
     if (!ctx->dSum) return fail(ctx, PTGPU_E_STATE, "no pass rendered yet");
     CK(cudaSetDevice(ctx->device));
     size_t npix = (size_t)ctx->bufW * ctx->bufH;
     float* tmp = nullptr;
     CK(cudaMalloc(&tmp, npix * 3 * sizeof(float)));
-    k_read_buffer<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pb, channel, (uint32_t)npix, tmp);
+    k_read_buffer<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pb, channel, ctx->bufW, ctx->bufH, tmp);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(out_rgb, tmp, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(tmp);
     CK(e);
+    return PTGPU_OK;
+}
+
+// Exact copy of the Welford buffer out of / into the device (checkpoint and resume of an IterativeRender loop).
+int ptgpu_export_buffer(ptgpu_ctx* ctx, int32_t* width, int32_t* height, double* M_rgb, double* V_rgb, int32_t* samples) {
+    if (!ctx || !width || !height) return PTGPU_E_ARG;
+    if (!ctx->dSum) return fail(ctx, PTGPU_E_STATE, "no pass rendered yet");
+    CK(cudaSetDevice(ctx->device));
+    *width = ctx->bufW; *height = ctx->bufH;
+    const size_t npix = (size_t)ctx->bufW * ctx->bufH;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (M_rgb) CK(cudaMemcpy(M_rgb, ctx->pb.M, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (V_rgb) CK(cudaMemcpy(V_rgb, ctx->pb.V, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (samples) CK(cudaMemcpy(samples, ctx->pb.samples, npix * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return PTGPU_OK;
+}
+int ptgpu_import_buffer(ptgpu_ctx* ctx, int32_t width, int32_t height, const double* M_rgb, const double* V_rgb, const int32_t* samples) {
+    if (!ctx || width <= 1 || height <= 1 || !M_rgb || !V_rgb || !samples) return PTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_image(ctx, width, height);
+    if (rc != PTGPU_OK) return rc;
+    const size_t npix = (size_t)width * height;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->pb.M, M_rgb, npix * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->pb.V, V_rgb, npix * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->pb.samples, samples, npix * sizeof(int32_t), cudaMemcpyHostToDevice));
     return PTGPU_OK;
 }
 

@@ -326,3 +326,55 @@ def test_renderer_api_roundtrip(bindings, tmp_path):
     assert (hw.renderer_image(64, 48, 3) == 2).all()
     c = hw.renderer_counters()
     assert c["cameraSamples"] == 2 * 64 * 48 * 4 and c["kernelLaunches"] > 0
+
+
+def test_albedo_and_normal_channels(orc, bindings, device):
+    """Channel.AlbedoChannel / NormalChannel of Buffer.Image (Buffer.cs:99-124, 222-282) against the same formulas in numpy on
+    the exported FP64 means."""
+    hw, _, _ = _worlds(orc, bindings, "c1")
+    device.upload(hw)
+    device.reset_buffer()
+    W, H = 48, 40
+    for i in range(2):
+        device.render_pass(hw.make_pass(W, H, 2, pass_index=i), want_mean=False)
+    M, _, n = device.export_buffer()
+    assert M.shape == (H, W, 3) and (n == 2).all()
+    albedo = device.read_buffer(W, H, 4).astype(np.float64)
+    mx = M.max(axis=2, keepdims=True)
+    ref = np.where(mx != 0, np.clip(M / np.where(mx != 0, mx, 1), 0, 1), 0.0)
+    np.testing.assert_allclose(albedo, ref, rtol=2e-7, atol=1e-12)
+    normal = device.read_buffer(W, H, 5).astype(np.float64)
+    P = np.zeros((H + 2, W + 2, 3)); P[1:-1, 1:-1] = M  # pixels outside the frame are `new Pixel()`
+    r, g = P[..., 0], P[..., 1]
+    nx = (r[:-2, :-2] + 2 * r[1:-1, :-2] + r[2:, :-2] - r[:-2, 2:] - 2 * r[1:-1, 2:] - r[2:, 2:]) / 8.0
+    ny = (g[:-2, :-2] + 2 * g[:-2, 1:-1] + g[:-2, 2:] - g[2:, :-2] - 2 * g[2:, 1:-1] - g[2:, 2:]) / 8.0
+    ln = np.sqrt(nx * nx + ny * ny + 1.0)
+    refn = np.stack([(nx / ln + 1) * 0.5, (ny / ln + 1) * 0.5, 1.0 / ln], axis=2)
+    np.testing.assert_allclose(normal, refn, rtol=3e-7, atol=1e-7)
+
+
+def test_checkpoint_round_trip_and_resume(orc, bindings, device):
+    """ptgpu_export_buffer / ptgpu_import_buffer: the Welford state survives a round trip bit for bit and a resumed loop
+    continues counting from it."""
+    hw, _, _ = _worlds(orc, bindings, "c2")
+    device.upload(hw)
+    device.reset_buffer()
+    W, H = 40, 32
+    for i in range(3):
+        device.render_pass(hw.make_pass(W, H, 2, pass_index=i), want_mean=False)
+    M, V, n = device.export_buffer()
+    assert (n == 3).all() and np.isfinite(M).all() and (V >= 0).all()
+    other = bindings.Device(0)
+    try:
+        other.upload(hw)
+        other.import_buffer(M, V, n)
+        M2, V2, n2 = other.export_buffer()
+        assert np.array_equal(M2.view(np.int64), M.view(np.int64)) and np.array_equal(V2.view(np.int64), V.view(np.int64)) and np.array_equal(n2, n)
+        other.render_pass(hw.make_pass(W, H, 2, pass_index=3), want_mean=False)
+        device.render_pass(hw.make_pass(W, H, 2, pass_index=3), want_mean=False)
+        Ma, _, na = other.export_buffer()
+        Mb, _, nb = device.export_buffer()
+        assert (na == 4).all() and (nb == 4).all()
+        np.testing.assert_allclose(Ma, Mb, rtol=1e-4, atol=1e-6)  # same samples; only the float atomics' order differs
+    finally:
+        other.close()
