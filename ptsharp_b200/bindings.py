@@ -103,6 +103,8 @@ _HOST_EXTRA = {
     "last_error": (C.c_char_p, [C.c_void_p]),
     "flatten": (C.c_void_p, [C.c_void_p]),
     "flat_bytes": (C.c_uint64, [C.c_void_p]),
+    "save_flat": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "load_flat": (C.c_void_p, [C.c_void_p, C.c_char_p]),
     "make_pass": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.POINTER(Pass)]),
     "tree_stats": (C.c_int, [C.c_void_p, C.c_int, c_ll_p, c_float_p]),
     "tree_dump": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_double_p, c_int_p, c_int_p, c_int_p]),
@@ -154,6 +156,18 @@ class HostWorld(World):
         if not p:
             raise PtgpuError("flatten: " + self._err())
         self._flat = p
+        return p
+
+    def save_flat(self, path: str):
+        """Write the flattened scene (flatten() first) to a flat-scene file."""
+        if self.lib.pth_save_flat(self.h, os.fsencode(path)) != 0:
+            raise RuntimeError(self._err())
+
+    def load_flat(self, path: str) -> int:
+        """Replace this world's flat scene by the one in `path`; returns the ptgpu_flat_scene pointer for Device.upload_flat."""
+        p = self.lib.pth_load_flat(self.h, os.fsencode(path))
+        if not p:
+            raise RuntimeError(self._err())
         return p
 
     def flat_bytes(self) -> int:

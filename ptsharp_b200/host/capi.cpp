@@ -109,6 +109,20 @@ const ptgpu_flat_scene* pth_flatten(pth_world* w) {
     } catch (const std::exception& e) { w->error = e.what(); return nullptr; }
 }
 uint64_t pth_flat_bytes(pth_world* w) { return w->flat ? w->flat->Bytes() : 0; }
+// Flat-scene file I/O (SaveFlatScene / LoadFlatScene).  Load replaces the world's flat scene and returns its view.
+int pth_save_flat(pth_world* w, const char* path) {
+    try {
+        if (!w->flat) throw std::runtime_error("flatten the scene first");
+        SaveFlatScene(*w->flat, path);
+        return 0;
+    } catch (const std::exception& e) { w->error = e.what(); return -1; }
+}
+const ptgpu_flat_scene* pth_load_flat(pth_world* w, const char* path) {
+    try {
+        w->flat = LoadFlatScene(path);
+        return &w->flat->view;
+    } catch (const std::exception& e) { w->error = e.what(); return nullptr; }
+}
 // Fill a ptgpu_pass from the world's camera and sampler.
 void pth_make_pass(pth_world* w, int width, int height, int spp, int stratified, unsigned seed, unsigned passIndex, int sampleBase,
                    int sampleStride, ptgpu_pass* out) {

@@ -631,6 +631,92 @@ void Camera::SetFocus(const Vector& focalPoint, double aperture) {  // Camera.cs
 }
 
 // ---------------------------------------------------------------------------------------------------- flattener
+void FlatScene::Bind(uint32_t sceneTree, uint32_t numSceneShapes) {
+    ptgpu_flat_scene& v = view;
+    const double env[3] = {v.envColor[0], v.envColor[1], v.envColor[2]};
+    const int32_t envTex = v.envTexture;
+    const double envAngle = v.envTextureAngle;
+    std::memset(&v, 0, sizeof(v));
+    v.abiVersion = PTGPU_ABI_VERSION;
+    v.sceneTree = sceneTree;
+    v.numSceneShapes = numSceneShapes;
+    v.numShapes = (uint32_t)shapes.size(); v.shapes = shapes.data();
+    v.numLights = (uint32_t)lights.size(); v.lights = lights.data();
+    v.numTrees = (uint32_t)trees.size(); v.trees = trees.data();
+    v.numNodes = nodes.size(); v.nodes = nodes.data();
+    v.numLeafItems = leafItems.size(); v.leafItems = leafItems.data();
+    v.numSpheres = (uint32_t)spheres.size(); v.spheres = spheres.data();
+    v.numCubes = (uint32_t)cubes.size(); v.cubes = cubes.data();
+    v.numPlanes = (uint32_t)planes.size(); v.planes = planes.data();
+    v.numCylinders = (uint32_t)cylinders.size(); v.cylinders = cylinders.data();
+    v.numMeshes = (uint32_t)meshes.size(); v.meshes = meshes.data();
+    v.numTriangles = triGeom.size(); v.triGeom = triGeom.data(); v.triShade = triShade.data();
+    v.numInstances = (uint32_t)instances.size(); v.instances = instances.data();
+    v.numSdfShapes = (uint32_t)sdfShapes.size(); v.sdfShapes = sdfShapes.data();
+    v.numSdfOps = (uint32_t)sdfOps.size(); v.sdfOps = sdfOps.data();
+    v.numVolumes = (uint32_t)volumes.size(); v.volumes = volumes.data();
+    v.numVolumeWindows = (uint32_t)volumeWindows.size(); v.volumeWindows = volumeWindows.data();
+    v.numVolumeData = volumeData.size(); v.volumeData = volumeData.data();
+    v.numMaterials = (uint32_t)materials.size(); v.materials = materials.data();
+    v.numTextures = (uint32_t)textures.size(); v.textures = textures.data();
+    v.numTexels = texels.size() / 4; v.texels = texels.data();
+    v.envColor[0] = env[0]; v.envColor[1] = env[1]; v.envColor[2] = env[2];
+    v.envTexture = envTex; v.envTextureAngle = envAngle;
+}
+
+// Flat-scene file: "PTFS", format version, ABI version, the scalar header, then the 21 arrays in header
+// order as (u64 count, u32 element size, bytes).  Little-endian, the in-memory layout of include/ptgpu.h.
+namespace {
+constexpr uint32_t kFlatMagic = 0x53465450u, kFlatFormat = 1;
+template <class T> void put_vec(std::FILE* f, const std::vector<T>& v) {
+    const uint64_t n = v.size(); const uint32_t es = (uint32_t)sizeof(T);
+    if (std::fwrite(&n, 8, 1, f) != 1 || std::fwrite(&es, 4, 1, f) != 1 || (n && std::fwrite(v.data(), sizeof(T), n, f) != n)) throw std::runtime_error("flat scene: write failed");
+}
+template <class T> void get_vec(std::FILE* f, std::vector<T>& v) {
+    uint64_t n = 0; uint32_t es = 0;
+    if (std::fread(&n, 8, 1, f) != 1 || std::fread(&es, 4, 1, f) != 1) throw std::runtime_error("flat scene: truncated file");
+    if (es != sizeof(T)) throw std::runtime_error("flat scene: element size mismatch (written by another ABI)");
+    v.resize(n);
+    if (n && std::fread(v.data(), sizeof(T), n, f) != n) throw std::runtime_error("flat scene: truncated file");
+}
+template <class F> void each_array(FlatScene& s, F&& fn) {
+    fn(s.shapes); fn(s.lights); fn(s.trees); fn(s.nodes); fn(s.leafItems); fn(s.spheres); fn(s.cubes); fn(s.planes); fn(s.cylinders); fn(s.meshes);
+    fn(s.triGeom); fn(s.triShade); fn(s.instances); fn(s.sdfShapes); fn(s.sdfOps); fn(s.volumes); fn(s.volumeWindows); fn(s.volumeData);
+    fn(s.materials); fn(s.textures); fn(s.texels);
+}
+}  // namespace
+void SaveFlatScene(const FlatScene& scene, const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("flat scene: cannot open " + path);
+    try {
+        const ptgpu_flat_scene& v = scene.view;
+        const uint32_t head[5] = {kFlatMagic, kFlatFormat, (uint32_t)PTGPU_ABI_VERSION, v.sceneTree, v.numSceneShapes};
+        const double env[4] = {v.envColor[0], v.envColor[1], v.envColor[2], v.envTextureAngle};
+        const int32_t envTex = v.envTexture;
+        if (std::fwrite(head, 4, 5, f) != 5 || std::fwrite(env, 8, 4, f) != 4 || std::fwrite(&envTex, 4, 1, f) != 1) throw std::runtime_error("flat scene: write failed");
+        each_array(const_cast<FlatScene&>(scene), [&](auto& vec) { put_vec(f, vec); });
+    } catch (...) { std::fclose(f); throw; }
+    std::fclose(f);
+}
+std::unique_ptr<FlatScene> LoadFlatScene(const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("flat scene: cannot open " + path);
+    auto fs = std::make_unique<FlatScene>();
+    try {
+        uint32_t head[5]; double env[4]; int32_t envTex;
+        if (std::fread(head, 4, 5, f) != 5 || std::fread(env, 8, 4, f) != 4 || std::fread(&envTex, 4, 1, f) != 1) throw std::runtime_error("flat scene: truncated file");
+        if (head[0] != kFlatMagic) throw std::runtime_error("flat scene: bad magic");
+        if (head[1] != kFlatFormat || head[2] != (uint32_t)PTGPU_ABI_VERSION) throw std::runtime_error("flat scene: format / ABI version mismatch");
+        each_array(*fs, [&](auto& vec) { get_vec(f, vec); });
+        if (fs->triShade.size() != fs->triGeom.size()) throw std::runtime_error("flat scene: triangle arrays differ in length");
+        fs->view.envColor[0] = env[0]; fs->view.envColor[1] = env[1]; fs->view.envColor[2] = env[2];
+        fs->view.envTextureAngle = env[3]; fs->view.envTexture = envTex;
+        fs->Bind(head[3], head[4]);
+    } catch (...) { std::fclose(f); throw; }
+    std::fclose(f);
+    return fs;
+}
+
 uint64_t FlatScene::Bytes() const {
     auto sz = [](const auto& v) { return (uint64_t)v.size() * sizeof(v[0]); };
     return sz(shapes) + sz(lights) + sz(trees) + sz(nodes) + sz(leafItems) + sz(spheres) + sz(cubes) + sz(planes) + sz(cylinders) +
@@ -794,31 +880,8 @@ std::unique_ptr<FlatScene> Flatten(const Scene& scene) {
         for (size_t i = 0; i < n; i++)
             if (scene.Shapes[i] == l) { f.lights.push_back((uint32_t)i); break; }
     uint32_t sceneTree = fl.AddTree(*scene.tree, 0);
+    f.Bind(sceneTree, (uint32_t)n);
     ptgpu_flat_scene& v = f.view;
-    std::memset(&v, 0, sizeof(v));
-    v.abiVersion = PTGPU_ABI_VERSION;
-    v.sceneTree = sceneTree;
-    v.numSceneShapes = (uint32_t)n;
-    v.numShapes = (uint32_t)f.shapes.size(); v.shapes = f.shapes.data();
-    v.numLights = (uint32_t)f.lights.size(); v.lights = f.lights.data();
-    v.numTrees = (uint32_t)f.trees.size(); v.trees = f.trees.data();
-    v.numNodes = f.nodes.size(); v.nodes = f.nodes.data();
-    v.numLeafItems = f.leafItems.size(); v.leafItems = f.leafItems.data();
-    v.numSpheres = (uint32_t)f.spheres.size(); v.spheres = f.spheres.data();
-    v.numCubes = (uint32_t)f.cubes.size(); v.cubes = f.cubes.data();
-    v.numPlanes = (uint32_t)f.planes.size(); v.planes = f.planes.data();
-    v.numCylinders = (uint32_t)f.cylinders.size(); v.cylinders = f.cylinders.data();
-    v.numMeshes = (uint32_t)f.meshes.size(); v.meshes = f.meshes.data();
-    v.numTriangles = f.triGeom.size(); v.triGeom = f.triGeom.data(); v.triShade = f.triShade.data();
-    v.numInstances = (uint32_t)f.instances.size(); v.instances = f.instances.data();
-    v.numSdfShapes = (uint32_t)f.sdfShapes.size(); v.sdfShapes = f.sdfShapes.data();
-    v.numSdfOps = (uint32_t)f.sdfOps.size(); v.sdfOps = f.sdfOps.data();
-    v.numVolumes = (uint32_t)f.volumes.size(); v.volumes = f.volumes.data();
-    v.numVolumeWindows = (uint32_t)f.volumeWindows.size(); v.volumeWindows = f.volumeWindows.data();
-    v.numVolumeData = f.volumeData.size(); v.volumeData = f.volumeData.data();
-    v.numMaterials = (uint32_t)f.materials.size(); v.materials = f.materials.data();
-    v.numTextures = (uint32_t)f.textures.size(); v.textures = f.textures.data();
-    v.numTexels = f.texels.size() / 4; v.texels = f.texels.data();
     v.envColor[0] = scene.Color.r; v.envColor[1] = scene.Color.g; v.envColor[2] = scene.Color.b;
     v.envTexture = fl.TextureId(scene.Texture);
     if (v.envTexture >= 0) {  // TextureId may have grown the arrays

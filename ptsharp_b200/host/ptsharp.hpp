@@ -284,14 +284,18 @@ struct FlatScene {
     std::vector<float> texels;
     ptgpu_flat_scene view{};
     uint64_t Bytes() const;
+    void Bind(uint32_t sceneTree, uint32_t numSceneShapes);  // point `view` at the vectors (keeps the env fields)
 };
+// Flat-scene file: what a .NET box running the real PTSharp would dump for this GPU-only harness, and the reverse.
+void SaveFlatScene(const FlatScene& scene, const std::string& path);
+std::unique_ptr<FlatScene> LoadFlatScene(const std::string& path);
 // Scene must be Compile()d.  Throws std::runtime_error on unsupported graphs (nested TransformedShape, ...).
 std::unique_ptr<FlatScene> Flatten(const Scene& scene);
 ptgpu_camera FlattenCamera(const Camera& c);
 
 // ---- render driver ---------------------------------------------------------------------------------------------------
 // Buffer.cs channels, read back from the device-resident buffer.
-enum Channel { ColorChannel = 0, VarianceChannel = 1, StandardDeviationChannel = 2, SamplesChannel = 3 };
+enum Channel { ColorChannel = 0, VarianceChannel = 1, StandardDeviationChannel = 2, SamplesChannel = 3, AlbedoChannel = 4, NormalChannel = 5 };
 
 class Renderer {  // Renderer.cs:15-56, 199-338, 702-765
 public:

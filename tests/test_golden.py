@@ -96,3 +96,28 @@ def test_device_matches_golden_replay(bindings, name):
     rel = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
     assert (rel > 1e-4).mean() < 2e-3, f"{(rel > 1e-4).mean():.4f} of the pixels differ"
     assert abs(cnt["segments"] - int(g["segments"])) <= max(2, int(g["segments"]) // 1000)
+
+
+@pytest.mark.gpu
+def test_device_matches_golden_through_flat_file(bindings, tmp_path):
+    """Scene -> flat-scene file -> another process' world -> device: same hits as the committed vectors (the route a .NET
+    box dumping PTSharp scenes for this library would take)."""
+    g = _load("c3")
+    builder, kw = CASES["c3"]
+    hw = bindings.HostWorld()
+    builder(hw, **kw)
+    hw.flatten()
+    path = str(tmp_path / "c3.ptfs")
+    hw.save_flat(path)
+    other = bindings.HostWorld()
+    flat = other.load_flat(path)
+    dev = bindings.Device(0)
+    try:
+        dev.upload_flat(flat)
+        h = dev.intersect_batch(g["o"], g["d"])
+    finally:
+        dev.close()
+    hit = g["shape"] >= 0
+    np.testing.assert_array_equal(h["shape"], g["shape"])
+    np.testing.assert_array_equal(h["prim"], g["prim"])
+    np.testing.assert_array_equal(h["t"][hit].view(np.int64), g["t"][hit].view(np.int64))
