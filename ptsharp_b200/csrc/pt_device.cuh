@@ -24,6 +24,9 @@
 #ifndef PT_PREFETCH
 #define PT_PREFETCH 0
 #endif
+#ifndef PT_LEAF_PIPELINE
+#define PT_LEAF_PIPELINE 0
+#endif
 #ifndef PT_SHORTCUT
 #define PT_SHORTCUT 1
 #endif
@@ -254,8 +257,9 @@ PT_D double triangle_intersect_exact(V3 v1, V3 e1, V3 e2, V3 o, V3 d) {
 //   u + v > 1    <=>  (a + b) / det > 1                       unless a + b is within 1e-13 relative of det
 //   t < EPS      <=>  c / det < 1e-9                          unless within 1e-13 relative of it
 // and the excluded borderline cases (a == det, near-equalities) are sent to the exact sequence above.
-PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) {
-    const float4 A = __ldg(g), B4 = __ldg(g + 1), C4 = __ldg(g + 2);
+PT_D double triangle_intersect_regs(float4 A, float4 B4, float4 C4, V3 o, V3 d);
+PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) { return triangle_intersect_regs(__ldg(g), __ldg(g + 1), __ldg(g + 2), o, d); }
+PT_D double triangle_intersect_regs(float4 A, float4 B4, float4 C4, V3 o, V3 d) {
     const V3 v1 = v3(A.x, A.y, A.z), e1 = v3(B4.x, B4.y, B4.z), e2 = v3(C4.x, C4.y, C4.z);
     // all four FP32 dot products up front (a warp pays for its slowest lane anyway), then one decision
     const V3 h = vcross(d, e2);
@@ -739,6 +743,28 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& 
 // The triangles [tPos, tEnd) of a micro leaf, at most `budget` of them.  Triangles are stored in sorted order, and the
 // reference keeps the FIRST shape in array order among equal T (Tree.cs:122), hence the position tie-break.
 PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, double& best, int32_t& prim, uint32_t& bestPos, int budget) {
+#if PT_LEAF_PIPELINE
+    // software pipeline: the next triangle's three quads are in flight while this one is tested (the tests of a micro leaf are
+    // otherwise four serialised memory round trips)
+    if (!(tPos < tEnd) || budget <= 0) return;
+    const float4* g = S.leafGeom + (size_t)tPos * 3;
+    float4 A = __ldg(g), B4 = __ldg(g + 1), C4 = __ldg(g + 2);
+#pragma unroll 1
+    for (int k = 0; k < budget && tPos < tEnd; k++) {
+        const bool more = tPos + 1 < tEnd && k + 1 < budget;
+        float4 nA = A, nB = B4, nC = C4;
+        if (more) { nA = __ldg(g + 3); nB = __ldg(g + 4); nC = __ldg(g + 5); }
+        DBG_ADD(4, 1);
+        const double t = triangle_intersect_regs(A, B4, C4, o, d);
+        if (t <= best && t < kHitInf) {  // rare (a T of INF never replaces NoHit)
+            const uint32_t pos = __float_as_uint(B4.w);
+            if (t < best || pos < bestPos) { best = t; prim = (int32_t)__float_as_uint(A.w); bestPos = pos; }
+        }
+        A = nA; B4 = nB; C4 = nC;
+        g += 3;
+        tPos++;
+    }
+#else
 #pragma unroll 1
     for (int k = 0; k < budget && tPos < tEnd; k++) {
         const float4* g = S.leafGeom + (size_t)tPos * 3;
@@ -750,6 +776,7 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
         }
         tPos++;
     }
+#endif
 }
 
 // The analytic subset (the split tracer is only used for scenes without SDFShape / Volume).
