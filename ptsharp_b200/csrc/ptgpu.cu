@@ -733,7 +733,8 @@ struct ptgpu_ctx {
     cudaStream_t stream = nullptr;
     std::string error;
     // scene
-    std::vector<void*> sceneAllocs;
+    std::vector<std::pair<void*, uint64_t>> sceneAllocs;   // (pointer, bytes) of the resident scene
+    std::vector<std::pair<void*, uint64_t>> scenePool;     // buffers of the previous scene, reused by the next upload of similar size
     DScene scene{};
     DLight* dLights = nullptr;
     bool haveScene = false;
@@ -782,25 +783,51 @@ static int fail(ptgpu_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
+// Scene buffers come from a small pool: re-uploading a scene of the same shape (a new frame of an animation, bench.py's
+// end-to-end step) reuses the previous allocations; cudaMalloc / cudaFree next to tens of GB of queues cost 0.2-1.5 s.
+static int scene_alloc(ptgpu_ctx* ctx, uint64_t bytes, void** out) {
+    int best = -1;
+    for (size_t i = 0; i < ctx->scenePool.size(); i++) {
+        const uint64_t b = ctx->scenePool[i].second;
+        if (b >= bytes && b <= bytes + bytes / 4 + 4096 && (best < 0 || b < ctx->scenePool[best].second)) best = (int)i;
+    }
+    if (best >= 0) {
+        *out = ctx->scenePool[best].first;
+        ctx->sceneAllocs.push_back(ctx->scenePool[best]);
+        ctx->scenePool.erase(ctx->scenePool.begin() + best);
+        return PTGPU_OK;
+    }
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    ctx->sceneAllocs.push_back({p, bytes});
+    *out = p;
+    return PTGPU_OK;
+}
 template <class T>
 static int upload(ptgpu_ctx* ctx, const T* host, uint64_t count, const T** dev) {
     *dev = nullptr;
     uint64_t bytes = (count ? count : 1) * sizeof(T);
     void* p = nullptr;
-    CK(cudaMalloc(&p, bytes));
-    ctx->sceneAllocs.push_back(p);
+    int rc = scene_alloc(ctx, bytes, &p);
+    if (rc != PTGPU_OK) return rc;
     ctx->sceneBytes += count * sizeof(T);
     if (count) CK(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     *dev = reinterpret_cast<const T*>(p);
     return PTGPU_OK;
 }
 
-static void free_scene(ptgpu_ctx* ctx) {
-    for (void* p : ctx->sceneAllocs) cudaFree(p);
+// The resident scene's buffers go to the pool (release = true: to the driver).
+static void free_scene(ptgpu_ctx* ctx, bool release = false) {
+    for (auto& a : ctx->sceneAllocs) ctx->scenePool.push_back(a);
     ctx->sceneAllocs.clear();
+    if (release) { for (auto& a : ctx->scenePool) cudaFree(a.first); ctx->scenePool.clear(); }
     ctx->haveScene = false;
     ctx->sceneBytes = 0;
     ctx->dLights = nullptr;
+}
+static void trim_scene_pool(ptgpu_ctx* ctx) {  // after an upload: what the new scene did not reuse goes back to the driver
+    for (auto& a : ctx->scenePool) cudaFree(a.first);
+    ctx->scenePool.clear();
 }
 static void free_split(Lane& L) {
     SplitState& W = L.split;
@@ -965,7 +992,7 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_scene(ctx);
+    free_scene(ctx, true);
     free_queues(ctx);
     free_image(ctx);
     for (int k = 0; k < kMaxLanes; k++) {
@@ -988,7 +1015,7 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
     if (!ctx || !s) return PTGPU_E_ARG;
     if (s->abiVersion != PTGPU_ABI_VERSION) return fail(ctx, PTGPU_E_ARG, "flat scene ABI version mismatch");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaDeviceSynchronize());  // every lane idle: the previous scene's buffers are reused, not freed
     free_scene(ctx);
     // limits the kernels were compiled with
     for (uint32_t i = 0; i < s->numTrees; i++) {
@@ -1340,6 +1367,7 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
             cudaGetLastError();
         }
     }
+    trim_scene_pool(ctx);
     ctx->haveScene = true;
     return PTGPU_OK;
 }
