@@ -35,7 +35,7 @@ def build_gpu(force=False, verbose=False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libptgpu.so")
     srcs = [os.path.join(PKG, "csrc", "ptgpu.cu"), os.path.join(PKG, "csrc", "pt_device.cuh"),
-            os.path.join(ROOT, "include", "ptgpu.h")]
+            os.path.join(PKG, "csrc", "mesh_derive.hpp"), os.path.join(ROOT, "include", "ptgpu.h")]
     if force or _newer(srcs, out):
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0]]
         subprocess.check_call(cmd)

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "../../include/ptgpu.h"
+#include "mesh_derive.hpp"
 
 #define PT_D __device__ __forceinline__
 #define PT_HD __host__ __device__ __forceinline__
@@ -602,21 +603,54 @@ PT_D bool tree_box_maybe_hit(const ptgpu_tree& t, V3 o, const RayAux& ra) {
     return box_line_hit(t.bmin[0] - p, t.bmin[1] - p, t.bmin[2] - p, t.bmax[0] + p, t.bmax[1] + p, t.bmax[2] + p, o, ra);
 }
 
+PT_D uint4 stk_entry(double ts, uint32_t node, uint32_t culled) { return make_uint4((uint32_t)__double2loint(ts), (uint32_t)__double2hiint(ts), node, culled); }
+
+// Where the 16-byte stack entries live.  PtrStack: a plain array (local memory, or the per-ray global array of the scene level).
+struct PtrStack {
+    uint4* p;
+    PT_D uint4 get(int i) const { return p[i]; }
+    PT_D void put(int i, const uint4& v) { p[i] = v; }
+    PT_D void reset() {}
+    PT_D void shrink(int) {}
+};
+// HybridStack<N>: the top (up to) N entries in shared memory, older ones spilled to the thread's local array.  ncu on the
+// all-local version of k_mesh: the interleaved local layout turns one lane's 16-byte entry into four 4-byte sector touches, the
+// stack made 52 % of the kernel's L1 sector traffic and 40 % of its pops missed L1 (a pop is on the ray's critical path).
+// Invariant: entry j lives in shared slot j % N for lo < j <= sp (sp - lo <= N), in loc[j] for j <= lo.
+template <int N>
+struct HybridStack {
+    uint4* sh;      // this thread's slot 0; slots are `stride` uint4 apart (one row of the block per slot)
+    uint4* loc;
+    int stride;
+    int lo;
+    PT_D uint4 get(int i) const { return i > lo ? sh[(i % N) * stride] : loc[i]; }
+    PT_D void put(int i, const uint4& v) {  // i == sp + 1 (push) or 0 after reset()
+        if (i - lo > N) { loc[lo + 1] = sh[((lo + 1) % N) * stride]; lo++; }
+        sh[(i % N) * stride] = v;
+    }
+    PT_D void reset() { lo = -1; }
+    PT_D void shrink(int sp) { lo = min(lo, sp); }  // after pops: keeps sp - lo >= 0 so a later push lands above lo
+};
+
 // Resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
-PT_D bool mesh_pop(KdCursor& c, double bestT, const uint4* stk) {
+template <class Stk>
+PT_D bool mesh_pop_t(KdCursor& c, double bestT, Stk& stk) {
     while (c.sp > 0) {
-        const uint4 e = stk[c.sp];
+        const uint4 e = stk.get(c.sp);
         --c.sp;
         const double ts = stk_t(e);
         if (bestT <= ts) continue;  // `if (h1.T <= tsplit) return h1`
         if (e.w) continue;          // its Node.Intersect returns NoHit
         c.node = e.z;
         c.tmin = ts;
-        c.tmax = netmin(stk_t(stk[c.sp]), bestT);
+        c.tmax = netmin(stk_t(stk.get(c.sp)), bestT);
+        stk.shrink(c.sp);
         return true;
     }
+    stk.shrink(0);
     return false;
 }
+PT_D bool mesh_pop(KdCursor& c, double bestT, uint4* stk) { PtrStack ps{stk}; return mesh_pop_t(c, bestT, ps); }
 
 // Node.Intersect step on Scene.tree (16-byte reference nodes, no culling) with the 16-byte stack.
 PT_D int scene_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 d, uint4* stk, int stackEnt, uint32_t& leafFirst, uint32_t& leafCount) {
@@ -661,13 +695,7 @@ __device__ unsigned long long g_dbg[8];  // 0 items, 1 real steps, 2 virtual ste
 #define DBG_ADD(i, v)
 #endif
 enum { MESH_INTERIOR = 0, MESH_LEAF = 1, MESH_DONE = 2 };
-static constexpr uint32_t kNodeVirtual = 0x80000000u, kNodeRefLeaf = 0x40000000u, kNodeIndexMask = 0x3FFFFFFFu;
-// A child reference (30 bits) is either a node index (< 2^29) or a micro leaf named in place, saving the round trip
-// to a record that would only hold (first, count):  bit 29 = 1 | bit 28 = root of a reference leaf | bits 27:26 = count - 1
-// | bits 25:0 = first triangle in leafGeom.
-static constexpr uint32_t kRefLeaf = 1u << 29, kRefLeafRoot = 1u << 28, kRefFirstMask = (1u << 26) - 1u;
-PT_HD uint32_t leaf_ref(uint32_t first, uint32_t count, bool root) { return kRefLeaf | (root ? kRefLeafRoot : 0u) | ((count - 1u) << 26) | first; }
-static constexpr int kVirtualDepthMax = 12;  // levels of bounds-only nodes below a reference leaf (4 * 2^12 triangles)
+// record layout constants (kNodeVirtual, kNodeRefLeaf, kRefLeaf, leaf_ref, kVirtualDepthMax ...): mesh_derive.hpp
 static constexpr int kMeshStackEnt = kMeshStack + kVirtualDepthMax + 1;
 
 // One step at c.node (whose bounds are known to be hit).  Node records (4 x uint4, q0 = {split, a, b}):
@@ -677,8 +705,9 @@ static constexpr int kMeshStackEnt = kMeshStack + kVirtualDepthMax + 1;
 //   micro leaf          no record: named in the parent's child reference (leaf_ref)
 // kNodeRefLeaf / kRefLeafRoot mark the root of a reference leaf (where the tie-break position restarts).
 // MESH_LEAF: triangles [tFirst, tFirst + tCount).
-PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
-                   uint32_t& tCount) {
+template <class Stk>
+PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& c, V3 o, V3 d, Stk& stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
+                     uint32_t& tCount) {
     if (c.node & kRefLeaf) {
         if (c.node & kRefLeafRoot) bestPos = 0;
         tFirst = c.node & kRefFirstMask; tCount = ((c.node >> 26) & 3u) + 1u;
@@ -712,7 +741,7 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& 
         const bool leftNear = !(tnR < tnL);
         const uint32_t nearC = leftNear ? left : right, farC = leftNear ? right : left;
         const bool hitNear = leftNear ? hitL : hitR, hitFar = leftNear ? hitR : hitL;
-        if (hitNear && hitFar) { c.sp++; stk_put(stk + c.sp, (double)(leftNear ? tnR : tnL), farC, 0u); }
+        if (hitNear && hitFar) { c.sp++; stk.put(c.sp, stk_entry((double)(leftNear ? tnR : tnL), farC, 0u)); }
         c.node = hitNear ? nearC : farC;
         go = hitNear || hitFar;
     } else {
@@ -730,14 +759,19 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& 
             else { c.node = second; c.tmin = tsplit; c.tmax = netmin(c.tmax, bestT); go = true; }
         } else {
             c.sp++;
-            stk_put(stk + c.sp, tsplit, second, hitSecond ? 0u : 1u);
+            stk.put(c.sp, stk_entry(tsplit, second, hitSecond ? 0u : 1u));
             c.node = first;
             c.tmax = tsplit;
             go = hitFirst;
         }
     }
     if (go) return MESH_INTERIOR;
-    return mesh_pop(c, bestT, stk) ? MESH_INTERIOR : MESH_DONE;
+    return mesh_pop_t(c, bestT, stk) ? MESH_INTERIOR : MESH_DONE;
+}
+PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& c, V3 o, V3 d, uint4* stk, double bestT, uint32_t& bestPos, uint32_t& tFirst,
+                   uint32_t& tCount) {
+    PtrStack ps{stk};
+    return mesh_step_t(nodes, ra, c, o, d, ps, bestT, bestPos, tFirst, tCount);
 }
 
 // The triangles [tPos, tEnd) of a micro leaf, at most `budget` of them.  Triangles are stored in sorted order, and the
@@ -1165,14 +1199,22 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
 }
 
 // Mesh.Intersect for every work item of `q`; the Hit goes to W.mBest / W.mPrim of the item's ray.
-PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
+#ifndef PT_SMEM_STACK
+#define PT_SMEM_STACK 0   // entries of the walk's kd stack kept in shared memory per thread (0 = all in local memory)
+#endif
+PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor, uint4* smem) {
     const uint32_t n = *q.count;
     int st = ST_IDLE;
     uint32_t ray = 0;
     V3 co = v3(0, 0, 0), cd = v3(0, 0, 1);
     RayBox ra = ray_box(co, cd);
     KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
-    uint4 mStk[kMeshStackEnt];
+    uint4 mLoc[kMeshStackEnt];
+#if PT_SMEM_STACK > 0
+    HybridStack<PT_SMEM_STACK> mStk{smem + threadIdx.x, mLoc, (int)blockDim.x, -1};
+#else
+    PtrStack mStk{mLoc};
+#endif
     uint32_t tPos = 0, tEnd = 0, mBestPos = 0;
     double mBest = kHitInf;
     int32_t mPrim = -1;
@@ -1202,7 +1244,8 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     dbgRoot = mc.node;
                     DBG_ADD(0, 1);
 #endif
-                    stk_put(mStk, mc.tmax, 0u, 0u);
+                    mStk.reset();
+                    mStk.put(0, stk_entry(mc.tmax, 0u, 0u));
                     mBest = kHitInf; mPrim = -1; mBestPos = 0;
                     st = ST_MESH_NODE;
                 }
@@ -1214,7 +1257,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                 if (k > 0 && __popc(__ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE)) < PT_BURST_VOTE) break;
                 if (st == ST_MESH_NODE) {
                     uint32_t first, count;
-                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
+                    const int r = mesh_step_t(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
                     if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
                     else if (r == MESH_DONE) st = ST_MESH_DONE;
                 }
@@ -1224,7 +1267,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 #pragma unroll 1
                 for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
                     uint32_t first, count;
-                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
+                    const int r = mesh_step_t(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
 #ifdef PT_DEBUG_STEPS
                     dbgSteps++;
 #endif
@@ -1242,7 +1285,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 #endif
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
                 if (tPos >= tEnd) {
-                    st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
+                    st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
                     if (st == ST_MESH_NODE) prefetch_node(S.meshNodes, mc.node);
                 }
             }

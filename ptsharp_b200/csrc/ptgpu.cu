@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -482,11 +483,13 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
 #ifndef PT_MESH_WARPS_PER_SM
 #define PT_MESH_WARPS_PER_SM 40
 #endif
+static constexpr size_t kMeshSmemBytes = (size_t)PT_SMEM_STACK * PT_MESH_BLOCK * sizeof(uint4);
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
 #if PT_MESH_RAYS == 2
     mesh_walk2(S, W, q, cursor);
 #else
-    mesh_walk(S, W, q, cursor);
+    extern __shared__ uint4 smemStack[];  // PT_SMEM_STACK rows of blockDim.x entries
+    mesh_walk(S, W, q, cursor, smemStack);
 #endif
 }
 
@@ -734,6 +737,9 @@ struct ptgpu_ctx {
     std::string error;
     // scene
     std::vector<std::pair<void*, uint64_t>> sceneAllocs;   // (pointer, bytes) of the resident scene
+    std::vector<std::pair<void*, uint64_t>> stage;         // pinned host staging buffers (pointer, capacity), reused across uploads
+    size_t stageNext = 0;
+    double deriveMs = 0;                                   // host time of the last derive_mesh
     std::vector<std::pair<void*, uint64_t>> scenePool;     // buffers of the previous scene, reused by the next upload of similar size
     DScene scene{};
     DLight* dLights = nullptr;
@@ -802,6 +808,21 @@ static int scene_alloc(ptgpu_ctx* ctx, uint64_t bytes, void** out) {
     ctx->sceneAllocs.push_back({p, bytes});
     *out = p;
     return PTGPU_OK;
+}
+// Pinned host staging, slot by slot in request order (the same scene shape asks for the same sizes again).
+static void* stage_alloc(ptgpu_ctx* ctx, uint64_t bytes) {
+    const size_t slot = ctx->stageNext++;
+    if (slot >= ctx->stage.size()) ctx->stage.push_back({nullptr, 0});
+    auto& b = ctx->stage[slot];
+    if (b.second < bytes) {
+        if (b.first) cudaFreeHost(b.first);
+        b = {nullptr, 0};
+        const uint64_t cap = bytes + bytes / 8 + 4096;
+        void* p = nullptr;
+        if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        b = {p, cap};
+    }
+    return b.first;
 }
 template <class T>
 static int upload(ptgpu_ctx* ctx, const T* host, uint64_t count, const T** dev) {
@@ -904,13 +925,13 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
             uint32_t items = 0;
             cudaMemcpyAsync(&items, L.mq[cur].count, 4, cudaMemcpyDeviceToHost, st);
             cudaEventRecord(ctx->evC, st);
-            k_mesh<<<gridMesh, PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            k_mesh<<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
             cudaEventRecord(ctx->evD, st); cudaEventSynchronize(ctx->evD);
             float ms = 0; cudaEventElapsedTime(&ms, ctx->evC, ctx->evD);
             ctx->meshMs += ms; ctx->meshItems += items; ctx->meshLaunches++;
             if (detail) fprintf(stderr, "k_mesh round %d items %u  %.3f ms  (%.1f Mitems/s)\n", round, items, ms, items / ms / 1e3);
         } else
-            k_mesh<<<gridMesh, PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            k_mesh<<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
         resume(L.mq[cur], L.mq[cur ^ 1]);
         ctx->launches += 2;
         cur ^= 1;
@@ -921,6 +942,28 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
 extern "C" {
 
 int ptgpu_abi_version(void) { return PTGPU_ABI_VERSION; }
+
+// Diagnostic (not part of include/ptgpu.h): run the host-side derivation of ptgpu_upload_scene without a device and return
+// its time in ms and an FNV-1a hash of the derived buffers (tools/derive_time.py; negative = failure).
+extern "C" double ptgpu_debug_derive(const ptgpu_flat_scene* s, uint64_t* hashOut, uint64_t* nodeRecords, uint64_t* leafTriangles) {
+    MeshDerived dv;
+    std::string err;
+    std::vector<void*> bufs;
+    auto t0 = std::chrono::steady_clock::now();
+    const bool ok = derive_mesh(s, dv, err, [&](uint64_t bytes) -> void* { void* p = std::malloc(bytes); bufs.push_back(p); return p; });
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ok) {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](const void* p, uint64_t bytes) { const uint64_t* w = static_cast<const uint64_t*>(p); for (uint64_t i = 0; i < bytes / 8; i++) { h ^= w[i]; h *= 1099511628211ull; } };
+        mix(dv.mn, dv.mnRecords * 64); mix(dv.lg, dv.lgCount * sizeof(ptgpu_tri_geom));
+        for (const ptgpu_tree& t : dv.trees) { h ^= t.root; h *= 1099511628211ull; }
+        if (hashOut) *hashOut = h;
+        if (nodeRecords) *nodeRecords = dv.mnRecords;
+        if (leafTriangles) *leafTriangles = dv.lgCount;
+    }
+    for (void* p : bufs) std::free(p);
+    return ok ? ms : -1.0;
+}
 
 const char* ptgpu_last_error(ptgpu_ctx* ctx) {
     if (ctx) return ctx->error.c_str();
@@ -958,6 +1001,11 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     ctx->numSMs = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if (kMeshSmemBytes > 0) {  // k_mesh keeps the top of every thread's kd stack in shared memory: carve out what its resident blocks need
+        const size_t perSM = (size_t)(PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) * (kMeshSmemBytes + 1024);
+        const int pct = (int)std::min<size_t>(100, (perSM * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
+        if ((e = cudaFuncSetAttribute(k_mesh, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_mesh carveout)", e);
+    }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
     // queueCapacity = path records in flight over all lanes (default 2^27, allocated on demand); flags bits 0-3 = number of lanes (0 = default)
     {
@@ -993,6 +1041,8 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx, true);
+    for (auto& b : ctx->stage) if (b.first) cudaFreeHost(b.first);
+    ctx->stage.clear();
     free_queues(ctx);
     free_image(ctx);
     for (int k = 0; k < kMaxLanes; k++) {
@@ -1101,181 +1151,25 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
         D.texels = t;
     }
 #undef UP
-    {   // padded triangle bounds per kd node (see box_line_hit in pt_device.cuh).  Nodes are stored parent-before-child,
-        // so one reverse sweep folds children into parents.  Scene-tree nodes get an unbounded box (never culled).
-        const uint64_t nn = s->numNodes;
-        std::vector<float> nb(nn * 8);
-        std::vector<uint8_t> isMeshNode(nn, 0);
-        for (uint32_t m = 0; m < s->numMeshes; m++) {
-            const ptgpu_tree& t = s->trees[s->meshes[m].tree];
-            // nodes of a tree are contiguous from its root up to the next tree's root
-            uint64_t end = nn;
-            for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > t.root && s->trees[k].root < end) end = s->trees[k].root;
-            for (uint64_t i = t.root; i < end; i++) isMeshNode[i] = 1;
-        }
-        const float BIG = 3.0e38f;
-        for (uint64_t ii = nn; ii-- > 0;) {
-            float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
-            const ptgpu_node& n = s->nodes[ii];
-            if (!isMeshNode[ii]) { for (int k = 0; k < 3; k++) { lo[k] = -BIG; hi[k] = BIG; } }
-            else if ((n.a & 3u) == 0) {
-                for (uint32_t k = 0; k < n.b; k++) {
-                    const ptgpu_tri_geom& g = s->triGeom[s->leafItems[(n.a >> 2) + k]];
-                    for (int c = 0; c < 3; c++) {
-                        float p0 = g.v1[c], p1 = g.v1[c] + g.e1[c], p2 = g.v1[c] + g.e2[c];
-                        lo[c] = std::min(lo[c], std::min(p0, std::min(p1, p2)));
-                        hi[c] = std::max(hi[c], std::max(p0, std::max(p1, p2)));
-                    }
-                }
-                // padding: 1e-4 of the box size plus 1e-5 of the coordinate magnitude (the FP32 triangle test errs by
-                // ~1e-7 of |origin - vertex|; the origin-dependent part is added per ray)
-                float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
-                for (int c = 0; c < 3; c++) {
-                    float padv = 1e-4f * ext + 1e-5f * std::max(std::fabs(lo[c]), std::fabs(hi[c])) + 1e-7f;
-                    lo[c] -= padv; hi[c] += padv;
-                }
-            } else {
-                const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
-                const float* r = &nb[(uint64_t)n.b * 8];
-                for (int c = 0; c < 3; c++) { lo[c] = std::min(l[c], r[c]); hi[c] = std::max(l[4 + c], r[4 + c]); }
-            }
-            float* o = &nb[ii * 8];
-            o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = 0; o[4] = hi[0]; o[5] = hi[1]; o[6] = hi[2]; o[7] = 0;
-        }
-        // Mesh nodes (see mesh_step in pt_device.cuh): 64-byte records = the reference node + both children's padded
-        // bounds.  The triangles of every reference leaf are sorted along a Morton curve and hung under bounds-only
-        // binary nodes ending in micro leaves of <= 4 triangles; each triangle carries its global index and its
-        // position in the reference leaf (tie-break of Tree.cs:122).
-        std::vector<ptgpu_tri_geom> lg;
-        lg.reserve(s->numLeafItems);
-        std::vector<uint32_t> mn(nn * 16, 0u);           // grows with the bounds-only nodes
-        std::vector<std::pair<uint32_t, uint32_t>> order;  // (morton, position in leaf)
-        std::vector<float> cen;
-        auto bitsToFloat = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
-        auto floatBits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
-        auto spread = [](uint32_t x) { x &= 1023u; x = (x | (x << 16)) & 0x030000FFu; x = (x | (x << 8)) & 0x0300F00Fu; x = (x | (x << 4)) & 0x030C30C3u; return (x | (x << 2)) & 0x09249249u; };
-        int virtualDepth = 0;
-        // padded bounds of triangles lg[t0, t1)
-        auto tri_bounds = [&](uint32_t t0, uint32_t t1, float* out8) {
-            float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
-            for (uint32_t t = t0; t < t1; t++) {
-                const ptgpu_tri_geom& g = lg[t];
-                for (int c = 0; c < 3; c++) {
-                    float p0 = g.v1[c], p1 = g.v1[c] + g.e1[c], p2 = g.v1[c] + g.e2[c];
-                    lo[c] = std::min(lo[c], std::min(p0, std::min(p1, p2)));
-                    hi[c] = std::max(hi[c], std::max(p0, std::max(p1, p2)));
-                }
-            }
-            float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
-            for (int c = 0; c < 3; c++) {  // same padding rule as the reference nodes' bounds
-                float padv = 1e-4f * ext + 1e-5f * std::max(std::fabs(lo[c]), std::fabs(hi[c])) + 1e-7f;
-                out8[c] = lo[c] - padv; out8[4 + c] = hi[c] + padv;
-            }
-            out8[3] = out8[7] = 0;
-        };
-        // child reference for triangles lg[t0, t1): a micro leaf named in place, or a new bounds-only node (appended)
-        struct Build { uint64_t idx; uint32_t t0, t1; int depth; };
-        auto fill_virtual = [&](uint64_t rootIdx, uint32_t t0, uint32_t t1) {  // record rootIdx becomes a bounds-only node over lg[t0, t1), t1 - t0 > 4
-            std::vector<Build> todo{{rootIdx, t0, t1, 0}};
-            while (!todo.empty()) {
-                Build bld = todo.back(); todo.pop_back();
-                virtualDepth = std::max(virtualDepth, bld.depth + 1);
-                const uint32_t n = bld.t1 - bld.t0, mid = bld.t0 + (n + 1) / 2;
-                uint32_t refs[2];
-                const uint32_t lo2[2] = {bld.t0, mid}, hi2[2] = {mid, bld.t1};
-                for (int side = 0; side < 2; side++) {
-                    const uint32_t cn = hi2[side] - lo2[side];
-                    if (cn <= 4) refs[side] = leaf_ref(lo2[side], cn, false);
-                    else {
-                        refs[side] = (uint32_t)(mn.size() / 16);
-                        mn.resize(mn.size() + 16, 0u);
-                        todo.push_back({refs[side], lo2[side], hi2[side], bld.depth + 1});
-                    }
-                }
-                uint32_t* o = &mn[bld.idx * 16];
-                o[2] = refs[0] << 2; o[3] = (o[3] & kNodeRefLeaf) | kNodeVirtual | refs[1];
-                float lb[8], rb[8];
-                tri_bounds(bld.t0, mid, lb); tri_bounds(mid, bld.t1, rb);
-                const float pk[12] = {lb[0], lb[1], lb[2], lb[4], lb[5], lb[6], rb[0], rb[1], rb[2], rb[4], rb[5], rb[6]};
-                for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
-            }
-        };
-        std::vector<uint32_t> ref(nn);                   // how a parent (or the tree) refers to reference node i
-        for (uint64_t i = 0; i < nn; i++) ref[i] = (uint32_t)i;
-        // pass 1: reference leaves -> sorted triangles + (for > 4 triangles) a bounds-only subtree rooted at record i
-        for (uint64_t i = 0; i < nn; i++) {
-            if (!isMeshNode[i]) continue;
-            const ptgpu_node& n = s->nodes[i];
-            if ((n.a & 3u) != 0) continue;
-            const uint32_t first = n.a >> 2, count = n.b;
-            float lo[3] = {BIG, BIG, BIG}, hi[3] = {-BIG, -BIG, -BIG};
-            cen.resize((size_t)count * 3);
-            for (uint32_t k = 0; k < count; k++) {
-                const ptgpu_tri_geom& g = s->triGeom[s->leafItems[first + k]];
-                for (int c = 0; c < 3; c++) {
-                    float v = g.v1[c] + (g.e1[c] + g.e2[c]) * (1.0f / 3.0f);
-                    cen[(size_t)k * 3 + c] = v; lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v);
-                }
-            }
-            order.clear();
-            for (uint32_t k = 0; k < count; k++) {
-                uint32_t q[3];
-                for (int c = 0; c < 3; c++) {
-                    float e = hi[c] - lo[c];
-                    float f = e > 0 ? (cen[(size_t)k * 3 + c] - lo[c]) / e : 0.f;
-                    q[c] = (uint32_t)std::min(1023.f, std::max(0.f, f * 1023.f));
-                }
-                order.push_back({spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), k});
-            }
-            std::sort(order.begin(), order.end());
-            const uint32_t t0 = (uint32_t)lg.size();
-            for (uint32_t k = 0; k < count; k++) {
-                const uint32_t pos = order[k].second, tri = s->leafItems[first + pos];
-                ptgpu_tri_geom g = s->triGeom[tri];
-                g.pad0 = bitsToFloat(tri); g.pad1 = bitsToFloat(pos); g.pad2 = 0.f;
-                lg.push_back(g);
-            }
-            if (lg.size() > (size_t)kRefFirstMask) return fail(ctx, PTGPU_E_LIMIT, "mesh too large for the 26-bit leaf triangle index");
-            if (count == 0) {  // cannot come out of Node.Split (an empty side is rejected) except for an empty mesh: one degenerate triangle
-                ptgpu_tri_geom z; std::memset(&z, 0, sizeof(z));
-                lg.push_back(z);
-                ref[i] = leaf_ref(t0, 1, true);
-                continue;
-            }
-            if (count <= 4) ref[i] = leaf_ref(t0, count, true);
-            else { mn[i * 16 + 3] = kNodeRefLeaf; fill_virtual(i, t0, t0 + count); }
-        }
-        // pass 2: reference interior nodes with both children's padded bounds
-        for (uint64_t i = 0; i < nn; i++) {
-            if (!isMeshNode[i]) continue;
-            const ptgpu_node& n = s->nodes[i];
-            if ((n.a & 3u) == 0) continue;
-            uint32_t* o = &mn[i * 16];
-            std::memcpy(o, &n.split, 8);
-            o[2] = (ref[n.a >> 2] << 2) | (n.a & 3u); o[3] = ref[n.b];
-            const float* l = &nb[(uint64_t)(n.a >> 2) * 8];
-            const float* r = &nb[(uint64_t)n.b * 8];
-            const float pk[12] = {l[0], l[1], l[2], l[4], l[5], l[6], r[0], r[1], r[2], r[4], r[5], r[6]};
-            for (int k = 0; k < 12; k++) o[4 + k] = floatBits(pk[k]);
-        }
-        // the roots the split tracer / trace_rays start from
-        std::vector<ptgpu_tree> treesPatched(s->trees, s->trees + s->numTrees);
-        for (uint32_t m = 0; m < s->numMeshes; m++) treesPatched[s->meshes[m].tree].root = ref[s->trees[s->meshes[m].tree].root];
+    {   // derived mesh data (see derive_mesh): 64-byte node records, sorted leaf triangles, patched tree roots
+        MeshDerived dv;
+        std::string err;
+        ctx->stageNext = 0;  // pinned staging owned by the handle: the derivation writes straight into DMA-able memory
+        auto t0 = std::chrono::steady_clock::now();
+        if (!derive_mesh(s, dv, err, [&](uint64_t bytes) -> void* { return stage_alloc(ctx, bytes); })) return fail(ctx, PTGPU_E_LIMIT, err);
+        ctx->deriveMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         {
             const ptgpu_tree* dt = nullptr;
-            if ((rc = upload(ctx, treesPatched.data(), (uint64_t)treesPatched.size(), &dt)) != PTGPU_OK) return rc;
-            CK(cudaStreamSynchronize(ctx->stream));
+            if ((rc = upload(ctx, dv.trees.data(), (uint64_t)dv.trees.size(), &dt)) != PTGPU_OK) return rc;
             D.trees = dt;
         }
-        if (mn.size() / 16 >= (uint64_t)kRefLeaf) return fail(ctx, PTGPU_E_LIMIT, "mesh too large for the 29-bit node index");
-        if (virtualDepth > kVirtualDepthMax) return fail(ctx, PTGPU_E_LIMIT, "a kd leaf holds more triangles than the bounds-only hierarchy supports");
         const uint4* dmn = nullptr;
-        if ((rc = upload(ctx, reinterpret_cast<const uint4*>(mn.data()), (uint64_t)mn.size() / 4, &dmn)) != PTGPU_OK) return rc;
+        if ((rc = upload(ctx, reinterpret_cast<const uint4*>(dv.mn), dv.mnRecords * 4, &dmn)) != PTGPU_OK) return rc;
         D.meshNodes = dmn;
-        ctx->meshNodeBytes = (uint64_t)mn.size() * 4;
+        ctx->meshNodeBytes = dv.mnRecords * 64;
         const float4* dl = nullptr;
-        if ((rc = upload(ctx, reinterpret_cast<const float4*>(lg.data()), (uint64_t)lg.size() * 3, &dl)) != PTGPU_OK) return rc;
-        CK(cudaStreamSynchronize(ctx->stream));  // the staging vectors are locals
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(dv.lg), dv.lgCount * 3, &dl)) != PTGPU_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));  // dv.trees is a local; the pinned staging is rewritten by the next upload
         D.leafGeom = dl;
     }
     D.sceneTree = s->sceneTree; D.numSceneShapes = s->numSceneShapes; D.numLights = s->numLights; D.numShapes = s->numShapes;

@@ -97,3 +97,29 @@ def test_flat_scene_file_round_trip(bindings, tmp_path):
     import pytest
     with pytest.raises(RuntimeError):
         bindings.HostWorld().load_flat(path)
+
+
+def _derive(bindings, flat):
+    lib = bindings.gpu_lib()
+    lib.ptgpu_debug_derive.restype = C.c_double
+    lib.ptgpu_debug_derive.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    h, nr, nt = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert lib.ptgpu_debug_derive(flat, C.byref(h), C.byref(nr), C.byref(nt)) >= 0
+    return h.value, nr.value, nt.value
+
+
+def test_mesh_derivation_is_thread_count_invariant(bindings, monkeypatch):
+    """ptgpu_upload_scene derives the walk's node records / sorted leaf triangles on all host threads (csrc/mesh_derive.hpp):
+    the bytes must not depend on the thread count and must equal the
+    single-threaded derivation the earlier GPU parity runs were made with (hash frozen from that implementation)."""
+    from ptsharp_b200 import scenes
+    hw = bindings.HostWorld()
+    scenes.build_c3(hw, freq_a=24, freq_b=12)
+    flat = hw.flatten()
+    monkeypatch.setenv("PTGPU_HOST_THREADS", "1")
+    one = _derive(bindings, flat)
+    monkeypatch.setenv("PTGPU_HOST_THREADS", "7")
+    many = _derive(bindings, flat)
+    assert one == many
+    assert many[1:] == (14883, 46795)            # node records (reference + bounds-only), leaf triangles
+    assert many[0] == 0xF03E2BC40DFF34E1, hex(many[0])
