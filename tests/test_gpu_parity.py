@@ -378,3 +378,126 @@ def test_checkpoint_round_trip_and_resume(orc, bindings, device):
         np.testing.assert_allclose(Ma, Mb, rtol=1e-4, atol=1e-6)  # same samples; only the float atomics' order differs
     finally:
         other.close()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json full sizes
+@pytest.fixture(scope="module")
+def full_c3(orc, bindings):
+    """configs[2] at its real size: the 1 000 000-triangle displaced icospheres (the scene bench.py times)."""
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    cfg = scenes.build_c3(hw)
+    scenes.build_c3(ow)
+    assert cfg.triangles == 1_000_000 and (cfg.width, cfg.height) == (1920, 1080)
+    return hw, ow, cfg
+
+
+def test_full_size_c3_closest_hit_bit_exact(full_c3, device):
+    """Tree.Intersect on the full 1 M-triangle kd-trees: camera rays over the whole frame plus rays leaving the surfaces in
+    random directions, hit shape / triangle / T / position / normal bit for bit against the oracle."""
+    hw, ow, cfg = full_c3
+    device.upload(hw)
+    o, d = _ray_batch(ow, W=192, H=108, n_secondary=30000, seed=17)
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    assert (c["prim"] >= 0).sum() > 10000
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["prim"], c["prim"])
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["inside"], c["inside"])
+
+
+def test_full_size_c3_replay_window(orc, full_c3, device):
+    """One keyed camera sample per pixel of a 240x135 frame of the full scene: per-pixel radiance and ray counts against
+    the oracle on the same Philox stream."""
+    hw, ow, cfg = full_c3
+    device.upload(hw)
+    W, H = 240, 135
+    device.reset_counters()
+    img = device.render_pass(hw.make_pass(W, H, 1, pass_index=0)).astype(np.float64)
+    cnt = device.counters()
+    ref, _, ocnt = ow.render(W, H, 1, passes=1, threads=os.cpu_count() or 1, rng_mode=orc.RNG_KEYED, seed=0x50545348)
+    rel = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert (rel.max(axis=2) > 1e-4).mean() < 1e-3
+    assert abs(cnt["segments"] - ocnt["segments"]) <= 5e-4 * ocnt["segments"] + 4
+    assert abs(cnt["shadowRays"] - ocnt["shadowRays"]) <= 5e-4 * ocnt["shadowRays"] + 4
+    assert cnt["nanSamples"] == 0
+
+
+def test_full_size_c3_frame_properties(full_c3, device):
+    """Size-independent properties on the full 1920x1080 frame (too large for the CPU oracle): the pass is a pure function
+    of (pixel, global sample index, pass) — a re-run is bit-identical, batch size does not matter, and a 2-way sample
+    partition sums to the unpartitioned pass — and the counters are consistent with the sampler's bounds."""
+    import torch
+    hw, _, cfg = full_c3
+    device.upload(hw)
+    W, H, spp = cfg.width, cfg.height, 2
+    bufs = [torch.zeros(W * H * 3, device="cuda") for _ in range(3)]
+    device.reset_counters()
+    device.accumulate_device(hw.make_pass(W, H, spp, pass_index=5), bufs[0].data_ptr())
+    cnt = device.counters()
+    device.accumulate_device(hw.make_pass(W, H, spp, pass_index=5), bufs[1].data_ptr())
+    for r in range(2):
+        device.accumulate_device(hw.make_pass(W, H, 1, pass_index=5, sample_base=r, sample_stride=2), bufs[2].data_ptr())
+    device.counters()
+    torch.cuda.synchronize()
+    a, b, c = (t.cpu().numpy() for t in bufs)
+    assert np.isfinite(a).all() and a.min() >= 0 and a.sum() > 0
+    # identical up to the order of the atomic float adds into a pixel (2 samples per pixel and a few path vertices each)
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(a, c, rtol=1e-5, atol=1e-5)
+    n = W * H * spp
+    assert cnt["cameraSamples"] == n
+    assert n <= cnt["segments"] <= 5 * n            # NewSampler(1, 4): one camera segment + at most 4 bounces
+    assert 0 < cnt["shadowRays"] <= cnt["segments"]  # LightModeRandom: at most one shadow ray per path vertex
+    assert cnt["nanSamples"] == 0
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_full_size_replay_c1_c2(orc, bindings, device, name):
+    """configs[0] (512x512, NewSampler(16, 4)) and configs[1] (Cornell 1024x1024, LightModeAll, 8 bounces) at their full
+    frame size, one keyed camera sample per pixel: every pixel against the oracle, ray counts identical or within the odd
+    libm-ulp branch flip."""
+    builder = {"c1": scenes.build_c1, "c2": scenes.build_c2}[name]
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    cfg = builder(hw)
+    builder(ow)
+    assert (cfg.width, cfg.height) == {"c1": (512, 512), "c2": (1024, 1024)}[name]
+    device.upload(hw)
+    W, H = cfg.width, cfg.height
+    device.reset_counters()
+    img = device.render_pass(hw.make_pass(W, H, 1, pass_index=0)).astype(np.float64)
+    cnt = device.counters()
+    ref, _, ocnt = ow.render(W, H, 1, passes=1, threads=os.cpu_count() or 1, rng_mode=orc.RNG_KEYED, seed=0x50545348)
+    rel = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert (rel.max(axis=2) > 1e-4).mean() < 1e-3
+    assert cnt["cameraSamples"] == W * H
+    assert abs(cnt["segments"] - ocnt["segments"]) <= 5e-4 * ocnt["segments"] + 4
+    assert abs(cnt["shadowRays"] - ocnt["shadowRays"]) <= 5e-4 * ocnt["shadowRays"] + 4
+
+
+@pytest.mark.parametrize("name", ["c4", "c5"])
+def test_full_size_scene_closest_hit_c4_c5(orc, bindings, device, name):
+    """configs[3] (200 TransformedShape instances of a 50 k-triangle mesh = 10 M triangles, 2 x 1024^2 textures + normal map)
+    and configs[4] (SDF + Cylinder + 64^3 Volume) with their full scene data: closest hits bit for bit."""
+    builder = {"c4": scenes.build_c4, "c5": scenes.build_c5}[name]
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    cfg = builder(hw)
+    builder(ow)
+    if name == "c4":
+        assert cfg.triangles >= 9_500_000 and (cfg.width, cfg.height) == (3840, 2160)
+    device.upload(hw)
+    o, d = _ray_batch(ow, W=128, H=72, n_secondary=8000 if name == "c5" else 20000, seed=29)
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    assert hit.sum() > 5000
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["prim"], c["prim"])
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["inside"], c["inside"])
+    if name == "c4":
+        np.testing.assert_allclose(g["normal"][hit], c["normal"][hit], rtol=1e-5, atol=2e-6)
+    else:
+        np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
