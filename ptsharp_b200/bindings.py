@@ -117,6 +117,9 @@ _HOST_EXTRA = {
     "renderer_image": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
     "renderer_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "renderer_ctx": (C.c_void_p, [C.c_void_p]),
+    "load_model": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
+    "mesh_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "mesh_get": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p]),
 }
 
 
@@ -172,6 +175,40 @@ class HostWorld(World):
 
     def flat_bytes(self) -> int:
         return int(self.lib.pth_flat_bytes(self.h))
+
+    # ---- model loaders and Mesh utilities (host/loaders.cpp; OBJ.cs, STL.cs, Mesh.cs:141-289) ----
+    def load_obj(self, path: str, mat: int) -> int:
+        return self._model(0, path, mat)
+
+    def load_stl(self, path: str, mat: int) -> int:
+        return self._model(1, path, mat)
+
+    def _model(self, kind: int, path: str, mat: int) -> int:
+        s = self.lib.pth_load_model(self.h, kind, os.fsencode(path), mat)
+        if s < 0:
+            raise RuntimeError(self._err())
+        return s
+
+    def _mesh_op(self, shape: int, op: int, args) -> None:
+        a = np.ascontiguousarray(np.asarray(list(args) + [0.0], dtype=np.float64))
+        if self.lib.pth_mesh_op(self.h, shape, op, a.ctypes.data_as(c_double_p)) != 0:
+            raise RuntimeError(self._err())
+
+    def mesh_smooth_normals(self, shape): self._mesh_op(shape, 0, [])
+    def mesh_smooth_normals_threshold(self, shape, radians): self._mesh_op(shape, 1, [radians])
+    def mesh_move_to(self, shape, position, anchor): self._mesh_op(shape, 2, list(position) + list(anchor))
+    def mesh_fit_inside(self, shape, bmin, bmax, anchor): self._mesh_op(shape, 3, list(bmin) + list(bmax) + list(anchor))
+    def mesh_transform(self, shape, m16): self._mesh_op(shape, 4, list(np.asarray(m16, dtype=np.float64).ravel()))
+    def mesh_set_material(self, shape, mat): self._mesh_op(shape, 5, [mat])
+
+    def mesh_triangles(self, shape: int):
+        """(V, N, T) of a Mesh, each (ntri, 3, 3) float32."""
+        n = self.lib.pth_mesh_get(self.h, shape, None, None, None)
+        if n < 0:
+            raise RuntimeError(self._err())
+        V, N, T = (np.empty((n, 3, 3), np.float32) for _ in range(3))
+        self.lib.pth_mesh_get(self.h, shape, V.ctypes.data_as(c_float_p), N.ctypes.data_as(c_float_p), T.ctypes.data_as(c_float_p))
+        return V, N, T
 
     def make_pass(self, width, height, spp, stratified=False, seed=0x50545348, pass_index=0, sample_base=0,
                   sample_stride=1, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0) -> Pass:

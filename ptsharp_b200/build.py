@@ -45,9 +45,9 @@ def build_gpu(force=False, verbose=False) -> str:
 def build_host(force=False) -> str:
     gpu = build_gpu()
     out = os.path.join(LIBDIR, "libpthost.so")
-    srcs = [os.path.join(PKG, "host", f) for f in ("host.cpp", "capi.cpp", "ptsharp.hpp")] + [os.path.join(ROOT, "include", "ptgpu.h")]
+    srcs = [os.path.join(PKG, "host", f) for f in ("host.cpp", "capi.cpp", "loaders.cpp", "ptsharp.hpp")] + [os.path.join(ROOT, "include", "ptgpu.h")]
     if force or _newer(srcs + [gpu], out):
-        cmd = ["g++"] + CXX_FLAGS + ["-o", out, srcs[0], srcs[1], "-L" + LIBDIR, "-lptgpu", "-Wl,-rpath,$ORIGIN"]
+        cmd = ["g++"] + CXX_FLAGS + ["-o", out, srcs[0], srcs[1], srcs[2], "-L" + LIBDIR, "-lptgpu", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return out
 

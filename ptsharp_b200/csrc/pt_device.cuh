@@ -813,6 +813,56 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
 #endif
 }
 
+// The triangle tests of every lane that sits in a micro leaf, spread over ALL lanes of the warp.  ncu on the per-lane
+// leaf loop: 40 % of k_mesh's issued instructions were leaf / triangle code running at 8-9 of 32 lanes (a third of the warp
+// is in a leaf at a time, and a lane with 2 triangles idles while its neighbour tests 4).  Here the (lane, triangle) pairs
+// of the warp are numbered 0 .. total-1 (prefix sum of the per-lane counts, <= 4 each, from three ballots); in round r lane
+// j tests pair 32 r + j: it finds the owner lane by bisection on the inclusive prefix (5 shuffles), pulls the owner's ray
+// with 6 shuffles and runs the unchanged triangle test; the rare hits go back to their owners one by one.  The result per
+// ray is the lexicographic minimum of (T, position in the reference leaf) over its micro leaf and the running best - what
+// the in-order loop of leaf_work gives (Tree.cs:119-126: strict <, first shape in array order wins a tie).
+PT_D void coop_leaf(const DScene& S, bool inLeaf, V3 co, V3 cd, uint32_t& tPos, uint32_t tEnd, double& best, int32_t& prim, uint32_t& bestPos) {
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t cnt = inLeaf ? (tEnd - tPos) : 0u;  // 0..4
+    const unsigned b0 = __ballot_sync(full, cnt & 1u), b1 = __ballot_sync(full, cnt & 2u), b2 = __ballot_sync(full, cnt & 4u);
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t excl = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+    const uint32_t incl = excl + cnt;
+    const uint32_t total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+#pragma unroll 1
+    for (uint32_t base = 0; base < total; base += 32u) {  // warp-uniform
+        const uint32_t u = base + lane;
+        int owner = 0;  // first lane whose inclusive prefix exceeds u
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t v = __shfl_sync(full, incl, owner + step - 1);
+            if (v <= u) owner += step;
+        }
+        const uint32_t oExcl = __shfl_sync(full, excl, owner), oPos = __shfl_sync(full, tPos, owner);
+        const V3 o = v3(__shfl_sync(full, co.x, owner), __shfl_sync(full, co.y, owner), __shfl_sync(full, co.z, owner));
+        const V3 d = v3(__shfl_sync(full, cd.x, owner), __shfl_sync(full, cd.y, owner), __shfl_sync(full, cd.z, owner));
+        double t = kHitInf;
+        uint32_t hitPos = 0, hitTri = 0;
+        if (u < total) {
+            const float4* g = S.leafGeom + (size_t)(oPos + (u - oExcl)) * 3;
+            DBG_ADD(4, 1);
+            t = triangle_intersect(g, o, d);
+            if (t < kHitInf) { hitTri = __float_as_uint(__ldg(g).w); hitPos = __float_as_uint(__ldg(g + 1).w); }  // rare
+        }
+        unsigned cand = __ballot_sync(full, t < kHitInf);  // a T of INF never replaces NoHit
+        while (cand) {                                     // warp-uniform: ~2 hits per 32 tests
+            const int w = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            const int ow = __shfl_sync(full, owner, w);
+            const double tw = __hiloint2double(__shfl_sync(full, __double2hiint(t), w), __shfl_sync(full, __double2loint(t), w));
+            const uint32_t pw = __shfl_sync(full, hitPos, w), iw = __shfl_sync(full, hitTri, w);
+            if ((int)lane == ow && tw <= best && (tw < best || pw < bestPos)) { best = tw; prim = (int32_t)iw; bestPos = pw; }
+        }
+    }
+    if (inLeaf) tPos = tEnd;
+}
+
 // The analytic subset (the split tracer is only used for scenes without SDFShape / Volume).
 PT_D double primitive_intersect_analytic(const DScene& S, const ptgpu_shape& sh, V3 o, V3 d) {
     switch (sh.type) {
@@ -1199,6 +1249,12 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
 }
 
 // Mesh.Intersect for every work item of `q`; the Hit goes to W.mBest / W.mPrim of the item's ray.
+#ifndef PT_COOP_LEAF
+#define PT_COOP_LEAF 0       // 1: the triangle tests of a LEAF turn are spread over all lanes of the warp (coop_leaf)
+#endif
+#ifndef PT_COOP_LEAF_MIN
+#define PT_COOP_LEAF_MIN 5   // run a LEAF turn once this many lanes sit in a micro leaf (or no lane is walking nodes)
+#endif
 #ifndef PT_SMEM_STACK
 #define PT_SMEM_STACK 0   // entries of the walk's kd stack kept in shared memory per thread (0 = all in local memory)
 #endif
@@ -1250,7 +1306,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     st = ST_MESH_NODE;
                 }
             }
-        } else if (nNode >= nLeaf) {
+        } else if (PT_COOP_LEAF ? !(nLeaf >= PT_COOP_LEAF_MIN || nNode == 0) : (nNode >= nLeaf)) {
 #if PT_BURST_VOTE
 #pragma unroll 1
             for (int k = 0; k < PT_NODE_BURST; k++) {
@@ -1278,12 +1334,17 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
             }
 #endif
         } else {
+#if PT_COOP_LEAF
+            coop_leaf(S, st == ST_MESH_LEAF, co, cd, tPos, tEnd, mBest, mPrim, mBestPos);
+#endif
             if (st == ST_MESH_LEAF) {
 #ifdef PT_DEBUG_STEPS
                 dbgLeaves++;
                 DBG_ADD(3, 1);
 #endif
+#if !PT_COOP_LEAF
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
+#endif
                 if (tPos >= tEnd) {
                     st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
                     if (st == ST_MESH_NODE) prefetch_node(S.meshNodes, mc.node);

@@ -63,6 +63,43 @@ int pth_mesh(pth_world* w, int ntri, const float* V, const float* N, const float
     }
     return push(w, Mesh::NewMesh(std::move(tris)));
 }
+// OBJ.Load / STL.Load (host/loaders.cpp): kind 0 = OBJ, 1 = STL.  Returns the shape id, or -1 with pth_last_error set.
+int pth_load_model(pth_world* w, int kind, const char* path, int mat) {
+    try {
+        const Material& m = w->materials[(size_t)mat];
+        return push(w, kind == 0 ? OBJ::Load(path, m) : STL::Load(path, m));
+    } catch (const std::exception& e) { w->error = e.what(); return -1; }
+}
+// Mesh utilities.  op 0 SmoothNormals, 1 SmoothNormalsThreshold(a[0] radians), 2 MoveTo(position a[0..2], anchor a[3..5]),
+// 3 FitInside(box min a[0..2], max a[3..5], anchor a[6..8]), 4 Transform(matrix a[0..15]), 5 SetMaterial(material (int)a[0])
+int pth_mesh_op(pth_world* w, int shape, int op, const double* a) {
+    Mesh* m = dynamic_cast<Mesh*>(w->shapes[(size_t)shape].get());
+    if (!m) { w->error = "pth_mesh_op: shape is not a Mesh"; return -1; }
+    try {
+        switch (op) {
+            case 0: m->SmoothNormals(); break;
+            case 1: m->SmoothNormalsThreshold(a[0]); break;
+            case 2: m->MoveTo(V3(a), V3(a + 3)); break;
+            case 3: m->FitInside(Box(V3(a), V3(a + 3)), V3(a + 6)); break;
+            case 4: m->Transform(M16(a)); break;
+            case 5: m->SetMaterial(w->materials[(size_t)a[0]]); break;
+            default: w->error = "pth_mesh_op: unknown op"; return -1;
+        }
+    } catch (const std::exception& e) { w->error = e.what(); return -1; }
+    return 0;
+}
+// Triangles of a Mesh (V, N, T: 9 floats per triangle each; null = only count them).
+int pth_mesh_get(pth_world* w, int shape, float* V, float* N, float* T) {
+    Mesh* m = dynamic_cast<Mesh*>(w->shapes[(size_t)shape].get());
+    if (!m) { w->error = "pth_mesh_get: shape is not a Mesh"; return -1; }
+    for (size_t i = 0; i < m->Triangles.size(); i++) {
+        const Triangle& t = m->Triangles[i];
+        const Vector* vs[3][3] = {{&t.V1, &t.V2, &t.V3}, {&t.N1, &t.N2, &t.N3}, {&t.T1, &t.T2, &t.T3}};
+        float* outs[3] = {V, N, T};
+        for (int a = 0; a < 3; a++) if (outs[a]) for (int k = 0; k < 3; k++) { outs[a][i * 9 + k * 3] = vs[a][k]->x; outs[a][i * 9 + k * 3 + 1] = vs[a][k]->y; outs[a][i * 9 + k * 3 + 2] = vs[a][k]->z; }
+    }
+    return (int)m->Triangles.size();
+}
 int pth_transformed(pth_world* w, int shape, const double* m16) { return push(w, TransformedShape::NewTransformedShape(w->shapes[(size_t)shape], M16(m16))); }
 int pth_sdf_sphere(pth_world* w, double r) { return pushSdf(w, NewSphereSDF(r)); }
 int pth_sdf_cube(pth_world* w, const double* size) { return pushSdf(w, NewCubeSDF(V3(size))); }

@@ -57,6 +57,7 @@ struct Box {  // Box.cs:5-58
     Box Extend(const Box& b) const;
     Vector Size() const;
     Vector Center() const;
+    Vector Anchor(const Vector& anchor) const;  // Box.cs:48
     double OuterRadius() const;
 };
 
@@ -70,6 +71,7 @@ struct Matrix {  // Matrix.cs:8-231 (row-major)
     Matrix Mul(const Matrix& b) const;
     Matrix Inverse() const;
     Vector MulPosition(const Vector& b) const;
+    Vector MulDirection(const Vector& b) const;  // Matrix.cs:144-150 (normalised)
     Box MulBox(const Box& box) const;
 };
 
@@ -161,7 +163,17 @@ struct Mesh : IShape {  // Mesh.cs
     void Compile() override;
     Box BoundingBox() const override;
     Material MaterialAt(const Vector&) const override { return Material(); }  // Mesh.cs:132-135
+    // authoring utilities the example scenes call on loaded meshes (host/loaders.cpp); each drops the cached box and tree
+    void SmoothNormals();                              // Mesh.cs:191-229
+    void SmoothNormalsThreshold(double radians);       // Mesh.cs:141-189 (incl. its prefix-list quirk)
+    void MoveTo(const Vector& position, const Vector& anchor);  // Mesh.cs:237-241
+    void FitInside(const Box& box, const Vector& anchor);       // Mesh.cs:243-252
+    void Transform(const Matrix& matrix);              // Mesh.cs:254-274
+    void SetMaterial(const Material& material);        // Mesh.cs:276-289
 };
+// Model loaders (host/loaders.cpp).  Both return a Mesh whose triangles went through Triangle.FixNormals.
+struct OBJ { static std::shared_ptr<Mesh> Load(const std::string& path, const Material& parent); };   // OBJ.cs:11-163
+struct STL { static std::shared_ptr<Mesh> Load(const std::string& path, const Material& material); }; // STL.cs:37-223
 struct TransformedShape : IShape {  // TransformedShape.cs
     ShapePtr Shape; Matrix M, Inv;
     static ShapePtr NewTransformedShape(ShapePtr s, const Matrix& m);
