@@ -73,6 +73,9 @@ PT_D double netmin(double a, double b) {
     if (a != b) return (a != a) ? a : (a < b ? a : b);
     return (__double2hiint(a) < 0) ? a : b;
 }
+// netmin(a, b) when b is known to be a positive number (a running best.T: EPS <= T <= 1e9, never NaN): one comparison.
+// a < b -> a; a >= b -> b (a == b > 0: the same value either way); a NaN -> `a >= b` is false -> a, the NaN, as Math.Min does.
+PT_D double netmin_best(double a, double bestT) { return !(a >= bestT) ? a : bestT; }
 PT_D float netmaxf(float a, float b) {
     if (a != b) return (a != a) ? a : (b < a ? a : b);
     return (__float_as_int(b) < 0) ? a : b;
@@ -643,7 +646,7 @@ PT_D bool mesh_pop_t(KdCursor& c, double bestT, Stk& stk) {
         if (e.w) continue;          // its Node.Intersect returns NoHit
         c.node = e.z;
         c.tmin = ts;
-        c.tmax = netmin(stk_t(stk.get(c.sp)), bestT);
+        c.tmax = netmin_best(stk_t(stk.get(c.sp)), bestT);
         stk.shrink(c.sp);
         return true;
     }
@@ -756,7 +759,7 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
         else if (PT_SHORTCUT && !hitFirst) {
             // the near child returns NoHit: what the pop of (second, tsplit) would do, without the stack round trip
             if (bestT <= tsplit || !hitSecond) go = false;
-            else { c.node = second; c.tmin = tsplit; c.tmax = netmin(c.tmax, bestT); go = true; }
+            else { c.node = second; c.tmin = tsplit; c.tmax = netmin_best(c.tmax, bestT); go = true; }
         } else {
             c.sp++;
             stk.put(c.sp, stk_entry(tsplit, second, hitSecond ? 0u : 1u));
@@ -878,7 +881,7 @@ PT_D double primitive_intersect_analytic(const DScene& S, const ptgpu_shape& sh,
 #define PT_LEAF_BURST 8
 #endif
 #ifndef PT_NODE_BURST
-#define PT_NODE_BURST 8
+#define PT_NODE_BURST 4   // 4: +1.2 % over 8 on C3 (bench.py, 128 spp); 16: -8 %
 #endif
 #ifndef PT_GLUE_PRIO
 #define PT_GLUE_PRIO 33   // run the GLUE class as soon as this many lanes wait in it (33 = only when it is the plurality)
