@@ -19,7 +19,7 @@ for n in names:
     t0 = time.time(); cfg = scenes.BUILDERS[n](hw); flat = hw.flatten(); build = time.time() - t0
     dev = Device(0); dev.upload_flat(flat)
     spp = spp_override or DEFAULT_SPP[n]
-    dev.render_pass(hw.make_pass(cfg.width, cfg.height, 1, pass_index=0), want_mean=False)  # warm-up
+    dev.render_pass(hw.make_pass(cfg.width, cfg.height, spp, pass_index=0), want_mean=False)  # warm-up at the measured spp: queues grow on demand
     dev.reset_counters()
     dev.render_pass(hw.make_pass(cfg.width, cfg.height, spp, pass_index=1), want_mean=False)
     c = dev.counters(); ms = c['lastPassMs']
