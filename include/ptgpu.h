@@ -161,6 +161,17 @@ typedef struct ptgpu_pass {
      *   that many more samples, stopping at the first one IsFirefly() rejects (Renderer.cs:430-441, 474-497). */
     int32_t adaptiveSamples, fireflySamples;
     double fireflyThreshold;     /* Renderer.FireflyThreshold, 1 in NewRenderer (Renderer.cs:47) */
+    /* serialRules != 0: the extra passes follow the serial Render() (Renderer.cs:150-191, what IterativeRender runs when
+     * NumCPU == 1) instead of RenderParallel:
+     *   adaptive: a pixel gets AdaptiveSamples * (int)pow(clamp(StandardDeviation().MaxComponent() / adaptiveThreshold, 0, 1),
+     *     adaptiveExponent) more samples (fu, fv = xi: uniform sub-pixel jitter), i.e. AdaptiveSamples of them iff its deviation
+     *     reaches the threshold (every pixel when the exponent is 0; a negative exponent is rejected with PTGPU_E_ARG);
+     *   firefly: pixels above fireflyThreshold (evaluated after the adaptive samples) get fireflySamples more samples with
+     *     fu = (x + xi) * (1.0f / w) - no IsFirefly() rejection in the serial path.
+     * Each extra sample is its own Buffer.AddSample. */
+    int32_t serialRules, reserved0;
+    double adaptiveThreshold;    /* Renderer.AdaptiveThreshold, 1 in NewRenderer (Renderer.cs:44) */
+    double adaptiveExponent;     /* Renderer.AdaptiveExponent, 1 in NewRenderer (Renderer.cs:45) */
 } ptgpu_pass;
 
 typedef struct ptgpu_params {

@@ -25,6 +25,7 @@ c_uint_p = C.POINTER(C.c_uint)
 _EXTRA = {
     "num_lights": (C.c_int, [C.c_void_p]),
     "set_extra": (None, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
+    "set_serial": (None, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "last_samples": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "camera_get": (None, [C.c_void_p, c_float_p, c_double_p]),
     "intersect_batch": (None, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p, c_float_p,
@@ -108,6 +109,10 @@ class OracleWorld(World):
 
     def set_extra(self, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0):
         self.lib.orc_set_extra(self.h, adaptive_samples, firefly_samples, float(firefly_threshold))
+
+    def set_serial(self, serial=True, adaptive_threshold=1.0, adaptive_exponent=1.0):
+        """The extra samples follow the serial Render() (Renderer.cs:150-191)."""
+        self.lib.orc_set_serial(self.h, int(serial), float(adaptive_threshold), float(adaptive_exponent))
 
     def last_samples(self, W, H):
         """Pixel.Samples of the Buffer the last render() filled."""

@@ -22,6 +22,8 @@ struct orc_world {
     bool compiled = false;
     int adaptiveSamples = 0, fireflySamples = 0;
     double fireflyThreshold = 1;
+    int serialRules = 0;
+    double adaptiveThreshold = 1, adaptiveExponent = 1;
     std::vector<int> lastSamples;  // Pixel.Samples of the last orc_render
 };
 
@@ -157,6 +159,10 @@ void orc_sampler(orc_world* w, int firstHit, int maxBounces, int directLighting,
 void orc_set_extra(orc_world* w, int adaptiveSamples, int fireflySamples, double fireflyThreshold) {
     w->adaptiveSamples = adaptiveSamples; w->fireflySamples = fireflySamples; w->fireflyThreshold = fireflyThreshold;
 }
+// serial != 0: the extra samples follow the serial Render() (Renderer.cs:150-191) with Renderer.AdaptiveThreshold / AdaptiveExponent.
+void orc_set_serial(orc_world* w, int serial, double adaptiveThreshold, double adaptiveExponent) {
+    w->serialRules = serial; w->adaptiveThreshold = adaptiveThreshold; w->adaptiveExponent = adaptiveExponent;
+}
 
 int orc_last_samples(orc_world* w, int n, int* out) {
     if ((size_t)n != w->lastSamples.size()) return -1;
@@ -237,6 +243,7 @@ void orc_render(orc_world* w, int W, int H, int spp, int passes, int stratified,
         opt.sampleBase = sampleBase;
         opt.sampleStride = sampleStride > 0 ? sampleStride : 1;
         opt.AdaptiveSamples = w->adaptiveSamples; opt.FireflySamples = w->fireflySamples; opt.FireflyThreshold = w->fireflyThreshold;
+        opt.SerialRules = w->serialRules != 0; opt.AdaptiveThreshold = w->adaptiveThreshold; opt.AdaptiveExponent = w->adaptiveExponent;
         if (window) { opt.x0 = window[0]; opt.y0 = window[1]; opt.x1 = window[2]; opt.y1 = window[3]; }
         Counters c = RenderPass(w->scene, w->camera, w->sampler, buf, opt);
         total.cameraSamples += c.cameraSamples;

@@ -370,6 +370,8 @@ struct RenderOptions {
     int AdaptiveSamples = 0;          // Renderer.cs:23
     int FireflySamples = 0;           // Renderer.cs:27
     double FireflyThreshold = 1;      // Renderer.cs:47
+    bool SerialRules = false;         // the extra samples follow the serial Render() (Renderer.cs:150-191) instead of RenderParallel
+    double AdaptiveThreshold = 1, AdaptiveExponent = 1;  // Renderer.cs:44-45
     // optional window (bounded CPU-baseline samples): pixels outside it are skipped
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
 };
@@ -482,7 +484,54 @@ static inline Counters RenderPass(Scene& scene, const Camera& camera, const Defa
         cn.cameraSamples++;
         return sampler.Sample(scene, ray, rng, cn);
     };
-    if (opt.AdaptiveSamples > 0) {
+    if (opt.SerialRules) {
+        // Renderer.cs:150-191 (the serial Render(), what IterativeRender runs when NumCPU == 1).  Per pixel, after its main sample:
+        //   samples = AdaptiveSamples * (int)Math.Pow(Math.Clamp(StandardDeviation.MaxComponent / AdaptiveThreshold, 0, 1), AdaptiveExponent)
+        //   more samples with fu, fv = rand.NextDouble() (:153-165); then, if the deviation exceeds FireflyThreshold, FireflySamples
+        //   more with fu = (x + rand) * invWidth, invWidth = 1.0f / w (:97, :172-186) and no IsFirefly test.  Pixels are independent
+        //   of each other here, so the two stages run frame-wide one after the other.
+        auto deviation = [&](size_t i) { return buf.Pixels[i].Variance().Pow((double)0.5f).MaxComponent(); };
+        for (int stage = 0; stage < 2; stage++) {
+            const int nExtra = stage == 0 ? opt.AdaptiveSamples : opt.FireflySamples;
+            if (nExtra <= 0) continue;
+            std::vector<uint32_t> list;
+            for (size_t i = 0; i < buf.Pixels.size(); i++) {
+                int y = (int)(i / (size_t)w), x = (int)(i % (size_t)w);
+                if (x < wx0 || x >= wx1 || y < wy0 || y >= wy1) continue;
+                bool pick;
+                if (stage == 0) {
+                    double v = deviation(i) / opt.AdaptiveThreshold;
+                    v = v < 0 ? 0.0 : (v > 1 ? 1.0 : v);
+                    v = std::pow(v, opt.AdaptiveExponent);
+                    pick = (int)v >= 1;
+                } else pick = deviation(i) > opt.FireflyThreshold;
+                if (pick) list.push_back((uint32_t)i);
+            }
+            std::vector<Colour> fresh(list.size());
+            for (int j = 0; j < nExtra; j++) {
+                parallelFor(list.size(), [&](size_t a, size_t b, int tid) {
+                    Rng rng; rng.mode = opt.rngMode;
+                    if (opt.rngMode == RNG_SEQUENTIAL) rng.SeedSequential(((uint64_t)opt.seed << 32) ^ ((uint64_t)opt.pass << 20) ^ (stage ? 0xF1000 : 0xA1000) ^ ((uint64_t)j << 8) ^ (uint64_t)tid);
+                    Counters cn;
+                    for (size_t i = a; i < b; i++) {
+                        int y = (int)(list[i] / (uint32_t)w), x = (int)(list[i] % (uint32_t)w);
+                        if (stage == 0) fresh[i] = extraSample(x, y, kAdaptiveBase + (uint32_t)j, rng, cn);
+                        else {
+                            rng.SetSample(opt.seed, opt.pass, list[i], kFireflyBase + (uint32_t)j);
+                            rng.Enter(0, 0, 0, 0);
+                            const double xo = rng.NextDouble(), yo = rng.NextDouble();
+                            const double fu = ((double)x + xo) * (double)(1.0f / (float)w), fv = ((double)y + yo) * (double)(1.0f / (float)h);
+                            Ray ray = camera.CastRay(x, y, w, h, fu, fv, rng);
+                            cn.cameraSamples++;
+                            fresh[i] = sampler.Sample(scene, ray, rng, cn);
+                        }
+                    }
+                    perThread[(size_t)tid].segments += cn.segments; perThread[(size_t)tid].shadowRays += cn.shadowRays; perThread[(size_t)tid].cameraSamples += cn.cameraSamples;
+                });
+                for (size_t i = 0; i < list.size(); i++) buf.Pixels[list[i]].AddSample(fresh[i]);
+            }
+        }
+    } else if (opt.AdaptiveSamples > 0) {
         // Renderer.cs:340-364: AdaptiveSamples more samples for EVERY pixel, each its own Buffer.AddSample.  (The second loop,
         // :376-388, re-renders as many samples only to fill a dictionary nothing reads: no effect on the Buffer, omitted.)
         parallelFor((size_t)w * h, [&](size_t a, size_t b, int tid) {
@@ -497,7 +546,7 @@ static inline Counters RenderPass(Scene& scene, const Camera& camera, const Defa
             perThread[(size_t)tid].segments += cn.segments; perThread[(size_t)tid].shadowRays += cn.shadowRays; perThread[(size_t)tid].cameraSamples += cn.cameraSamples;
         });
     }
-    if (opt.FireflySamples > 0) {
+    if (!opt.SerialRules && opt.FireflySamples > 0) {
         // Renderer.cs:418-468.  Every pixel whose StandardDeviation().MaxComponent() > FireflyThreshold takes up to
         // FireflySamples more samples and stops at the first one IsFirefly() rejects.  The reference lets every pixel's loop
         // read its neighbours' running means while other threads update them; here the iterations are synchronous (all

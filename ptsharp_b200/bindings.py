@@ -36,7 +36,8 @@ class Pass(C.Structure):
                 ("maxBounces", C.c_int32), ("directLighting", C.c_int32), ("softShadows", C.c_int32),
                 ("lightMode", C.c_int32), ("specularMode", C.c_int32), ("seed", C.c_uint32), ("passIndex", C.c_uint32),
                 ("camera", Camera), ("adaptiveSamples", C.c_int32), ("fireflySamples", C.c_int32),
-                ("fireflyThreshold", C.c_double)]
+                ("fireflyThreshold", C.c_double), ("serialRules", C.c_int32), ("reserved0", C.c_int32),
+                ("adaptiveThreshold", C.c_double), ("adaptiveExponent", C.c_double)]
 
 
 class Params(C.Structure):
@@ -211,11 +212,13 @@ class HostWorld(World):
         return V, N, T
 
     def make_pass(self, width, height, spp, stratified=False, seed=0x50545348, pass_index=0, sample_base=0,
-                  sample_stride=1, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0) -> Pass:
+                  sample_stride=1, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0, serial_rules=False,
+                  adaptive_threshold=1.0, adaptive_exponent=1.0) -> Pass:
         p = Pass()
         self.lib.pth_make_pass(self.h, width, height, spp, int(stratified), seed, pass_index, sample_base, sample_stride,
                                C.byref(p))
         p.adaptiveSamples, p.fireflySamples, p.fireflyThreshold = adaptive_samples, firefly_samples, firefly_threshold
+        p.serialRules, p.adaptiveThreshold, p.adaptiveExponent = int(serial_rules), adaptive_threshold, adaptive_exponent
         return p
 
     def tree_stats(self, which=-1):

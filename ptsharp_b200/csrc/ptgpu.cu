@@ -166,7 +166,7 @@ PT_D void bounce(V3 rayDir, const Surface& sf, double u, double v, int mode, Rng
 // ====================================================================================================== pipeline state
 struct PassD {  // ptgpu_pass plus derived values, passed by value to kernels
     int32_t width, height, spp, stratified, sppRoot;
-    int32_t subpixelJitter;  // 1: fu, fv = xi1, xi2 (adaptive / firefly passes, Renderer.cs:351-353, 432)
+    int32_t subpixelJitter;  // 1: fu, fv = xi1, xi2 (adaptive / firefly passes, Renderer.cs:351-353, 432); 2: fu = (x + xi) * (1.0f / w) (serial firefly, Renderer.cs:97-98, 179-180)
     int32_t sampleBase, sampleStride;
     int32_t firstHitSamples, maxBounces, directLighting, softShadows, lightMode, specularMode;
     uint32_t seed, passIndex;
@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
             fv = ((double)(s % (uint32_t)P.sppRoot) + 0.5) / (double)P.sppRoot;
         } else {
             double xo = rng_next(rng), yo = rng_next(rng);
-            if (P.subpixelJitter) { fu = xo; fv = yo; }
+            if (P.subpixelJitter == 1) { fu = xo; fv = yo; }
+            else if (P.subpixelJitter == 2) { fu = ((double)x + xo) * (double)(1.0f / (float)P.width); fv = ((double)y + yo) * (double)(1.0f / (float)P.height); }
             else { fu = ((double)x + xo) / (double)P.width; fv = ((double)y + yo) / (double)P.height; }
         }
         V3 o, d;
@@ -560,7 +561,10 @@ __global__ void k_read_buffer(PixelBuf pb, int channel, int w, int h, float* __r
 }
 
 // Firefly pass (Renderer.cs:418-468).  Pixels whose StandardDeviation().MaxComponent() exceeds the threshold.
-__global__ void k_firefly_select(PixelBuf pb, double threshold, uint32_t npix, uint32_t* __restrict__ list, uint32_t* __restrict__ listCount) {
+// mode 0: deviation > threshold (Renderer.cs:426 / :174).  mode 1: the serial Render()'s adaptive rule (Renderer.cs:153-158):
+// (int)pow(clamp(deviation / threshold, 0, 1), exponent) >= 1.
+__global__ void k_firefly_select(PixelBuf pb, double threshold, uint32_t npix, uint32_t* __restrict__ list, uint32_t* __restrict__ listCount, int mode = 0,
+                                 double exponent = 1.0) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         int32_t ns = pb.samples[i];
         double mx = 0;
@@ -569,7 +573,15 @@ __global__ void k_firefly_select(PixelBuf pb, double threshold, uint32_t npix, u
             double sd = pow(v, (double)0.5f);
             mx = c == 0 ? sd : netmax(mx, sd);
         }
-        if (mx > threshold) {
+        bool pick;
+        if (mode == 0) pick = mx > threshold;
+        else {
+            double v = mx / threshold;
+            v = v < 0 ? 0.0 : (v > 1 ? 1.0 : v);  // Math.Clamp
+            v = pow(v, exponent);
+            pick = (int)v >= 1;
+        }
+        if (pick) {
             auto g = cg::coalesced_threads();
             uint32_t base = 0;
             if (g.thread_rank() == 0) base = atomicAdd(listCount, g.size());
@@ -610,7 +622,7 @@ __global__ void k_firefly_apply(float* __restrict__ sum, const uint32_t* __restr
     const uint32_t n = *listCount;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t pixel = list[i];
-        const bool rej = reject[i];
+        const bool rej = reject ? reject[i] : false;
         if (!rej) {
             int32_t ns = pb.samples[pixel] + 1;
             pb.samples[pixel] = ns;
@@ -1519,7 +1531,31 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
     if (out_mean_rgb) CK(cudaMemcpyAsync(out_mean_rgb, ctx->dMean, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     // Extra samples use their own ranges of the global sample index so that no Philox stream is reused.
     const int kAdaptiveBase = 1 << 20, kFireflyBase = 1 << 21;
-    if (pass->adaptiveSamples > 0) {  // Renderer.cs:340-364
+    if (pass->serialRules) {  // Renderer.cs:150-191: the extra samples of the serial Render()
+        if (pass->adaptiveSamples > 0 && pass->adaptiveExponent < 0) return fail(ctx, PTGPU_E_ARG, "serialRules: a negative AdaptiveExponent is not supported");
+        uint32_t* lc = ctx->dCounts + 8;  // [8], [9]: list counts
+        for (int stage = 0; stage < 2; stage++) {
+            const int nExtra = stage == 0 ? pass->adaptiveSamples : pass->fireflySamples;
+            if (nExtra <= 0) continue;
+            PassD Q = P;
+            Q.stratified = 0; Q.subpixelJitter = stage == 0 ? 1 : 2; Q.sampleStride = 1;
+            CK(cudaMemsetAsync(lc, 0, 2 * sizeof(uint32_t), st));
+            CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
+            if (stage == 0) k_firefly_select<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->pb, pass->adaptiveThreshold, (uint32_t)npix, ctx->dList[0], lc, 1, pass->adaptiveExponent);
+            else k_firefly_select<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->pb, pass->fireflyThreshold, (uint32_t)npix, ctx->dList[0], lc, 0, 1.0);
+            ctx->launches++;
+            int cur = 0;
+            for (int j = 0; j < nExtra; j++) {  // every listed pixel takes all nExtra samples, each its own AddSample
+                Q.sampleBase = (stage == 0 ? kAdaptiveBase : kFireflyBase) + j;
+                rc = run_pass(ctx, Q, 1, ctx->dSum, st, ctx->dList[cur], lc + cur);
+                if (rc != PTGPU_OK) return rc;
+                CK(cudaMemsetAsync(lc + (cur ^ 1), 0, sizeof(uint32_t), st));
+                k_firefly_apply<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, ctx->dList[cur], lc + cur, nullptr, ctx->pb, ctx->dList[cur ^ 1], lc + (cur ^ 1));
+                ctx->launches++;
+                cur ^= 1;
+            }
+        }
+    } else if (pass->adaptiveSamples > 0) {  // Renderer.cs:340-364
         PassD Q = P;
         Q.stratified = 0; Q.subpixelJitter = 1; Q.sampleStride = 1;
         for (int j = 0; j < pass->adaptiveSamples; j++) {
@@ -1531,7 +1567,7 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
             ctx->launches++;
         }
     }
-    if (pass->fireflySamples > 0) {  // Renderer.cs:418-468
+    if (!pass->serialRules && pass->fireflySamples > 0) {  // Renderer.cs:418-468
         PassD Q = P;
         Q.stratified = 0; Q.subpixelJitter = 1; Q.sampleStride = 1;
         uint32_t* lc = ctx->dCounts + 8;  // [8], [9]: list counts

@@ -172,6 +172,7 @@ void pth_make_pass(pth_world* w, int width, int height, int spp, int stratified,
     out->seed = seed; out->passIndex = passIndex;
     out->camera = FlattenCamera(w->camera);
     out->adaptiveSamples = 0; out->fireflySamples = 0; out->fireflyThreshold = 1.0;
+    out->serialRules = 0; out->reserved0 = 0; out->adaptiveThreshold = 1.0; out->adaptiveExponent = 1.0;
 }
 
 // kd-tree dump in the oracle's canonical pre-order form (builder parity tests).  which = -1: scene tree, else the

@@ -906,14 +906,16 @@ static void Check(ptgpu_ctx* ctx, int rc, const char* what) {
         throw std::runtime_error(std::string(what) + ": " + (e ? e : "unknown error"));
     }
 }
-Renderer Renderer::NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sampler, int w, int h, bool) {  // Renderer.cs:35-56
+Renderer Renderer::NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sampler, int w, int h, bool multithreaded) {  // Renderer.cs:35-56
     Renderer r;
+    r.NumCPU = multithreaded ? 0 : 1;  // 0 = "ProcessorCount": the parallel path
     r.scene_ = &scene; r.camera_ = &camera; r.sampler_ = &sampler; r.w_ = w; r.h_ = h;
     return r;
 }
 Renderer::Renderer(Renderer&& o) noexcept
     : SamplesPerPixel(o.SamplesPerPixel), StratifiedSampling(o.StratifiedSampling), AdaptiveSamples(o.AdaptiveSamples),
-      FireflySamples(o.FireflySamples), FireflyThreshold(o.FireflyThreshold), Device(o.Device), Seed(o.Seed), scene_(o.scene_), camera_(o.camera_),
+      FireflySamples(o.FireflySamples), FireflyThreshold(o.FireflyThreshold), AdaptiveThreshold(o.AdaptiveThreshold), AdaptiveExponent(o.AdaptiveExponent),
+      NumCPU(o.NumCPU), Device(o.Device), Seed(o.Seed), scene_(o.scene_), camera_(o.camera_),
       sampler_(o.sampler_), w_(o.w_), h_(o.h_), passIndex_(o.passIndex_), ctx_(o.ctx_), flat_(std::move(o.flat_)) {
     o.ctx_ = nullptr;
 }
@@ -941,11 +943,19 @@ ptgpu_pass Renderer::MakePass() const {
     p.seed = Seed; p.passIndex = passIndex_;
     p.camera = FlattenCamera(*camera_);
     p.adaptiveSamples = AdaptiveSamples; p.fireflySamples = FireflySamples; p.fireflyThreshold = FireflyThreshold;
+    p.serialRules = 0; p.adaptiveThreshold = AdaptiveThreshold; p.adaptiveExponent = AdaptiveExponent;
     return p;
 }
 void Renderer::RenderParallel(float* out) {
     EnsureUploaded();
     ptgpu_pass p = MakePass();
+    Check(ctx_, ptgpu_render_pass(ctx_, &p, out), "ptgpu_render_pass");
+    passIndex_++;
+}
+void Renderer::Render(float* out) {  // Renderer.cs:80-198
+    EnsureUploaded();
+    ptgpu_pass p = MakePass();
+    p.serialRules = 1;
     Check(ctx_, ptgpu_render_pass(ctx_, &p, out), "ptgpu_render_pass");
     passIndex_++;
 }
@@ -963,7 +973,7 @@ ptgpu_counters Renderer::Counters() {
 }
 void Renderer::IterativeRender(const std::string& pathTemplate, int iter) {  // Renderer.cs:702-765
     for (int i = 1; i <= iter; i++) {
-        RenderParallel(nullptr);
+        if (NumCPU == 1) Render(nullptr); else RenderParallel(nullptr);  // Renderer.cs:712-719
         std::string path = pathTemplate;
         size_t k = path.find("{0}");
         if (k != std::string::npos) path.replace(k, 3, std::to_string(i));

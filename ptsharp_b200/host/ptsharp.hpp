@@ -315,6 +315,8 @@ public:
     bool StratifiedSampling = false;
     int AdaptiveSamples = 0, FireflySamples = 0;  // Renderer.cs:340-468, run on the device after the main pass
     double FireflyThreshold = 1;                  // Renderer.cs:47
+    double AdaptiveThreshold = 1, AdaptiveExponent = 1;  // Renderer.cs:44-45 (read by the serial Render() only, :153-158)
+    int NumCPU = 0;                               // Renderer.cs:38: 1 when NewRenderer(..., multithreaded = false) -> IterativeRender runs the serial Render()
     int Device = 0;
     uint32_t Seed = 0x50545348u;
     static Renderer NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sampler, int w, int h, bool multithreaded);
@@ -323,6 +325,8 @@ public:
     Renderer(const Renderer&) = delete;
     // One pass (Renderer.RenderParallel): returns this pass's mean image (w*h*3) if out != nullptr.
     void RenderParallel(float* outMeanRgb = nullptr);
+    // One pass with the serial Render()'s rules for the extra samples (Renderer.cs:80-198); the main pass is the same.
+    void Render(float* outMeanRgb = nullptr);
     // `iter` passes; after each the Color channel is written as binary PPM to pathTemplate ("{0}" -> pass number).
     // (The reference writes PNG through SkiaSharp, Renderer.cs:721-729; image encoding is out of scope.)
     void IterativeRender(const std::string& pathTemplate, int iter);

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(bindings):
 def test_struct_layouts_match_header(bindings):
     # sizes the C compiler gives the ABI structs (see include/ptgpu.h)
     assert C.sizeof(bindings.Camera) == 72
-    assert C.sizeof(bindings.Pass) == 56 + 72 + 16
+    assert C.sizeof(bindings.Pass) == 56 + 72 + 16 + 24
     assert C.sizeof(bindings.Params) == 16
     assert C.sizeof(bindings.Counters) == 104
 

@@ -255,6 +255,45 @@ def test_adaptive_and_firefly_passes(orc, bindings, device):
     assert abs(cnt["cameraSamples"] - ocnt["cameraSamples"]) <= 0.01 * ocnt["cameraSamples"]
 
 
+def test_serial_render_rules(orc, bindings, device):
+    """The serial Render() (Renderer.cs:150-191, what IterativeRender runs when NumCPU == 1): AdaptiveSamples more samples only for
+    pixels whose deviation reaches AdaptiveThreshold (`samples = AdaptiveSamples * (int)v`), then FireflySamples more for pixels above
+    FireflyThreshold with fu = (x + xi) * (1.0f / w) and no IsFirefly test.  Two passes: after the first every deviation is 0."""
+    hw, ow, _ = _worlds(orc, bindings, "c1")
+    device.upload(hw)
+    W, H, spp, A, F, athr, fthr = 64, 48, 2, 2, 3, 0.08, 0.15
+    device.reset_buffer()
+    device.reset_counters()
+    ns_pass = []
+    for i in range(2):
+        device.render_pass(hw.make_pass(W, H, spp, pass_index=i, adaptive_samples=A, firefly_samples=F, firefly_threshold=fthr, serial_rules=True,
+                                        adaptive_threshold=athr, adaptive_exponent=1.0), want_mean=False)
+        ns_pass.append(device.read_buffer(W, H, 3)[..., 0].astype(np.int64))
+    cnt = device.counters()
+    mean = device.read_buffer(W, H, 0).astype(np.float64)
+    var = device.read_buffer(W, H, 1).astype(np.float64)
+    ns = ns_pass[1]
+    device.reset_buffer()
+    ow.set_extra(A, F, fthr)
+    ow.set_serial(True, athr, 1.0)
+    ref, rvar, ocnt = ow.render(W, H, spp, passes=2, threads=os.cpu_count() or 1, rng_mode=orc.RNG_KEYED)
+    rns = ow.last_samples(W, H)
+    ow.set_extra(0, 0, 1.0)
+    ow.set_serial(False)
+    assert (ns_pass[0] == 1).all()                                   # one sample in the buffer: Variance() is 0, nothing is picked
+    assert set(np.unique(ns)) <= {2, 2 + A, 2 + F, 2 + A + F} and (ns == 2).any() and (ns > 2).any()
+    assert (ns != rns).mean() < 0.01
+    same = ns == rns
+    rel = np.abs(mean - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert (rel.max(axis=2)[same] > 1e-4).mean() < 5e-3
+    relv = np.abs(var - rvar) / np.maximum(np.abs(rvar), 1e-3)
+    assert (relv.max(axis=2)[same] > 1e-3).mean() < 1e-2
+    assert abs(cnt["cameraSamples"] - ocnt["cameraSamples"]) <= 0.01 * ocnt["cameraSamples"]
+    with pytest.raises(bindings.PtgpuError):                         # (int)pow(v < 1, negative) is unbounded: rejected
+        device.render_pass(hw.make_pass(W, H, spp, adaptive_samples=1, serial_rules=True, adaptive_exponent=-1.0), want_mean=False)
+    device.reset_buffer()
+
+
 def test_buffer_welford_matches_reference_formula(orc, bindings, device):
     """Buffer.AddSample over several passes (Buffer.cs:33-57) against numpy on the per-pass means."""
     hw, _, _ = _worlds(orc, bindings, "c1")

@@ -162,3 +162,23 @@ def test_light_registration_and_struct_identity(orc):  # Scene.cs:29-38, SURVEY 
     V = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], np.float32)
     w.add(w.mesh(V, light))                                               # Mesh.MaterialAt is `new Material()`: not a light
     assert w.num_lights() == 2
+
+
+def test_serial_render_adaptive_rule(orc):  # Renderer.cs:153-158: samples = AdaptiveSamples * (int)pow(clamp(sd / threshold, 0, 1), exponent)
+    from ptsharp_b200 import scenes
+    ow = orc.OracleWorld()
+    scenes.build_c1(ow)
+    W, H = 24, 16
+    ow.set_extra(3, 0, 1.0)
+    ow.set_serial(True, 0.05, 1.0)
+    ow.render(W, H, 1, passes=1, threads=2, rng_mode=orc.RNG_KEYED)
+    assert (ow.last_samples(W, H) == 1).all()        # first pass: one sample per pixel, deviation 0, (int)0 = 0 extra samples
+    ow.set_serial(True, 0.05, 0.0)
+    ow.render(W, H, 1, passes=1, threads=2, rng_mode=orc.RNG_KEYED)
+    assert (ow.last_samples(W, H) == 1 + 3).all()    # exponent 0: pow(v, 0) = 1 for every pixel
+    ow.set_serial(True, 0.05, 1.0)
+    ow.render(W, H, 1, passes=2, threads=2, rng_mode=orc.RNG_KEYED)
+    ns = ow.last_samples(W, H)
+    assert set(np.unique(ns)) == {2, 5}              # second pass: only the pixels whose deviation reached the threshold
+    ow.set_extra(0, 0, 1.0)
+    ow.set_serial(False)
