@@ -573,3 +573,66 @@ def test_loaded_model_renders_like_the_oracle(orc, bindings, device, tmp_path):
     np.testing.assert_array_equal(g["prim"], c["prim"])
     np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
     np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+
+
+def _random_scene(w, rng, n_mesh, n_inst, n_analytic):
+    """A random scene through the shared authoring verbs: small displaced icospheres (some instanced under random rotate /
+    non-uniform scale / translate matrices), spheres, cubes, cylinders, transformed cylinders, a floor plane and a light."""
+    from ptsharp_b200 import hostmath as hm
+    mats = [w.DiffuseMaterial(tuple(rng.random(3))), w.GlossyMaterial(tuple(rng.random(3)), 1.3 + rng.random(), 0.1 * rng.random()),
+            w.ClearMaterial(1.5, 0.0), w.SpecularMaterial(tuple(rng.random(3)), 2.0)]
+    pick = lambda: mats[int(rng.integers(len(mats)))]
+    w.add(w.plane((0, -1.0, 0), (0, 1, 0), mats[0]))
+    meshes = []
+    for _ in range(n_mesh):
+        c = rng.uniform(-2.5, 2.5, 3); c[1] = rng.uniform(-0.5, 1.5)
+        V = scenes.displaced_icosphere(int(rng.integers(2, 7)), float(rng.uniform(0.3, 0.9)), tuple(c), amplitude=float(rng.uniform(0, 0.15)), k=float(rng.uniform(3, 12)))
+        m = w.mesh(V, pick())
+        meshes.append(m)
+        w.add(m)
+    for _ in range(n_inst):
+        base = scenes.displaced_icosphere(int(rng.integers(2, 5)), 0.5, (0, 0, 0), amplitude=0.1)
+        m = w.mesh(base, pick())
+        axis = rng.normal(size=3)
+        M = hm.mul(hm.translate(hm.vec(rng.uniform(-3, 3, 3))), hm.mul(hm.rotate(hm.vec(axis), float(rng.uniform(0, 6.28))), hm.scale(hm.vec(rng.uniform(0.4, 1.8, 3)))))
+        w.add(w.transformed(m, M))
+    for _ in range(n_analytic):
+        kind = int(rng.integers(4))
+        p = rng.uniform(-3, 3, 3)
+        if kind == 0: w.add(w.sphere(tuple(p), float(rng.uniform(0.2, 0.8)), pick()))
+        elif kind == 1: w.add(w.cube(tuple(p - rng.uniform(0.1, 0.6, 3)), tuple(p + rng.uniform(0.1, 0.6, 3)), pick()))
+        elif kind == 2: w.add(w.cylinder(float(rng.uniform(0.1, 0.5)), float(rng.uniform(-1, 0)), float(rng.uniform(0.1, 1)), pick()))
+        else: w.add(w.transformed_cylinder(tuple(p), tuple(p + rng.uniform(-1, 1, 3)), float(rng.uniform(0.05, 0.3)), pick()))
+    w.add(w.sphere((0, 6, 0), 0.8, w.LightMaterial((1, 1, 1), 30)))
+    w.look_at((0, 2.0, -7.0), (0, 0.3, 0), (0, 1, 0), 45)
+    w.sampler(1, 3)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_scenes_closest_hit_bit_exact(orc, bindings, device, seed):
+    """Randomised scenes (meshes of different sizes, instances under general affine matrices, every analytic shape, many shapes per
+    Scene.tree leaf): closest hits of camera rays and of rays leaving the surfaces, bit for bit against the oracle."""
+    n_mesh, n_inst, n_analytic = [(2, 0, 3), (1, 6, 4), (0, 12, 0), (5, 5, 10), (3, 0, 20), (0, 0, 12)][seed - 1]
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    _random_scene(hw, np.random.default_rng(1000 + seed), n_mesh, n_inst, n_analytic)
+    _random_scene(ow, np.random.default_rng(1000 + seed), n_mesh, n_inst, n_analytic)
+    device.upload(hw)
+    o, d = _ray_batch(ow, W=96, H=72, n_secondary=9000, seed=seed)
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    assert hit.sum() > 4000
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["prim"], c["prim"])
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["inside"], c["inside"])
+    # and one keyed camera sample per pixel through the whole sampler
+    W, H = 80, 60
+    device.reset_counters()
+    img = device.render_pass(hw.make_pass(W, H, 1, pass_index=0)).astype(np.float64)
+    cnt = device.counters()
+    ref, _, ocnt = ow.render(W, H, 1, passes=1, threads=os.cpu_count() or 1, rng_mode=orc.RNG_KEYED, seed=0x50545348)
+    rel = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert (rel.max(axis=2) > 1e-4).mean() < 2e-3
+    assert abs(cnt["segments"] - ocnt["segments"]) <= 1e-3 * ocnt["segments"] + 4
