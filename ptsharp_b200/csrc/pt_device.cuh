@@ -22,12 +22,6 @@
 #define PT_HD __host__ __device__ __forceinline__
 #define PT_DN __device__ __noinline__
 
-#ifndef PT_PREFETCH
-#define PT_PREFETCH 0
-#endif
-#ifndef PT_LEAF_PIPELINE
-#define PT_LEAF_PIPELINE 0
-#endif
 #ifndef PT_SHORTCUT
 #define PT_SHORTCUT 1
 #endif
@@ -677,20 +671,6 @@ PT_D int scene_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 
     return KD_INTERIOR;
 }
 
-#ifndef PT_PREFETCH2
-#define PT_PREFETCH2 0
-#endif
-PT_D void prefetch_l1(const void* p) {
-#if PT_PREFETCH2
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-// A lane usually waits a scheduling turn or two between learning what it will touch next and touching it: ask for it now.
-PT_D void prefetch_node(const uint4* __restrict__ nodes, uint32_t node) { if (!(node & (1u << 29))) prefetch_l1(nodes + (size_t)node * 4); }
-PT_D void prefetch_leaf(const float4* __restrict__ geom, uint32_t first, uint32_t count) {
-    prefetch_l1(geom + (size_t)first * 3);
-    if (count > 2) prefetch_l1(geom + (size_t)first * 3 + 6);
-}
 #ifdef PT_DEBUG_STEPS
 __device__ unsigned long long g_dbg[8];  // 0 items, 1 real steps, 2 virtual steps, 3 leaf visits, 4 triangle tests, 5 pops, 6 pushes
 #define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
@@ -729,10 +709,6 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
     bool hitR = box_line_hit_fast(__uint_as_float(q2.z), __uint_as_float(q2.w), __uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z),
                                   __uint_as_float(q3.w), ra, tnR);
     const uint32_t left = a >> 2, right = b & kNodeIndexMask;
-#if PT_PREFETCH
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (size_t)left * 4));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (size_t)right * 4));
-#endif
     bool go;
     if (axis == 0) {
         // bounds-only node.  tn* are strict lower bounds of the T of any triangle below the child (the padded box contains
@@ -780,28 +756,6 @@ PT_D int mesh_step(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor& 
 // The triangles [tPos, tEnd) of a micro leaf, at most `budget` of them.  Triangles are stored in sorted order, and the
 // reference keeps the FIRST shape in array order among equal T (Tree.cs:122), hence the position tie-break.
 PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, double& best, int32_t& prim, uint32_t& bestPos, int budget) {
-#if PT_LEAF_PIPELINE
-    // software pipeline: the next triangle's three quads are in flight while this one is tested (the tests of a micro leaf are
-    // otherwise four serialised memory round trips)
-    if (!(tPos < tEnd) || budget <= 0) return;
-    const float4* g = S.leafGeom + (size_t)tPos * 3;
-    float4 A = __ldg(g), B4 = __ldg(g + 1), C4 = __ldg(g + 2);
-#pragma unroll 1
-    for (int k = 0; k < budget && tPos < tEnd; k++) {
-        const bool more = tPos + 1 < tEnd && k + 1 < budget;
-        float4 nA = A, nB = B4, nC = C4;
-        if (more) { nA = __ldg(g + 3); nB = __ldg(g + 4); nC = __ldg(g + 5); }
-        DBG_ADD(4, 1);
-        const double t = triangle_intersect_regs(A, B4, C4, o, d);
-        if (t <= best && t < kHitInf) {  // rare (a T of INF never replaces NoHit)
-            const uint32_t pos = __float_as_uint(B4.w);
-            if (t < best || pos < bestPos) { best = t; prim = (int32_t)__float_as_uint(A.w); bestPos = pos; }
-        }
-        A = nA; B4 = nB; C4 = nC;
-        g += 3;
-        tPos++;
-    }
-#else
 #pragma unroll 1
     for (int k = 0; k < budget && tPos < tEnd; k++) {
         const float4* g = S.leafGeom + (size_t)tPos * 3;
@@ -813,7 +767,6 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
         }
         tPos++;
     }
-#endif
 }
 
 // The triangle tests of every lane that sits in a micro leaf, spread over ALL lanes of the warp.  ncu on the per-lane
@@ -891,12 +844,6 @@ PT_D double primitive_intersect_analytic(const DScene& S, const ptgpu_shape& sh,
 #endif
 #ifndef PT_SPLIT_FETCH_MIN
 #define PT_SPLIT_FETCH_MIN 8   // mesh_walk refills idle lanes once this many wait (or nothing else is left to do)
-#endif
-#ifndef PT_BURST_VOTE
-#define PT_BURST_VOTE 0     // mesh_walk: leave a NODE burst once fewer than this many lanes are still walking (0 = off)
-#endif
-#ifndef PT_SPLIT_FETCH_MIN2
-#define PT_SPLIT_FETCH_MIN2 16  // mesh_walk2 (64 rays per warp)
 #endif
 #ifndef PT_LEAF_UNROLL
 #define PT_LEAF_UNROLL 1
@@ -1310,18 +1257,6 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                 }
             }
         } else if (PT_COOP_LEAF ? !(nLeaf >= PT_COOP_LEAF_MIN || nNode == 0) : (nNode >= nLeaf)) {
-#if PT_BURST_VOTE
-#pragma unroll 1
-            for (int k = 0; k < PT_NODE_BURST; k++) {
-                if (k > 0 && __popc(__ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE)) < PT_BURST_VOTE) break;
-                if (st == ST_MESH_NODE) {
-                    uint32_t first, count;
-                    const int r = mesh_step_t(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
-                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
-                    else if (r == MESH_DONE) st = ST_MESH_DONE;
-                }
-            }
-#else
             if (st == ST_MESH_NODE) {
 #pragma unroll 1
                 for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
@@ -1330,12 +1265,10 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 #ifdef PT_DEBUG_STEPS
                     dbgSteps++;
 #endif
-                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; prefetch_leaf(S.leafGeom, first, count); }
+                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
                     else if (r == MESH_DONE) st = ST_MESH_DONE;
                 }
-                if (st == ST_MESH_NODE) prefetch_node(S.meshNodes, mc.node);
             }
-#endif
         } else {
 #if PT_COOP_LEAF
             coop_leaf(S, st == ST_MESH_LEAF, co, cd, tPos, tEnd, mBest, mPrim, mBestPos);
@@ -1348,10 +1281,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 #if !PT_COOP_LEAF
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
 #endif
-                if (tPos >= tEnd) {
-                    st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
-                    if (st == ST_MESH_NODE) prefetch_node(S.meshNodes, mc.node);
-                }
+                if (tPos >= tEnd) st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
             }
         }
 #ifdef PT_DEBUG_STEPS
@@ -1361,85 +1291,6 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
         }
 #endif
         if (st == ST_MESH_DONE) { W.mBest[ray] = mBest; W.mPrim[ray] = mPrim; st = ST_IDLE; }
-    }
-}
-
-// mesh_walk with TWO rays per lane.  A warp's NODE and LEAF populations are about equal whatever the rays are, so with
-// one ray per lane a burst starts with half the lanes.  Here a lane owns two rays; the warp votes over all 64, and a lane
-// takes part in the winning class if EITHER of its rays is in it (the active ray lives in registers, the parked one is
-// swapped in when needed), which lifts the expected share of busy lanes from 1/2 to 3/4.
-struct WalkRay {
-    V3 co, cd;
-    RayBox ra;
-    KdCursor mc;
-    uint32_t tPos, tEnd, bestPos, ray, stackOff;
-    double best;
-    int32_t prim;
-    int st;
-};
-PT_D void walk_swap(WalkRay& a, WalkRay& b, bool p) {
-#define SW(f) { auto t_ = a.f; a.f = p ? b.f : a.f; b.f = p ? t_ : b.f; }
-    SW(co.x) SW(co.y) SW(co.z) SW(cd.x) SW(cd.y) SW(cd.z) SW(ra.ix) SW(ra.iy) SW(ra.iz) SW(ra.cx) SW(ra.cy) SW(ra.cz) SW(ra.P)
-    SW(mc.node) SW(mc.sp) SW(mc.tmin) SW(mc.tmax) SW(tPos) SW(tEnd) SW(bestPos) SW(ray) SW(stackOff) SW(best) SW(prim) SW(st)
-#undef SW
-}
-PT_D void mesh_walk2(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
-    const uint32_t n = *q.count;
-    WalkRay A, B;
-    A.co = B.co = v3(0, 0, 0); A.cd = B.cd = v3(0, 0, 1);
-    A.ra = B.ra = ray_box(A.co, A.cd);
-    A.mc.node = B.mc.node = 0; A.mc.sp = B.mc.sp = 0; A.mc.tmin = A.mc.tmax = B.mc.tmin = B.mc.tmax = 0;
-    A.tPos = A.tEnd = A.bestPos = A.ray = B.tPos = B.tEnd = B.bestPos = B.ray = 0;
-    A.best = B.best = kHitInf; A.prim = B.prim = -1;
-    A.st = B.st = ST_IDLE;
-    A.stackOff = 0; B.stackOff = kMeshStackEnt;
-    uint4 mStk[2 * kMeshStackEnt];
-    bool drained = false;  // the cursor ran past n: nothing left to fetch
-    for (;;) {
-        const int nIdle = drained ? 0 : __popc(__ballot_sync(0xFFFFFFFFu, A.st == ST_IDLE)) + __popc(__ballot_sync(0xFFFFFFFFu, B.st == ST_IDLE));
-        const int nLeaf = __popc(__ballot_sync(0xFFFFFFFFu, A.st == ST_MESH_LEAF)) + __popc(__ballot_sync(0xFFFFFFFFu, B.st == ST_MESH_LEAF));
-        const int nNode = __popc(__ballot_sync(0xFFFFFFFFu, A.st == ST_MESH_NODE)) + __popc(__ballot_sync(0xFFFFFFFFu, B.st == ST_MESH_NODE));
-        if (nIdle + nLeaf + nNode == 0) break;
-        const int cls = (nIdle >= PT_SPLIT_FETCH_MIN2 || nLeaf + nNode == 0) ? ST_IDLE : (nNode >= nLeaf ? ST_MESH_NODE : ST_MESH_LEAF);
-        walk_swap(A, B, A.st != cls && B.st == cls);
-        if (cls == ST_IDLE) {
-            if (A.st == ST_IDLE) {
-                auto g = cooperative_groups::coalesced_threads();
-                uint32_t base = 0;
-                if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
-                const uint32_t i = g.shfl(base, 0) + g.thread_rank();
-                if (i >= n) A.st = ST_EXIT;
-                else {
-                    const float4 a = q.a[i], b = q.b[i];
-                    const double2 c = q.c[i];
-                    A.co = v3(a.x, a.y, a.z); A.cd = v3(b.x, b.y, b.z); A.ray = __float_as_uint(a.w);
-                    A.ra = ray_box(A.co, A.cd);
-                    A.mc.node = __float_as_uint(b.w); A.mc.tmin = c.x; A.mc.tmax = c.y; A.mc.sp = 0;
-                    stk_put(mStk + A.stackOff, A.mc.tmax, 0u, 0u);
-                    A.best = kHitInf; A.prim = -1; A.bestPos = 0;
-                    A.st = ST_MESH_NODE;
-                }
-            }
-            if (__any_sync(0xFFFFFFFFu, A.st == ST_EXIT)) drained = true;
-            if (drained) { if (A.st == ST_IDLE) A.st = ST_EXIT; if (B.st == ST_IDLE) B.st = ST_EXIT; }
-        } else if (cls == ST_MESH_NODE) {
-            if (A.st == ST_MESH_NODE) {
-                uint4* stk = mStk + A.stackOff;
-#pragma unroll 1
-                for (int k = 0; k < PT_NODE_BURST && A.st == ST_MESH_NODE; k++) {
-                    uint32_t first, count;
-                    const int r = mesh_step(S.meshNodes, A.ra, A.mc, A.co, A.cd, stk, A.best, A.bestPos, first, count);
-                    if (r == MESH_LEAF) { A.tPos = first; A.tEnd = first + count; A.st = ST_MESH_LEAF; }
-                    else if (r == MESH_DONE) A.st = ST_MESH_DONE;
-                }
-            }
-        } else {
-            if (A.st == ST_MESH_LEAF) {
-                leaf_work(S, A.co, A.cd, A.tPos, A.tEnd, A.best, A.prim, A.bestPos, PT_LEAF_BURST);
-                if (A.tPos >= A.tEnd) A.st = mesh_pop(A.mc, A.best, mStk + A.stackOff) ? ST_MESH_NODE : ST_MESH_DONE;
-            }
-        }
-        if (A.st == ST_MESH_DONE) { W.mBest[A.ray] = A.best; W.mPrim[A.ray] = A.prim; A.st = drained ? ST_EXIT : ST_IDLE; }
     }
 }
 

@@ -475,9 +475,6 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
 // Small blocks: the warps of a launch finish at very different times (a few grazing rays take ~1000 steps) and a block's
 // registers are only returned when its last warp exits.  The walk is latency-bound, so occupancy pays: 2-warp blocks
 // (32 blocks/SM is the hardware limit) at 48 registers = 40 warps/SM measured 4 % faster than 32 warps at 57 registers.
-#ifndef PT_MESH_RAYS
-#define PT_MESH_RAYS 1
-#endif
 #ifndef PT_MESH_BLOCK
 #define PT_MESH_BLOCK 64
 #endif
@@ -486,12 +483,8 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
 #endif
 static constexpr size_t kMeshSmemBytes = (size_t)PT_SMEM_STACK * PT_MESH_BLOCK * sizeof(uint4);
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
-#if PT_MESH_RAYS == 2
-    mesh_walk2(S, W, q, cursor);
-#else
     extern __shared__ uint4 smemStack[];  // PT_SMEM_STACK rows of blockDim.x entries
     mesh_walk(S, W, q, cursor, smemStack);
-#endif
 }
 
 __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
