@@ -830,6 +830,15 @@ PT_D double primitive_intersect_analytic(const DScene& S, const ptgpu_shape& sh,
     }
 }
 
+#ifndef PT_MARCH_SPLIT
+#define PT_MARCH_SPLIT 1   // C5 (2 spp pass): 1365 ms with both bursts every turn at 2 / 4 steps, 1010 ms with separate turns at 16 / 64
+#endif
+#ifndef PT_SDF_BURST
+#define PT_SDF_BURST 16   // SDF sphere-tracing steps per MARCH turn of trace_rays
+#endif
+#ifndef PT_VOL_BURST
+#define PT_VOL_BURST 64   // Volume marching steps per MARCH turn
+#endif
 #ifndef PT_LEAF_BURST
 #define PT_LEAF_BURST 8
 #endif
@@ -888,15 +897,18 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
         const unsigned marchMask = __ballot_sync(0xFFFFFFFFu, st == ST_SDF || st == ST_VOLUME);
         const int nLeaf = __popc(leafMask), nNode = __popc(nodeMask), nMarch = __popc(marchMask);
         const int nGlue = 32 - nLeaf - nNode - nMarch - __popc(exitMask);
+        // PT_MARCH_SPLIT: SDF and Volume lanes take separate turns (the larger group first) instead of both bursts in every turn
+        bool sdfTurn = true;
+        if (PT_MARCH_SPLIT) sdfTurn = __popc(__ballot_sync(0xFFFFFFFFu, st == ST_SDF)) * 2 >= nMarch;
 
         if (nMarch > 0 && nMarch >= nGlue && nMarch >= nLeaf && nMarch >= nNode) {
             // MARCH class: one SDF sphere-tracing step / a few Volume marching steps per turn.  The loop state lives in
             // the (idle) mesh-traversal variables of the lane: mc.tmin = t, mc.tmax = t2 | tmax, mc.sp = iteration
             // counter, mc.node = flags, mBest = Volume step.
-            if (st == ST_SDF) {  // SDFShape.Intersect loop body (SDF.cs:47-74); mc.node bit0 = `jump`
+            if (st == ST_SDF && sdfTurn) {  // SDFShape.Intersect loop body (SDF.cs:47-74); mc.node bit0 = `jump`
                 const ptgpu_sdf_shape& sh = S.sdfShapes[marchData];
 #pragma unroll 1
-                for (int k = 0; k < 2 && st == ST_SDF; k++) {
+                for (int k = 0; k < PT_SDF_BURST && st == ST_SDF; k++) {
                     if (mc.sp >= 1000) { mBest = kHitInf; st = ST_MESH_DONE; break; }
                     mc.sp++;
                     double dist = sdf_evaluate(S.sdfOps + sh.progFirst, sh.progCount, ray_at(co, cd, mc.tmin));
@@ -907,11 +919,11 @@ PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor,
                     mc.tmin += dist;
                     if (mc.tmin > mc.tmax) { mBest = kHitInf; st = ST_MESH_DONE; }
                 }
-            } else if (st == ST_VOLUME) {  // Volume.Intersect (Volume.cs:169-197), one Sign() per step
+            } else if (st == ST_VOLUME && (!PT_MARCH_SPLIT || !sdfTurn)) {  // Volume.Intersect (Volume.cs:169-197), one Sign() per step
                 // mc.node: bits 0-15 = sign + 1, bit 16 = refining, bits 17-31 = pending sign + 1; mc.sp = refine counter
                 const ptgpu_volume& v = S.volumes[marchData];
 #pragma unroll 1
-                for (int k = 0; k < 4 && st == ST_VOLUME; k++) {
+                for (int k = 0; k < PT_VOL_BURST && st == ST_VOLUME; k++) {
                     const bool refining = (mc.node >> 16) & 1u;
                     if (!refining) {
                         if (!(mc.tmin <= mc.tmax)) { mBest = kHitInf; st = ST_MESH_DONE; break; }  // `t <= tmax` loop test
