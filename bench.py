@@ -295,7 +295,7 @@ def main():
         out = np.empty((H, W, 3), np.float32)
         pinned = torch.from_numpy(out).pin_memory() if hasattr(torch.Tensor, "pin_memory") else None
         host_out = pinned.numpy() if pinned is not None else out
-        scene_bytes = hw.flat_bytes()
+        scene_bytes = dev.scene_bytes()  # everything ptgpu_upload_scene copies host -> device: the flat scene and the records derived from it
         n_e2e = max(1, min(args.steps, 2))
         barrier()
         t0 = time.perf_counter()
@@ -313,6 +313,7 @@ def main():
             b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM); e2e_samples = float(b[1])
         e2e = {"value": e2e_samples / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(scene_bytes + 128),
                "d2h_bytes_per_step": int(npix * 3 * 4), "steps": n_e2e,
+               "flat_scene_bytes": int(hw.flat_bytes()),
                "api": "ptgpu_upload_scene + ptgpu_render_pass (what Renderer.RenderParallel calls), host buffers, wall clock"}
 
     base = None
