@@ -285,7 +285,7 @@ def main():
             "avg_launch_ms": kms / max(klaunches, 1), "kernel_ms_in_profiled_pass": kms, "share_of_step": kms / total_stage,
             "pipeline": {"bytes_per_bounce": B_PER_BOUNCE_NEE, "bytes_per_sample": B_PER_SAMPLE,
                          "achieved": pipeline_bytes / sec / 1e9, "frac": pipeline_bytes / sec / 1e9 / peak},
-            "note": "latency/divergence-bound kd-tree walk: HBM traffic is the streamed queues plus the part of the 300 MB "
+            "note": "latency/divergence-bound kd-tree walk: HBM traffic is the streamed queues plus the part of the 221 MB "
                     "scene working set that misses the 126 MB L2; see profiles/ for SIMT efficiency, issue utilisation and hit rates",
         }
 
