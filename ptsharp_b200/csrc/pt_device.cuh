@@ -580,7 +580,7 @@ PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3
 PT_D void stk_put(uint4* e, double ts, uint32_t node, uint32_t culled) { *e = make_uint4((uint32_t)__double2loint(ts), (uint32_t)__double2hiint(ts), node, culled); }
 PT_D double stk_t(const uint4& e) { return __hiloint2double((int)e.y, (int)e.x); }
 
-PT_D bool box_line_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, V3 o, const RayAux& ra) {
+PT_D bool box_line_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, V3 o, const RayAux& ra, float* entry = nullptr) {
     // fminf/fmaxf ignore NaNs (0 * inf when the origin lies on a slab plane of a zero direction): conservative
     const float x1 = (lox - ra.pad - o.x) * ra.ix, x2 = (hix + ra.pad - o.x) * ra.ix;
     const float y1 = (loy - ra.pad - o.y) * ra.iy, y2 = (hiy + ra.pad - o.y) * ra.iy;
@@ -588,6 +588,7 @@ PT_D bool box_line_hit(float lox, float loy, float loz, float hix, float hiy, fl
     const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
     const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
     const float slack = 1e-5f * fabsf(tf) + 1e-30f;
+    if (entry) *entry = tn - 1e-5f * fabsf(tn) - 1e-30f;  // a lower bound of the parameter at which the ray enters the padded box (NaN: no bound)
     return !(tn > tf + slack) && !(tf < -slack);  // NaN comparisons are false -> treated as a hit
 }
 
@@ -1074,6 +1075,9 @@ struct SplitState {      // per ray of the launch, SoA
     double* mBest; int32_t* mPrim;                                              // Hit of the pending Mesh.Intersect
     uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
 };
+#ifndef PT_BEST_CLIP
+#define PT_BEST_CLIP 1   // scene_advance: no mesh walk beyond the running best of the Scene.tree traversal (see there)
+#endif
 struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root node)  c = (tmin, tmax)
     float4* a; float4* b; double2* c; uint32_t* count;
 };
@@ -1119,6 +1123,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
         V3 co = o, cd = d;
         uint4* sstk = W.sceneStack + (size_t)ray * W.stackEnt;
         const RayAux worldAux = ray_aux(o, d);
+        const float dirLen = vlenf(d);  // 1 for every ray the renderer makes; ptgpu_intersect_batch takes directions as given
         int st;
         if (RESUME) {
             best.t = W.bestT[ray]; best.tInner = W.bestTInner[ray]; best.shape = W.bestShape[ray]; best.prim = W.bestPrim[ray];
@@ -1169,7 +1174,14 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         // FP32 pre-test in world space: a ray that misses the padded world bounds of the instanced mesh gives a
                         // shapeRay that misses the mesh's Box (Tree.cs:36-41) -> NoHit, without the FP64 transform
                         const float4 wlo = __ldg(S.instBounds + 2 * (size_t)sh.data), whi = __ldg(S.instBounds + 2 * (size_t)sh.data + 1);
+#if PT_BEST_CLIP
+                        // ... and an instance entered beyond the running best cannot change it: its Hit's T is the world-space distance to a
+                        // point inside these bounds (TransformedShape.cs:69: parameter x |direction|), and the fold only takes T < best.T
+                        float entry;
+                        if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux, &entry) || (double)(entry * dirLen) > best.t * (1.0 + 1e-4)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
+#else
                         if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
+#endif
                         const ptgpu_instance& inst = S.instances[sh.data];
                         co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
                         sh = S.shapes[inst.shape];
@@ -1180,6 +1192,18 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         double tmin = 0, tmax = -1;
                         const RayAux ra = ray_aux(co, cd);
                         if (tree_box_maybe_hit(mt, co, ra)) box_intersect(mt.bmin, mt.bmax, co, cd, tmin, tmax);
+#if PT_BEST_CLIP
+                        // The fold below only takes a mesh Hit with T < best.T (Tree.cs:121-125).  Every triangle lies inside the tree's
+                        // box, so a box entered beyond best.T cannot give one: no walk.  Otherwise the walk's tmax is cut to best.T: it
+                        // then visits a prefix of the cells the reference visits, in the same order, and a Hit below best.T lies in that
+                        // prefix - so the Hit that gets folded is the same.  (1e-5 relative margin against the FP32 rounding of
+                        // the triangle test's T; object-space T of an instance is not comparable with best.T, so instances are left alone.)
+                        if (curInst < 0 && !(tmax < tmin || tmax <= 0)) {
+                            const double lim = best.t * (1.0 + 1e-5);
+                            if (tmin > lim) tmax = -1;
+                            else if (tmax > lim) tmax = lim;
+                        }
+#endif
                         if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
                         else if (MODE == SCENE_FINISH) { mesh_walk_single(S, co, cd, mt.root, tmin, tmax, mBest, mPrim); st = ST_MESH_DONE; }
                         else {
