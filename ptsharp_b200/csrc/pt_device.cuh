@@ -21,6 +21,17 @@
 #define PT_D __device__ __forceinline__
 #define PT_HD __host__ __device__ __forceinline__
 #define PT_DN __device__ __noinline__
+// k_shade was 215 KB of SASS with every libm call, Philox refill and texture fetch inlined at each call site, and ncu showed
+// 41 % of its stall samples in `no_instructions` (instruction-cache misses of divergent warps).  PT_COMPACT = 1 keeps ONE copy of
+// those bodies (PT_DC = noinline, scalar arguments and results only: nothing forces a value into local memory).
+#ifndef PT_COMPACT
+#define PT_COMPACT 1
+#endif
+#if PT_COMPACT
+#define PT_DC __device__ __noinline__
+#else
+#define PT_DC __device__ __forceinline__
+#endif
 
 #ifndef PT_SHORTCUT
 #define PT_SHORTCUT 1
@@ -56,6 +67,10 @@ PT_D float vlenf(V3 a) { return sqrtf(vdotf(a, a)); }
 PT_D V3 vnorm(V3 a) { float l = vlenf(a); return v3(a.x / l, a.y / l, a.z / l); }
 PT_D bool veq(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 PT_D bool vzero(V3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+PT_DC double2 sincos_c(double a) { double s_, c_; sincos(a, &s_, &c_); return make_double2(s_, c_); }  // (sin, cos)
+PT_DC double acos_c(double x) { return acos(x); }
+PT_DC V3 vnorm_c(V3 a) { return vnorm(a); }  // shading code: one copy of the three IEEE divisions + sqrt
+PT_DC double atan2_c(double y, double x) { return atan2(y, x); }
 PT_D float vaxis(V3 a, uint32_t axis) { return axis == 1 ? a.x : (axis == 2 ? a.y : a.z); }
 
 // System.Math.Min/Max (.NET Core 3.0+): NaN-propagating, -0 < +0.  CUDA fmin/fmax drop NaNs, so hand-written.
@@ -525,9 +540,43 @@ PT_D RayAux ray_aux(V3 o, V3 d) {
 }
 // The same slab test with fewer instructions for the mesh walk: t = lo * i - o * i by FMA, and the per-ray padding applied
 // once to the interval ends as P = pad * max|i| (>= pad * |i| on every axis: only more conservative).
-struct RayBox { float ix, iy, iz, cx, cy, cz, P; };
+#ifndef PT_MERGED_STEP
+#define PT_MERGED_STEP 0   // 1: reference and bounds-only nodes share one instruction stream in mesh_step_t
+#endif
+#ifndef PT_RCP_DIV
+#define PT_RCP_DIV 0   // 1: tsplit of a mesh-tree step by kd_div (per-ray correctly rounded reciprocals); 0: a plain FP64 division per step
+#endif
+struct RayBox {
+    float ix, iy, iz, cx, cy, cz, P;
+#if PT_RCP_DIV
+    double rx, ry, rz;  // RN(1 / (double)d) per axis (IEEE division, once per ray)
+    bool rok;           // every |d| component is a normal float: the reciprocals are finite, non-zero and normal
+#endif
+};
+// `tsplit = (split - o[axis]) / d[axis]` (Tree.cs:86-98) without a division per node.  nvcc's own div.rn.f64 fast path is
+// y = Newton-refined reciprocal, q0 = RN(a y), r = RN(a - b q0) (exact), q = RN(q0 + r y); with y = RN(1/b) that last step is
+// Markstein's correction, which returns RN(a/b) — the value the reference's double division produces — whenever nothing
+// leaves the normal range.  That is guaranteed here by construction: b is a float widened to double (24-bit significand,
+// |b| in [2^-126, 2^128) when `rok`), and the fast path is only taken for |a| in [2^-127, 2^128) (a = split - o is a difference
+// of float-valued numbers, so this is every non-zero a but subnormal-float ones), hence |q| in [2^-255, 2^255] and the residual
+// is >= 2^-310.  Everything else (a = 0, NaN, infinities, zero / subnormal direction components) takes the plain division.
+// tests/test_gpu_parity.py::test_kd_div_matches_ieee_division compares it with `/` bit for bit on 2^33 operand pairs.
+PT_D double kd_div(double a, double b, double rcp, bool rok) {
+    const uint32_t ea = ((uint32_t)__double2hiint(a) & 0x7FFFFFFFu) - 0x38000000u;  // biased exponent 896 = 2^-127
+    if (rok && ea < 0x0FF00000u) {                                                  // ... up to 1151 = 2^128 (exclusive)
+        const double q0 = a * rcp;
+        const double r = fma(-b, q0, a);
+        return fma(r, rcp, q0);
+    }
+    return a / b;
+}
 PT_D RayBox ray_box(V3 o, V3 d) {
     RayBox a;
+#if PT_RCP_DIV
+    a.rx = 1.0 / (double)d.x; a.ry = 1.0 / (double)d.y; a.rz = 1.0 / (double)d.z;
+    const float tiny = 1.17549435e-38f;  // FLT_MIN; false for NaN, true for inf -> checked with the upper bound
+    a.rok = fabsf(d.x) >= tiny && fabsf(d.y) >= tiny && fabsf(d.z) >= tiny && fabsf(d.x) < INFINITY && fabsf(d.y) < INFINITY && fabsf(d.z) < INFINITY;
+#endif
     a.ix = 1.0f / d.x; a.iy = 1.0f / d.y; a.iz = 1.0f / d.z;
     a.cx = o.x * a.ix; a.cy = o.y * a.iy; a.cz = o.z * a.iz;  // NaN when o = 0 and d = 0 on an axis: the min/max below ignore NaNs
     const float pad = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
@@ -711,6 +760,39 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
                                   __uint_as_float(q3.w), ra, tnR);
     const uint32_t left = a >> 2, right = b & kNodeIndexMask;
     bool go;
+#if PT_MERGED_STEP
+    // One instruction stream for both node kinds (the lanes of a NODE turn hold reference and bounds-only nodes side by side, and
+    // two branches would each be issued for the whole warp).  A bounds-only node is the "both children" case of Node.Intersect with
+    // near / far in place of first / second, the far child's entry bound in place of tsplit, and tmin / tmax left alone; its lanes
+    // run the reference arithmetic on whatever q0 holds and drop the result in the selects below.
+    const bool isRef = axis != 0;
+    const double split = __hiloint2double((int)q0.y, (int)q0.x);
+    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+#if PT_RCP_DIV
+    const double tsplit = kd_div(split - oa, da, axis == 1 ? ra.rx : (axis == 2 ? ra.ry : ra.rz), ra.rok);
+#else
+    const double tsplit = (split - oa) / da;
+#endif
+    // bounds-only: a child with best.T <= tn cannot improve or tie the running best (see the comment in the other variant)
+    hitL = hitL && (isRef || !(bestT <= (double)tnL));
+    hitR = hitR && (isRef || !(bestT <= (double)tnR));
+    const bool leftFirst = isRef ? ((oa < split) || (oa == split && da <= 0)) : !(tnR < tnL);
+    const uint32_t first = leftFirst ? left : right, second = leftFirst ? right : left;
+    const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
+    const double key = isRef ? tsplit : (double)(leftFirst ? tnR : tnL);
+    const bool onlyFirst = isRef && (tsplit > c.tmax || tsplit <= 0);
+    const bool onlySecond = isRef && !onlyFirst && tsplit < c.tmin;
+    const bool both = !onlyFirst && !onlySecond;
+    const bool skipFirst = both && !hitFirst;                          // the near child returns NoHit: what the pop of (second, key) would do
+    const bool resume = skipFirst && hitSecond && !(bestT <= key);
+    if (both && hitFirst && (isRef || hitSecond)) { c.sp++; stk.put(c.sp, stk_entry(key, second, hitSecond ? 0u : 1u)); }
+    c.node = (onlySecond || skipFirst) ? second : first;
+    go = onlyFirst ? hitFirst : (onlySecond ? hitSecond : (skipFirst ? resume : true));
+    if (isRef) {
+        if (resume) { c.tmin = key; c.tmax = netmin_best(c.tmax, bestT); }
+        else if (both && hitFirst) c.tmax = key;
+    }
+#else
     if (axis == 0) {
         // bounds-only node.  tn* are strict lower bounds of the T of any triangle below the child (the padded box contains
         // the triangles with a margin far above the FP32 error of the triangle test), so a child with best.T <= tn cannot
@@ -727,7 +809,11 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
     } else {
         const double split = __hiloint2double((int)q0.y, (int)q0.x);
         const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
+#if PT_RCP_DIV
+        const double tsplit = kd_div(split - oa, da, axis == 1 ? ra.rx : (axis == 2 ? ra.ry : ra.rz), ra.rok);
+#else
         const double tsplit = (split - oa) / da;
+#endif
         const bool leftFirst = (oa < split) || (oa == split && da <= 0);
         const uint32_t first = leftFirst ? left : right, second = leftFirst ? right : left;
         const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
@@ -745,6 +831,7 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
             go = hitFirst;
         }
     }
+#endif
     if (go) return MESH_INTERIOR;
     return mesh_pop_t(c, bestT, stk) ? MESH_INTERIOR : MESH_DONE;
 }
@@ -1334,7 +1421,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 struct Col { double r, g, b; };
 PT_D void modf_net(double in, int& dec, double& frac) { double tr = trunc(in); dec = (int)tr; frac = in - tr; }  // Util.cs:108-113
 PT_D double fract_net(double x) { int d; double f; modf_net(x, d, f); return f; }                                 // Texture.cs:218-222
-PT_D Col tex_bilinear(const DScene& S, const ptgpu_texture& tx, double u, double v) {  // Texture.cs:188-216
+PT_D Col tex_bilinear(const float4* __restrict__ texels, const ptgpu_texture& tx, double u, double v) {  // Texture.cs:188-216
     if (u == 1) u -= kEPS;
     if (v == 1) v -= kEPS;
     double w = (double)tx.width - 1, h = (double)tx.height - 1;
@@ -1342,7 +1429,7 @@ PT_D Col tex_bilinear(const DScene& S, const ptgpu_texture& tx, double u, double
     modf_net(u * w, X, x);
     modf_net(v * h, Y, y);
     int x0 = X, y0 = Y, x1 = x0 + 1, y1 = y0 + 1;
-    const float4* T = S.texels + tx.texelOffset;
+    const float4* T = texels + tx.texelOffset;
     float4 c00 = __ldg(T + (size_t)y0 * tx.width + x0), c01 = __ldg(T + (size_t)y1 * tx.width + x0);
     float4 c10 = __ldg(T + (size_t)y0 * tx.width + x1), c11 = __ldg(T + (size_t)y1 * tx.width + x1);
     double w00 = (1 - x) * (1 - y), w10 = x * (1 - y), w01 = (1 - x) * y, w11 = x * y;
@@ -1353,15 +1440,16 @@ PT_D Col tex_bilinear(const DScene& S, const ptgpu_texture& tx, double u, double
     c.r = c.r + (double)c11.x * w11; c.g = c.g + (double)c11.y * w11; c.b = c.b + (double)c11.z * w11;
     return c;
 }
-PT_D Col tex_sample(const DScene& S, int32_t id, double u, double v) {  // Texture.cs:224-229
-    const ptgpu_texture tx = S.textures[id];
+PT_DC Col tex_sample_c(const ptgpu_texture* __restrict__ textures, const float4* __restrict__ texels, int32_t id, double u, double v) {  // Texture.cs:224-229
+    const ptgpu_texture tx = textures[id];
     u = fract_net(fract_net(u) + 1);
     v = fract_net(fract_net(v) + 1);
-    return tex_bilinear(S, tx, u, 1 - v);
+    return tex_bilinear(texels, tx, u, 1 - v);
 }
+PT_D Col tex_sample(const DScene& S, int32_t id, double u, double v) { return tex_sample_c(S.textures, S.texels, id, u, v); }
 PT_D V3 tex_normal_sample(const DScene& S, int32_t id, double u, double v) {  // Texture.cs:231-237
     Col c = tex_sample(S, id, u, v);
-    return vnorm(v3d(c.r * 2 - 1, c.g * 2 - 1, c.b * 2 - 1));
+    return vnorm_c(v3d(c.r * 2 - 1, c.g * 2 - 1, c.b * 2 - 1));
 }
 PT_D int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 PT_D V3 tex_bump_sample(const DScene& S, int32_t id, double u, double v) {  // Texture.cs:239-251 (row read clamped)
@@ -1427,13 +1515,13 @@ PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
         V3 ns = tex_normal_sample(S, pm.normalTexture, (double)b.x, (double)b.y);
         if (!vzero(ns)) {
             V3 dt1 = v3(s.t2[0] - s.t1[0], s.t2[1] - s.t1[1], 0.f), dt2 = v3(s.t3[0] - s.t1[0], s.t3[1] - s.t1[1], 0.f);
-            V3 T = vnorm(vsub(vmuls(e1, (double)dt2.y), vmuls(e2, (double)dt1.y)));
-            V3 B = vnorm(vsub(vmuls(e2, (double)dt1.x), vmuls(e1, (double)dt2.x)));
+            V3 T = vnorm_c(vsub(vmuls(e1, (double)dt2.y), vmuls(e2, (double)dt1.y)));
+            V3 B = vnorm_c(vsub(vmuls(e2, (double)dt1.x), vmuls(e1, (double)dt2.x)));
             V3 N = vcross(T, B);
             double X = (double)T.x * (double)ns.x + (double)B.x * (double)ns.y + (double)N.x * (double)ns.z;
             double Y = (double)T.y * (double)ns.x + (double)B.y * (double)ns.y + (double)N.y * (double)ns.z;
             double Z = (double)T.z * (double)ns.x + (double)B.z * (double)ns.y + (double)N.z * (double)ns.z;
-            n = vnorm(v3d(X, Y, Z));  // Matrix.MulDirection
+            n = vnorm_c(v3d(X, Y, Z));  // Matrix.MulDirection
         }
     }
     if (pm.bumpTexture >= 0) {
@@ -1441,19 +1529,19 @@ PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
         V3 bump = tex_bump_sample(S, pm.bumpTexture, (double)b.x, (double)b.y);
         if (!vzero(bump)) {
             V3 dt1 = v3(s.t2[0] - s.t1[0], s.t2[1] - s.t1[1], 0.f), dt2 = v3(s.t3[0] - s.t1[0], s.t3[1] - s.t1[1], 0.f);
-            V3 tangent = vnorm(vsub(vmuls(e1, (double)dt2.y), vmuls(e2, (double)dt1.y)));
-            V3 bitangent = vnorm(vsub(vmuls(e2, (double)dt1.x), vmuls(e1, (double)dt2.x)));
+            V3 tangent = vnorm_c(vsub(vmuls(e1, (double)dt2.y), vmuls(e2, (double)dt1.y)));
+            V3 bitangent = vnorm_c(vsub(vmuls(e2, (double)dt1.x), vmuls(e1, (double)dt2.x)));
             n = vadd(n, vmuls(tangent, (double)bump.x * pm.bumpMultiplier));
             n = vadd(n, vmuls(bitangent, (double)bump.y * pm.bumpMultiplier));
         }
     }
-    return vnorm(n);
+    return vnorm_c(n);
 }
 
 // IShape.NormalAt for a non-transformed shape entry (prim = global triangle index for meshes).
 PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p) {
     switch (sh.type) {
-        case PTGPU_SPHERE: return vnorm(vsub(p, ld3(S.spheres[sh.data].center)));  // Sphere.cs:78-81
+        case PTGPU_SPHERE: return vnorm_c(vsub(p, ld3(S.spheres[sh.data].center)));  // Sphere.cs:78-81
         case PTGPU_CUBE: {                                                          // Cube.cs:57-69
             const ptgpu_cube& c = S.cubes[sh.data];
             if (fabs((double)p.x - (double)c.min[0]) < kEPS) return v3(-1, 0, 0);
@@ -1470,7 +1558,7 @@ PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p)
             const double epsilon = 0.0001;
             if (fabs((double)p.z - c.z0) > epsilon && fabs((double)p.z - c.z1) > epsilon) {
                 V3 center = v3d(0, 0, (c.z0 + c.z1) / 2);
-                V3 normal = vnorm(vsub(p, center));
+                V3 normal = vnorm_c(vsub(p, center));
                 if (vdot(normal, vsub(p, v3d(0, 0, c.z0))) < 0) normal = vneg(normal);
                 return normal;
             }
@@ -1499,8 +1587,8 @@ PT_D Mat shape_material(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3
         switch (sh.type) {
             case PTGPU_SPHERE: {  // Sphere.cs:62-69 (sic: (p.X, 0, p.Y))
                 V3 q = vsub(p, ld3(S.spheres[sh.data].center));
-                double u = atan2((double)q.z, (double)q.x);
-                double v = atan2((double)q.y, (double)vlenf(v3(q.x, 0.f, q.y)));
+                double u = atan2_c((double)q.z, (double)q.x);
+                double v = atan2_c((double)q.y, (double)vlenf(v3(q.x, 0.f, q.y)));
                 u = 1 - (u + kPi) / (2 * kPi);
                 v = (v + kPi / 2) / kPi;
                 uv = v3d(u, v, 0);
@@ -1512,7 +1600,7 @@ PT_D Mat shape_material(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3
                 uv = v3(q.x, q.z, 0.f);
                 break;
             }
-            case PTGPU_CYLINDER: uv = vnorm(v3d(-(double)p.y, (double)p.x, 0)); break;  // Cylinder.cs:114-118
+            case PTGPU_CYLINDER: uv = vnorm_c(v3d(-(double)p.y, (double)p.x, 0)); break;  // Cylinder.cs:114-118
             case PTGPU_MESH: {                                                           // Triangle.cs:128-136
                 const float4* g = S.triGeom + (size_t)prim * 3;
                 float4 a = __ldg(g), b4 = __ldg(g + 1), c4 = __ldg(g + 2);
@@ -1543,25 +1631,28 @@ struct Surface {  // HitInfo (Hit.cs:58-75)
 // Hit.Info (Hit.cs:26-55) / the HitInfo TransformedShape.Intersect pre-fills (TransformedShape.cs:52-70).
 PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
     Surface sf;
-    const ptgpu_shape sh = S.shapes[h.shape];
-    if (sh.type == PTGPU_TRANSFORMED) {
-        const ptgpu_instance& inst = S.instances[sh.data];
-        V3 so = mat_pos(inst.inv, o), sd = mat_dir(inst.inv, d);
-        const ptgpu_shape inner = S.shapes[inst.shape];
-        V3 shapePosition = ray_at(so, sd, h.tInner);
-        V3 shapeNormal = shape_normal(S, inner, h.prim, shapePosition);
-        sf.position = mat_pos(inst.m, shapePosition);
-        V3 normal = mat_dir_transposed(inst.inv, shapeNormal);
-        sf.mat = shape_material(S, inner, h.prim, shapePosition);
-        sf.inside = false;
-        if (vdot(shapeNormal, sd) > 0) { normal = vneg(normal); sf.inside = true; }
-        sf.normal = normal;
-        return sf;
+    ptgpu_shape sh = S.shapes[h.shape];
+    const bool xf = sh.type == PTGPU_TRANSFORMED;
+    const ptgpu_instance* inst = nullptr;
+    V3 so = o, sd = d;
+    double t = h.t;
+    if (xf) {  // the shape's own frame: one copy of shape_normal / shape_material serves both cases
+        inst = S.instances + sh.data;
+        so = mat_pos(inst->inv, o); sd = mat_dir(inst->inv, d);
+        sh = S.shapes[inst->shape];
+        t = h.tInner;
     }
-    V3 position = ray_at(o, d, h.t);
+    const V3 position = ray_at(so, sd, t);
     V3 normal = shape_normal(S, sh, h.prim, position);
     sf.mat = shape_material(S, sh, h.prim, position);
     sf.inside = false;
+    if (xf) {
+        sf.position = mat_pos(inst->m, position);
+        V3 wn = mat_dir_transposed(inst->inv, normal);
+        if (vdot(normal, sd) > 0) { wn = vneg(wn); sf.inside = true; }
+        sf.normal = wn;
+        return sf;
+    }
     if (vdot(normal, d) > 0) {
         normal = vneg(normal);
         sf.inside = true;

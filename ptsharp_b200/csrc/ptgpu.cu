@@ -42,7 +42,7 @@ struct Rng {
     uint32_t cache[4];
     uint32_t cachedBlock;
 };
-PT_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+PT_DC uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; i++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -51,7 +51,7 @@ PT_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
 }
 PT_D void rng_set_sample(Rng& r, uint32_t seed, uint32_t pass, uint32_t pixel, uint32_t sample) { r.k0 = seed; r.k1 = pass; r.c0 = pixel; r.c1 = sample; }
 // Counter word 3: [31:20] first-hit index+1 | [19:14] depth | [13:6] sub-stream | [5:0] block of two draws.
@@ -65,7 +65,8 @@ PT_D void rng_enter(Rng& r, uint32_t pathBits, uint32_t first, uint32_t depth, u
 PT_D double rng_next(Rng& r) {  // Random.Shared.NextDouble(): 53 random bits / 2^53
     uint32_t block = r.draw >> 1;
     if (block != r.cachedBlock) {
-        philox4x32_10(r.c0, r.c1, r.c2, r.c3 | (block & 0x3Fu), r.k0, r.k1, r.cache);
+        const uint4 o = philox4x32_10(r.c0, r.c1, r.c2, r.c3 | (block & 0x3Fu), r.k0, r.k1);
+        r.cache[0] = o.x; r.cache[1] = o.y; r.cache[2] = o.z; r.cache[3] = o.w;
         r.cachedBlock = block;
     }
     uint32_t hi = (r.draw & 1) ? r.cache[2] : r.cache[0], lo = (r.draw & 1) ? r.cache[3] : r.cache[1];
@@ -80,27 +81,26 @@ PT_D V3 random_unit_vector(Rng& rng) {
     double z = rng_next(rng) * 2.0 - 1.0;
     double a = rng_next(rng) * 2.0 * kPi;
     double r = sqrt(1.0 - z * z);
-    double s, c;
-    sincos(a, &s, &c);
-    return v3d(r * s, r * c, z);
+    const double2 sc = sincos_c(a);
+    return v3d(r * sc.x, r * sc.y, z);
 }
 // Util.Cone (Util.cs:17-32)
 PT_D V3 cone(V3 direction, double theta, double u, double v, Rng& rng) {
     if (theta < kEPS) return direction;
-    theta = theta * (1 - (2 * acos(u) / kPi));
-    double m1, m2;
-    sincos(theta, &m1, &m2);
+    theta = theta * (1 - (2 * acos_c(u) / kPi));
+    const double2 m = sincos_c(theta);
+    const double m1 = m.x, m2 = m.y;
     double a = v * 2 * kPi;
     V3 q = random_unit_vector(rng);
     V3 s = vcross(direction, q);
     V3 t = vcross(direction, s);
-    double sa, ca;
-    sincos(a, &sa, &ca);
+    const double2 sca = sincos_c(a);
+    const double sa = sca.x, ca = sca.y;
     V3 d = v3(0, 0, 0);
     d = vadd(d, vmuls(s, m1 * ca));
     d = vadd(d, vmuls(t, m1 * sa));
     d = vadd(d, vmuls(direction, m2));
-    return vnorm(d);
+    return vnorm_c(d);
 }
 // Vector.Reflect (Vector.cs:497): n.Reflect(i) = i - n * (2 * n.i)
 PT_D V3 reflect(V3 n, V3 i) { return vsub(i, vmuls(n, 2 * vdot(n, i))); }
@@ -134,24 +134,23 @@ PT_D void bounce(V3 rayDir, const Surface& sf, double u, double v, int mode, Rng
     bool refl = false;
     if (mode == 0) refl = rng_next(rng) < p;
     else if (mode == 2) refl = true;
-    if (refl) {
-        outO = sf.position;
-        outD = cone(reflect(n, rayDir), sf.mat.gloss, u, v, rng);
+    if (refl || sf.mat.transparent) {  // one copy of cone() for the reflected and the refracted ray
+        V3 base;
+        if (refl) { outO = sf.position; base = reflect(n, rayDir); pOut = p; }
+        else {
+            base = refract(n, rayDir, n1, n2);
+            outO = vadd(sf.position, vmuls(base, 1e-4));  // Ray.cs:78, the only epsilon offset in the code base
+            pOut = 1 - p;
+        }
+        outD = cone(base, sf.mat.gloss, u, v, rng);
         reflected = true;
-        pOut = p;
-    } else if (sf.mat.transparent) {
-        V3 rd = refract(n, rayDir, n1, n2);
-        outO = vadd(sf.position, vmuls(rd, 1e-4));  // Ray.cs:78, the only epsilon offset in the code base
-        outD = cone(rd, sf.mat.gloss, u, v, rng);
-        reflected = true;
-        pOut = 1 - p;
     } else {  // Ray.WeightedBounce (Ray.cs:28-35)
         double radius = sqrt(u);
         double theta = 2 * kPi * v;
-        V3 s = vnorm(vcross(n, random_unit_vector(rng)));
+        V3 s = vnorm_c(vcross(n, random_unit_vector(rng)));
         V3 t = vcross(n, s);
-        double st, ct;
-        sincos(theta, &st, &ct);
+        const double2 sct = sincos_c(theta);
+        const double st = sct.x, ct = sct.y;
         V3 d = v3(0, 0, 0);
         d = vadd(d, vmuls(s, radius * ct));
         d = vadd(d, vmuls(t, radius * st));
@@ -203,17 +202,17 @@ PT_D void cast_ray(const ptgpu_camera& cam, int x, int y, int w, int h, double u
     dir = vadd(dir, vmuls(cu, -px * aspect));
     dir = vadd(dir, vmuls(cv, -py));
     dir = vadd(dir, vmuls(cw, cam.m));
-    dir = vnorm(dir);
+    dir = vnorm_c(dir);
     V3 p = cp;
     if (cam.apertureRadius > 0) {
         V3 focalPoint = vadd(cp, vmuls(dir, cam.focalDistance));
         double angle = rng_next(rng) * 2 * kPi;
         double radius = rng_next(rng) * cam.apertureRadius;
-        double sa, ca;
-        sincos(angle, &sa, &ca);
+        const double2 sca = sincos_c(angle);
+        const double sa = sca.x, ca = sca.y;
         p = vadd(p, vmuls(cu, ca * radius));
         p = vadd(p, vmuls(cv, sa * radius));
-        dir = vnorm(vsub(focalPoint, p));
+        dir = vnorm_c(vsub(focalPoint, p));
     }
     o = p;
     d = dir;
@@ -277,15 +276,85 @@ __global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_trace(DScene S, Ray
 // Radius; anything else -> bounding box centre / outer radius.  Precomputed at upload into DLight.
 struct DLight { float center[3]; uint32_t shape; double radius; uint32_t classTyped; uint32_t isCylinder; };
 
+// Shade order.  k_shade runs one thread per hit record, and which code a record needs (Hit.Info of a triangle / cube / sphere,
+// the BRDF of its material, NEE or not) follows the surface that was hit: in ray order a warp holds a mix of them (ncu: 9.4 of 32
+// lanes per instruction, 41 % of the stall samples `no_instructions`: the divergent warps miss the instruction cache).  The hit
+// records of a launch are therefore visited bin by bin (bin = shape type x material of the surface, 0 = miss); inside a bin
+// the order stays close to ray order (2048-record chunks, warp-contiguous), so the gathers still touch whole sectors.
+// Results do not depend on the order: every draw is keyed by its place in the path tree (rng_enter).
+static constexpr int kShadeBins = 32, kBinChunk = 2048;
+PT_D uint32_t shade_bin(const DScene& S, int32_t shape) {
+    if (shape < 0) return 0u;
+    ptgpu_shape sh = S.shapes[shape];
+    if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+    const uint32_t which = sh.type == PTGPU_MESH ? sh.data * 7u : 0u;  // a Mesh carries its materials per triangle: one bin per mesh
+    return 1u + ((uint32_t)sh.type * 5u + (uint32_t)(sh.material + 1) + which) % (uint32_t)(kShadeBins - 1);
+}
+// bins[0..31] += records per bin
+__global__ void __launch_bounds__(256) k_bin_count(DScene S, const int32_t* __restrict__ shape, const uint32_t* __restrict__ count, uint32_t* __restrict__ bins) {
+    __shared__ uint32_t h[kShadeBins];
+    if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t b = shade_bin(S, shape[i]);
+        const unsigned m = __match_any_sync(__activemask(), b);
+        if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h[b], (uint32_t)__popc(m));
+    }
+    __syncthreads();
+    if (threadIdx.x < kShadeBins && h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+}
+// bins[b] = first slot of bin b (exclusive prefix sum), in place
+__global__ void k_bin_scan(uint32_t* __restrict__ bins) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t c = bins[lane];
+    uint32_t incl = c;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
+    bins[lane] = incl - c;
+}
+// perm[slot] = record index, bin by bin
+__global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __restrict__ shape, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursors,
+                                                    uint32_t* __restrict__ perm) {
+    __shared__ uint32_t h[kShadeBins], base[kShadeBins];
+    const uint32_t n = *count;
+    constexpr int kPer = kBinChunk / 256;
+    for (uint32_t c0 = blockIdx.x * (uint32_t)kBinChunk; c0 < n; c0 += gridDim.x * (uint32_t)kBinChunk) {
+        if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t bin[kPer], rank[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+            const uint32_t i = c0 + k * 256 + threadIdx.x;
+            bin[k] = i < n ? shade_bin(S, shape[i]) : 0xFFFFFFFFu;
+            const unsigned m = __match_any_sync(0xFFFFFFFFu, bin[k]);
+            const int leader = __ffs(m) - 1;
+            uint32_t off = 0;
+            if ((int)(threadIdx.x & 31) == leader && i < n) off = atomicAdd(&h[bin[k]], (uint32_t)__popc(m));
+            rank[k] = __shfl_sync(0xFFFFFFFFu, off, leader) + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < kShadeBins) base[threadIdx.x] = h[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], h[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+            const uint32_t i = c0 + k * 256 + threadIdx.x;
+            if (i < n) perm[base[bin[k]] + rank[k]] = i;
+        }
+        __syncthreads();
+    }
+}
+
 // K3.  One thread per hit record: Hit.Info, emission, then the (u, v, mode) loop of Sampler.cs:97-131.
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
                                                 HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
-                                                float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow) {
+                                                float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow,
+                                                const uint32_t* __restrict__ perm) {
     const uint32_t n = *count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = perm ? perm[j] : j;  // shade order (see k_bin_scatter)
         float4 a = q.od0[i], b = q.od1[i], c = q.bt[i];
         const V3 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z);
         const uint32_t pixel = f2u(a.w), meta = f2u(b.w), pathBits = f2u(c.w), sample = q.smp[i];
@@ -297,8 +366,8 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
         if (h.shape < 0) {  // sampleEnvironment (Sampler.cs:177-189)
             double er = S.envColor[0], eg = S.envColor[1], eb = S.envColor[2];
             if (S.envTexture >= 0) {
-                double u = atan2((double)d.z, (double)d.x) + S.envTextureAngle;
-                double v = atan2((double)d.y, (double)vlenf(v3(d.x, 0.f, d.z)));
+                double u = atan2_c((double)d.z, (double)d.x) + S.envTextureAngle;
+                double v = atan2_c((double)d.y, (double)vlenf(v3(d.x, 0.f, d.z)));
                 u = (u + kPi) / (2 * kPi);
                 v = (v + kPi / 2) / kPi;
                 Col e = tex_sample(S, S.envTexture, u, v);
@@ -380,15 +449,15 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
                                     double x = rng_next(rng) * 2 - 1;
                                     double y = rng_next(rng) * 2 - 1;
                                     if (x * x + y * y <= 1) {
-                                        V3 l = vnorm(vsub(center, sf.position));
-                                        V3 uu = vnorm(vcross(l, random_unit_vector(rng)));
+                                        V3 l = vnorm_c(vsub(center, sf.position));
+                                        V3 uu = vnorm_c(vcross(l, random_unit_vector(rng)));
                                         V3 vv = vcross(l, uu);
                                         point = vadd(vadd(center, vmuls(uu, x * radius)), vmuls(vv, y * radius));
                                         break;
                                     }
                                 }
                             }
-                            V3 rayDirection = vnorm(vsub(point, sf.position));
+                            V3 rayDirection = vnorm_c(vsub(point, sf.position));
                             double diffuse = vdot(rayDirection, sf.normal);
                             if (diffuse <= 0) continue;
                             if (!L.classTyped) continue;  // `hit.Shape != light` is always true for struct shapes
@@ -716,6 +785,41 @@ __global__ void k_keyed_draw(uint32_t seed, uint32_t pass, uint32_t pixel, uint3
     for (uint32_t i = 0; i <= drawIndex; i++) v = rng_next(rng);
     *out = v;
 }
+// kd_div (pt_device.cuh) against the IEEE division on `n` operand pairs: b runs over float bit patterns (index + offset, so 2^32
+// consecutive pairs visit every float), a is a difference of two floats of nearby magnitude (what split - o[axis] is), a random
+// double of the float range, or b times a random 53-bit significand's worth of near-midpoint quotients.
+__global__ void k_check_kd_div(uint64_t seed, uint64_t offset, uint64_t n, unsigned long long* out) {
+    unsigned long long bad = 0, fast = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + (i + offset) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const float bf = __uint_as_float((uint32_t)(i + offset));
+        const double b = (double)bf;
+        double a;
+        const uint32_t mode = (uint32_t)(z >> 62);
+        if (mode == 0) {
+            const float f1 = __uint_as_float((uint32_t)z & 0xBFFFFFFFu | 0x20000000u);      // exponents 2^-63 .. 2^64
+            const float f2 = __uint_as_float(((uint32_t)z & 0xFF800000u) | ((uint32_t)(z >> 32) & 0x007FFFFFu));
+            a = (double)f1 - (double)f2;                                                      // same sign and exponent: cancellation
+        } else if (mode == 1) {
+            a = (double)__uint_as_float((uint32_t)z) - (double)__uint_as_float((uint32_t)(z >> 32) & 0xBFFFFFFFu);
+        } else if (mode == 2) {
+            a = __longlong_as_double((long long)((z & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(896 + (z >> 52) % 255) << 52)));
+        } else {
+            // a = RN(b * m) for a random significand m: quotients that sit next to representable numbers
+            a = b * __longlong_as_double((long long)((z & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+        }
+        const float tiny = 1.17549435e-38f;
+        const bool rok = fabsf(bf) >= tiny && fabsf(bf) < INFINITY;
+        const double q = kd_div(a, b, 1.0 / b, rok), want = a / b;
+        const uint32_t ea = ((uint32_t)__double2hiint(a) & 0x7FFFFFFFu) - 0x38000000u;
+        fast += (rok && ea < 0x0FF00000u) ? 1 : 0;
+        const bool same = __double_as_longlong(q) == __double_as_longlong(want) || (q != q && want != want);
+        bad += same ? 0 : 1;
+    }
+    if (bad) atomicAdd(out, bad);
+    if (fast) atomicAdd(out + 1, fast);
+}
 
 // ====================================================================================================== host side
 static constexpr int kMaxLanes = 8;
@@ -734,6 +838,8 @@ struct Lane {
     SplitState split{};           // split tracer (scene_advance / mesh_walk): per-ray scene-level state and the two mesh work queues
     MeshQueue mq[2]{};
     uint64_t splitCap = 0;
+    uint32_t* perm = nullptr;     // shade order of the current launch (capRays entries)
+    uint32_t* bins = nullptr;     // kShadeBins counters / cursors
 };
 struct ptgpu_ctx {
     int device = 0;
@@ -870,6 +976,7 @@ static void free_queues(ptgpu_ctx* ctx) {
         for (int i = 0; i < 2; i++) { cudaFree(L.rq[i].od0); cudaFree(L.rq[i].od1); cudaFree(L.rq[i].bt); cudaFree(L.rq[i].smp); L.rq[i] = RayQueue{}; }
         cudaFree(L.hq.t); cudaFree(L.hq.tInner); cudaFree(L.hq.shape); cudaFree(L.hq.prim); L.hq = HitQueue{};
         cudaFree(L.sq.so); cudaFree(L.sq.sd); cudaFree(L.sq.sc); L.sq = ShadowQueue{};
+        cudaFree(L.perm); cudaFree(L.bins); L.perm = nullptr; L.bins = nullptr;
         L.capRays = 0; L.capShadow = 0;
         free_split(L);
     }
@@ -1290,6 +1397,9 @@ static int ensure_queues(ptgpu_ctx* ctx, Lane& L, uint64_t needRays, uint64_t ne
         CK(cudaMalloc(&L.hq.tInner, cap * sizeof(double)));
         CK(cudaMalloc(&L.hq.shape, cap * sizeof(int32_t)));
         CK(cudaMalloc(&L.hq.prim, cap * sizeof(int32_t)));
+        cudaFree(L.perm); L.perm = nullptr;
+        CK(cudaMalloc(&L.perm, cap * sizeof(uint32_t)));
+        if (!L.bins) CK(cudaMalloc(&L.bins, kShadeBins * sizeof(uint32_t)));
         L.capRays = cap;
     }
     if (needShadow > L.capShadow) {
@@ -1429,8 +1539,17 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 ctx->launches++;
             }
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
+            static const bool shadeOrder = !(std::getenv("PTGPU_SHADE_ORDER") && std::atoi(std::getenv("PTGPU_SHADE_ORDER")) == 0);  // development switch
+            if (shadeOrder) {
+                CK(cudaMemsetAsync(L.bins, 0, kShadeBins * sizeof(uint32_t), stream));
+                k_bin_count<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, counts + cur, L.bins);
+                k_bin_scan<<<1, 32, 0, stream>>>(L.bins);
+                k_bin_scatter<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, counts + cur, L.bins, L.perm);
+                ctx->launches += 3;
+            }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
-                                                   L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow);
+                                                   L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow,
+                                                   shadeOrder ? L.perm : nullptr);
             k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)L.capRays, counts + 3);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 2;
@@ -1738,6 +1857,23 @@ int ptgpu_keyed_draw(ptgpu_ctx* ctx, uint32_t seed, uint32_t pass, uint32_t pixe
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
     CK(e);
+    return PTGPU_OK;
+}
+
+int ptgpu_check_kd_div(ptgpu_ctx* ctx, uint64_t seed, uint64_t offset, uint64_t n, uint64_t* mismatches, uint64_t* fastPath) {
+    if (!ctx || !mismatches || !fastPath) return PTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    cudaMemsetAsync(d, 0, 16, ctx->stream);
+    k_check_kd_div<<<148 * 8, 256, 0, ctx->stream>>>(seed, offset, n, d);
+    ctx->launches++;
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CK(e);
+    *mismatches = h[0]; *fastPath = h[1];
     return PTGPU_OK;
 }
 
