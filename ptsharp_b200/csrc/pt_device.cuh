@@ -1328,6 +1328,15 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
 #ifndef PT_COOP_LEAF_MIN
 #define PT_COOP_LEAF_MIN 5   // run a LEAF turn once this many lanes sit in a micro leaf (or no lane is walking nodes)
 #endif
+#ifndef PT_TURN_RULE
+#define PT_TURN_RULE 0    // which class a warp of mesh_walk runs next: 0 the larger one; 1 LEAF once PT_LEAF_MIN lanes wait in a micro leaf; 2 NODE while PT_NODE_MIN lanes walk nodes
+#endif
+#ifndef PT_LEAF_MIN
+#define PT_LEAF_MIN 8
+#endif
+#ifndef PT_NODE_MIN
+#define PT_NODE_MIN 8
+#endif
 #ifndef PT_SMEM_STACK
 #define PT_SMEM_STACK 0   // entries of the walk's kd stack kept in shared memory per thread (0 = all in local memory)
 #endif
@@ -1379,7 +1388,8 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     st = ST_MESH_NODE;
                 }
             }
-        } else if (PT_COOP_LEAF ? !(nLeaf >= PT_COOP_LEAF_MIN || nNode == 0) : (nNode >= nLeaf)) {
+        } else if (PT_COOP_LEAF ? !(nLeaf >= PT_COOP_LEAF_MIN || nNode == 0)
+                   : (PT_TURN_RULE == 1 ? !(nLeaf >= PT_LEAF_MIN || nNode == 0) : (PT_TURN_RULE == 2 ? (nNode >= PT_NODE_MIN || nLeaf == 0) : (nNode >= nLeaf)))) {
             if (st == ST_MESH_NODE) {
 #pragma unroll 1
                 for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {

@@ -282,50 +282,81 @@ struct DLight { float center[3]; uint32_t shape; double radius; uint32_t classTy
 // records of a launch are therefore visited bin by bin (bin = shape type x material of the surface, 0 = miss); inside a bin
 // the order stays close to ray order (2048-record chunks, warp-contiguous), so the gathers still touch whole sectors.
 // Results do not depend on the order: every draw is keyed by its place in the path tree (rng_enter).
-static constexpr int kShadeBins = 32, kBinChunk = 2048;
-PT_D uint32_t shade_bin(const DScene& S, int32_t shape) {
+#ifndef PT_SHADE_SUB
+#define PT_SHADE_SUB 64   // patches per surface bin (1 = order by surface only).  8-spp C3 pass: 1 -> 61.05 ms, 64 -> 60.54, 256 -> 60.9
+#endif
+static constexpr int kSurfaceBins = 32, kShadeSub = PT_SHADE_SUB, kShadeBins = kSurfaceBins * kShadeSub, kBinChunk = 2048;
+// Bin of a hit record: surface (shape type x material, one per Mesh; 0 = miss) x patch.  The patch of a triangle hit is its index
+// within the mesh scaled to kShadeSub (mesh triangles are stored in a spatial order, so a patch is a piece of surface a few
+// thousand triangles large): the rays a launch appends then start patch by patch, and the mesh walks and shadow rays of the next
+// launches work on one neighbourhood of the kd-tree at a time.
+PT_D uint32_t shade_bin(const DScene& S, int32_t shape, int32_t prim) {
     if (shape < 0) return 0u;
     ptgpu_shape sh = S.shapes[shape];
     if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
-    const uint32_t which = sh.type == PTGPU_MESH ? sh.data * 7u : 0u;  // a Mesh carries its materials per triangle: one bin per mesh
-    return 1u + ((uint32_t)sh.type * 5u + (uint32_t)(sh.material + 1) + which) % (uint32_t)(kShadeBins - 1);
+    uint32_t which = 0u, sub = 0u;
+    if (sh.type == PTGPU_MESH) {
+        which = sh.data * 7u;  // a Mesh carries its materials per triangle: one surface bin per mesh
+        if (kShadeSub > 1 && prim >= 0) {
+            const ptgpu_mesh m = S.meshes[sh.data];
+            sub = (uint32_t)((float)((uint32_t)prim - m.triFirst) * __fdividef((float)kShadeSub, (float)(m.triCount ? m.triCount : 1u)));  // any monotone map will do
+            if (sub >= (uint32_t)kShadeSub) sub = kShadeSub - 1;
+        }
+    }
+    const uint32_t surface = 1u + ((uint32_t)sh.type * 5u + (uint32_t)(sh.material + 1) + which) % (uint32_t)(kSurfaceBins - 1);
+    return surface * (uint32_t)kShadeSub + sub;
 }
-// bins[0..31] += records per bin
-__global__ void __launch_bounds__(256) k_bin_count(DScene S, const int32_t* __restrict__ shape, const uint32_t* __restrict__ count, uint32_t* __restrict__ bins) {
+// bins[b] += records of bin b
+__global__ void __launch_bounds__(256) k_bin_count(DScene S, const int32_t* __restrict__ shape, const int32_t* __restrict__ prim, const uint32_t* __restrict__ count,
+                                                  uint32_t* __restrict__ bins) {
     __shared__ uint32_t h[kShadeBins];
-    if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
+    for (int b = threadIdx.x; b < kShadeBins; b += 256) h[b] = 0;
     __syncthreads();
     const uint32_t n = *count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t b = shade_bin(S, shape[i]);
+        const uint32_t b = shade_bin(S, shape[i], prim[i]);
         const unsigned m = __match_any_sync(__activemask(), b);
         if ((m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&h[b], (uint32_t)__popc(m));
     }
     __syncthreads();
-    if (threadIdx.x < kShadeBins && h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+    for (int b = threadIdx.x; b < kShadeBins; b += 256) if (h[b]) atomicAdd(&bins[b], h[b]);
 }
-// bins[b] = first slot of bin b (exclusive prefix sum), in place
-__global__ void k_bin_scan(uint32_t* __restrict__ bins) {
-    const uint32_t lane = threadIdx.x;
-    const uint32_t c = bins[lane];
-    uint32_t incl = c;
+// bins[b] = first slot of bin b (exclusive prefix sum), in place; one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* __restrict__ bins) {
+    constexpr int kPer = (kShadeBins + 1023) / 1024;
+    __shared__ uint32_t warpSum[32];
+    uint32_t v[kPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; k++) { const int b = threadIdx.x * kPer + k; v[k] = b < kShadeBins ? bins[b] : 0u; sum += v[k]; }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
     for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += t; }
-    bins[lane] = incl - c;
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warpSum[lane], wi = w;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane >= d) wi += t; }
+        warpSum[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warpSum[warp] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < kPer; k++) { const int b = threadIdx.x * kPer + k; if (b < kShadeBins) bins[b] = run; run += v[k]; }
 }
 // perm[slot] = record index, bin by bin
-__global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __restrict__ shape, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursors,
-                                                    uint32_t* __restrict__ perm) {
-    __shared__ uint32_t h[kShadeBins], base[kShadeBins];
+__global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __restrict__ shape, const int32_t* __restrict__ prim, const uint32_t* __restrict__ count,
+                                                    uint32_t* __restrict__ cursors, uint32_t* __restrict__ perm) {
+    __shared__ uint32_t h[kShadeBins];  // records of the chunk per bin, then the chunk's first slot in each bin
     const uint32_t n = *count;
     constexpr int kPer = kBinChunk / 256;
+    for (int b = threadIdx.x; b < kShadeBins; b += 256) h[b] = 0;
+    __syncthreads();
     for (uint32_t c0 = blockIdx.x * (uint32_t)kBinChunk; c0 < n; c0 += gridDim.x * (uint32_t)kBinChunk) {
-        if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
-        __syncthreads();
         uint32_t bin[kPer], rank[kPer];
 #pragma unroll
         for (int k = 0; k < kPer; k++) {
             const uint32_t i = c0 + k * 256 + threadIdx.x;
-            bin[k] = i < n ? shade_bin(S, shape[i]) : 0xFFFFFFFFu;
+            bin[k] = i < n ? shade_bin(S, shape[i], prim[i]) : 0xFFFFFFFFu;
             const unsigned m = __match_any_sync(0xFFFFFFFFu, bin[k]);
             const int leader = __ffs(m) - 1;
             uint32_t off = 0;
@@ -333,12 +364,22 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __
             rank[k] = __shfl_sync(0xFFFFFFFFu, off, leader) + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
         }
         __syncthreads();
-        if (threadIdx.x < kShadeBins) base[threadIdx.x] = h[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], h[threadIdx.x]) : 0u;
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {  // the first record of a bin in this chunk (rank 0) reserves the chunk's run in the bin
+            const uint32_t i = c0 + k * 256 + threadIdx.x;
+            if (i < n && rank[k] == 0) h[bin[k]] = atomicAdd(&cursors[bin[k]], h[bin[k]]);
+        }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kPer; k++) {
             const uint32_t i = c0 + k * 256 + threadIdx.x;
-            if (i < n) perm[base[bin[k]] + rank[k]] = i;
+            if (i < n) perm[h[bin[k]] + rank[k]] = i;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {  // leave the table zeroed for the next chunk (only the touched bins)
+            const uint32_t i = c0 + k * 256 + threadIdx.x;
+            if (i < n && rank[k] == 0) h[bin[k]] = 0;
         }
         __syncthreads();
     }
@@ -346,7 +387,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __
 
 // K3.  One thread per hit record: Hit.Info, emission, then the (u, v, mode) loop of Sampler.cs:97-131.
 #ifndef PT_SHADE_MINBLOCKS
-#define PT_SHADE_MINBLOCKS 4
+#define PT_SHADE_MINBLOCKS 8   // 64 registers: 6.8 ms vs 7.0 ms (4 blocks, 128 registers) per 8-spp C3 pass with the shade order on
 #endif
 __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
                                                 HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
@@ -1542,9 +1583,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             static const bool shadeOrder = !(std::getenv("PTGPU_SHADE_ORDER") && std::atoi(std::getenv("PTGPU_SHADE_ORDER")) == 0);  // development switch
             if (shadeOrder) {
                 CK(cudaMemsetAsync(L.bins, 0, kShadeBins * sizeof(uint32_t), stream));
-                k_bin_count<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, counts + cur, L.bins);
-                k_bin_scan<<<1, 32, 0, stream>>>(L.bins);
-                k_bin_scatter<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, counts + cur, L.bins, L.perm);
+                k_bin_count<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, L.hq.prim, counts + cur, L.bins);
+                k_bin_scan<<<1, 1024, 0, stream>>>(L.bins);
+                k_bin_scatter<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, L.hq.prim, counts + cur, L.bins, L.perm);
                 ctx->launches += 3;
             }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),

@@ -219,6 +219,42 @@ def test_replay_counts_identical(orc, bindings, device):
     assert cnt["shadowRays"] == ocnt["shadowRays"]
 
 
+_ORDER_SNIPPET = """
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from ptsharp_b200 import scenes
+from ptsharp_b200.bindings import HostWorld, Device
+hw = HostWorld()
+scenes.build_c3(hw, freq_a=12, freq_b=6)
+dev = Device(0)
+dev.upload(hw)
+img = dev.render_pass(hw.make_pass(160, 90, 4, pass_index=3))
+c = dev.counters()
+np.save({out!r}, img)
+print(c["segments"], c["shadowRays"], c["cameraSamples"])
+"""
+
+
+def test_shade_order_does_not_change_the_pass(tmp_path):
+    """k_shade visits the hit records of a launch bin by bin (k_bin_count / k_bin_scan / k_bin_scatter, csrc/ptgpu.cu).  Every
+    draw is keyed by its place in the path tree, so the pass must not depend on that order: the same pass with the order switched
+    off (PTGPU_SHADE_ORDER=0, read when the library first renders, hence the two processes) gives the same ray counts and the same
+    image up to the rounding of the unordered float additions into the pass accumulator."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs, counts = [], []
+    for flag in ("1", "0"):
+        out = str(tmp_path / f"order{flag}.npy")
+        env = dict(os.environ, PTGPU_SHADE_ORDER=flag)
+        r = subprocess.run([sys.executable, "-c", _ORDER_SNIPPET.format(root=root, out=out)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out).astype(np.float64))
+        counts.append(r.stdout.split())
+    assert counts[0] == counts[1]
+    rel = np.abs(outs[0] - outs[1]) / np.maximum(np.abs(outs[1]), 1e-3)
+    assert rel.max() < 1e-4, rel.max()
+
+
 def test_stratified_branch(orc, bindings, device):
     """Renderer.cs:231-246: sppRoot^2 samples at strata centres, each its own Buffer.AddSample."""
     hw, ow, _ = _worlds(orc, bindings, "c1")
