@@ -283,9 +283,15 @@ struct DLight { float center[3]; uint32_t shape; double radius; uint32_t classTy
 // the order stays close to ray order (2048-record chunks, warp-contiguous), so the gathers still touch whole sectors.
 // Results do not depend on the order: every draw is keyed by its place in the path tree (rng_enter).
 #ifndef PT_SHADE_SUB
-#define PT_SHADE_SUB 64   // patches per surface bin (1 = order by surface only).  8-spp C3 pass: 1 -> 61.05 ms, 64 -> 60.54, 256 -> 60.9
+#define PT_SHADE_SUB 32   // patches per surface bin (1 = order by surface only).  8-spp C3 pass with 32 surface bins: 1 -> 61.05 ms, 64 -> 60.54, 256 -> 60.9
 #endif
-static constexpr int kSurfaceBins = 32, kShadeSub = PT_SHADE_SUB, kShadeBins = kSurfaceBins * kShadeSub, kBinChunk = 2048;
+#ifndef PT_BIN_INSTANCE_MUL
+#define PT_BIN_INSTANCE_MUL 3u   // 0: every instance of a shape in the shape's bin
+#endif
+#ifndef PT_SURFACE_BINS
+#define PT_SURFACE_BINS 128   // x PT_SHADE_SUB patches = 4096 bins (16 KB shared histogram).  C4 2-spp pass: 32 x 64 -> 161.5 ms, 128 x 32 -> 157.8 (instances hashed in: 165 without); C3 unchanged
+#endif
+static constexpr int kSurfaceBins = PT_SURFACE_BINS, kShadeSub = PT_SHADE_SUB, kShadeBins = kSurfaceBins * kShadeSub, kBinChunk = 2048;
 // Bin of a hit record: surface (shape type x material, one per Mesh; 0 = miss) x patch.  The patch of a triangle hit is its index
 // within the mesh scaled to kShadeSub (mesh triangles are stored in a spatial order, so a patch is a piece of surface a few
 // thousand triangles large): the rays a launch appends then start patch by patch, and the mesh walks and shadow rays of the next
@@ -293,10 +299,10 @@ static constexpr int kSurfaceBins = 32, kShadeSub = PT_SHADE_SUB, kShadeBins = k
 PT_D uint32_t shade_bin(const DScene& S, int32_t shape, int32_t prim) {
     if (shape < 0) return 0u;
     ptgpu_shape sh = S.shapes[shape];
-    if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
     uint32_t which = 0u, sub = 0u;
+    if (sh.type == PTGPU_TRANSFORMED) { which = (sh.data + 1u) * PT_BIN_INSTANCE_MUL; sh = S.shapes[S.instances[sh.data].shape]; }  // instances of one mesh sit in different places
     if (sh.type == PTGPU_MESH) {
-        which = sh.data * 7u;  // a Mesh carries its materials per triangle: one surface bin per mesh
+        which += sh.data * 7u;  // a Mesh carries its materials per triangle: one surface bin per mesh
         if (kShadeSub > 1 && prim >= 0) {
             const ptgpu_mesh m = S.meshes[sh.data];
             sub = (uint32_t)((float)((uint32_t)prim - m.triFirst) * __fdividef((float)kShadeSub, (float)(m.triCount ? m.triCount : 1u)));  // any monotone map will do
