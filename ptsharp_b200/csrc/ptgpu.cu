@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
 #define PT_MESH_WARPS_PER_SM 40
 #endif
 static constexpr size_t kMeshSmemBytes = (size_t)PT_SMEM_STACK * PT_MESH_BLOCK * sizeof(uint4);
+// 40 warps x 48 registers is the register file: each of the four sub-partitions holds 16 K registers = 10 warps of 48 (42 warps would need 40 registers).
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
     extern __shared__ uint4 smemStack[];  // PT_SMEM_STACK rows of blockDim.x entries
     mesh_walk(S, W, q, cursor, smemStack);
