@@ -714,7 +714,13 @@ PT_D int scene_step(const ptgpu_node* __restrict__ nodes, KdCursor& c, V3 o, V3 
     if (tsplit > c.tmax || tsplit <= 0) c.node = first;
     else if (tsplit < c.tmin) c.node = second;
     else {
-        if (c.sp + 1 < stackEnt) { c.sp++; stk_put(stk + c.sp, tsplit, second, 0u); }
+        if (c.sp + 1 < stackEnt) {
+            // entry 0 (the sentinel with the root tmax, see mesh_pop) is written with the first push above it: until then c.tmax IS the
+            // root tmax (only this branch changes it), and after a pop back to level 0 it is netmin(root tmax, best.T), which gives the
+            // same netmin(.., best.T) at every later pop because best.T only decreases.  Rays that never push never touch their stack.
+            if (c.sp == 0) stk_put(stk, c.tmax, 0u, 0u);
+            c.sp++; stk_put(stk + c.sp, tsplit, second, 0u);
+        }
         c.node = first;
         c.tmax = tsplit;
     }
@@ -1227,7 +1233,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
             box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
             if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-            else { sc.node = sceneTree.root; sc.sp = 0; stk_put(sstk, sc.tmax, 0u, 0u); st = ST_SCENE_NODE; }
+            else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }  // sentinel: written by scene_step with the first push
         }
         for (;;) {
             if (st == ST_MESH_DONE) {  // fold the shape's Hit into the leaf's running best (Tree.cs:121-125)
