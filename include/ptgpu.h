@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define PTGPU_ABI_VERSION 1
+#define PTGPU_ABI_VERSION 2
+#define PTGPU_MAX_DEVICES 8
 
 enum {
     PTGPU_OK = 0,
@@ -169,15 +170,29 @@ typedef struct ptgpu_pass {
      *   firefly: pixels above fireflyThreshold (evaluated after the adaptive samples) get fireflySamples more samples with
      *     fu = (x + xi) * (1.0f / w) - no IsFirefly() rejection in the serial path.
      * Each extra sample is its own Buffer.AddSample. */
-    int32_t serialRules, reserved0;
+    int32_t serialRules;
+    /* PTGPU_PASS_* bits.  RUSSIAN_ROULETTE: the `russianRoulette` branch of DefaultSampler.sample (Sampler.cs:133-142), which the
+     * reference never enables (its only caller passes the default `false`): at depth >= 4 a vertex survives with
+     * probability p = min(max colour component of the material, 0.95) and its children carry 1/p.  Unbiased, NOT part of parity mode. */
+    int32_t flags;
     double adaptiveThreshold;    /* Renderer.AdaptiveThreshold, 1 in NewRenderer (Renderer.cs:44) */
     double adaptiveExponent;     /* Renderer.AdaptiveExponent, 1 in NewRenderer (Renderer.cs:45) */
 } ptgpu_pass;
 
+enum { PTGPU_PASS_RUSSIAN_ROULETTE = 1 };
+
 typedef struct ptgpu_params {
-    int32_t device;              /* CUDA ordinal */
+    int32_t device;              /* CUDA ordinal (used when numDevices == 0) */
     int32_t flags;               /* bits 0-3: number of lanes (independent streams + queues the batches of a pass go round), 0 = default (1) */
     uint64_t queueCapacity;      /* path records in flight over all lanes; 0 = default (2^27 ~ 64 spp of a 1920x1080 frame per batch; queues are allocated on demand, ~50 GB when full) */
+    /* Multi-GPU inside the handle (SURVEY 8b "Threading", 8e): numDevices > 1 replicates the scene on devices[0..numDevices) and
+     * ptgpu_render_pass splits the samples of every pixel over them (device k draws global samples sampleBase + (k + j*numDevices)
+     * * sampleStride); devices[0] owns the Buffer and folds the peers' float sum buffers over NVLink peer access inside the
+     * Buffer.AddSample kernel (one fused reduce + Welford per pass, no host copy).  A single-process host (the C# Renderer) thus
+     * drives every GPU of the box through the same seven calls. */
+    int32_t numDevices;          /* 0 or 1: single device */
+    int32_t devices[PTGPU_MAX_DEVICES];
+    int32_t reserved;
 } ptgpu_params;
 
 typedef struct ptgpu_counters {
@@ -191,11 +206,20 @@ typedef struct ptgpu_counters {
     double meshMs;               /* of traceMs + shadowMs: time in the mesh-walk kernel (k_mesh), 0 when the scene has no meshes */
     uint64_t meshItems;          /* Mesh.Intersect calls (work items of k_mesh) in that time */
     uint64_t meshLaunches;       /* k_mesh launches in that time */
+    uint64_t traceLaunches;      /* k_trace launches of the last profiled pass (scenes without meshes) */
+    uint64_t queueOverflows;     /* passes since create/reset in which a ray or shadow queue overflowed (records dropped: that pass is not added to the Buffer) */
+    uint64_t devices;            /* GPUs behind this handle */
 } ptgpu_counters;
 
 typedef struct ptgpu_ctx ptgpu_ctx;
 
 int ptgpu_abi_version(void);
+/* sizeof() of the ABI structs as this library was compiled, for bindings to check their marshalling against:
+ * 0 ptgpu_params, 1 ptgpu_pass, 2 ptgpu_camera, 3 ptgpu_counters, 4 ptgpu_flat_scene, 5 ptgpu_node, 6 ptgpu_tree, 7 ptgpu_shape,
+ * 8 ptgpu_sphere, 9 ptgpu_cube, 10 ptgpu_plane, 11 ptgpu_cylinder, 12 ptgpu_mesh, 13 ptgpu_tri_geom, 14 ptgpu_tri_shade,
+ * 15 ptgpu_instance, 16 ptgpu_sdf_op, 17 ptgpu_sdf_shape, 18 ptgpu_volume_window, 19 ptgpu_volume, 20 ptgpu_material,
+ * 21 ptgpu_texture; anything else: -1. */
+int ptgpu_abi_sizeof(int which);
 int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out);
 void ptgpu_destroy(ptgpu_ctx* ctx);
 const char* ptgpu_last_error(ptgpu_ctx* ctx);   /* ctx may be NULL: error of the last failed ptgpu_create */
@@ -207,8 +231,11 @@ uint64_t ptgpu_scene_bytes(ptgpu_ctx* ctx);     /* bytes of scene data resident 
  * width*height*3 floats, may be NULL) receives this pass's per-pixel mean, i.e. the value handed to AddSample. */
 int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rgb);
 
-/* Multi-GPU building blocks.  d_sum_rgb is a DEVICE pointer (width*height*3 floats) the pass's radiance is ADDED to;
- * stream is a cudaStream_t (NULL = default stream).  No Buffer update. */
+/* Multi-process multi-GPU building blocks (one rank per GPU, e.g. torchrun; a single-process host uses ptgpu_params.devices
+ * instead).  d_sum_rgb is a DEVICE pointer (width*height*3 floats) the pass's radiance is ADDED to; stream is a cudaStream_t the
+ * work is ordered on: it starts after everything already queued on that stream and the stream continues after it.  NULL = the
+ * legacy default stream (cudaStreamLegacy, what torch's default stream is).  No Buffer update.  A queue overflow is reported by
+ * ptgpu_get_counters().queueOverflows. */
 int ptgpu_accumulate_device(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* d_sum_rgb, void* stream);
 /* Buffer.AddSample(x, y, sum/divisor) for every pixel; d_sum_rgb is a DEVICE pointer. */
 int ptgpu_add_sample_device(ptgpu_ctx* ctx, int32_t width, int32_t height, const float* d_sum_rgb, double divisor, void* stream);

@@ -26,6 +26,7 @@ _EXTRA = {
     "num_lights": (C.c_int, [C.c_void_p]),
     "set_extra": (None, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
     "set_serial": (None, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
+    "set_task_sample": (None, [C.c_void_p, C.c_int, C.c_int]),
     "last_samples": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "camera_get": (None, [C.c_void_p, c_float_p, c_double_p]),
     "intersect_batch": (None, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p, c_float_p,
@@ -113,6 +114,10 @@ class OracleWorld(World):
     def set_serial(self, serial=True, adaptive_threshold=1.0, adaptive_exponent=1.0):
         """The extra samples follow the serial Render() (Renderer.cs:150-191)."""
         self.lib.orc_set_serial(self.h, int(serial), float(adaptive_threshold), float(adaptive_exponent))
+
+    def set_task_sample(self, stride=1, offset=0):
+        """render() only renders every `stride`-th non-empty 32x32 task of the frame (a bounded, evenly spread timing sample)."""
+        self.lib.orc_set_task_sample(self.h, int(stride), int(offset))
 
     def last_samples(self, W, H):
         """Pixel.Samples of the Buffer the last render() filled."""

@@ -23,6 +23,7 @@ struct orc_world {
     int adaptiveSamples = 0, fireflySamples = 0;
     double fireflyThreshold = 1;
     int serialRules = 0;
+    int taskStride = 1, taskOffset = 0;  // orc_set_task_sample
     double adaptiveThreshold = 1, adaptiveExponent = 1;
     std::vector<int> lastSamples;  // Pixel.Samples of the last orc_render
 };
@@ -225,6 +226,9 @@ void orc_cast_rays(orc_world* w, int W, int H, int n, const int* x, const int* y
     }
 }
 
+// Bounded samples for timing: render only every stride-th non-empty 32x32 task of the frame (stride <= 1: all of them).
+void orc_set_task_sample(orc_world* w, int stride, int offset) { w->taskStride = stride; w->taskOffset = stride > 1 ? ((offset % stride) + stride) % stride : 0; }
+
 // `passes` calls of RenderParallel on a fresh Buffer; mean = Pixel.M, var = Pixel.Variance() (Buffer.cs:46-55).
 // window = {x0,y0,x1,y1} or NULL.  counters = {cameraSamples, segments, shadowRays}.
 void orc_render(orc_world* w, int W, int H, int spp, int passes, int stratified, int threads, int rngMode, unsigned seed,
@@ -245,6 +249,7 @@ void orc_render(orc_world* w, int W, int H, int spp, int passes, int stratified,
         opt.AdaptiveSamples = w->adaptiveSamples; opt.FireflySamples = w->fireflySamples; opt.FireflyThreshold = w->fireflyThreshold;
         opt.SerialRules = w->serialRules != 0; opt.AdaptiveThreshold = w->adaptiveThreshold; opt.AdaptiveExponent = w->adaptiveExponent;
         if (window) { opt.x0 = window[0]; opt.y0 = window[1]; opt.x1 = window[2]; opt.y1 = window[3]; }
+        opt.taskStride = w->taskStride > 1 ? w->taskStride : 1; opt.taskOffset = w->taskOffset;
         Counters c = RenderPass(w->scene, w->camera, w->sampler, buf, opt);
         total.cameraSamples += c.cameraSamples;
         total.segments += c.segments;

@@ -374,6 +374,9 @@ struct RenderOptions {
     double AdaptiveThreshold = 1, AdaptiveExponent = 1;  // Renderer.cs:44-45
     // optional window (bounded CPU-baseline samples): pixels outside it are skipped
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+    // optional task sample (bounded CPU-baseline samples of a large frame): of the non-empty 32x32 tasks of the whole frame, in queue
+    // order, only every taskStride-th one starting at taskOffset is rendered - a strided sample that covers the frame evenly
+    int taskStride = 1, taskOffset = 0;
 };
 
 // One camera sample of the non-stratified branch (Renderer.cs:294-304), incl. the fu/fv quirk.
@@ -417,6 +420,15 @@ static inline Counters RenderPass(Scene& scene, const Camera& camera, const Defa
                 t.y1 = std::min(t.y0 + sub_tile_size, y_end);
                 tasks.push_back(t);
             }
+    }
+    if (opt.taskStride > 1) {  // bounded sample: keep every taskStride-th task that has pixels
+        std::vector<Task> kept;
+        size_t k = 0;
+        for (const Task& t : tasks) {
+            if (t.x1 <= t.x0 || t.y1 <= t.y0) continue;
+            if ((int)(k++ % (size_t)opt.taskStride) == opt.taskOffset) kept.push_back(t);
+        }
+        tasks.swap(kept);
     }
     std::atomic<size_t> next{0};
     int nthreads = std::max(1, opt.threads);

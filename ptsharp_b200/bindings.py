@@ -36,19 +36,25 @@ class Pass(C.Structure):
                 ("maxBounces", C.c_int32), ("directLighting", C.c_int32), ("softShadows", C.c_int32),
                 ("lightMode", C.c_int32), ("specularMode", C.c_int32), ("seed", C.c_uint32), ("passIndex", C.c_uint32),
                 ("camera", Camera), ("adaptiveSamples", C.c_int32), ("fireflySamples", C.c_int32),
-                ("fireflyThreshold", C.c_double), ("serialRules", C.c_int32), ("reserved0", C.c_int32),
+                ("fireflyThreshold", C.c_double), ("serialRules", C.c_int32), ("flags", C.c_int32),
                 ("adaptiveThreshold", C.c_double), ("adaptiveExponent", C.c_double)]
 
 
+MAX_DEVICES = 8
+PASS_RUSSIAN_ROULETTE = 1
+
+
 class Params(C.Structure):
-    _fields_ = [("device", C.c_int32), ("flags", C.c_int32), ("queueCapacity", C.c_uint64)]
+    _fields_ = [("device", C.c_int32), ("flags", C.c_int32), ("queueCapacity", C.c_uint64), ("numDevices", C.c_int32),
+                ("devices", C.c_int32 * MAX_DEVICES), ("reserved", C.c_int32)]
 
 
 class Counters(C.Structure):
     _fields_ = [("cameraSamples", C.c_uint64), ("segments", C.c_uint64), ("shadowRays", C.c_uint64),
                 ("nanSamples", C.c_uint64), ("kernelLaunches", C.c_uint64), ("lastPassMs", C.c_double),
                 ("traceMs", C.c_double), ("shadeMs", C.c_double), ("shadowMs", C.c_double), ("raygenMs", C.c_double),
-                ("meshMs", C.c_double), ("meshItems", C.c_uint64), ("meshLaunches", C.c_uint64)]
+                ("meshMs", C.c_double), ("meshItems", C.c_uint64), ("meshLaunches", C.c_uint64), ("traceLaunches", C.c_uint64),
+                ("queueOverflows", C.c_uint64), ("devices", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -56,7 +62,7 @@ class Counters(C.Structure):
 
 # every symbol include/ptgpu.h declares (tests check the library exports all of them)
 PTGPU_SYMBOLS = [
-    "ptgpu_abi_version", "ptgpu_create", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_upload_scene", "ptgpu_scene_bytes",
+    "ptgpu_abi_version", "ptgpu_abi_sizeof", "ptgpu_create", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_upload_scene", "ptgpu_scene_bytes",
     "ptgpu_render_pass", "ptgpu_accumulate_device", "ptgpu_add_sample_device", "ptgpu_read_buffer", "ptgpu_reset_buffer",
     "ptgpu_intersect_batch", "ptgpu_cast_rays", "ptgpu_keyed_draw", "ptgpu_check_kd_div", "ptgpu_get_counters", "ptgpu_reset_counters",
     "ptgpu_set_profiling", "ptgpu_export_buffer", "ptgpu_import_buffer",
@@ -72,6 +78,8 @@ def gpu_lib() -> C.CDLL:
         path = os.environ.get("PTGPU_LIB") or _build.build_gpu()  # PTGPU_LIB: development override (tuning variants)
         lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
         lib.ptgpu_abi_version.restype = C.c_int
+        lib.ptgpu_abi_sizeof.restype = C.c_int
+        lib.ptgpu_abi_sizeof.argtypes = [C.c_int]
         lib.ptgpu_create.restype = C.c_int
         lib.ptgpu_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
         lib.ptgpu_destroy.restype = None
@@ -113,6 +121,7 @@ _HOST_EXTRA = {
     "builder_friendly_order": (None, [C.c_int, c_float_p, C.c_double, C.c_int, C.c_int, c_int_p]),
     "renderer_new": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "renderer_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "renderer_devices": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "renderer_set_extra": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "renderer_render": (C.c_int, [C.c_void_p, c_float_p]),
     "renderer_iterative": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
@@ -214,12 +223,14 @@ class HostWorld(World):
 
     def make_pass(self, width, height, spp, stratified=False, seed=0x50545348, pass_index=0, sample_base=0,
                   sample_stride=1, adaptive_samples=0, firefly_samples=0, firefly_threshold=1.0, serial_rules=False,
-                  adaptive_threshold=1.0, adaptive_exponent=1.0) -> Pass:
+                  adaptive_threshold=1.0, adaptive_exponent=1.0, russian_roulette=False) -> Pass:
         p = Pass()
         self.lib.pth_make_pass(self.h, width, height, spp, int(stratified), seed, pass_index, sample_base, sample_stride,
                                C.byref(p))
         p.adaptiveSamples, p.fireflySamples, p.fireflyThreshold = adaptive_samples, firefly_samples, firefly_threshold
         p.serialRules, p.adaptiveThreshold, p.adaptiveExponent = int(serial_rules), adaptive_threshold, adaptive_exponent
+        if russian_roulette:
+            p.flags |= PASS_RUSSIAN_ROULETTE  # opt-in, not part of parity mode (ptgpu.h)
         return p
 
     def tree_stats(self, which=-1):
@@ -241,6 +252,12 @@ class HostWorld(World):
     # Renderer.cs mirror ------------------------------------------------------------------------------------------
     def new_renderer(self, width, height, device=0):
         if self.lib.pth_renderer_new(self.h, width, height, device) != 0:
+            raise PtgpuError(self._err())
+
+    def renderer_devices(self, devices):
+        """Renderer.Devices: split every pass over these GPUs inside the handle (single process)."""
+        a = (C.c_int * len(devices))(*devices)
+        if self.lib.pth_renderer_devices(self.h, len(devices), a) != 0:
             raise PtgpuError(self._err())
 
     def renderer_set(self, samples_per_pixel, stratified=False, seed=0x50545348):
@@ -277,10 +294,16 @@ class HostWorld(World):
 class Device:
     """One ptgpu_ctx: a CUDA device with an uploaded scene, its wavefront queues and its image Buffer."""
 
-    def __init__(self, device: int = 0, queue_capacity: int = 0):
+    def __init__(self, device: int = 0, queue_capacity: int = 0, devices=None):
+        """devices: a list of CUDA ordinals -> one handle that splits every pass over them (ptgpu_params.devices)."""
         self.lib = gpu_lib()
         self.h = C.c_void_p()
-        p = Params(device, 0, queue_capacity)
+        p = Params()
+        p.device, p.flags, p.queueCapacity = device, 0, queue_capacity
+        if devices:
+            p.numDevices = len(devices)
+            for k, d in enumerate(devices):
+                p.devices[k] = d
         rc = self.lib.ptgpu_create(C.byref(p), C.byref(self.h))
         if rc != 0:
             e = self.lib.ptgpu_last_error(None)

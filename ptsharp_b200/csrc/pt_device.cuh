@@ -924,6 +924,21 @@ PT_D double primitive_intersect_analytic(const DScene& S, const ptgpu_shape& sh,
     }
 }
 
+// Shadow rays: Hit.T of the light itself along the ray, i.e. what light.Intersect(ray) returns when Tree.Intersect reaches it
+// (the same device function, so the same bits).  Sphere / Cube / Plane only (the class-typed analytic lights); -1 = not
+// evaluated up front (SDFShape / Volume lights: no cut-off for their shadow rays).
+PT_D double light_hit_t(const DScene& S, int32_t lightShape, V3 o, V3 d) {
+    const ptgpu_shape sh = S.shapes[lightShape];
+    switch (sh.type) {
+        case PTGPU_SPHERE: return sphere_intersect(S.spheres[sh.data], o, d);
+        case PTGPU_CUBE: return cube_intersect(S.cubes[sh.data], o, d);
+        case PTGPU_PLANE: return plane_intersect(S.planes[sh.data], o, d);
+        default: return -1.0;
+    }
+}
+// Beyond this parameter a shape's Hit cannot matter to a shadow ray whose light sits at tL (see scene_advance).
+PT_D double shadow_clip(double tL) { return tL > 0 ? tL * (1.0 + 1e-4) : 1e300; }
+
 #ifndef PT_MARCH_SPLIT
 #define PT_MARCH_SPLIT 1   // C5 (2 spp pass): 1365 ms with both bursts every turn at 2 / 4 steps, 1010 ms with separate turns at 16 / 64
 #endif
@@ -1173,11 +1188,12 @@ struct SplitState {      // per ray of the launch, SoA
 #endif
 struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root node)  c = (tmin, tmax)
     float4* a; float4* b; double2* c; uint32_t* count;
+    float* lim;          // shadow launches only: the walk may stop at the first Hit with T < lim (a float at or below the light's tL; <= 0: never)
 };
 
 // Mesh.Intersect by one thread, start to end (the tail rounds of scenes where rays enter many meshes: a few thousand rays,
 // latency-bound whatever the scheduling, not worth a k_mesh launch each).
-PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double tmin, double tmax, double& best, int32_t& prim) {
+PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double tmin, double tmax, double& best, int32_t& prim, double anyLim = -1.0) {
     const RayBox ra = ray_box(co, cd);
     KdCursor mc; mc.node = root; mc.tmin = tmin; mc.tmax = tmax; mc.sp = 0;
     uint4 stk[kMeshStackEnt];
@@ -1191,6 +1207,7 @@ PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double 
         if (r == MESH_LEAF) {
             uint32_t tPos = first;
             leaf_work(S, co, cd, tPos, first + count, best, prim, bestPos, 4);
+            if (best < anyLim) break;  // shadow ray: closer than the light (see scene_advance)
             if (!mesh_pop(mc, best, stk)) break;
         }
     }
@@ -1200,8 +1217,16 @@ PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double 
 // MODE 0: rays [0, n) start.  MODE 1: the n rays named by the items of `in` continue after their mesh walk.  MODE 2: the
 // same rays, whose mesh walks have NOT run yet, are carried to their end by this thread (mesh walks inline, no more items).
 enum { SCENE_START = 0, SCENE_RESUME = 1, SCENE_FINISH = 2 };
-template <int MODE, class Source, class Sink>
-PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink) {
+// SHADOW = true: the rays are sampleLight's visibility rays (Sampler.cs:261-265), whose only use is `hit.Shape == light`.
+// `lightOf(i)` names the light; its own Hit.T along the ray, tL, is evaluated from the ray every round (the light is an analytic
+// class-typed shape) and the walk - same order, same arithmetic - stops at the first fold that leaves best.T < tL: the
+// running best only decreases, so the closest hit can no longer be the light (exact any-hit cut-off).  A ray that
+// misses the light altogether (tL = INF) is Black without a walk.  Meshes entered beyond tL (1e-4 relative margin, far above the
+// FP32 error of any T) are not walked: their Hit has T > tL, so it can neither be the light nor hide a closer one; and mesh work
+// items carry tL so the walk itself stops at the first triangle hit below it (k_mesh<true>).
+struct NoLight { PT_D int32_t operator()(uint32_t) const { return -1; } };
+template <int MODE, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
+PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink, LightOf lightOf = LightOf()) {
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         constexpr bool RESUME = MODE != SCENE_START;
@@ -1217,7 +1242,14 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
         uint4* sstk = W.sceneStack + (size_t)ray * W.stackEnt;
         const RayAux worldAux = ray_aux(o, d);
         const float dirLen = vlenf(d);  // 1 for every ray the renderer makes; ptgpu_intersect_batch takes directions as given
+        const double tL = SHADOW ? light_hit_t(S, lightOf(ray), o, d) : -1.0;
+        const double clipL = shadow_clip(tL);
         int st;
+        if (SHADOW && MODE == SCENE_START && !(tL < kHitInf)) {  // the ray misses the light: hit.Shape != light whatever is hit
+            best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
+            sink(ray, best);
+            continue;
+        }
         if (RESUME) {
             best.t = W.bestT[ray]; best.tInner = W.bestTInner[ray]; best.shape = W.bestShape[ray]; best.prim = W.bestPrim[ray];
             sc.node = W.scNode[ray]; sc.sp = W.scSp[ray]; sc.tmin = W.scTmin[ray]; sc.tmax = W.scTmax[ray];
@@ -1225,7 +1257,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             if (MODE == SCENE_FINISH) {  // the pending mesh walk first (the item holds the ray in the mesh's space)
                 const float4 ia = in.a[k], ib = in.b[k];
                 const double2 ic = in.c[k];
-                mesh_walk_single(S, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z), __float_as_uint(ib.w), ic.x, ic.y, mBest, mPrim);
+                mesh_walk_single(S, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z), __float_as_uint(ib.w), ic.x, ic.y, mBest, mPrim, SHADOW ? (double)in.lim[k] : -1.0);
             } else { mBest = W.mBest[ray]; mPrim = W.mPrim[ray]; }
             if (curInst >= 0) { const ptgpu_instance& inst = S.instances[curInst]; co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d); }
             st = ST_MESH_DONE;
@@ -1247,7 +1279,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                     }
                 }
                 if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
-                st = ST_SCENE_LEAF;
+                st = (SHADOW && best.t < tL) ? ST_FINISH : ST_SCENE_LEAF;  // occluded: the closest hit is closer than the light
             }
             if (st == ST_SCENE_NODE) {
                 uint32_t first, count;
@@ -1271,7 +1303,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         // ... and an instance entered beyond the running best cannot change it: its Hit's T is the world-space distance to a
                         // point inside these bounds (TransformedShape.cs:69: parameter x |direction|), and the fold only takes T < best.T
                         float entry;
-                        if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux, &entry) || (double)(entry * dirLen) > best.t * (1.0 + 1e-4)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
+                        if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux, &entry) || (double)(entry * dirLen) > netmin_best(clipL, best.t) * (1.0 + 1e-4)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
 #else
                         if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
 #endif
@@ -1292,13 +1324,13 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         // prefix - so the Hit that gets folded is the same.  (1e-5 relative margin against the FP32 rounding of
                         // the triangle test's T; object-space T of an instance is not comparable with best.T, so instances are left alone.)
                         if (curInst < 0 && !(tmax < tmin || tmax <= 0)) {
-                            const double lim = best.t * (1.0 + 1e-5);
+                            const double lim = SHADOW ? netmin_best(clipL, best.t * (1.0 + 1e-5)) : best.t * (1.0 + 1e-5);
                             if (tmin > lim) tmax = -1;
                             else if (tmax > lim) tmax = lim;
                         }
 #endif
                         if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
-                        else if (MODE == SCENE_FINISH) { mesh_walk_single(S, co, cd, mt.root, tmin, tmax, mBest, mPrim); st = ST_MESH_DONE; }
+                        else if (MODE == SCENE_FINISH) { mesh_walk_single(S, co, cd, mt.root, tmin, tmax, mBest, mPrim, (SHADOW && curInst < 0) ? tL : -1.0); st = ST_MESH_DONE; }
                         else {
                             auto g = cooperative_groups::coalesced_threads();
                             uint32_t base = 0;
@@ -1307,6 +1339,8 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.a[slot] = make_float4(co.x, co.y, co.z, __uint_as_float(ray));
                             out.b[slot] = make_float4(cd.x, cd.y, cd.z, __uint_as_float(mt.root));
                             out.c[slot] = make_double2(tmin, tmax);
+                            // a float at or below tL (object-space T of an instance is not comparable with tL: no cut-off there)
+                            if (SHADOW) out.lim[slot] = (curInst < 0 && tL > 0) ? __double2float_rd(tL) : -1.0f;
                             W.bestT[ray] = best.t; W.bestTInner[ray] = best.tInner; W.bestShape[ray] = best.shape; W.bestPrim[ray] = best.prim;
                             W.scNode[ray] = sc.node; W.scSp[ray] = sc.sp; W.scTmin[ray] = sc.tmin; W.scTmax[ray] = sc.tmax;
                             W.sPos[ray] = sPos; W.sEnd[ray] = sEnd; W.curShape[ray] = curShape; W.curInst[ray] = curInst;
@@ -1346,7 +1380,9 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
 #ifndef PT_SMEM_STACK
 #define PT_SMEM_STACK 0   // entries of the walk's kd stack kept in shared memory per thread (0 = all in local memory)
 #endif
+template <bool ANYHIT>
 PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor, uint4* smem) {
+    float anyLim = -1.0f;  // ANYHIT (shadow rays): stop at the first Hit below it
     const uint32_t n = *q.count;
     int st = ST_IDLE;
     uint32_t ray = 0;
@@ -1384,6 +1420,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     co = v3(a.x, a.y, a.z); cd = v3(b.x, b.y, b.z); ray = __float_as_uint(a.w);
                     ra = ray_box(co, cd);
                     mc.node = __float_as_uint(b.w); mc.tmin = c.x; mc.tmax = c.y; mc.sp = 0;
+                    if (ANYHIT) anyLim = q.lim[i];
 #ifdef PT_DEBUG_STEPS
                     dbgRoot = mc.node;
                     DBG_ADD(0, 1);
@@ -1420,7 +1457,8 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 #if !PT_COOP_LEAF
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
 #endif
-                if (tPos >= tEnd) st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
+                if (ANYHIT && mBest < (double)anyLim) st = ST_MESH_DONE;  // Mesh.Intersect's T can only be <= this: closer than the light
+                else if (tPos >= tEnd) st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
             }
         }
 #ifdef PT_DEBUG_STEPS
@@ -1525,6 +1563,7 @@ PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
     double u, v, w;
     tri_barycentric(v1, e1, e2, p, u, v, w);
     V3 n = vadd(vadd(vmuls(ld3(s.n1), u), vmuls(ld3(s.n2), v)), vmuls(ld3(s.n3), w));
+    if (s.material < 0) return vnorm_c(n);  // `new Material()`: no textures
     const ptgpu_material& pm = S.materials[s.material];
     if (pm.normalTexture >= 0) {
         V3 b = tri_blend_uv(s, u, v, w);

@@ -25,10 +25,14 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifndef PT_SPLIT
 #define PT_SPLIT 1
+#endif
+#ifndef PT_ANYHIT
+#define PT_ANYHIT 1   // 0: shadow rays take the full closest-hit walk (A/B switch for the exact any-hit cut-off, see scene_advance)
 #endif
 #include "pt_device.cuh"
 
@@ -168,6 +172,7 @@ struct PassD {  // ptgpu_pass plus derived values, passed by value to kernels
     int32_t subpixelJitter;  // 1: fu, fv = xi1, xi2 (adaptive / firefly passes, Renderer.cs:351-353, 432); 2: fu = (x + xi) * (1.0f / w) (serial firefly, Renderer.cs:97-98, 179-180)
     int32_t sampleBase, sampleStride;
     int32_t firstHitSamples, maxBounces, directLighting, softShadows, lightMode, specularMode;
+    int32_t russianRoulette;  // PTGPU_PASS_RUSSIAN_ROULETTE (opt-in, not part of parity mode)
     uint32_t seed, passIndex;
     ptgpu_camera cam;
 };
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __
 __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
                                                 HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
                                                 float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow,
-                                                const uint32_t* __restrict__ perm) {
+                                                const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow) {
     const uint32_t n = *count;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t i = perm ? perm[j] : j;  // shade order (see k_bin_scatter)
@@ -460,7 +465,17 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
                     const float pf = (float)p * invnn;
                     const float cr = br * wr * pf, cgn = bg * wg * pf, cb = bb * wb * pf;
                     // child path segment (traced only while depth+1 <= MaxBounces, Sampler.cs:57)
-                    const bool pushRay = (int)depth + 1 <= P.maxBounces;
+                    bool pushRay = (int)depth + 1 <= P.maxBounces;
+                    float rr = 1.f;
+                    if (pushRay && P.russianRoulette && depth >= 2) {
+                        // Opt-in Russian roulette (ptgpu_pass.flags; the reference's own `russianRoulette` branch, Sampler.cs:133-142, is never
+                        // enabled and does not terminate anything).  The child survives with probability q = the largest component of its local
+                        // weight (material colour x branch probability), clamped to [minReflectance = 0.05, 1], and carries 1/q: unbiased.  The
+                        // vertex's own next-event estimate below is not affected.  Sub-stream 255 is reserved for this draw.
+                        const float q = fminf(fmaxf(fmaxf(wr, fmaxf(wg, wb)) * (float)p, 0.05f), 1.f);
+                        rng_enter(rng, cBits, cFirst, depth + 1, 255);
+                        if (rng_next(rng) >= (double)q) pushRay = false; else rr = 1.f / q;
+                    }
                     if (pushRay) {
                         auto g2 = cg::coalesced_threads();
                         uint32_t base = 0;
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
                         if (slot < capRays) {
                             nq.od0[slot] = make_float4(no.x, no.y, no.z, u2f(pixel));
                             nq.od1[slot] = make_float4(nd.x, nd.y, nd.z, u2f((depth + 1) | ((reflected ? 1u : 0u) << 6) | (cFirst << 7)));
-                            nq.bt[slot] = make_float4(cr, cgn, cb, u2f(cBits));
+                            nq.bt[slot] = make_float4(cr * rr, cgn * rr, cb * rr, u2f(cBits));
                             nq.smp[slot] = sample;
                         }
                     }
@@ -531,7 +546,7 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
                                 sq.so[slot] = make_float4(sf.position.x, sf.position.y, sf.position.z, u2f(pixel));
                                 sq.sd[slot] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, u2f(L.shape));
                                 sq.sc[slot] = make_float4(cr * (float)lm.cr * m, cgn * (float)lm.cg * m, cb * (float)lm.cb * m, 0.f);
-                            }
+                            } else *overflow = 1u;  // dropped: the pass is reported and not added to the Buffer
                         }
                     }
                 }
@@ -577,7 +592,7 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
     constexpr bool RESUME = MODE != SCENE_START;
     uint32_t n = RESUME ? *in.count : *scount;
     if (!RESUME && n > capShadow) n = capShadow;
-    scene_advance<MODE>(S, W, n, in, out,
+    scene_advance<MODE, PT_ANYHIT != 0>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) {
                               const uint32_t light = f2u(sq.sd[i].w);
@@ -585,7 +600,8 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
                                   float4 c = sq.sc[i];
                                   accumulate(sum, cnt, f2u(sq.so[i].w), c.x, c.y, c.z);
                               }
-                          });
+                          },
+                          [&](uint32_t i) { return (int32_t)f2u(sq.sd[i].w); });
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
 }
 // Small blocks: the warps of a launch finish at very different times (a few grazing rays take ~1000 steps) and a block's
@@ -599,9 +615,11 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
 #endif
 static constexpr size_t kMeshSmemBytes = (size_t)PT_SMEM_STACK * PT_MESH_BLOCK * sizeof(uint4);
 // 40 warps x 48 registers is the register file: each of the four sub-partitions holds 16 K registers = 10 warps of 48 (42 warps would need 40 registers).
+// ANYHIT: the items are Mesh.Intersect calls of shadow rays, each with the light's own T (see scene_advance in pt_device.cuh).
+template <bool ANYHIT>
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
     extern __shared__ uint4 smemStack[];  // PT_SMEM_STACK rows of blockDim.x entries
-    mesh_walk(S, W, q, cursor, smemStack);
+    mesh_walk<ANYHIT>(S, W, q, cursor, smemStack);
 }
 
 __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
@@ -610,14 +628,21 @@ __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow)
 
 // K5.  c /= spp; Buffer.AddSample (Renderer.cs:307-309, Buffer.cs:33-44), Welford state in FP64 like Colour.
 struct PixelBuf { double* M; double* V; int32_t* samples; };
-__global__ void k_add_sample(const float* __restrict__ sum, double divisor, uint32_t npix, PixelBuf pb, float* __restrict__ meanOut) {
+// `overflow` (one flag per lane, may be NULL): a queue overflowed in this pass, so its sum is incomplete and the Buffer is left alone.
+// meanOut receives s * meanScale, added to what it holds when meanAdd is set (the stratified branch reports the mean over its strata).
+struct SumSet { const float* p[PTGPU_MAX_DEVICES]; int n; };  // the pass accumulators of every device of the handle (peers read over NVLink)
+__global__ void k_add_sample(SumSet sums, double divisor, uint32_t npix, PixelBuf pb, float* __restrict__ meanOut, const uint32_t* __restrict__ overflow,
+                             int numFlags, float meanScale, int meanAdd) {
+    for (int k = 0; k < numFlags; k++) if (overflow[k * 16]) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         int32_t ns = pb.samples[i] + 1;
         pb.samples[i] = ns;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            double s = (double)sum[(size_t)i * 3 + c] / divisor;
-            if (meanOut) meanOut[(size_t)i * 3 + c] = (float)s;
+            float acc = sums.p[0][(size_t)i * 3 + c];
+            for (int k = 1; k < sums.n; k++) acc += sums.p[k][(size_t)i * 3 + c];  // the multi-GPU reduce, fused into Buffer.AddSample
+            double s = (double)acc / divisor;
+            if (meanOut) meanOut[(size_t)i * 3 + c] = (meanAdd ? meanOut[(size_t)i * 3 + c] : 0.f) + (float)s * meanScale;
             if (ns == 1) { pb.M[(size_t)i * 3 + c] = s; continue; }
             double m = pb.M[(size_t)i * 3 + c];
             double M2 = m + (s - m) / (double)ns;
@@ -892,6 +917,15 @@ struct Lane {
 struct ptgpu_ctx {
     int device = 0;
     int numSMs = 148;
+    // multi-GPU inside the handle: the handle the caller holds is the root (devices[0]); peers are full contexts of their own
+    // device (scene replica, queues, pass accumulator) driven by one host thread each during a pass
+    std::vector<ptgpu_ctx*> peers;
+    std::vector<float*> peerStage;        // root-side copies of the peers' accumulators when peer access is not available
+    std::vector<char> peerDirect;         // the root can read peer k's memory (cudaDeviceEnablePeerAccess)
+    cudaEvent_t evPeerDone = nullptr;     // on a peer: its share of the pass is in its dSum
+    uint32_t* laneCounts = nullptr;       // kMaxLanes x 16 counters, lane k at + 16 k (so the overflow flags are one strided array)
+    uint64_t overflowPasses = 0;
+    uint64_t traceLaunches = 0;
     cudaStream_t stream = nullptr;
     std::string error;
     // scene
@@ -1012,7 +1046,7 @@ static void trim_scene_pool(ptgpu_ctx* ctx) {  // after an upload: what the new 
 static void free_split(Lane& L) {
     SplitState& W = L.split;
     void* ps[] = {W.bestT, W.bestTInner, W.bestShape, W.bestPrim, W.scNode, W.scSp, W.scTmin, W.scTmax, W.sPos, W.sEnd, W.curShape, W.curInst, W.mBest, W.mPrim,
-                  W.sceneStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c};
+                  W.sceneStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c, L.mq[0].lim, L.mq[1].lim};
     for (void* p : ps) cudaFree(p);
     W = SplitState{};
     L.mq[0] = L.mq[1] = MeshQueue{};
@@ -1052,6 +1086,7 @@ static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
     W.stackEnt = stackEnt;
     for (int i = 0; i < 2; i++) {
         CK(cudaMalloc(&L.mq[i].a, cap * sizeof(float4))); CK(cudaMalloc(&L.mq[i].b, cap * sizeof(float4))); CK(cudaMalloc(&L.mq[i].c, cap * sizeof(double2)));
+        CK(cudaMalloc(&L.mq[i].lim, cap * sizeof(float)));
         L.mq[i].count = L.counts + 10 + i;
     }
     L.splitCap = cap;
@@ -1062,7 +1097,7 @@ static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
 #ifndef PT_FINISH_MAX
 #define PT_FINISH_MAX 65536   // pending mesh walks at or below which the remaining rounds run as one SCENE_FINISH launch
 #endif
-template <class StartFn, class ResumeFn, class FinishFn>
+template <bool ANYHIT = false, class StartFn, class ResumeFn, class FinishFn>
 static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, ResumeFn resume, FinishFn finish) {
     uint32_t* cursor = L.counts + 12;
     CK(cudaMemsetAsync(L.counts + 10, 0, 3 * sizeof(uint32_t), st));
@@ -1085,13 +1120,13 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
             uint32_t items = 0;
             cudaMemcpyAsync(&items, L.mq[cur].count, 4, cudaMemcpyDeviceToHost, st);
             cudaEventRecord(ctx->evC, st);
-            k_mesh<<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
             cudaEventRecord(ctx->evD, st); cudaEventSynchronize(ctx->evD);
             float ms = 0; cudaEventElapsedTime(&ms, ctx->evC, ctx->evD);
             ctx->meshMs += ms; ctx->meshItems += items; ctx->meshLaunches++;
             if (detail) fprintf(stderr, "k_mesh round %d items %u  %.3f ms  (%.1f Mitems/s)\n", round, items, ms, items / ms / 1e3);
         } else
-            k_mesh<<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+            k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
         resume(L.mq[cur], L.mq[cur ^ 1]);
         ctx->launches += 2;
         cur ^= 1;
@@ -1131,10 +1166,69 @@ const char* ptgpu_last_error(ptgpu_ctx* ctx) {
     return g_createError.c_str();
 }
 
+int ptgpu_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(ptgpu_params); case 1: return (int)sizeof(ptgpu_pass); case 2: return (int)sizeof(ptgpu_camera);
+        case 3: return (int)sizeof(ptgpu_counters); case 4: return (int)sizeof(ptgpu_flat_scene); case 5: return (int)sizeof(ptgpu_node);
+        case 6: return (int)sizeof(ptgpu_tree); case 7: return (int)sizeof(ptgpu_shape); case 8: return (int)sizeof(ptgpu_sphere);
+        case 9: return (int)sizeof(ptgpu_cube); case 10: return (int)sizeof(ptgpu_plane); case 11: return (int)sizeof(ptgpu_cylinder);
+        case 12: return (int)sizeof(ptgpu_mesh); case 13: return (int)sizeof(ptgpu_tri_geom); case 14: return (int)sizeof(ptgpu_tri_shade);
+        case 15: return (int)sizeof(ptgpu_instance); case 16: return (int)sizeof(ptgpu_sdf_op); case 17: return (int)sizeof(ptgpu_sdf_shape);
+        case 18: return (int)sizeof(ptgpu_volume_window); case 19: return (int)sizeof(ptgpu_volume); case 20: return (int)sizeof(ptgpu_material);
+        case 21: return (int)sizeof(ptgpu_texture);
+        default: return -1;
+    }
+}
+
+static int create_one(const ptgpu_params* params, int dev, ptgpu_ctx** out);
+
+// ptgpu_params.numDevices > 1: one context per device; the first is the handle the caller holds (the root), the others its peers.
 int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     if (!out) return PTGPU_E_ARG;
     *out = nullptr;
-    int dev = params ? params->device : 0;
+    const int nd = params ? params->numDevices : 0;
+    if (nd < 0 || nd > PTGPU_MAX_DEVICES) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_createError = "numDevices out of range";
+        return PTGPU_E_ARG;
+    }
+    if (nd <= 1) return create_one(params, nd == 1 ? params->devices[0] : (params ? params->device : 0), out);
+    for (int a = 0; a < nd; a++)
+        for (int b = a + 1; b < nd; b++)
+            if (params->devices[a] == params->devices[b]) {
+                std::lock_guard<std::mutex> lk(g_mu);
+                g_createError = "devices[] names a device twice";
+                return PTGPU_E_ARG;
+            }
+    ptgpu_ctx* root = nullptr;
+    int rc = create_one(params, params->devices[0], &root);
+    if (rc != PTGPU_OK) return rc;
+    for (int k = 1; k < nd; k++) {
+        ptgpu_ctx* peer = nullptr;
+        rc = create_one(params, params->devices[k], &peer);
+        if (rc != PTGPU_OK) { ptgpu_destroy(root); return rc; }
+        cudaEventCreateWithFlags(&peer->evPeerDone, cudaEventDisableTiming);
+        root->peers.push_back(peer);
+        // NVLink peer access root -> peer: the Buffer.AddSample kernel of the root reads the peers' accumulators in place
+        int can = 0;
+        cudaSetDevice(root->device);
+        bool direct = false;
+        if (cudaDeviceCanAccessPeer(&can, root->device, peer->device) == cudaSuccess && can) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(peer->device, 0);
+            direct = pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled;
+            cudaGetLastError();
+        }
+        if (std::getenv("PTGPU_NO_PEER_ACCESS")) direct = false;  // development switch: exercise the staged copy
+        root->peerDirect.push_back(direct ? 1 : 0);
+        root->peerStage.push_back(nullptr);
+    }
+    cudaSetDevice(root->device);
+    *out = root;
+    return PTGPU_OK;
+}
+
+static int create_one(const ptgpu_params* params, int dev, ptgpu_ctx** out) {
+    *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -1164,7 +1258,8 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
     if (kMeshSmemBytes > 0) {  // k_mesh keeps the top of every thread's kd stack in shared memory: carve out what its resident blocks need
         const size_t perSM = (size_t)(PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) * (kMeshSmemBytes + 1024);
         const int pct = (int)std::min<size_t>(100, (perSM * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
-        if ((e = cudaFuncSetAttribute(k_mesh, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_mesh carveout)", e);
+        if ((e = cudaFuncSetAttribute(k_mesh<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_mesh carveout)", e);
+        if ((e = cudaFuncSetAttribute(k_mesh<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_mesh carveout)", e);
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
     // queueCapacity = path records in flight over all lanes (default 2^27, allocated on demand); flags bits 0-3 = number of lanes (0 = default)
@@ -1180,12 +1275,13 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
         if (ctx->capRays > (1ull << 30)) ctx->capRays = 1ull << 30;
         if (ctx->capRays == 0) ctx->capRays = 1;
     }
+    if ((e = cudaMalloc(&ctx->laneCounts, kMaxLanes * 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(ctx->laneCounts, 0, kMaxLanes * 16 * sizeof(uint32_t));
     for (int k = 0; k < ctx->numLanes; k++) {
         Lane& L = ctx->lanes[k];
         if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
         if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-        if ((e = cudaMalloc(&L.counts, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
-        cudaMemset(L.counts, 0, 16 * sizeof(uint32_t));
+        L.counts = ctx->laneCounts + 16 * k;
     }
     if ((e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->dCounts, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -1198,7 +1294,11 @@ int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out) {
 
 void ptgpu_destroy(ptgpu_ctx* ctx) {
     if (!ctx) return;
+    for (ptgpu_ctx* p : ctx->peers) ptgpu_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
+    for (float* p : ctx->peerStage) cudaFree(p);
+    ctx->peerStage.clear();
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx, true);
     for (auto& b : ctx->stage) if (b.first) cudaFreeHost(b.first);
@@ -1209,8 +1309,9 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
         Lane& L = ctx->lanes[k];
         if (L.stream) cudaStreamDestroy(L.stream);
         if (L.done) cudaEventDestroy(L.done);
-        cudaFree(L.counts);
     }
+    cudaFree(ctx->laneCounts);
+    if (ctx->evPeerDone) cudaEventDestroy(ctx->evPeerDone);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     cudaFree(ctx->dCounts);
     cudaFree(ctx->dCounters);
@@ -1221,9 +1322,103 @@ void ptgpu_destroy(ptgpu_ctx* ctx) {
 
 uint64_t ptgpu_scene_bytes(ptgpu_ctx* ctx) { return ctx ? ctx->sceneBytes : 0; }
 
+// Index ranges of a flat scene (a PTFS file written elsewhere, or a foreign flattener): everything the upload and the kernels
+// dereference.  Returns an empty string when the scene is consistent.
+static std::string validate_flat_scene(const ptgpu_flat_scene* s) {
+    auto bad = [](const char* what, uint64_t i) { return std::string("flat scene: ") + what + " (element " + std::to_string(i) + ")"; };
+    if (s->numTrees == 0 || s->sceneTree >= s->numTrees) return "flat scene: sceneTree out of range";
+    if (s->numSceneShapes > s->numShapes) return "flat scene: numSceneShapes > numShapes";
+    auto mat_ok = [&](int32_t m) { return m >= -1 && (m < 0 || (uint32_t)m < s->numMaterials); };
+    for (uint32_t i = 0; i < s->numShapes; i++) {
+        const ptgpu_shape& sh = s->shapes[i];
+        uint32_t lim = 0;
+        switch (sh.type) {
+            case PTGPU_SPHERE: lim = s->numSpheres; break;
+            case PTGPU_CUBE: lim = s->numCubes; break;
+            case PTGPU_PLANE: lim = s->numPlanes; break;
+            case PTGPU_CYLINDER: lim = s->numCylinders; break;
+            case PTGPU_MESH: lim = s->numMeshes; break;
+            case PTGPU_TRANSFORMED: lim = s->numInstances; break;
+            case PTGPU_SDF: lim = s->numSdfShapes; break;
+            case PTGPU_VOLUME: lim = s->numVolumes; break;
+            default: return bad("unknown shape type", i);
+        }
+        if (sh.data >= lim) return bad("shape data index out of range", i);
+        if (!mat_ok(sh.material)) return bad("shape material out of range", i);
+    }
+    for (uint32_t i = 0; i < s->numLights; i++) if (s->lights[i] >= s->numSceneShapes) return bad("light index out of range", i);
+    for (uint32_t i = 0; i < s->numInstances; i++) if (s->instances[i].shape >= s->numShapes) return bad("instance shape out of range", i);
+    for (uint32_t i = 0; i < s->numMeshes; i++) {
+        const ptgpu_mesh& m = s->meshes[i];
+        if (m.tree >= s->numTrees || m.tree == s->sceneTree) return bad("mesh tree out of range", i);
+        if ((uint64_t)m.triFirst + m.triCount > s->numTriangles) return bad("mesh triangle range out of range", i);
+    }
+    for (uint64_t i = 0; i < s->numTriangles; i++) {
+        if (!mat_ok(s->triShade[i].material)) return bad("triangle material out of range", i);
+    }
+    for (uint32_t i = 0; i < s->numTrees; i++) if (s->trees[i].root >= s->numNodes) return bad("tree root out of range", i);
+    // which tree owns a node decides what its leaf items index: nodes of a tree are contiguous from its root to the next root
+    std::vector<std::pair<uint32_t, uint32_t>> roots;  // (root, tree)
+    for (uint32_t i = 0; i < s->numTrees; i++) roots.push_back({s->trees[i].root, i});
+    std::sort(roots.begin(), roots.end());
+    for (size_t r = 0; r < roots.size(); r++) {
+        const uint64_t b = roots[r].first, e = r + 1 < roots.size() ? roots[r + 1].first : s->numNodes;
+        const bool sceneTree = roots[r].second == s->sceneTree;
+        for (uint64_t i = b; i < e; i++) {
+            const ptgpu_node& n = s->nodes[i];
+            if (n.a & 3u) {
+                if ((n.a >> 2) <= i || (n.a >> 2) >= e || n.b <= i || n.b >= e) return bad("kd node child out of its tree (children follow their parent)", i);
+            } else {
+                if ((uint64_t)(n.a >> 2) + n.b > s->numLeafItems) return bad("kd leaf range out of range", i);
+                for (uint32_t k = 0; k < n.b; k++) {
+                    const uint32_t item = s->leafItems[(n.a >> 2) + k];
+                    if (sceneTree ? item >= s->numSceneShapes : item >= s->numTriangles) return bad("kd leaf item out of range", i);
+                }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < s->numSdfShapes; i++)
+        if ((uint64_t)s->sdfShapes[i].progFirst + s->sdfShapes[i].progCount > s->numSdfOps) return bad("SDF program range out of range", i);
+    for (uint32_t i = 0; i < s->numVolumes; i++) {
+        const ptgpu_volume& v = s->volumes[i];
+        if (v.w <= 0 || v.h <= 0 || v.d <= 0) return bad("volume dimensions", i);
+        if ((uint64_t)v.windowFirst + v.windowCount > s->numVolumeWindows) return bad("volume window range out of range", i);
+        if (v.dataOffset + (uint64_t)v.w * v.h * v.d > s->numVolumeData) return bad("volume data range out of range", i);
+    }
+    for (uint32_t i = 0; i < s->numVolumeWindows; i++) if (!mat_ok(s->volumeWindows[i].material)) return bad("volume window material out of range", i);
+    auto tex_ok = [&](int32_t t) { return t >= -1 && (t < 0 || (uint32_t)t < s->numTextures); };
+    for (uint32_t i = 0; i < s->numMaterials; i++) {
+        const ptgpu_material& m = s->materials[i];
+        if (!tex_ok(m.texture) || !tex_ok(m.normalTexture) || !tex_ok(m.bumpTexture) || !tex_ok(m.glossTexture)) return bad("material texture out of range", i);
+    }
+    if (!tex_ok(s->envTexture)) return "flat scene: envTexture out of range";
+    for (uint32_t i = 0; i < s->numTextures; i++) {
+        const ptgpu_texture& t = s->textures[i];
+        if (t.width < 1 || t.height < 1 || t.texelOffset + (uint64_t)t.width * t.height > s->numTexels) return bad("texture texel range out of range", i);
+    }
+    return std::string();
+}
+
+static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv, bool derive);
+
 int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
     if (!ctx || !s) return PTGPU_E_ARG;
     if (s->abiVersion != PTGPU_ABI_VERSION) return fail(ctx, PTGPU_E_ARG, "flat scene ABI version mismatch");
+    {
+        const std::string why = validate_flat_scene(s);
+        if (!why.empty()) return fail(ctx, PTGPU_E_ARG, why);
+    }
+    MeshDerived dv;  // derived once on the host (pinned staging of the root), copied to every device of the handle
+    int rc = upload_one(ctx, s, dv, true);
+    for (size_t k = 0; rc == PTGPU_OK && k < ctx->peers.size(); k++) {
+        rc = upload_one(ctx->peers[k], s, dv, false);
+        if (rc != PTGPU_OK) ctx->error = "device " + std::to_string(ctx->peers[k]->device) + ": " + ctx->peers[k]->error;
+    }
+    cudaSetDevice(ctx->device);
+    return rc;
+}
+
+static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv, bool derive) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());  // every lane idle: the previous scene's buffers are reused, not freed
     free_scene(ctx);
@@ -1312,12 +1507,13 @@ int ptgpu_upload_scene(ptgpu_ctx* ctx, const ptgpu_flat_scene* s) {
     }
 #undef UP
     {   // derived mesh data (see derive_mesh): 64-byte node records, sorted leaf triangles, patched tree roots
-        MeshDerived dv;
-        std::string err;
-        ctx->stageNext = 0;  // pinned staging owned by the handle: the derivation writes straight into DMA-able memory
-        auto t0 = std::chrono::steady_clock::now();
-        if (!derive_mesh(s, dv, err, [&](uint64_t bytes) -> void* { return stage_alloc(ctx, bytes); })) return fail(ctx, PTGPU_E_LIMIT, err);
-        ctx->deriveMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (derive) {
+            std::string err;
+            ctx->stageNext = 0;  // pinned staging owned by the handle: the derivation writes straight into DMA-able memory
+            auto t0 = std::chrono::steady_clock::now();
+            if (!derive_mesh(s, dv, err, [&](uint64_t bytes) -> void* { return stage_alloc(ctx, bytes); })) return fail(ctx, PTGPU_E_LIMIT, err);
+            ctx->deriveMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
         {
             const ptgpu_tree* dt = nullptr;
             if ((rc = upload(ctx, dv.trees.data(), (uint64_t)dv.trees.size(), &dt)) != PTGPU_OK) return rc;
@@ -1490,6 +1686,16 @@ static int make_passd(ptgpu_ctx* ctx, const ptgpu_pass* p, PassD& P) {
     int nroot = (int)std::sqrt((double)p->firstHitSamples);
     int modes0 = (p->specularMode == PTGPU_SPECULAR_NAIVE) ? 1 : 2;
     if (nroot * nroot * modes0 > 4094) return fail(ctx, PTGPU_E_LIMIT, "firstHitSamples too large for the 12-bit first-hit index");
+    // Philox addressing (rng_enter): one path bit per depth under SpecularModeAll; sub-streams 1..254 name the light under
+    // LightModeAll (255 = Russian roulette); global sample indices from 2^20 on belong to the adaptive / firefly extra samples.
+    if (p->specularMode == PTGPU_SPECULAR_ALL && p->maxBounces > 32) return fail(ctx, PTGPU_E_LIMIT, "SpecularModeAll: maxBounces must be <= 32 (one path bit per depth)");
+    if (p->lightMode == PTGPU_LIGHT_ALL && p->directLighting && ctx->scene.numLights > 254) return fail(ctx, PTGPU_E_LIMIT, "LightModeAll: more than 254 lights");
+    {
+        const long long stride = p->sampleStride ? p->sampleStride : 1;
+        const long long last = (long long)p->sampleBase + (long long)(p->spp - 1) * stride;
+        if (p->sampleBase < 0 || stride < 1 || last >= (1ll << 20)) return fail(ctx, PTGPU_E_LIMIT, "global sample indices must stay in [0, 2^20): spp x ranks too large for one pass");
+    }
+    P.russianRoulette = (p->flags & PTGPU_PASS_RUSSIAN_ROULETTE) ? 1 : 0;
     P.width = p->width; P.height = p->height; P.spp = p->spp; P.stratified = p->stratified; P.subpixelJitter = 0;
     P.sppRoot = (int)std::sqrt((double)p->spp);
     P.sampleBase = p->sampleBase; P.sampleStride = p->sampleStride ? p->sampleStride : 1;
@@ -1524,7 +1730,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     uint64_t batch = ctx->capRays / maxGrow;
     if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's branching factor");
     uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
-    const uint64_t shadowCeil = ctx->capRays * 4;
+    const uint64_t shadowCeil = std::min<uint64_t>(ctx->capRays * 4, 0xFFFF0000ull);  // slots are 32-bit
     if (capShadow > shadowCeil) {  // shrink the batch so the shadow queue stays bounded
         batch = shadowCeil / (childGrow * (lightsPer ? lightsPer : 1));
         if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's light count");
@@ -1552,7 +1758,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     }
     const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
     float ms = 0;
-    if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = ctx->meshMs = 0; ctx->meshItems = ctx->meshLaunches = 0; }
+    if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = ctx->meshMs = 0; ctx->meshItems = ctx->meshLaunches = ctx->traceLaunches = 0; }
     // fork: the lanes' streams continue from the caller's stream ...
     if (!prof) {
         CK(cudaEventRecord(ctx->evFork, callerStream));
@@ -1585,6 +1791,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             } else {
                 k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.rq[cur], counts + cur, counts + 4, L.hq, ctx->dCounters);
                 ctx->launches++;
+                if (prof) ctx->traceLaunches++;
             }
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
             static const bool shadeOrder = !(std::getenv("PTGPU_SHADE_ORDER") && std::atoi(std::getenv("PTGPU_SHADE_ORDER")) == 0);  // development switch
@@ -1597,13 +1804,13 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             }
             k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
                                                    L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow,
-                                                   shadeOrder ? L.perm : nullptr);
+                                                   shadeOrder ? L.perm : nullptr, counts + 3);
             k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)L.capRays, counts + 3);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 2;
             if (lightsPer) {
                 if (ctx->useSplit) {
-                    rc = run_split(ctx, L, stream,
+                    rc = run_split<PT_ANYHIT != 0>(ctx, L, stream,
                                    [&](const MeshQueue& out) { k_scene_shadow<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, out, out, d_sum, ctx->dCounters); },
                                    [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, out, d_sum, ctx->dCounters); },
                                    [&](const MeshQueue& in) { k_scene_shadow<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, in, d_sum, ctx->dCounters); });
@@ -1628,6 +1835,28 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     return PTGPU_OK;
 }
 
+// Queue-overflow flags (counts[3] of every lane; set by k_clamp_count for the ray queue and by k_shade for the shadow queue).
+static int clear_overflow(ptgpu_ctx* ctx, cudaStream_t st) {
+    for (int k = 0; k < ctx->numLanes; k++) CK(cudaMemsetAsync(ctx->lanes[k].counts + 3, 0, sizeof(uint32_t), st));
+    return PTGPU_OK;
+}
+// After the work is known to be complete: true when a queue overflowed since the last clear.
+static bool take_overflow(ptgpu_ctx* ctx) {
+    uint32_t h[kMaxLanes * 16];
+    if (cudaMemcpy(h, ctx->laneCounts, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
+    bool any = false;
+    for (int k = 0; k < ctx->numLanes; k++) any = any || h[k * 16 + 3] != 0;
+    if (any) {
+        ctx->overflowPasses++;
+        for (int k = 0; k < ctx->numLanes; k++) cudaMemset(ctx->lanes[k].counts + 3, 0, sizeof(uint32_t));
+    }
+    return any;
+}
+
+// NULL = the legacy default stream (the stream torch's default stream is): the pass is ordered after everything already queued on
+// the caller's stream (e.g. the zero-fill of d_sum_rgb) and the stream continues after it (e.g. with the NCCL reduce).
+static cudaStream_t caller_stream(void* stream) { return stream ? (cudaStream_t)stream : cudaStreamLegacy; }
+
 int ptgpu_accumulate_device(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* d_sum_rgb, void* stream) {
     if (!ctx || !pass || !d_sum_rgb) return PTGPU_E_ARG;
     if (!ctx->haveScene) return fail(ctx, PTGPU_E_STATE, "no scene uploaded");
@@ -1635,7 +1864,7 @@ int ptgpu_accumulate_device(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* d_sum
     PassD P;
     int rc = make_passd(ctx, pass, P);
     if (rc != PTGPU_OK) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = caller_stream(stream);
     CK(cudaEventRecord(ctx->ev0, st));
     int nSlots = P.stratified ? P.sppRoot * P.sppRoot : P.spp;
     rc = run_pass(ctx, P, nSlots, d_sum_rgb, st);
@@ -1644,16 +1873,85 @@ int ptgpu_accumulate_device(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* d_sum
     return PTGPU_OK;
 }
 
+static SumSet one_sum(const float* p) { SumSet s; std::memset(&s, 0, sizeof(s)); s.p[0] = p; s.n = 1; return s; }
+
 int ptgpu_add_sample_device(ptgpu_ctx* ctx, int32_t width, int32_t height, const float* d_sum_rgb, double divisor, void* stream) {
     if (!ctx || !d_sum_rgb) return PTGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_image(ctx, width, height);
     if (rc != PTGPU_OK) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = caller_stream(stream);
     if (st != ctx->stream) CK(cudaStreamSynchronize(ctx->stream));  // buffer allocation memsets
-    k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(d_sum_rgb, divisor, (uint32_t)((size_t)width * height), ctx->pb, ctx->dMean);
+    k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(one_sum(d_sum_rgb), divisor, (uint32_t)((size_t)width * height), ctx->pb, ctx->dMean, nullptr, 0, 1.f, 0);
     ctx->launches++;
     CK(cudaGetLastError());
+    return PTGPU_OK;
+}
+
+// The pass accumulator of a peer device (the root's comes with ensure_image).
+static int ensure_sum(ptgpu_ctx* ctx, int w, int h) {
+    if (ctx->bufW == w && ctx->bufH == h && ctx->dSum) return PTGPU_OK;
+    free_image(ctx);
+    CK(cudaMalloc(&ctx->dSum, (size_t)w * h * 3 * sizeof(float)));
+    ctx->bufW = w; ctx->bufH = h;
+    return PTGPU_OK;
+}
+
+// The main pass of a multi-device handle: device k of N draws samples k, k + N, k + 2N, ... of the pass's sample sequence into its
+// own accumulator (one host thread per peer: a pass may synchronise its stream between rounds), then the root's Buffer.AddSample
+// kernel sums the N accumulators — the peers' through NVLink peer access — and applies Welford: reduce and update in one kernel.
+static int render_main_multi(ptgpu_ctx* ctx, const PassD& P, cudaStream_t st) {
+    const int N = 1 + (int)ctx->peers.size();
+    const size_t npix = (size_t)P.width * P.height;
+    std::vector<int> rcs((size_t)N, PTGPU_OK);
+    auto share = [&](int k) { return P.spp / N + (k < P.spp % N ? 1 : 0); };
+    auto run_one = [&](ptgpu_ctx* c, int k) -> int {
+        if (cudaSetDevice(c->device) != cudaSuccess) { c->error = "cudaSetDevice failed"; return PTGPU_E_CUDA; }
+        int rc = c == ctx ? PTGPU_OK : ensure_sum(c, P.width, P.height);
+        if (rc != PTGPU_OK) return rc;
+        if (cudaMemsetAsync(c->dSum, 0, npix * 3 * sizeof(float), c->stream) != cudaSuccess) { c->error = "cudaMemsetAsync failed"; return PTGPU_E_CUDA; }
+        if ((rc = clear_overflow(c, c->stream)) != PTGPU_OK) return rc;
+        PassD Q = P;
+        Q.spp = share(k); Q.sampleBase = P.sampleBase + k * P.sampleStride; Q.sampleStride = P.sampleStride * N;
+        if (Q.spp > 0 && (rc = run_pass(c, Q, Q.spp, c->dSum, c->stream)) != PTGPU_OK) return rc;
+        if (c != ctx && cudaEventRecord(c->evPeerDone, c->stream) != cudaSuccess) { c->error = "cudaEventRecord failed"; return PTGPU_E_CUDA; }
+        return PTGPU_OK;
+    };
+    std::vector<std::thread> threads;
+    for (int k = 1; k < N; k++) threads.emplace_back([&, k] { rcs[(size_t)k] = run_one(ctx->peers[(size_t)k - 1], k); });
+    rcs[0] = run_one(ctx, 0);
+    for (auto& t : threads) t.join();
+    CK(cudaSetDevice(ctx->device));
+    for (int k = 0; k < N; k++)
+        if (rcs[(size_t)k] != PTGPU_OK) {
+            if (k > 0) ctx->error = "device " + std::to_string(ctx->peers[(size_t)k - 1]->device) + ": " + ctx->peers[(size_t)k - 1]->error;
+            return rcs[(size_t)k];
+        }
+    SumSet sums;
+    std::memset(&sums, 0, sizeof(sums));
+    sums.p[0] = ctx->dSum; sums.n = N;
+    for (int k = 1; k < N; k++) {
+        ptgpu_ctx* c = ctx->peers[(size_t)k - 1];
+        CK(cudaStreamWaitEvent(st, c->evPeerDone, 0));
+        if (ctx->peerDirect[(size_t)k - 1]) sums.p[k] = c->dSum;
+        else {  // no peer access between these two devices: one device-to-device copy into a root-side buffer
+            float*& stage = ctx->peerStage[(size_t)k - 1];
+            if (!stage) CK(cudaMalloc(&stage, npix * 3 * sizeof(float)));
+            CK(cudaMemcpyPeerAsync(stage, ctx->device, c->dSum, c->device, npix * 3 * sizeof(float), st));
+            sums.p[k] = stage;
+        }
+    }
+    k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(sums, (double)P.spp, (uint32_t)npix, ctx->pb, ctx->dMean, ctx->laneCounts + 3, ctx->numLanes, 1.f, 0);
+    ctx->launches++;
+    CK(cudaStreamSynchronize(st));  // the peers' accumulators are free again
+    bool overflow = false;
+    for (int k = 1; k < N; k++) {
+        ptgpu_ctx* c = ctx->peers[(size_t)k - 1];
+        cudaSetDevice(c->device);
+        overflow = take_overflow(c) || overflow;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (overflow) return fail(ctx, PTGPU_E_LIMIT, "ray queue overflow on a peer device (internal sizing error)");
     return PTGPU_OK;
 }
 
@@ -1668,9 +1966,12 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
     if (rc != PTGPU_OK) return rc;
     const size_t npix = (size_t)P.width * P.height;
     cudaStream_t st = ctx->stream;
+    const uint32_t* flags = ctx->laneCounts + 3;
+    const int nflags = ctx->numLanes;
     CK(cudaEventRecord(ctx->ev0, st));
+    if ((rc = clear_overflow(ctx, st)) != PTGPU_OK) return rc;
     if (P.stratified) {
-        // Renderer.cs:231-246: every stratum sample is its own Buffer.AddSample
+        // Renderer.cs:231-246: every stratum sample is its own Buffer.AddSample (root device only: one sample per pixel at a time)
         int nn = P.sppRoot * P.sppRoot;
         for (int k = 0; k < nn; k++) {
             PassD Q = P;
@@ -1678,18 +1979,21 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
             CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
             rc = run_pass(ctx, Q, 1, ctx->dSum, st);
             if (rc != PTGPU_OK) return rc;
-            k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, 1.0, (uint32_t)npix, ctx->pb, ctx->dMean);
+            k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(one_sum(ctx->dSum), 1.0, (uint32_t)npix, ctx->pb, ctx->dMean, flags, nflags, 1.f / (float)nn, k > 0);
             ctx->launches++;
         }
+    } else if (!ctx->peers.empty()) {
+        rc = render_main_multi(ctx, P, st);
+        if (rc != PTGPU_OK) return rc;
     } else {
         CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
         rc = run_pass(ctx, P, P.spp, ctx->dSum, st);
         if (rc != PTGPU_OK) return rc;
-        k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, (double)P.spp, (uint32_t)npix, ctx->pb, ctx->dMean);
+        k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(one_sum(ctx->dSum), (double)P.spp, (uint32_t)npix, ctx->pb, ctx->dMean, flags, nflags, 1.f, 0);
         ctx->launches++;
     }
     if (out_mean_rgb) CK(cudaMemcpyAsync(out_mean_rgb, ctx->dMean, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    // Extra samples use their own ranges of the global sample index so that no Philox stream is reused.
+    // Extra samples (root device) use their own ranges of the global sample index so that no Philox stream is reused.
     const int kAdaptiveBase = 1 << 20, kFireflyBase = 1 << 21;
     if (pass->serialRules) {  // Renderer.cs:150-191: the extra samples of the serial Render()
         if (pass->adaptiveSamples > 0 && pass->adaptiveExponent < 0) return fail(ctx, PTGPU_E_ARG, "serialRules: a negative AdaptiveExponent is not supported");
@@ -1723,7 +2027,7 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
             CK(cudaMemsetAsync(ctx->dSum, 0, npix * 3 * sizeof(float), st));
             rc = run_pass(ctx, Q, 1, ctx->dSum, st);
             if (rc != PTGPU_OK) return rc;
-            k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->dSum, 1.0, (uint32_t)npix, ctx->pb, nullptr);
+            k_add_sample<<<grid_for(ctx, 4), 256, 0, st>>>(one_sum(ctx->dSum), 1.0, (uint32_t)npix, ctx->pb, nullptr, flags, nflags, 1.f, 0);
             ctx->launches++;
         }
     }
@@ -1753,11 +2057,8 @@ int ptgpu_render_pass(ptgpu_ctx* ctx, const ptgpu_pass* pass, float* out_mean_rg
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->lastPassMs = ms;
-    for (int k = 0; k < ctx->numLanes; k++) {
-        uint32_t overflow = 0;
-        CK(cudaMemcpy(&overflow, ctx->lanes[k].counts + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (overflow) return fail(ctx, PTGPU_E_LIMIT, "ray queue overflow (internal sizing error)");
-    }
+    // the Buffer.AddSample kernels saw the flag and left the Buffer alone: the pass can be repeated with a larger queueCapacity
+    if (take_overflow(ctx)) return fail(ctx, PTGPU_E_LIMIT, "ray queue overflow (internal sizing error): the pass was not added to the Buffer");
     return PTGPU_OK;
 }
 
@@ -1947,6 +2248,17 @@ int ptgpu_get_counters(ptgpu_ctx* ctx, ptgpu_counters* out) {
     out->lastPassMs = ctx->lastPassMs;
     out->traceMs = ctx->traceMs; out->shadeMs = ctx->shadeMs; out->shadowMs = ctx->shadowMs; out->raygenMs = ctx->raygenMs;
     out->meshMs = ctx->meshMs; out->meshItems = ctx->meshItems; out->meshLaunches = ctx->meshLaunches;
+    out->traceLaunches = ctx->traceLaunches;
+    take_overflow(ctx);  // an overflow of a ptgpu_accumulate_device pass is reported here
+    out->queueOverflows = ctx->overflowPasses;
+    out->devices = 1 + ctx->peers.size();
+    for (ptgpu_ctx* p : ctx->peers) {  // the peers' shares of the passes
+        ptgpu_counters pc;
+        if (ptgpu_get_counters(p, &pc) != PTGPU_OK) { ctx->error = p->error; cudaSetDevice(ctx->device); return PTGPU_E_CUDA; }
+        out->cameraSamples += pc.cameraSamples; out->segments += pc.segments; out->shadowRays += pc.shadowRays; out->nanSamples += pc.nanSamples;
+        out->kernelLaunches += pc.kernelLaunches; out->queueOverflows += pc.queueOverflows;
+    }
+    if (!ctx->peers.empty()) CK(cudaSetDevice(ctx->device));
     return PTGPU_OK;
 }
 
@@ -1956,6 +2268,9 @@ int ptgpu_reset_counters(ptgpu_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters)));
     ctx->launches = 0;
+    ctx->overflowPasses = 0;
+    for (ptgpu_ctx* p : ctx->peers) { int rc = ptgpu_reset_counters(p); if (rc != PTGPU_OK) return rc; }
+    if (!ctx->peers.empty()) CK(cudaSetDevice(ctx->device));
     return PTGPU_OK;
 }
 

@@ -52,11 +52,16 @@ def reduce_sum_to_root(tensor, dst: int = 0):
     return tensor
 
 
-def render_pass_distributed(device, host_world, width: int, height: int, rs: RankSamples, d_sum, stream: int = 0,
+def render_pass_distributed(device, host_world, width: int, height: int, rs: RankSamples, d_sum, stream: Optional[int] = None,
                             pass_index: int = 0, seed: int = 0x50545348, rank: Optional[int] = None):
-    """One multi-GPU pass: accumulate this rank's samples into `d_sum` (a torch CUDA tensor of width*height*3 floats), reduce,
-    and on rank 0 apply Buffer.AddSample with the job's total spp."""
+    """One multi-process multi-GPU pass (one rank per GPU): accumulate this rank's samples into `d_sum` (a torch CUDA tensor of
+    width*height*3 floats), reduce, and on rank 0 apply Buffer.AddSample with the job's total spp.  Everything is ordered on
+    `stream` (a cudaStream_t handle); None = torch's current stream, the one `d_sum.zero_()` and the NCCL reduce are issued on.
+    (A single-process host uses ptgpu_params.devices instead: bindings.Device(devices=[...]).)"""
+    import torch
     import torch.distributed as dist
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream if d_sum.is_cuda else 0
     d_sum.zero_()
     if rs.spp > 0:
         p = host_world.make_pass(width, height, rs.spp, pass_index=pass_index, seed=seed, sample_base=rs.sample_base,

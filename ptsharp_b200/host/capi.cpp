@@ -172,7 +172,7 @@ void pth_make_pass(pth_world* w, int width, int height, int spp, int stratified,
     out->seed = seed; out->passIndex = passIndex;
     out->camera = FlattenCamera(w->camera);
     out->adaptiveSamples = 0; out->fireflySamples = 0; out->fireflyThreshold = 1.0;
-    out->serialRules = 0; out->reserved0 = 0; out->adaptiveThreshold = 1.0; out->adaptiveExponent = 1.0;
+    out->serialRules = 0; out->flags = w->sampler.RussianRoulette ? PTGPU_PASS_RUSSIAN_ROULETTE : 0; out->adaptiveThreshold = 1.0; out->adaptiveExponent = 1.0;
 }
 
 // kd-tree dump in the oracle's canonical pre-order form (builder parity tests).  which = -1: scene tree, else the
@@ -227,6 +227,12 @@ int pth_renderer_new(pth_world* w, int width, int height, int device) {
         w->renderer->Device = device;
         return 0;
     } catch (const std::exception& e) { w->error = e.what(); return -1; }
+}
+// Renderer.Devices: the GPUs one Renderer drives (multi-GPU inside the ptgpu handle); n <= 1 = the single device of pth_renderer_new.
+int pth_renderer_devices(pth_world* w, int n, const int* devices) {
+    if (!w->renderer) { w->error = "no renderer"; return -1; }
+    w->renderer->Devices.assign(devices, devices + (n > 0 ? n : 0));
+    return 0;
 }
 int pth_renderer_set(pth_world* w, int samplesPerPixel, int stratified, unsigned seed) {
     if (!w->renderer) { w->error = "no renderer"; return -1; }

@@ -915,14 +915,19 @@ Renderer Renderer::NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sam
 Renderer::Renderer(Renderer&& o) noexcept
     : SamplesPerPixel(o.SamplesPerPixel), StratifiedSampling(o.StratifiedSampling), AdaptiveSamples(o.AdaptiveSamples),
       FireflySamples(o.FireflySamples), FireflyThreshold(o.FireflyThreshold), AdaptiveThreshold(o.AdaptiveThreshold), AdaptiveExponent(o.AdaptiveExponent),
-      NumCPU(o.NumCPU), Device(o.Device), Seed(o.Seed), scene_(o.scene_), camera_(o.camera_),
+      NumCPU(o.NumCPU), Device(o.Device), Devices(std::move(o.Devices)), Seed(o.Seed), scene_(o.scene_), camera_(o.camera_),
       sampler_(o.sampler_), w_(o.w_), h_(o.h_), passIndex_(o.passIndex_), ctx_(o.ctx_), flat_(std::move(o.flat_)) {
     o.ctx_ = nullptr;
 }
 Renderer::~Renderer() { if (ctx_) ptgpu_destroy(ctx_); }
 void Renderer::EnsureUploaded() {
     if (!ctx_) {
-        ptgpu_params p{Device, 0, 0};
+        ptgpu_params p;
+        std::memset(&p, 0, sizeof(p));
+        p.device = Device;
+        if (Devices.size() > PTGPU_MAX_DEVICES) throw std::runtime_error("Renderer.Devices: at most 8 GPUs");
+        p.numDevices = (int)Devices.size();
+        for (size_t k = 0; k < Devices.size(); k++) p.devices[k] = Devices[k];
         int rc = ptgpu_create(&p, &ctx_);
         if (rc != PTGPU_OK) { const char* e = ptgpu_last_error(nullptr); throw std::runtime_error(std::string("ptgpu_create: ") + (e ? e : "?")); }
     }
@@ -944,6 +949,7 @@ ptgpu_pass Renderer::MakePass() const {
     p.camera = FlattenCamera(*camera_);
     p.adaptiveSamples = AdaptiveSamples; p.fireflySamples = FireflySamples; p.fireflyThreshold = FireflyThreshold;
     p.serialRules = 0; p.adaptiveThreshold = AdaptiveThreshold; p.adaptiveExponent = AdaptiveExponent;
+    p.flags = sampler_->RussianRoulette ? PTGPU_PASS_RUSSIAN_ROULETTE : 0;
     return p;
 }
 void Renderer::RenderParallel(float* out) {

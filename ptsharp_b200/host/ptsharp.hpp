@@ -261,6 +261,7 @@ enum SpecularMode { SpecularModeNaive = 0, SpecularModeFirst = 1, SpecularModeAl
 struct DefaultSampler {  // Sampler.cs:10-53
     int FirstHitSamples = 1, MaxBounces = 4;
     bool DirectLighting = true, SoftShadows = true;
+    bool RussianRoulette = false;  // opt-in extension (ptgpu_pass.flags): dead code in the reference (Sampler.cs:55, 133-142), off in parity mode
     ptsharp::LightMode LightMode = LightModeRandom;
     ptsharp::SpecularMode SpecularMode = SpecularModeNaive;
     static DefaultSampler NewSampler(int firstHitSamples, int maxBounces) {
@@ -318,6 +319,7 @@ public:
     double AdaptiveThreshold = 1, AdaptiveExponent = 1;  // Renderer.cs:44-45 (read by the serial Render() only, :153-158)
     int NumCPU = 0;                               // Renderer.cs:38: 1 when NewRenderer(..., multithreaded = false) -> IterativeRender runs the serial Render()
     int Device = 0;
+    std::vector<int> Devices;                     // more than one entry: the pass is split over these GPUs inside the handle (ptgpu_params.devices)
     uint32_t Seed = 0x50545348u;
     static Renderer NewRenderer(Scene& scene, Camera& camera, DefaultSampler& sampler, int w, int h, bool multithreaded);
     ~Renderer();

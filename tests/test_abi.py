@@ -20,15 +20,32 @@ def test_header_symbols_are_exported(bindings):
     assert set(declared) == set(bindings.PTGPU_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ptgpu_abi_version() == 1
+    assert lib.ptgpu_abi_version() == 2
 
 
-def test_struct_layouts_match_header(bindings):
-    # sizes the C compiler gives the ABI structs (see include/ptgpu.h)
-    assert C.sizeof(bindings.Camera) == 72
-    assert C.sizeof(bindings.Pass) == 56 + 72 + 16 + 24
-    assert C.sizeof(bindings.Params) == 16
-    assert C.sizeof(bindings.Counters) == 104
+ABI_STRUCTS = ["ptgpu_params", "ptgpu_pass", "ptgpu_camera", "ptgpu_counters", "ptgpu_flat_scene", "ptgpu_node", "ptgpu_tree", "ptgpu_shape",
+               "ptgpu_sphere", "ptgpu_cube", "ptgpu_plane", "ptgpu_cylinder", "ptgpu_mesh", "ptgpu_tri_geom", "ptgpu_tri_shade",
+               "ptgpu_instance", "ptgpu_sdf_op", "ptgpu_sdf_shape", "ptgpu_volume_window", "ptgpu_volume", "ptgpu_material", "ptgpu_texture"]
+# what a plain C compiler (hence a P/Invoke [StructLayout(LayoutKind.Sequential)] mirror) lays out for include/ptgpu.h
+ABI_SIZES = [56, 168, 72, 128, 376, 16, 32, 16, 32, 24, 24, 24, 16, 48, 64, 272, 136, 32, 24, 64, 96, 16]
+
+
+def test_struct_layouts_match_header(bindings, tmp_path):
+    """Every struct of the ABI: the size nvcc compiled into libptgpu (ptgpu_abi_sizeof) == the size gcc gives the same header as C
+    == the documented constant, and the ctypes mirrors the tests marshal through agree."""
+    import subprocess
+    lib = bindings.gpu_lib()
+    got = [lib.ptgpu_abi_sizeof(k) for k in range(len(ABI_STRUCTS))]
+    assert got == ABI_SIZES, dict(zip(ABI_STRUCTS, got))
+    assert lib.ptgpu_abi_sizeof(len(ABI_STRUCTS)) == -1
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "ptgpu.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n in ABI_STRUCTS) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    assert [int(x) for x in subprocess.check_output([str(exe)]).split()] == ABI_SIZES
+    for k, cls in ((0, bindings.Params), (1, bindings.Pass), (2, bindings.Camera), (3, bindings.Counters)):
+        assert C.sizeof(cls) == ABI_SIZES[k], cls
 
 
 def test_flatten_c1(bindings):
