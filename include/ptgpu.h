@@ -108,7 +108,9 @@ typedef struct ptgpu_material {
     int32_t transparent, texture, normalTexture, bumpTexture, glossTexture, pad;
 } ptgpu_material;
 
-/* ColorTexture (Texture.cs:96-100): Width, Height, Data (already Pow(2.2)'d, Texture.cs:163) as RGBA float. */
+/* ColorTexture (Texture.cs:96-100): Width, Height, Data (already Pow(2.2)'d, Texture.cs:163) as 4 doubles per texel (r, g, b, 1): the
+ * reference's Colour is 3 doubles, and FP32 texels perturb a normal-mapped / bump-mapped normal in its last bits, which is enough to
+ * flip the self-intersection of the next ray: texels keep the reference's precision. */
 typedef struct ptgpu_texture { int32_t width, height; uint64_t texelOffset; } ptgpu_texture;
 
 typedef struct ptgpu_flat_scene {
@@ -134,7 +136,7 @@ typedef struct ptgpu_flat_scene {
     uint64_t numVolumeData;    const double* volumeData;
     uint32_t numMaterials;     const ptgpu_material* materials;
     uint32_t numTextures;      const ptgpu_texture* textures;
-    uint64_t numTexels;        const float* texels;          /* 4 floats per texel */
+    uint64_t numTexels;        const double* texels;         /* 4 doubles per texel */
     double envColor[3];                                      /* Scene.Color (Scene.cs:11) */
     int32_t envTexture; int32_t pad0;                        /* Scene.Texture (Scene.cs:12) */
     double envTextureAngle;                                  /* Scene.TextureAngle (Scene.cs:13) */

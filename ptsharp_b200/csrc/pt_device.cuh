@@ -142,7 +142,7 @@ struct DScene {
     const double* volumeData;
     const ptgpu_material* materials;
     const ptgpu_texture* textures;
-    const float4* texels;
+    const double4* texels;        // 4 doubles per texel (the reference's Colour precision, see ptgpu.h)
     // Derived at upload for mesh trees (see "mesh traversal" below):
     const uint4* meshNodes;         // 4 x uint4 per node: reference kd nodes, bounds-only nodes and micro leaves (see mesh_step)
     const float4* instBounds;       // 2 x float4 per TransformedShape of a Mesh: padded WORLD-space bounds of the instance (FP32 pre-test)
@@ -1475,7 +1475,12 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
 struct Col { double r, g, b; };
 PT_D void modf_net(double in, int& dec, double& frac) { double tr = trunc(in); dec = (int)tr; frac = in - tr; }  // Util.cs:108-113
 PT_D double fract_net(double x) { int d; double f; modf_net(x, d, f); return f; }                                 // Texture.cs:218-222
-PT_D Col tex_bilinear(const float4* __restrict__ texels, const ptgpu_texture& tx, double u, double v) {  // Texture.cs:188-216
+struct Texel { double x, y, z; };
+PT_D Texel ld_texel(const double4* p) {  // two 128-bit loads (r, g) (b, -)
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    Texel t; t.x = a.x; t.y = a.y; t.z = b.x; return t;
+}
+PT_D Col tex_bilinear(const double4* __restrict__ texels, const ptgpu_texture& tx, double u, double v) {  // Texture.cs:188-216
     if (u == 1) u -= kEPS;
     if (v == 1) v -= kEPS;
     double w = (double)tx.width - 1, h = (double)tx.height - 1;
@@ -1483,18 +1488,18 @@ PT_D Col tex_bilinear(const float4* __restrict__ texels, const ptgpu_texture& tx
     modf_net(u * w, X, x);
     modf_net(v * h, Y, y);
     int x0 = X, y0 = Y, x1 = x0 + 1, y1 = y0 + 1;
-    const float4* T = texels + tx.texelOffset;
-    float4 c00 = __ldg(T + (size_t)y0 * tx.width + x0), c01 = __ldg(T + (size_t)y1 * tx.width + x0);
-    float4 c10 = __ldg(T + (size_t)y0 * tx.width + x1), c11 = __ldg(T + (size_t)y1 * tx.width + x1);
+    const double4* T = texels + tx.texelOffset;
+    const Texel c00 = ld_texel(T + (size_t)y0 * tx.width + x0), c01 = ld_texel(T + (size_t)y1 * tx.width + x0);
+    const Texel c10 = ld_texel(T + (size_t)y0 * tx.width + x1), c11 = ld_texel(T + (size_t)y1 * tx.width + x1);
     double w00 = (1 - x) * (1 - y), w10 = x * (1 - y), w01 = (1 - x) * y, w11 = x * y;
     Col c = {0, 0, 0};
-    c.r = c.r + (double)c00.x * w00; c.g = c.g + (double)c00.y * w00; c.b = c.b + (double)c00.z * w00;
-    c.r = c.r + (double)c10.x * w10; c.g = c.g + (double)c10.y * w10; c.b = c.b + (double)c10.z * w10;
-    c.r = c.r + (double)c01.x * w01; c.g = c.g + (double)c01.y * w01; c.b = c.b + (double)c01.z * w01;
-    c.r = c.r + (double)c11.x * w11; c.g = c.g + (double)c11.y * w11; c.b = c.b + (double)c11.z * w11;
+    c.r = c.r + c00.x * w00; c.g = c.g + c00.y * w00; c.b = c.b + c00.z * w00;
+    c.r = c.r + c10.x * w10; c.g = c.g + c10.y * w10; c.b = c.b + c10.z * w10;
+    c.r = c.r + c01.x * w01; c.g = c.g + c01.y * w01; c.b = c.b + c01.z * w01;
+    c.r = c.r + c11.x * w11; c.g = c.g + c11.y * w11; c.b = c.b + c11.z * w11;
     return c;
 }
-PT_DC Col tex_sample_c(const ptgpu_texture* __restrict__ textures, const float4* __restrict__ texels, int32_t id, double u, double v) {  // Texture.cs:224-229
+PT_DC Col tex_sample_c(const ptgpu_texture* __restrict__ textures, const double4* __restrict__ texels, int32_t id, double u, double v) {  // Texture.cs:224-229
     const ptgpu_texture tx = textures[id];
     u = fract_net(fract_net(u) + 1);
     v = fract_net(fract_net(v) + 1);
@@ -1515,9 +1520,9 @@ PT_D V3 tex_bump_sample(const DScene& S, int32_t id, double u, double v) {  // T
     int x1 = clampi(x - 1, 0, tx.width - 1), x2 = clampi(x + 1, 0, tx.width - 1);
     int y1 = clampi(y - 1, 0, tx.height - 1), y2 = clampi(y + 1, 0, tx.height - 1);
     int yr = clampi(y, 0, tx.height - 1), xr = clampi(x, 0, tx.width - 1);
-    const float4* T = S.texels + tx.texelOffset;
-    double cx = (double)__ldg(T + (size_t)yr * tx.width + x1).x - (double)__ldg(T + (size_t)yr * tx.width + x2).x;
-    double cy = (double)__ldg(T + (size_t)y1 * tx.width + xr).x - (double)__ldg(T + (size_t)y2 * tx.width + xr).x;
+    const double* T = reinterpret_cast<const double*>(S.texels + tx.texelOffset);  // the red channel of 4 neighbours
+    double cx = __ldg(T + 4 * ((size_t)yr * tx.width + x1)) - __ldg(T + 4 * ((size_t)yr * tx.width + x2));
+    double cy = __ldg(T + 4 * ((size_t)y1 * tx.width + xr)) - __ldg(T + 4 * ((size_t)y2 * tx.width + xr));
     return v3d(cx, cy, 0.0);
 }
 

@@ -224,10 +224,17 @@ PT_D void cast_ray(const ptgpu_camera& cam, int x, int y, int w, int h, double u
 }
 
 // ====================================================================================================== kernels
-// K1.  Camera samples [g0, g0+n) of the pass: g -> (pixel = g % npix, slot k = g / npix), global sample index
-// sampleBase + k*sampleStride.  Non-stratified: fu = (x+xi1)/w, fv = (y+xi2)/h are passed where CastRay expects a
+// K1.  Camera samples [g0, g0+n) of the pass, PIXEL-MAJOR: g -> (pixel = g / slots, slot k = g % slots), global sample index
+// sampleBase + k*sampleStride.  The samples of one pixel are neighbours in the queue, so a warp traces (nearly) one camera ray
+// 32 times - the reference's jitter is 1/w of a pixel (below) - and the lanes walk the same nodes, hit the same triangle and
+// run the same shading code; their bounce and shadow rays then leave from one point.  The order changes nothing else: every
+// draw is keyed by (pixel, global sample index, place in the path tree).
+// Non-stratified: fu = (x+xi1)/w, fv = (y+xi2)/h are passed where CastRay expects a
 // sub-pixel offset — the reference's behaviour (Renderer.cs:297-304), reproduced on purpose.
-__global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, uint32_t n, RayQueue q, uint32_t* __restrict__ count,
+#ifndef PT_PIXEL_MAJOR
+#define PT_PIXEL_MAJOR 1   // 0: sample-major (pixel = g % npix), the order of round 1 (A/B switch)
+#endif
+__global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, uint32_t n, uint32_t slots, RayQueue q, uint32_t* __restrict__ count,
                                                  DeviceCounters* cnt, const uint32_t* __restrict__ pixelList, const uint32_t* __restrict__ listCount) {
     const uint32_t npix = (uint32_t)P.width * (uint32_t)P.height;
     if (pixelList) {  // sparse pass: one sample for each listed pixel; this batch covers list[g0, g0+n)
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
     }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long g = g0 + i;
-        uint32_t pixel = (uint32_t)(g % npix), k = (uint32_t)(g / npix);
+        uint32_t pixel = PT_PIXEL_MAJOR ? (uint32_t)(g / slots) : (uint32_t)(g % npix), k = PT_PIXEL_MAJOR ? (uint32_t)(g % slots) : (uint32_t)(g / npix);
         if (pixelList) { pixel = pixelList[g0 + i]; k = 0; }
         int x = (int)(pixel % (uint32_t)P.width), y = (int)(pixel / (uint32_t)P.width);
         uint32_t sample = (uint32_t)(P.sampleBase + (int)k * P.sampleStride);
@@ -1501,8 +1508,8 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
     UP(materials, s->materials, s->numMaterials);
     UP(textures, s->textures, s->numTextures);
     {
-        const float4* t = nullptr;
-        if ((rc = upload(ctx, reinterpret_cast<const float4*>(s->texels), s->numTexels, &t)) != PTGPU_OK) return rc;
+        const double4* t = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const double4*>(s->texels), s->numTexels, &t)) != PTGPU_OK) return rc;
         D.texels = t;
     }
 #undef UP
@@ -1772,7 +1779,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         uint32_t n = (uint32_t)std::min<uint64_t>(batch, total - g0);
         int cur = 0;
         if (prof) cudaEventRecord(ctx->evA, stream);
-        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, L.rq[0], counts + 0, ctx->dCounters, pixelList, listCount);
+        k_raygen<<<gridGen, 256, 0, stream>>>(P, g0, n, (uint32_t)nSlots, L.rq[0], counts + 0, ctx->dCounters, pixelList, listCount);
         ctx->launches++;
         if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->raygenMs += ms; }
         for (int depth = 0; depth <= P.maxBounces; depth++) {

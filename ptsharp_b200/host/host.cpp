@@ -739,7 +739,7 @@ struct Flattener {
         if (it != texIds.end()) return it->second;
         ptgpu_texture pt;
         pt.width = t->Width; pt.height = t->Height; pt.texelOffset = f.texels.size() / 4;
-        for (const Colour& c : t->Data) { f.texels.push_back((float)c.r); f.texels.push_back((float)c.g); f.texels.push_back((float)c.b); f.texels.push_back(1.0f); }
+        for (const Colour& c : t->Data) { f.texels.push_back(c.r); f.texels.push_back(c.g); f.texels.push_back(c.b); f.texels.push_back(1.0); }
         int32_t id = (int32_t)f.textures.size();
         f.textures.push_back(pt);
         texIds[t.get()] = id;

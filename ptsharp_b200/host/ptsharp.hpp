@@ -294,7 +294,7 @@ struct FlatScene {
     std::vector<double> volumeData;
     std::vector<ptgpu_material> materials;
     std::vector<ptgpu_texture> textures;
-    std::vector<float> texels;
+    std::vector<double> texels;
     ptgpu_flat_scene view{};
     uint64_t Bytes() const;
     void Bind(uint32_t sceneTree, uint32_t numSceneShapes);  // point `view` at the vectors (keeps the env fields)
