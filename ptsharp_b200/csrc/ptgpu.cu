@@ -904,7 +904,7 @@ __global__ void k_check_kd_div(uint64_t seed, uint64_t offset, uint64_t n, unsig
 // ====================================================================================================== host side
 static constexpr int kMaxLanes = 8;
 #ifndef PT_LANES
-#define PT_LANES 1
+#define PT_LANES 2   // C3, 512 spp: 1 -> 362.2, 2 -> 367.7, 3 -> 363.8, 4 -> 362.7 Msamples/s (the tail of one batch's k_mesh overlaps the next batch)
 #endif
 struct Lane {
     cudaStream_t stream = nullptr;
