@@ -72,41 +72,49 @@ _gpu = None
 _host = None
 
 
+def _bind_gpu(lib: C.CDLL) -> C.CDLL:
+    lib.ptgpu_abi_version.restype = C.c_int
+    lib.ptgpu_abi_sizeof.restype = C.c_int
+    lib.ptgpu_abi_sizeof.argtypes = [C.c_int]
+    lib.ptgpu_create.restype = C.c_int
+    lib.ptgpu_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+    lib.ptgpu_destroy.restype = None
+    lib.ptgpu_destroy.argtypes = [C.c_void_p]
+    lib.ptgpu_last_error.restype = C.c_char_p
+    lib.ptgpu_last_error.argtypes = [C.c_void_p]
+    lib.ptgpu_upload_scene.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ptgpu_scene_bytes.restype = C.c_uint64
+    lib.ptgpu_scene_bytes.argtypes = [C.c_void_p]
+    lib.ptgpu_render_pass.argtypes = [C.c_void_p, C.POINTER(Pass), c_float_p]
+    lib.ptgpu_accumulate_device.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_void_p, C.c_void_p]
+    lib.ptgpu_add_sample_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p]
+    lib.ptgpu_read_buffer.argtypes = [C.c_void_p, C.c_int32, c_float_p]
+    lib.ptgpu_reset_buffer.argtypes = [C.c_void_p]
+    lib.ptgpu_export_buffer.argtypes = [C.c_void_p, c_int_p, c_int_p, c_double_p, c_double_p, c_int_p]
+    lib.ptgpu_import_buffer.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int_p]
+    lib.ptgpu_intersect_batch.argtypes = [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p,
+                                          c_float_p, c_float_p, c_int_p, c_int_p]
+    lib.ptgpu_cast_rays.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_int32, c_int_p, c_int_p, c_double_p, c_double_p,
+                                    c_int_p, c_float_p, c_float_p]
+    lib.ptgpu_keyed_draw.argtypes = [C.c_void_p] + [C.c_uint32] * 9 + [c_double_p]
+    lib.ptgpu_check_kd_div.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.ptgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    lib.ptgpu_reset_counters.argtypes = [C.c_void_p]
+    lib.ptgpu_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+    return lib
+
+
 def gpu_lib() -> C.CDLL:
     global _gpu
     if _gpu is None:
         path = os.environ.get("PTGPU_LIB") or _build.build_gpu()  # PTGPU_LIB: development override (tuning variants)
-        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
-        lib.ptgpu_abi_version.restype = C.c_int
-        lib.ptgpu_abi_sizeof.restype = C.c_int
-        lib.ptgpu_abi_sizeof.argtypes = [C.c_int]
-        lib.ptgpu_create.restype = C.c_int
-        lib.ptgpu_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
-        lib.ptgpu_destroy.restype = None
-        lib.ptgpu_destroy.argtypes = [C.c_void_p]
-        lib.ptgpu_last_error.restype = C.c_char_p
-        lib.ptgpu_last_error.argtypes = [C.c_void_p]
-        lib.ptgpu_upload_scene.argtypes = [C.c_void_p, C.c_void_p]
-        lib.ptgpu_scene_bytes.restype = C.c_uint64
-        lib.ptgpu_scene_bytes.argtypes = [C.c_void_p]
-        lib.ptgpu_render_pass.argtypes = [C.c_void_p, C.POINTER(Pass), c_float_p]
-        lib.ptgpu_accumulate_device.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_void_p, C.c_void_p]
-        lib.ptgpu_add_sample_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p]
-        lib.ptgpu_read_buffer.argtypes = [C.c_void_p, C.c_int32, c_float_p]
-        lib.ptgpu_reset_buffer.argtypes = [C.c_void_p]
-        lib.ptgpu_export_buffer.argtypes = [C.c_void_p, c_int_p, c_int_p, c_double_p, c_double_p, c_int_p]
-        lib.ptgpu_import_buffer.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int_p]
-        lib.ptgpu_intersect_batch.argtypes = [C.c_void_p, C.c_int32, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p,
-                                              c_float_p, c_float_p, c_int_p, c_int_p]
-        lib.ptgpu_cast_rays.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_int32, c_int_p, c_int_p, c_double_p, c_double_p,
-                                        c_int_p, c_float_p, c_float_p]
-        lib.ptgpu_keyed_draw.argtypes = [C.c_void_p] + [C.c_uint32] * 9 + [c_double_p]
-        lib.ptgpu_check_kd_div.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-        lib.ptgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
-        lib.ptgpu_reset_counters.argtypes = [C.c_void_p]
-        lib.ptgpu_set_profiling.argtypes = [C.c_void_p, C.c_int32]
-        _gpu = lib
+        _gpu = _bind_gpu(C.CDLL(path, mode=C.RTLD_GLOBAL))
     return _gpu
+
+
+def checker_lib(name: str = "nocull") -> C.CDLL:
+    """A checker build of libptgpu (ptsharp_b200/build.py VARIANTS) loaded BESIDE the product library: tests only."""
+    return _bind_gpu(C.CDLL(_build.build_variants()[name], mode=C.RTLD_LOCAL))
 
 
 _HOST_EXTRA = {
@@ -294,9 +302,10 @@ class HostWorld(World):
 class Device:
     """One ptgpu_ctx: a CUDA device with an uploaded scene, its wavefront queues and its image Buffer."""
 
-    def __init__(self, device: int = 0, queue_capacity: int = 0, devices=None):
-        """devices: a list of CUDA ordinals -> one handle that splits every pass over them (ptgpu_params.devices)."""
-        self.lib = gpu_lib()
+    def __init__(self, device: int = 0, queue_capacity: int = 0, devices=None, lib: Optional[C.CDLL] = None):
+        """devices: a list of CUDA ordinals -> one handle that splits every pass over them (ptgpu_params.devices).
+        lib: a checker build (checker_lib()) instead of the product library - tests only."""
+        self.lib = lib or gpu_lib()
         self.h = C.c_void_p()
         p = Params()
         p.device, p.flags, p.queueCapacity = device, 0, queue_capacity
@@ -372,17 +381,20 @@ class Device:
     def reset_buffer(self):
         self._ck(self.lib.ptgpu_reset_buffer(self.h), "ptgpu_reset_buffer")
 
-    def intersect_batch(self, o: np.ndarray, d: np.ndarray) -> dict:
+    def intersect_batch(self, o: np.ndarray, d: np.ndarray, full: bool = True) -> dict:
+        """Scene.Intersect (+ Hit.Info when `full`) on caller-supplied rays."""
         o = np.ascontiguousarray(o, dtype=np.float32); d = np.ascontiguousarray(d, dtype=np.float32)
         n = o.shape[0]
-        out = dict(shape=np.empty(n, np.int32), prim=np.empty(n, np.int32), t=np.empty(n, np.float64),
-                   normal=np.empty((n, 3), np.float32), position=np.empty((n, 3), np.float32),
-                   inside=np.empty(n, np.int32), material=np.empty(n, np.int32))
+        out = dict(shape=np.empty(n, np.int32), prim=np.empty(n, np.int32), t=np.empty(n, np.float64))
+        if full:
+            out.update(normal=np.empty((n, 3), np.float32), position=np.empty((n, 3), np.float32),
+                       inside=np.empty(n, np.int32), material=np.empty(n, np.int32))
+        fp = lambda k: out[k].ctypes.data_as(c_float_p) if k in out else None
+        ip = lambda k: out[k].ctypes.data_as(c_int_p) if k in out else None
         self._ck(self.lib.ptgpu_intersect_batch(
             self.h, n, o.ctypes.data_as(c_float_p), d.ctypes.data_as(c_float_p), out["shape"].ctypes.data_as(c_int_p),
             out["prim"].ctypes.data_as(c_int_p), out["t"].ctypes.data_as(c_double_p),
-            out["normal"].ctypes.data_as(c_float_p), out["position"].ctypes.data_as(c_float_p),
-            out["inside"].ctypes.data_as(c_int_p), out["material"].ctypes.data_as(c_int_p)), "ptgpu_intersect_batch")
+            fp("normal"), fp("position"), ip("inside"), ip("material")), "ptgpu_intersect_batch")
         return out
 
     def cast_rays(self, p: Pass, x, y, fu, fv, sample):

@@ -19,7 +19,8 @@ LIBDIR = os.path.join(PKG, "_lib")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+              "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+              "-Xlinker", "-Bsymbolic"]  # -Bsymbolic: the library's own calls to ptgpu_* bind inside it (a checker build may be loaded beside it)
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra",
              "-Wno-unused-parameter"]
 
@@ -42,6 +43,29 @@ def build_gpu(force=False, verbose=False) -> str:
     return out
 
 
+# Checker builds of the same source (tests only; never loaded by the product path).
+VARIANTS = {"nocull": ["-DPT_NO_CULL=1"]}
+
+
+def variant_path(name: str) -> str:
+    return os.path.join(LIBDIR, "variants", f"libptgpu_{name}.so")
+
+
+def build_variants(force=False) -> dict:
+    """libptgpu_nocull.so: every culling shortcut of the tracer compiled out (PT_NO_CULL in csrc/pt_device.cuh) - the arbiter the
+    GPU tests compare the product library with on 1e8 rays."""
+    os.makedirs(os.path.join(LIBDIR, "variants"), exist_ok=True)
+    srcs = [os.path.join(PKG, "csrc", "ptgpu.cu"), os.path.join(PKG, "csrc", "pt_device.cuh"),
+            os.path.join(PKG, "csrc", "mesh_derive.hpp"), os.path.join(ROOT, "include", "ptgpu.h")]
+    out = {}
+    for name, flags in VARIANTS.items():
+        path = variant_path(name)
+        if force or _newer(srcs, path):
+            subprocess.check_call([NVCC] + NVCC_FLAGS + flags + ["-o", path, srcs[0]])
+        out[name] = path
+    return out
+
+
 def build_host(force=False) -> str:
     gpu = build_gpu()
     out = os.path.join(LIBDIR, "libpthost.so")
@@ -53,7 +77,9 @@ def build_host(force=False) -> str:
 
 
 def build_all(force=False, verbose=False):
-    return build_gpu(force, verbose), build_host(force)
+    out = build_gpu(force, verbose), build_host(force)
+    build_variants(force)
+    return out
 
 
 if __name__ == "__main__":

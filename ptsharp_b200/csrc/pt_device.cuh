@@ -36,6 +36,19 @@
 #ifndef PT_SHORTCUT
 #define PT_SHORTCUT 1
 #endif
+// PT_NO_CULL = 1 builds the ARBITER of every shortcut this file takes (tests/test_gpu_parity.py::test_cull_matches_no_cull): no
+// padded-bounds test ever skips a subtree, a mesh or an instance (every reference leaf is tested in full), the division-free
+// triangle filter is replaced by the reference sequence, no walk is clipped to the running best and shadow rays take the full
+// closest-hit walk.  What remains is Tree.Intersect / Node.Intersect / IntersectShapes as written (Tree.cs:31-128).
+#ifndef PT_NO_CULL
+#define PT_NO_CULL 0
+#endif
+#ifndef PT_CULL_BOUNDS
+#define PT_CULL_BOUNDS (!PT_NO_CULL)   // padded-bounds tests may skip subtrees / meshes / instances
+#endif
+#ifndef PT_TRI_FILTER
+#define PT_TRI_FILTER (!PT_NO_CULL)    // division-free triangle filter in front of the reference sequence
+#endif
 
 namespace pt {
 
@@ -271,7 +284,14 @@ PT_D double triangle_intersect_exact(V3 v1, V3 e1, V3 e2, V3 o, V3 d) {
 //   t < EPS      <=>  c / det < 1e-9                          unless within 1e-13 relative of it
 // and the excluded borderline cases (a == det, near-equalities) are sent to the exact sequence above.
 PT_D double triangle_intersect_regs(float4 A, float4 B4, float4 C4, V3 o, V3 d);
-PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) { return triangle_intersect_regs(__ldg(g), __ldg(g + 1), __ldg(g + 2), o, d); }
+PT_D double triangle_intersect(const float4* __restrict__ g, V3 o, V3 d) {
+#if !PT_TRI_FILTER
+    const float4 A = __ldg(g), B4 = __ldg(g + 1), C4 = __ldg(g + 2);
+    return triangle_intersect_exact(v3(A.x, A.y, A.z), v3(B4.x, B4.y, B4.z), v3(C4.x, C4.y, C4.z), o, d);
+#else
+    return triangle_intersect_regs(__ldg(g), __ldg(g + 1), __ldg(g + 2), o, d);
+#endif
+}
 PT_D double triangle_intersect_regs(float4 A, float4 B4, float4 C4, V3 o, V3 d) {
     const V3 v1 = v3(A.x, A.y, A.z), e1 = v3(B4.x, B4.y, B4.z), e2 = v3(C4.x, C4.y, C4.z);
     // all four FP32 dot products up front (a warp pays for its slowest lane anyway), then one decision
@@ -584,6 +604,10 @@ PT_D RayBox ray_box(V3 o, V3 d) {
     return a;
 }
 PT_D bool box_line_hit_fast(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayBox& r, float& tnear) {
+#if !PT_CULL_BOUNDS
+    tnear = -INFINITY;
+    return true;
+#endif
     const float x1 = __fmaf_rn(lox, r.ix, -r.cx), x2 = __fmaf_rn(hix, r.ix, -r.cx);
     const float y1 = __fmaf_rn(loy, r.iy, -r.cy), y2 = __fmaf_rn(hiy, r.iy, -r.cy);
     const float z1 = __fmaf_rn(loz, r.iz, -r.cz), z2 = __fmaf_rn(hiz, r.iz, -r.cz);
@@ -630,6 +654,10 @@ PT_D void stk_put(uint4* e, double ts, uint32_t node, uint32_t culled) { *e = ma
 PT_D double stk_t(const uint4& e) { return __hiloint2double((int)e.y, (int)e.x); }
 
 PT_D bool box_line_hit(float lox, float loy, float loz, float hix, float hiy, float hiz, V3 o, const RayAux& ra, float* entry = nullptr) {
+#if !PT_CULL_BOUNDS
+    if (entry) *entry = -INFINITY;
+    return true;
+#endif
     // fminf/fmaxf ignore NaNs (0 * inf when the origin lies on a slab plane of a zero direction): conservative
     const float x1 = (lox - ra.pad - o.x) * ra.ix, x2 = (hix + ra.pad - o.x) * ra.ix;
     const float y1 = (loy - ra.pad - o.y) * ra.iy, y2 = (hiy + ra.pad - o.y) * ra.iy;
@@ -937,7 +965,7 @@ PT_D double light_hit_t(const DScene& S, int32_t lightShape, V3 o, V3 d) {
     }
 }
 // Beyond this parameter a shape's Hit cannot matter to a shadow ray whose light sits at tL (see scene_advance).
-PT_D double shadow_clip(double tL) { return tL > 0 ? tL * (1.0 + 1e-4) : 1e300; }
+PT_D double shadow_clip(double tL) { return tL > 0 ? tL : 1e300; }  // the 1e-4 margin is applied where it is compared
 
 #ifndef PT_MARCH_SPLIT
 #define PT_MARCH_SPLIT 1   // C5 (2 spp pass): 1365 ms with both bursts every turn at 2 / 4 steps, 1010 ms with separate turns at 16 / 64
@@ -1184,7 +1212,7 @@ struct SplitState {      // per ray of the launch, SoA
     uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
 };
 #ifndef PT_BEST_CLIP
-#define PT_BEST_CLIP 1   // scene_advance: no mesh walk beyond the running best of the Scene.tree traversal (see there)
+#define PT_BEST_CLIP (!PT_NO_CULL)   // scene_advance: no mesh walk beyond the running best of the Scene.tree traversal (see there)
 #endif
 struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root node)  c = (tmin, tmax)
     float4* a; float4* b; double2* c; uint32_t* count;
@@ -1301,9 +1329,14 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         const float4 wlo = __ldg(S.instBounds + 2 * (size_t)sh.data), whi = __ldg(S.instBounds + 2 * (size_t)sh.data + 1);
 #if PT_BEST_CLIP
                         // ... and an instance entered beyond the running best cannot change it: its Hit's T is the world-space distance to a
-                        // point inside these bounds (TransformedShape.cs:69: parameter x |direction|), and the fold only takes T < best.T
+                        // point inside these bounds (TransformedShape.cs:69: parameter x |direction|), and the fold only takes T < best.T.
+                        // That reads T as a distance, which only holds while the FP32 dot products behind every T are accurate: for an
+                        // origin millions of scene sizes away they are not (the no-cull arbiter found a reference hit 8 000 units in front
+                        // of its own mesh at |o| = 5e6), so the comparison is only made for origins within ~250 extents of the instance.
                         float entry;
-                        if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux, &entry) || (double)(entry * dirLen) > netmin_best(clipL, best.t) * (1.0 + 1e-4)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
+                        const bool hitBounds = box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux, &entry);
+                        const bool nearOrigin = worldAux.pad <= 1e-3f * fmaxf(fmaxf(whi.x - wlo.x, whi.y - wlo.y), whi.z - wlo.z);
+                        if (!hitBounds || (nearOrigin && (double)(entry * dirLen) > netmin_best(clipL, best.t) * (1.0 + 1e-4))) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
 #else
                         if (!box_line_hit(wlo.x, wlo.y, wlo.z, whi.x, whi.y, whi.z, o, worldAux)) { mBest = kHitInf; st = ST_MESH_DONE; continue; }
 #endif
@@ -1321,10 +1354,12 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         // The fold below only takes a mesh Hit with T < best.T (Tree.cs:121-125).  Every triangle lies inside the tree's
                         // box, so a box entered beyond best.T cannot give one: no walk.  Otherwise the walk's tmax is cut to best.T: it
                         // then visits a prefix of the cells the reference visits, in the same order, and a Hit below best.T lies in that
-                        // prefix - so the Hit that gets folded is the same.  (1e-5 relative margin against the FP32 rounding of
-                        // the triangle test's T; object-space T of an instance is not comparable with best.T, so instances are left alone.)
-                        if (curInst < 0 && !(tmax < tmin || tmax <= 0)) {
-                            const double lim = SHADOW ? netmin_best(clipL, best.t * (1.0 + 1e-5)) : best.t * (1.0 + 1e-5);
+                        // prefix - so the Hit that gets folded is the same.  (1e-4 relative margin against the FP32 rounding of
+                        // the triangle test's T, and only for origins within ~250 extents of the mesh - see the instance test above;
+                        // object-space T of an instance is not comparable with best.T, so instances are left alone.)
+                        const bool nearOrigin = ra.pad <= 1e-3f * fmaxf(fmaxf(mt.bmax[0] - mt.bmin[0], mt.bmax[1] - mt.bmin[1]), mt.bmax[2] - mt.bmin[2]);
+                        if (curInst < 0 && nearOrigin && !(tmax < tmin || tmax <= 0)) {
+                            const double lim = netmin_best(clipL, best.t) * (1.0 + 1e-4);
                             if (tmin > lim) tmax = -1;
                             else if (tmax > lim) tmax = lim;
                         }

@@ -32,7 +32,7 @@
 #define PT_SPLIT 1
 #endif
 #ifndef PT_ANYHIT
-#define PT_ANYHIT 1   // 0: shadow rays take the full closest-hit walk (A/B switch for the exact any-hit cut-off, see scene_advance)
+#define PT_ANYHIT (!PT_NO_CULL)   // 0: shadow rays take the full closest-hit walk (A/B switch for the exact any-hit cut-off, see scene_advance)
 #endif
 #include "pt_device.cuh"
 
@@ -803,8 +803,10 @@ __global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32
                            if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
                            localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
                        }
-                       Surface sf = hit_info(S, o, d, h);
-                       nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+                       if (normal3 || position3 || inside || material) {  // Hit.Info only when asked for
+                           Surface sf = hit_info(S, o, d, h);
+                           nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+                       }
                    }
                    prim[i] = localPrim;
                    if (normal3) { normal3[3 * i] = nn.x; normal3[3 * i + 1] = nn.y; normal3[3 * i + 2] = nn.z; }
@@ -834,8 +836,10 @@ __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uin
                                       if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
                                       localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
                                   }
-                                  Surface sf = hit_info(S, o, d, h);
-                                  nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+                                  if (B.normal3 || B.position3 || B.inside || B.material) {  // Hit.Info only when asked for
+                                      Surface sf = hit_info(S, o, d, h);
+                                      nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
+                                  }
                               }
                               B.prim[i] = localPrim;
                               if (B.normal3) { B.normal3[3 * i] = nn.x; B.normal3[3 * i + 1] = nn.y; B.normal3[3 * i + 2] = nn.z; }
@@ -2136,8 +2140,12 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
     int rc = PTGPU_OK;
     auto cleanup = [&]() { cudaFree(dO); cudaFree(dD); cudaFree(dN); cudaFree(dP); cudaFree(dS); cudaFree(dPr); cudaFree(dI); cudaFree(dM); cudaFree(dT); };
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return PTGPU_E_CUDA; } } while (0)
-    CKC(cudaMalloc(&dO, N * 12)); CKC(cudaMalloc(&dD, N * 12)); CKC(cudaMalloc(&dN, N * 12)); CKC(cudaMalloc(&dP, N * 12));
-    CKC(cudaMalloc(&dS, N * 4)); CKC(cudaMalloc(&dPr, N * 4)); CKC(cudaMalloc(&dI, N * 4)); CKC(cudaMalloc(&dM, N * 4)); CKC(cudaMalloc(&dT, N * 8));
+    CKC(cudaMalloc(&dO, N * 12)); CKC(cudaMalloc(&dD, N * 12));
+    if (normal3) CKC(cudaMalloc(&dN, N * 12));
+    if (position3) CKC(cudaMalloc(&dP, N * 12));
+    if (inside) CKC(cudaMalloc(&dI, N * 4));
+    if (material) CKC(cudaMalloc(&dM, N * 4));
+    CKC(cudaMalloc(&dS, N * 4)); CKC(cudaMalloc(&dPr, N * 4)); CKC(cudaMalloc(&dT, N * 8));
     CKC(cudaMemcpyAsync(dO, o3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemsetAsync(ctx->dCounts + 6, 0, sizeof(uint32_t), ctx->stream));

@@ -827,28 +827,32 @@ def test_replay_light_mode_all_two_lights_on_meshes(orc, bindings, device):
     assert cnt["shadowRays"] > 2 * 160 * 90  # up to three shadow rays per diffuse vertex (the lights it faces)
 
 
-def test_any_hit_cut_off_matches_the_full_closest_hit_walk(orc, bindings, device, tmp_path):
-    """The exact any-hit cut-off of the shadow rays (scene_advance<SHADOW>, k_mesh<ANYHIT>) against the same library built without it
-    (-DPT_ANYHIT=0: every shadow ray takes the full closest-hit walk, then `hit.Shape == light`): same ray counts, same image up to
-    the order of the float additions.  Skipped when the variant library was not built (tools/build_variants.py noanyhit=-DPT_ANYHIT=0)."""
-    import subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    variant = os.path.join(root, "ptsharp_b200", "_lib", "variants", "libptgpu_noanyhit.so")
-    if not os.path.exists(variant):
-        pytest.skip("variant library not built")
-    outs, counts = [], []
-    for lib in ("", variant):
-        out = str(tmp_path / f"anyhit{len(outs)}.npy")
-        env = dict(os.environ)
-        if lib:
-            env["PTGPU_LIB"] = lib
-        r = subprocess.run([sys.executable, "-c", _ORDER_SNIPPET.format(root=root, out=out)], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(np.load(out).astype(np.float64))
-        counts.append(r.stdout.split())
-    assert counts[0] == counts[1]
-    rel = np.abs(outs[0] - outs[1]) / np.maximum(np.abs(outs[1]), 1e-3)
-    assert rel.max() < 1e-4, rel.max()
+def test_any_hit_cut_off_matches_the_full_closest_hit_walk(orc, bindings, device):
+    """The exact any-hit cut-off of the shadow rays (scene_advance<SHADOW>, k_mesh<ANYHIT>) against the checker build without it
+    (libptgpu_nocull.so: every shadow ray takes the full closest-hit walk, then `hit.Shape == light`): same ray counts, same image
+    up to the order of the float additions - on the mesh scene, on the instanced scene and with three lights."""
+    from ptsharp_b200.authoring import LightModeAll
+    arbiter = bindings.Device(0, lib=bindings.checker_lib("nocull"))
+    try:
+        for name, res, lights_all in (("c3", (160, 90), False), ("c3", (128, 72), True), ("c4", (160, 90), False)):
+            hw, _, _ = _worlds(orc, bindings, name)
+            if lights_all:
+                hw.add(hw.sphere((4, 6, -3), 0.7, hw.LightMaterial((1.0, 0.8, 0.6), 40)))
+                hw.add(hw.cube((-3.5, 4.0, 1.0), (-2.5, 4.2, 2.0), hw.LightMaterial((0.6, 0.8, 1.0), 60)))
+                hw.sampler(1, 4, light_mode=LightModeAll)
+            W, H = res
+            outs, counts = [], []
+            for dev in (device, arbiter):
+                dev.upload(hw)
+                dev.reset_counters()
+                outs.append(dev.render_pass(hw.make_pass(W, H, 4, pass_index=3)).astype(np.float64))
+                c = dev.counters()
+                counts.append((c["segments"], c["shadowRays"], c["cameraSamples"]))
+            assert counts[0] == counts[1]
+            rel = np.abs(outs[0] - outs[1]) / np.maximum(np.abs(outs[1]), 1e-3)
+            assert rel.max() < 1e-4, (name, rel.max())
+    finally:
+        arbiter.close()
 
 
 def test_russian_roulette_is_unbiased(orc, bindings, device):
@@ -901,3 +905,68 @@ def test_multi_device_handle(orc, bindings):
         two.close()
     with pytest.raises(bindings.PtgpuError):
         bindings.Device(devices=[0, 0])
+
+
+def _fuzz_rays(rng, n, ow_hits, scale):
+    """n rays in six families: (a) random origins around the scene, (b) far origins (|o| = 10 .. 1e6 x scale) aimed at the scene,
+    (c) rays leaving surface points (the self-intersection regime), (d) rays grazing along the surface they start on,
+    (e) axis-parallel and near-axis-parallel directions, (f) origins on the kd split / box planes of round coordinates."""
+    k = n // 6
+    def dirs(m):
+        v = rng.normal(size=(m, 3)).astype(np.float32)
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    pos, nrm = ow_hits
+    oa = (rng.random((k, 3), dtype=np.float32) * 2 - 1) * scale * 1.5 + np.float32([0, 0.5 * scale, 0]); da = dirs(k)
+    dist = (10.0 ** rng.uniform(1, 6, size=(k, 1))).astype(np.float32) * scale
+    tgt = pos[rng.integers(0, len(pos), k)] + rng.normal(size=(k, 3)).astype(np.float32) * 0.05 * scale
+    ob = tgt + dirs(k) * dist
+    db = tgt - ob; db /= np.linalg.norm(db, axis=1, keepdims=True)
+    ic = rng.integers(0, len(pos), k); oc = pos[ic]; dc = dirs(k)
+    idd = rng.integers(0, len(pos), k); od = pos[idd]
+    tang = np.cross(nrm[idd], dirs(k)); tang /= np.maximum(np.linalg.norm(tang, axis=1, keepdims=True), 1e-9)
+    dd = tang + nrm[idd] * (rng.normal(size=(k, 1)) * 0.01).astype(np.float32); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    oe = (rng.random((k, 3), dtype=np.float32) * 2 - 1) * scale * 2; de = np.zeros((k, 3), np.float32)
+    ax = rng.integers(0, 3, k); de[np.arange(k), ax] = rng.choice(np.float32([-1, 1]), k)
+    de += (rng.random((k, 3), dtype=np.float32) < 0.5) * rng.normal(size=(k, 3)).astype(np.float32) * 1e-6
+    m = n - 5 * k
+    of = np.round((rng.random((m, 3), dtype=np.float32) * 2 - 1) * scale * 4) / 4; df = dirs(m)
+    return np.concatenate([oa, ob, oc, od, oe, of]).astype(np.float32), np.concatenate([da, db, dc, dd.astype(np.float32), de, df]).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["c3", "c4"])
+def test_cull_matches_no_cull(orc, bindings, device, name):
+    """Every shortcut of the tracer (padded subtree / mesh / instance bounds, the bounds-only hierarchy under the reference leaves,
+    the division-free triangle filter, walks clipped to the running best) against the SAME source compiled without them
+    (libptgpu_nocull.so, -DPT_NO_CULL=1: Tree.Intersect / IntersectShapes as written, every reference leaf tested in full): closest
+    hits - shape, triangle, T - bit for bit on 1e8 rays (PTGPU_FUZZ_RAYS to change) in six families including far origins up to
+    1e6 scene sizes and grazing rays.  The no-cull build is itself checked against the oracle on the first chunk."""
+    total = int(float(os.environ.get("PTGPU_FUZZ_RAYS", "1e8"))) // 2  # per scene
+    hw, ow, _ = _worlds(orc, bindings, name)
+    device.upload(hw)
+    arbiter = bindings.Device(0, lib=bindings.checker_lib("nocull"))
+    try:
+        arbiter.upload(hw)
+        o0, d0 = _ray_batch(ow, W=160, H=120, n_secondary=1, seed=1)
+        h0 = ow.intersect_batch(o0, d0)
+        ok = h0["shape"] >= 0
+        hits = (h0["position"][ok], h0["normal"][ok])
+        scale = 3.0 if name == "c3" else 25.0
+        rng = np.random.default_rng(2024)
+        chunk, done, nhit = 5_000_000, 0, 0
+        while done < total:
+            n = min(chunk, total - done)
+            o, d = _fuzz_rays(rng, n, hits, scale)
+            g, a = device.intersect_batch(o, d, full=False), arbiter.intersect_batch(o, d, full=False)
+            bad = (g["shape"] != a["shape"]) | (g["prim"] != a["prim"]) | ((g["t"].view(np.int64) != a["t"].view(np.int64)) & (a["shape"] >= 0))
+            assert not bad.any(), (name, done, int(bad.sum()), o[bad][:4], d[bad][:4], g["t"][bad][:4], a["t"][bad][:4])
+            if done == 0:  # the arbiter itself against the oracle (CPU: a slice)
+                c = ow.intersect_batch(o[::50], d[::50])
+                np.testing.assert_array_equal(a["shape"][::50], c["shape"])
+                np.testing.assert_array_equal(a["prim"][::50], c["prim"])
+                hit = c["shape"] >= 0
+                np.testing.assert_array_equal(a["t"][::50][hit].view(np.int64), c["t"][hit].view(np.int64))
+            nhit += int((a["shape"] >= 0).sum())
+            done += n
+        assert nhit > 0.2 * total
+    finally:
+        arbiter.close()
