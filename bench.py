@@ -10,7 +10,7 @@ A step = one pass (Renderer.RenderParallel, Renderer.cs:199-338) over the whole 
   value  device-timed throughput, scene resident in HBM, CUDA events, max over ranks;
   e2e    the same pass through the C ABI with HOST buffers: every step re-uploads the flat scene (host -> device) and reads
          the image back (device -> host);
-  roofline       the dominant kernel (k_mesh, or k_trace for scenes without meshes): algorithmic bytes per launch / launch
+  roofline       the dominant kernel (k_mesh / k_march, or k_scene_trace for scenes of analytic shapes only): algorithmic bytes per launch / launch
                  duration measured live with CUDA events on the launching stream, vs the measured HBM peak;
   cpu_baseline   the CPU restatement in oracle/ (kind "port": the C# reference cannot be built here) on all host cores, on a
                  bounded sample of the same workload: every k-th 32x32 task of the WHOLE frame (the reference's own task list,
@@ -49,8 +49,8 @@ WORKLOADS = {
 SAMPLERS = {"c1": "DefaultSampler.NewSampler(16,4)", "c2": "NewSampler(1,8) LightModeAll", "c3": "DefaultSampler.NewSampler(1,4)",
             "c4": "DefaultSampler.NewSampler(1,4)", "c5": "NewSampler(4,4) LightModeAll SpecularModeAll", "c3_small": "DefaultSampler.NewSampler(1,4)"}
 B_PER_BOUNCE_NEE, B_PER_BOUNCE, B_PER_SAMPLE = 208, 128, 24
-TRACE_BYTES_PER_RAY = 32 + 24  # k_trace: reads (o,pixel),(d,meta) = 2 x float4, writes the 24-byte hit record
-MESH_BYTES_PER_ITEM = 48 + 12  # k_mesh: reads the 48-byte work item (co, ray | cd, root | tmin, tmax), writes T (8) + triangle (4)
+TRACE_BYTES_PER_RAY = 32 + 24  # k_scene_trace: reads (o,pixel),(d,meta) = 2 x float4, writes the 24-byte hit record
+MESH_BYTES_PER_ITEM = 48 + 12  # k_mesh / k_march: reads the 48-byte work item (co, ray | cd, root | tmin, tmax), writes T (8) + triangle (4)
 TRAFFIC_FILES = ("r02_k_mesh_traffic.json", "r01_k_mesh_traffic.json")  # ncu --set full captures of k_mesh, newest first
 
 
@@ -303,15 +303,18 @@ def main():
         stage = {k: pc[k] for k in ("raygenMs", "traceMs", "shadeMs", "shadowMs", "meshMs")}
         total_stage = (pc["raygenMs"] + pc["traceMs"] + pc["shadeMs"] + pc["shadowMs"]) or 1.0
         pipeline_bytes = segs * B_PER_BOUNCE_NEE + samples * B_PER_SAMPLE
-        if pc["meshLaunches"] > 0:
-            # dominant kernel: k_mesh (Mesh.Intersect of every ray that enters a mesh box; trace AND shadow rays).
-            # Algorithmic HBM bytes per work item: the 48-byte item in, the 12-byte Hit (T, triangle) out; the kd
-            # nodes and triangles it walks are scene data, reported as measured traffic, not counted as algorithmic.
-            kname, unit_bytes, units, kms, klaunches = "k_mesh", MESH_BYTES_PER_ITEM, pc["meshItems"], pc["meshMs"], pc["meshLaunches"]
-        else:
-            # k_trace (the single-kernel tracer of scenes without meshes); k_shadow runs the same code on the shadow rays and is
-            # timed in shadowMs, not here
-            kname, unit_bytes, units, kms, klaunches = "k_trace", TRACE_BYTES_PER_RAY, pc["segments"], pc["traceMs"], pc["traceLaunches"]
+        # dominant kernel: the consumer of the deferred work items that takes the most time - k_mesh (Mesh.Intersect of every ray
+        # that enters a mesh box), k_march<SDF> / k_march<VOLUME> (the marching loops) - for trace AND shadow rays.  Algorithmic HBM
+        # bytes per work item: the 48-byte item in, the 12-byte Hit (T, triangle) out; the kd nodes, triangles, SDF programs and
+        # voxels it reads are scene data, reported as measured traffic, not counted as algorithmic.  Scenes without deferred shapes
+        # (only analytic primitives): k_scene_trace<START>, a streaming kernel reading a 32-byte ray and writing a 24-byte hit.
+        kinds = [("k_mesh", pc["meshMs"], pc["meshItems"], pc["meshLaunches"]), ("k_march<SDF>", pc["sdfMs"], pc["sdfItems"], pc["sdfLaunches"]),
+                 ("k_march<VOLUME>", pc["volumeMs"], pc["volumeItems"], pc["volumeLaunches"])]
+        kname, kms, units, klaunches = max(kinds, key=lambda k: k[1])
+        unit_bytes = MESH_BYTES_PER_ITEM
+        if kms <= 0:
+            kname, unit_bytes, units, kms, klaunches = "k_scene_trace<START>", TRACE_BYTES_PER_RAY, pc["segments"], pc["traceMs"], pc["traceLaunches"]
+        stage.update({"sdfMs": pc["sdfMs"], "volumeMs": pc["volumeMs"]})
         achieved = units * unit_bytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         traffic, traffic_src = None, None
         if kname == "k_mesh" and args.workload == "c3":

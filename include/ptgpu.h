@@ -206,11 +206,15 @@ typedef struct ptgpu_counters {
     double lastPassMs;           /* device time of the last render_pass / accumulate_device (CUDA events) */
     double traceMs, shadeMs, shadowMs, raygenMs;  /* per-stage device time of the last pass when profiling is on */
     double meshMs;               /* of traceMs + shadowMs: time in the mesh-walk kernel (k_mesh), 0 when the scene has no meshes */
-    uint64_t meshItems;          /* Mesh.Intersect calls (work items of k_mesh) in that time */
-    uint64_t meshLaunches;       /* k_mesh launches in that time */
-    uint64_t traceLaunches;      /* k_trace launches of the last profiled pass (scenes without meshes) */
+    uint64_t meshItems;          /* Mesh.Intersect calls (work items of k_mesh) of the last profiled pass */
+    uint64_t meshLaunches;       /* k_mesh launches of the last profiled pass */
+    uint64_t traceLaunches;      /* k_scene_trace<START> launches of the last profiled pass (= depths traced) */
     uint64_t queueOverflows;     /* passes since create/reset in which a ray or shadow queue overflowed (records dropped: that pass is not added to the Buffer) */
     uint64_t devices;            /* GPUs behind this handle */
+    double sdfMs;                /* like meshMs / meshItems / meshLaunches for k_march<SDF> (SDFShape.Intersect loops) ... */
+    uint64_t sdfItems, sdfLaunches;
+    double volumeMs;             /* ... and k_march<VOLUME> (Volume.Intersect loops) */
+    uint64_t volumeItems, volumeLaunches;
 } ptgpu_counters;
 
 typedef struct ptgpu_ctx ptgpu_ctx;

@@ -54,7 +54,8 @@ class Counters(C.Structure):
                 ("nanSamples", C.c_uint64), ("kernelLaunches", C.c_uint64), ("lastPassMs", C.c_double),
                 ("traceMs", C.c_double), ("shadeMs", C.c_double), ("shadowMs", C.c_double), ("raygenMs", C.c_double),
                 ("meshMs", C.c_double), ("meshItems", C.c_uint64), ("meshLaunches", C.c_uint64), ("traceLaunches", C.c_uint64),
-                ("queueOverflows", C.c_uint64), ("devices", C.c_uint64)]
+                ("queueOverflows", C.c_uint64), ("devices", C.c_uint64), ("sdfMs", C.c_double), ("sdfItems", C.c_uint64),
+                ("sdfLaunches", C.c_uint64), ("volumeMs", C.c_double), ("volumeItems", C.c_uint64), ("volumeLaunches", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

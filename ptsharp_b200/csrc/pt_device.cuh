@@ -134,6 +134,10 @@ PT_D V3 mat_dir_transposed(const double* __restrict__ m, V3 b) {
 }
 
 // ---------------------------------------------------------------------------------------------------- device scene
+// Derived per Volume at upload: the largest voxel of every 4x4x4 block of the grid, dilated by two voxels (vol_skip).
+static constexpr int kVolBlock = 4;
+struct VolBlocks { uint64_t first; int32_t nbx, nby, nbz; int32_t pad; };  // blocks -1 .. nb per axis; entry ((bz + 1) * (nby + 2) + by + 1) * (nbx + 2) + bx + 1
+
 struct DScene {
     const ptgpu_shape* shapes;
     const uint32_t* lights;
@@ -160,6 +164,8 @@ struct DScene {
     const uint4* meshNodes;         // 4 x uint4 per node: reference kd nodes, bounds-only nodes and micro leaves (see mesh_step)
     const float4* instBounds;       // 2 x float4 per TransformedShape of a Mesh: padded WORLD-space bounds of the instance (FP32 pre-test)
     const float4* leafGeom;         // 3 x float4 per leaf triangle in sorted order: (V1, triangle id) (e1, position in the leaf) (e2, -)
+    const VolBlocks* volBlocks;     // per Volume: where its table of block maxima sits in volBlockMax (see vol_skip)
+    const double* volBlockMax;
     uint32_t sceneTree, numSceneShapes, numLights, numShapes;
     double envColor[3];
     int32_t envTexture;
@@ -484,13 +490,80 @@ PT_D int vol_sign(const DScene& S, const ptgpu_volume& v, V3 a) {  // Volume.cs:
     }
     return (int)v.windowCount + 1;
 }
-PT_D double volume_intersect(const DScene& S, const ptgpu_volume& v, V3 o, V3 d) {  // Volume.cs:169-197
+// t after k more `t += step` of the marching loop (Volume.cs:175), in closed form.  step is a power of two (1/512, then /64 per
+// refinement) and at least one ulp of t, so inside a binade every one of those additions is exact and k of them equal ONE exact
+// addition of k * step; only the addition that carries t into the next binade can round, and it is performed as such.
+PT_D double vol_advance(double t, double step, long long k) {
+    while (k > 0) {
+        int e;
+        frexp(t, &e);
+        const double edge = ldexp(1.0, e);                          // the next power of two above t
+        const long long j0 = (long long)ceil((edge - t) / step);    // additions until t reaches it (exact: multiples of ulp(t))
+        if (k < j0) return t + (double)k * step;
+        t += (double)(j0 - 1) * step;
+        t += step;                                                  // the reference's own (possibly rounding) addition
+        k -= j0;
+    }
+    return t;
+}
+// Empty-space skipping that cannot change the result.  While the loop is in its `sign == 1` state (the last Sign() saw a value
+// below the first window, Volume.cs:118-119), a step whose Sample() is below windows[0].lo returns 1 again: nothing happens but
+// `t += step`.  Sample() is a convex combination of the 8 voxels around the sample's grid position (zero outside the grid), so it
+// is at most the largest voxel of the surrounding block; blockMax holds that maximum per 4x4x4 block, dilated by two voxels
+// (one for the `+1` corners, one against the FP32 rounding of Ray.Position, which moves a sample by < 1e-4 voxels).  If the block
+// the ray is in is below the window, every step up to the block's exit face (1e-3 voxels short of it) is skipped, with t advanced
+// exactly as the skipped additions would have.  Returns the number of steps skipped (0: take a normal step).
+#ifndef PT_VOL_SKIP
+#define PT_VOL_SKIP (!PT_NO_CULL)
+#endif
+PT_D long long vol_skip(const DScene& S, const ptgpu_volume& v, uint32_t volIndex, V3 co, V3 cd, double t, double step, double tend) {
+#if !PT_VOL_SKIP
+    return 0;
+#endif
+    if (!(step >= 1e-12)) return 0;  // after a handful of refinements (step /= 64 each, Volume.cs:183) step nears the ulp of t: plain steps
+    const VolBlocks vb = S.volBlocks[volIndex];
+    const double lo = v.windowCount ? S.volumeWindows[v.windowFirst].lo : 1e300;
+    // grid position of Ray.Position(t) as Volume.Sample maps it (Volume.cs:75-78, quirks included): linear in t
+    const double zq0 = (double)co.z / v.zscale, zq1 = (double)cd.z / v.zscale;
+    const double a0[3] = {(((double)co.x + 1) / 2) * (double)v.w, ((zq0 + 1) / 2) * (double)v.h, ((zq0 + 2) / 2) * (double)v.d};
+    const double a1[3] = {((double)cd.x / 2) * (double)v.w, (zq1 / 2) * (double)v.h, (zq1 / 2) * (double)v.d};
+    const int nb[3] = {vb.nbx, vb.nby, vb.nbz};
+    int b[3];
+    double texit = 1e300;
+    const double m = 1e-3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double p = a0[c] + a1[c] * t;
+        const double bf = floor(p / kVolBlock);
+        if (!(bf > -1e9 && bf < 1e9)) return 0;                       // NaN / huge: no skipping
+        if (p < bf * kVolBlock + m || p > (bf + 1) * kVolBlock - m) return 0;  // too close to a block face
+        b[c] = (int)bf;
+        if (a1[c] > 0) texit = fmin(texit, ((bf + 1) * kVolBlock - m - a0[c]) / a1[c]);
+        else if (a1[c] < 0) texit = fmin(texit, (bf * kVolBlock + m - a0[c]) / a1[c]);
+    }
+    double bm = 0;  // outside the table every voxel is outside the grid: Sample() = 0
+    if (b[0] >= -1 && b[0] <= nb[0] && b[1] >= -1 && b[1] <= nb[1] && b[2] >= -1 && b[2] <= nb[2])
+        bm = __ldg(S.volBlockMax + vb.first + ((size_t)(b[2] + 1) * (nb[1] + 2) + (b[1] + 1)) * (nb[0] + 2) + (b[0] + 1));
+    if (!(bm < lo)) return 0;
+    if (!(texit > t)) return 0;
+    // samples t, t + step, ..., t + (k - 1) step lie inside the block; one fewer against the rounding of the quotient
+    double kf = floor((texit - t) / step) - 1;
+    // the loop ends (NoHit) at the first t > tend: never skip to within two steps of it, the ordinary steps finish the march
+    kf = fmin(kf, floor((tend - t) / step) - 2);
+    if (!(kf >= 2)) return 0;
+    return (long long)fmin(kf, 1e15);
+}
+PT_D double volume_intersect(const DScene& S, const ptgpu_volume& v, V3 o, V3 d, uint32_t volIndex = 0xFFFFFFFFu) {  // Volume.cs:169-197
     double tmin, tmax;
     box_intersect(v.bmin, v.bmax, o, d, tmin, tmax);
     double step = (double)(1.0f / 512.0f);
     double start = netmax(step, tmin);
     int sign = -1;
     for (double t = start; t <= tmax; t += step) {
+        if (sign == 1 && volIndex != 0xFFFFFFFFu) {
+            const long long k = vol_skip(S, v, volIndex, o, d, t, step, tmax);
+            if (k > 0) { t = vol_advance(t, step, k - 1); continue; }  // k steps: k - 1 here, the loop's own `t += step`
+        }
         int s = vol_sign(S, v, ray_at(o, d, t));
         if (s == 0 || (sign >= 0 && s != sign)) {
             t -= step;
@@ -627,7 +700,7 @@ PT_D double primitive_intersect(const DScene& S, const ptgpu_shape& sh, V3 o, V3
         case PTGPU_PLANE: return plane_intersect(S.planes[sh.data], o, d);
         case PTGPU_CYLINDER: return cylinder_intersect(S.cylinders[sh.data], o, d);
         case PTGPU_SDF: return sdf_intersect(S, S.sdfShapes[sh.data], o, d);
-        case PTGPU_VOLUME: return volume_intersect(S, S.volumes[sh.data], o, d);
+        case PTGPU_VOLUME: return volume_intersect(S, S.volumes[sh.data], o, d, sh.data);
         default: return kHitInf;
     }
 }
@@ -967,254 +1040,53 @@ PT_D double light_hit_t(const DScene& S, int32_t lightShape, V3 o, V3 d) {
 // Beyond this parameter a shape's Hit cannot matter to a shadow ray whose light sits at tL (see scene_advance).
 PT_D double shadow_clip(double tL) { return tL > 0 ? tL : 1e300; }  // the 1e-4 margin is applied where it is compared
 
-#ifndef PT_MARCH_SPLIT
-#define PT_MARCH_SPLIT 1   // C5 (2 spp pass): 1365 ms with both bursts every turn at 2 / 4 steps, 1010 ms with separate turns at 16 / 64
-#endif
-#ifndef PT_SDF_BURST
-#define PT_SDF_BURST 16   // SDF sphere-tracing steps per MARCH turn of trace_rays
-#endif
-#ifndef PT_VOL_BURST
-#define PT_VOL_BURST 64   // Volume marching steps per MARCH turn
-#endif
 #ifndef PT_LEAF_BURST
 #define PT_LEAF_BURST 8
 #endif
 #ifndef PT_NODE_BURST
 #define PT_NODE_BURST 4   // 4: +1.2 % over 8 on C3 (bench.py, 128 spp); 16: -8 %
 #endif
-#ifndef PT_GLUE_PRIO
-#define PT_GLUE_PRIO 33   // run the GLUE class as soon as this many lanes wait in it (33 = only when it is the plurality)
-#endif
-#ifndef PT_GLUE_CHAIN
-#define PT_GLUE_CHAIN 1
-#endif
 #ifndef PT_SPLIT_FETCH_MIN
 #define PT_SPLIT_FETCH_MIN 8   // mesh_walk refills idle lanes once this many wait (or nothing else is left to do)
 #endif
-#ifndef PT_LEAF_UNROLL
-#define PT_LEAF_UNROLL 1
+#ifndef PT_SDF_BURST
+#define PT_SDF_BURST 16   // sphere-tracing steps between two refills of a warp of march_items
 #endif
-static constexpr int kLeafUnroll = PT_LEAF_UNROLL;
-enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT, ST_SDF, ST_VOLUME };
-
-// Scene.Intersect (Scene.cs:75-79) for rays [0, n): `source(i, o, d)` loads ray i, `sink(i, hit)` consumes its closest
-// hit.  `cursor` is a zero-initialised global counter shared by every warp of the launch.
-template <class Source, class Sink>
-PT_D void trace_rays(const DScene& S, uint32_t n, uint32_t* __restrict__ cursor, Source source, Sink sink) {
-    int st = ST_IDLE;
-    uint32_t rayIdx = 0;
-    V3 o = v3(0, 0, 0), d = v3(0, 0, 1);    // world-space ray
-    V3 co = o, cd = d;                       // ray in the space of the mesh being traversed (object space for instances)
-    HitRec best;
-    best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
-    // Scene tree (Scene.tree)
-    KdCursor sc; sc.node = 0; sc.tmin = sc.tmax = 0; sc.sp = 0;
-    uint4 sStk[kSceneStack + 1];             // entry 0 = sentinel (root tmax)
-    uint32_t sPos = 0, sEnd = 0;
-    // Mesh tree (Mesh.tree) of the shape being visited
-    KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
-    uint4 mStk[kMeshStackEnt];               // entry 0 = sentinel (root tmax)
-    uint32_t tPos = 0, tEnd = 0;             // remaining triangles of the current micro leaf
-    double mBest = kHitInf; int32_t mPrim = -1; uint32_t mBestPos = 0;
-    uint32_t curShape = 0; int32_t curInst = -1;
-    uint32_t marchData = 0;                  // sdfShapes[] / volumes[] index while in the MARCH class
-    RayBox ra = ray_box(co, cd);             // for the mesh being traversed
-    const ptgpu_tree sceneTree = S.trees[S.sceneTree];
-
-    // Scheduling.  Lanes fall into three classes: LEAF (testing triangles of a mesh leaf), NODE (walking a mesh tree) and
-    // GLUE (everything else: fetching a ray, the scene tree, per-shape set-up, folding a shape's hit, writing the
-    // result).  Executing a block costs the same whatever the number of lanes in it, so each iteration runs only the
-    // class most lanes are waiting in; the others accumulate until they win.  (ncu on the two-block version showed
-    // the glue code running at 1-3 lanes and taking ~30 % of all issued instructions.)
-    for (;;) {
-        const unsigned leafMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_LEAF);
-        const unsigned nodeMask = __ballot_sync(0xFFFFFFFFu, st == ST_MESH_NODE);
-        const unsigned exitMask = __ballot_sync(0xFFFFFFFFu, st == ST_EXIT);
-        if (exitMask == 0xFFFFFFFFu) break;
-        const unsigned marchMask = __ballot_sync(0xFFFFFFFFu, st == ST_SDF || st == ST_VOLUME);
-        const int nLeaf = __popc(leafMask), nNode = __popc(nodeMask), nMarch = __popc(marchMask);
-        const int nGlue = 32 - nLeaf - nNode - nMarch - __popc(exitMask);
-        // PT_MARCH_SPLIT: SDF and Volume lanes take separate turns (the larger group first) instead of both bursts in every turn
-        bool sdfTurn = true;
-        if (PT_MARCH_SPLIT) sdfTurn = __popc(__ballot_sync(0xFFFFFFFFu, st == ST_SDF)) * 2 >= nMarch;
-
-        if (nMarch > 0 && nMarch >= nGlue && nMarch >= nLeaf && nMarch >= nNode) {
-            // MARCH class: one SDF sphere-tracing step / a few Volume marching steps per turn.  The loop state lives in
-            // the (idle) mesh-traversal variables of the lane: mc.tmin = t, mc.tmax = t2 | tmax, mc.sp = iteration
-            // counter, mc.node = flags, mBest = Volume step.
-            if (st == ST_SDF && sdfTurn) {  // SDFShape.Intersect loop body (SDF.cs:47-74); mc.node bit0 = `jump`
-                const ptgpu_sdf_shape& sh = S.sdfShapes[marchData];
-#pragma unroll 1
-                for (int k = 0; k < PT_SDF_BURST && st == ST_SDF; k++) {
-                    if (mc.sp >= 1000) { mBest = kHitInf; st = ST_MESH_DONE; break; }
-                    mc.sp++;
-                    double dist = sdf_evaluate(S.sdfOps + sh.progFirst, sh.progCount, ray_at(co, cd, mc.tmin));
-                    const bool jump = mc.node & 1u;
-                    if (jump && dist < 0) { mc.tmin -= (double)0.001f; mc.node = 0; continue; }
-                    if (dist < (double)0.00001f) { mBest = mc.tmin; st = ST_MESH_DONE; break; }
-                    if (jump && dist < (double)0.001f) dist = (double)0.001f;
-                    mc.tmin += dist;
-                    if (mc.tmin > mc.tmax) { mBest = kHitInf; st = ST_MESH_DONE; }
-                }
-            } else if (st == ST_VOLUME && (!PT_MARCH_SPLIT || !sdfTurn)) {  // Volume.Intersect (Volume.cs:169-197), one Sign() per step
-                // mc.node: bits 0-15 = sign + 1, bit 16 = refining, bits 17-31 = pending sign + 1; mc.sp = refine counter
-                const ptgpu_volume& v = S.volumes[marchData];
-#pragma unroll 1
-                for (int k = 0; k < PT_VOL_BURST && st == ST_VOLUME; k++) {
-                    const bool refining = (mc.node >> 16) & 1u;
-                    if (!refining) {
-                        if (!(mc.tmin <= mc.tmax)) { mBest = kHitInf; st = ST_MESH_DONE; break; }  // `t <= tmax` loop test
-                        const int sign = (int)(mc.node & 0xFFFFu) - 1;
-                        const int sg = vol_sign(S, v, ray_at(co, cd, mc.tmin));
-                        if (sg == 0 || (sign >= 0 && sg != sign)) {
-                            mc.tmin -= mBest; mBest /= 64; mc.tmin += mBest;
-                            mc.node = (mc.node & 0xFFFFu) | (1u << 16) | ((uint32_t)(sg + 1) << 17);
-                            mc.sp = 0;
-                        } else { mc.node = (uint32_t)(sg + 1); mc.tmin += mBest; }
-                    } else if (mc.sp < 64) {
-                        if (vol_sign(S, v, ray_at(co, cd, mc.tmin)) == 0) { const double t = mc.tmin - mBest; mBest = t; st = ST_MESH_DONE; break; }
-                        mc.tmin += mBest; mc.sp++;
-                    } else {  // refinement found nothing: `sign = s`, then the outer loop's `t += step`
-                        mc.node = (mc.node >> 17);
-                        mc.tmin += mBest;
-                    }
-                }
-            }
-        } else if (nGlue > 0 && ((nGlue >= nLeaf && nGlue >= nNode) || nGlue >= PT_GLUE_PRIO)) {
-            // one GLUE turn carries a lane through consecutive glue states (fold a hit, analytic shapes, the next ray ...)
-            // until it needs a mesh walk or a march, so a ray costs ~one GLUE turn per mesh it enters
-#pragma unroll 1
-            for (int it = 0; it < PT_GLUE_CHAIN; it++) {
-                if (st == ST_MESH_NODE || st == ST_MESH_LEAF || st == ST_SDF || st == ST_VOLUME || st == ST_EXIT) break;
-                if (st == ST_MESH_DONE) {  // the shape's Hit is known: fold it into the leaf's running best (Tree.cs:121-125)
-                    double t = mBest, tInner = 0;
-                    if (curInst >= 0) {
-                        tInner = mBest;
-                        if (mBest < kHitInf) {  // TransformedShape.cs:47-69: hit.T = |Matrix.MulPosition(shapeRay.Position(T)) - r.Origin|
-                            const ptgpu_instance& inst = S.instances[curInst];
-                            V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
-                            t = (double)vlenf(vsub(position, o));
-                        }
-                    }
-                    if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
-                    st = ST_SCENE_LEAF;
-                }
-                if (st == ST_FINISH) {
-                    if (!(best.t < kHitInf)) best.shape = -1;  // Hit.Ok (Hit.cs:22)
-                    sink(rayIdx, best);
-                    st = ST_IDLE;
-                }
-                if (st == ST_IDLE) {
-                    auto g = cooperative_groups::coalesced_threads();
-                    uint32_t base = 0;
-                    if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
-                    rayIdx = g.shfl(base, 0) + g.thread_rank();
-                    if (rayIdx >= n) st = ST_EXIT;
-                    else {
-                        source(rayIdx, o, d);
-                        best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
-                        box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
-                        if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-                        else { sc.node = sceneTree.root; sc.sp = 0; stk_put(sStk, sc.tmax, 0u, 0u); st = ST_SCENE_NODE; }
-                    }
-                }
-                if (st == ST_SCENE_NODE) {
-    #pragma unroll 1
-                    for (int k = 0; k < 4 && st == ST_SCENE_NODE; k++) {
-                        uint32_t first, count;
-                        if (scene_step(S.nodes, sc, o, d, sStk, kSceneStack + 1, first, count) == KD_LEAF) {
-                            sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
-                        }
-                    }
-                }
-                if (st == ST_SCENE_LEAF) {
-                    if (sPos == sEnd) {
-                        st = mesh_pop(sc, best.t, sStk) ? ST_SCENE_NODE : ST_FINISH;
-                    } else {  // next shape of the leaf, in array order (Tree.cs:119-126)
-                        curShape = __ldg(S.leafItems + sPos);
-                        sPos++;
-                        ptgpu_shape sh = S.shapes[curShape];
-                        curInst = -1; co = o; cd = d;
-                        if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45: shapeRay = Matrix.Inverse().MulRay(r)
-                            curInst = (int32_t)sh.data;
-                            const ptgpu_instance& inst = S.instances[sh.data];
-                            co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
-                            sh = S.shapes[inst.shape];
-                        }
-                        if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
-                            const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
-                            mBest = kHitInf; mPrim = -1;
-                            ra = ray_box(co, cd);
-                            if (!tree_box_maybe_hit(mt, co, ray_aux(co, cd))) st = ST_MESH_DONE;  // clear miss: Box.Intersect would say so too
-                            else {
-                                box_intersect(mt.bmin, mt.bmax, co, cd, mc.tmin, mc.tmax);
-                                if (mc.tmax < mc.tmin || mc.tmax <= 0) st = ST_MESH_DONE;
-                                else { mc.node = mt.root; mc.sp = 0; stk_put(mStk, mc.tmax, 0u, 0u); st = ST_MESH_NODE; }
-                            }
-                        } else if (sh.type == PTGPU_SDF) {  // SDFShape.Intersect prologue (SDF.cs:34-46), loop in the MARCH class
-                            const ptgpu_sdf_shape& q = S.sdfShapes[sh.data];
-                            mPrim = -1; marchData = sh.data;
-                            double t1, t2;
-                            box_intersect(q.bmin, q.bmax, co, cd, t1, t2);
-                            if (t2 < t1 || t2 < 0) { mBest = kHitInf; st = ST_MESH_DONE; }
-                            else { mc.tmin = netmax((double)0.0001f, t1); mc.tmax = t2; mc.sp = 0; mc.node = 1u; st = ST_SDF; }
-                        } else if (sh.type == PTGPU_VOLUME) {  // Volume.Intersect prologue (Volume.cs:171-175)
-                            const ptgpu_volume& q = S.volumes[sh.data];
-                            mPrim = -1; marchData = sh.data;
-                            double tmin, tmax;
-                            box_intersect(q.bmin, q.bmax, co, cd, tmin, tmax);
-                            mBest = (double)(1.0f / 512.0f);  // step
-                            mc.tmin = netmax(mBest, tmin); mc.tmax = tmax; mc.sp = 0; mc.node = 0u;  // sign = -1
-                            st = ST_VOLUME;
-                        } else {
-                            mBest = primitive_intersect(S, sh, co, cd);
-                            mPrim = -1;
-                            st = ST_MESH_DONE;
-                        }
-                    }
-                }
-            }
-        } else if (nNode > nLeaf) {
-            if (st == ST_MESH_NODE) {
-#pragma unroll 1
-                for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
-                    uint32_t first, count;
-                    const int r = mesh_step(S.meshNodes, ra, mc, co, cd, mStk, mBest, mBestPos, first, count);
-                    if (r == MESH_LEAF) { tPos = first; tEnd = first + count; st = ST_MESH_LEAF; }
-                    else if (r == MESH_DONE) st = ST_MESH_DONE;
-                }
-            }
-        } else {
-            if (st == ST_MESH_LEAF) {
-                leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
-                if (tPos >= tEnd) st = mesh_pop(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
-            }
-        }
-    }
-}
+#ifndef PT_VOL_BURST
+#define PT_VOL_BURST 64   // Volume marching steps between two refills
+#endif
+enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT };
 
 // ---------------------------------------------------------------------------------------------------- split tracer
-// Scene.Intersect as two kinds of kernels (used when the scene has meshes and no SDF / Volume shapes).
+// Scene.Intersect (Scene.cs:75-79) as two kinds of kernels.
 //
-// In trace_rays the three work classes settle at a third of the lanes each: GLUE lanes (ray fetch, Scene.tree, analytic
-// shapes, TransformedShape set-up, FP64 Box.Intersect) drop out of step with the lanes walking a mesh.  Here the scene
-// level runs as a streaming kernel (`scene_advance`, one thread per ray, every lane busy) that carries each ray up to
-// the next Mesh it has to enter and emits a 48-byte work item; `mesh_walk` is a persistent kernel that only knows NODE
-// and LEAF work, so a warp alternates between the two with most of its lanes (a NODE burst ends in leaves, a LEAF burst
-// ends in nodes); the mesh's Hit is written back into the ray's record and the next `scene_advance` round folds it in and
-// continues with the ray's remaining shapes.  A ray takes as many rounds as it enters meshes.  The per-ray arithmetic
-// and visiting order are those of Tree.Intersect (Tree.cs:31-128), so hits are bit-identical to trace_rays.
+// A naive "one thread walks one ray to completion" kernel measured 2.2 active lanes per warp instruction on a 250k-triangle scene
+// (per-ray cost is heavy-tailed and a warp runs as long as its slowest lane); round 1's single persistent state machine with ray
+// replacement (LEAF / NODE / GLUE / MARCH classes voting per iteration) settled at a third of the lanes per class.  Here the scene
+// level - Scene.tree, the analytic shapes, TransformedShape set-up and fold, the FP64 Box.Intersect of every deferred shape - runs
+// as a streaming kernel (`scene_advance`, one thread per ray, every lane busy) that carries each ray up to the next shape whose
+// Intersect is a loop of its own and emits a 48-byte work item for it:
+//   Mesh      -> `mesh_walk`   (k_mesh):      Tree.Intersect of Mesh.tree; a persistent kernel that only knows NODE and LEAF work
+//   SDFShape  -> `march_items<SDF>`    (k_march): the sphere-tracing loop of SDF.cs:47-74, one loop body for the whole warp
+//   Volume    -> `march_items<VOLUME>` (k_march): the marching loop of Volume.cs:172-196
+// The shape's Hit is written into the ray's record and the next `scene_advance` round folds it in and continues with the ray's
+// remaining shapes.  A ray takes as many rounds as it enters deferred shapes.  The per-ray arithmetic and visiting order are
+// those of Tree.Intersect (Tree.cs:31-128), every loop is reproduced step for step, so hits are bit-identical to the reference.
+// Work items of the three kinds share one queue; the kind sits in the top two bits of the item's root word and every consumer
+// kernel takes the items of its kind.
+static constexpr uint32_t kItemKindShift = 30u, kItemMesh = 0u, kItemSdf = 1u, kItemVolume = 2u, kItemIndexMask = (1u << 30) - 1u;
 struct SplitState {      // per ray of the launch, SoA
     double* bestT; double* bestTInner; int32_t* bestShape; int32_t* bestPrim;   // running Hit of Scene.tree's traversal
     uint32_t* scNode; int32_t* scSp; double* scTmin; double* scTmax;            // Scene.tree cursor
     uint32_t* sPos; uint32_t* sEnd; uint32_t* curShape; int32_t* curInst;       // position in the current scene leaf
-    double* mBest; int32_t* mPrim;                                              // Hit of the pending Mesh.Intersect
+    double* mBest; int32_t* mPrim;                                              // Hit of the pending deferred Intersect
     uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
+    unsigned long long* kindItems;                                              // [3] work items consumed per kind (counters; [0] is filled in by the host)
 };
 #ifndef PT_BEST_CLIP
 #define PT_BEST_CLIP (!PT_NO_CULL)   // scene_advance: no mesh walk beyond the running best of the Scene.tree traversal (see there)
 #endif
-struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, root node)  c = (tmin, tmax)
+struct MeshQueue {       // work items: a = (co.xyz, ray)  b = (cd.xyz, kind | root node or shape data index)  c = (tmin, tmax)
     float4* a; float4* b; double2* c; uint32_t* count;
     float* lim;          // shadow launches only: the walk may stop at the first Hit with T < lim (a float at or below the light's tL; <= 0: never)
 };
@@ -1282,12 +1154,20 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             best.t = W.bestT[ray]; best.tInner = W.bestTInner[ray]; best.shape = W.bestShape[ray]; best.prim = W.bestPrim[ray];
             sc.node = W.scNode[ray]; sc.sp = W.scSp[ray]; sc.tmin = W.scTmin[ray]; sc.tmax = W.scTmax[ray];
             sPos = W.sPos[ray]; sEnd = W.sEnd[ray]; curShape = W.curShape[ray]; curInst = W.curInst[ray];
-            if (MODE == SCENE_FINISH) {  // the pending mesh walk first (the item holds the ray in the mesh's space)
-                const float4 ia = in.a[k], ib = in.b[k];
+            const float4 ia = in.a[k], ib = in.b[k];  // the item holds the ray in the shape's space (TransformedShape.cs:45): no second Matrix.MulRay
+            if (curInst >= 0) { co = v3(ia.x, ia.y, ia.z); cd = v3(ib.x, ib.y, ib.z); }
+            if (MODE == SCENE_FINISH) {  // the pending walk / march first
                 const double2 ic = in.c[k];
-                mesh_walk_single(S, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z), __float_as_uint(ib.w), ic.x, ic.y, mBest, mPrim, SHADOW ? (double)in.lim[k] : -1.0);
+                const uint32_t tag = __float_as_uint(ib.w);
+                if ((tag >> kItemKindShift) == kItemMesh)
+                    mesh_walk_single(S, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z), tag, ic.x, ic.y, mBest, mPrim, SHADOW ? (double)in.lim[k] : -1.0);
+                else {  // a pending SDFShape / Volume march: the whole Intersect inline (same prologue, same loop)
+                    ptgpu_shape msh;
+                    msh.type = (tag >> kItemKindShift) == kItemSdf ? PTGPU_SDF : PTGPU_VOLUME; msh.data = tag & kItemIndexMask; msh.material = -1; msh.flags = 0;
+                    mBest = primitive_intersect(S, msh, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z));
+                    mPrim = -1;
+                }
             } else { mBest = W.mBest[ray]; mPrim = W.mPrim[ray]; }
-            if (curInst >= 0) { const ptgpu_instance& inst = S.instances[curInst]; co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d); }
             st = ST_MESH_DONE;
         } else {
             best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
@@ -1381,6 +1261,41 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             W.sPos[ray] = sPos; W.sEnd[ray] = sEnd; W.curShape[ray] = curShape; W.curInst[ray] = curInst;
                             break;
                         }
+                    } else if (sh.type == PTGPU_SDF || sh.type == PTGPU_VOLUME) {
+                        // SDFShape.Intersect / Volume.Intersect: the prologue here (SDF.cs:34-46, Volume.cs:171-175), the loop in march_items
+                        double t0, t1;
+                        bool go;
+                        if (sh.type == PTGPU_SDF) {
+                            const ptgpu_sdf_shape& q = S.sdfShapes[sh.data];
+                            double b1, b2;
+                            box_intersect(q.bmin, q.bmax, co, cd, b1, b2);
+                            go = !(b2 < b1 || b2 < 0);
+                            t0 = netmax((double)0.0001f, b1); t1 = b2;
+                        } else {
+                            const ptgpu_volume& q = S.volumes[sh.data];
+                            double b1, b2;
+                            box_intersect(q.bmin, q.bmax, co, cd, b1, b2);
+                            t0 = netmax((double)(1.0f / 512.0f), b1); t1 = b2;
+                            go = t0 <= t1;  // the `t <= tmax` test of the first iteration (false for NaN bounds as well)
+                        }
+                        mBest = kHitInf;
+                        if (!go) st = ST_MESH_DONE;
+                        else if (MODE == SCENE_FINISH) { mBest = primitive_intersect(S, sh, co, cd); st = ST_MESH_DONE; }
+                        else {
+                            auto g = cooperative_groups::coalesced_threads();
+                            uint32_t base = 0;
+                            if (g.thread_rank() == 0) base = atomicAdd(out.count, g.size());
+                            const uint32_t slot = g.shfl(base, 0) + g.thread_rank();
+                            const uint32_t kind = sh.type == PTGPU_SDF ? kItemSdf : kItemVolume;
+                            out.a[slot] = make_float4(co.x, co.y, co.z, __uint_as_float(ray));
+                            out.b[slot] = make_float4(cd.x, cd.y, cd.z, __uint_as_float((kind << kItemKindShift) | sh.data));
+                            out.c[slot] = make_double2(t0, t1);
+                            if (SHADOW) out.lim[slot] = -1.0f;
+                            W.bestT[ray] = best.t; W.bestTInner[ray] = best.tInner; W.bestShape[ray] = best.shape; W.bestPrim[ray] = best.prim;
+                            W.scNode[ray] = sc.node; W.scSp[ray] = sc.sp; W.scTmin[ray] = sc.tmin; W.scTmax[ray] = sc.tmax;
+                            W.sPos[ray] = sPos; W.sEnd[ray] = sEnd; W.curShape[ray] = curShape; W.curInst[ray] = curInst;
+                            break;
+                        }
                     } else {
                         mBest = primitive_intersect_analytic(S, sh, co, cd);
                         st = ST_MESH_DONE;
@@ -1451,6 +1366,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                 if (i >= n) st = ST_EXIT;
                 else {
                     const float4 a = q.a[i], b = q.b[i];
+                    if ((__float_as_uint(b.w) >> kItemKindShift) != kItemMesh) continue;  // an SDFShape / Volume item: march_items takes it; this lane stays idle for a turn
                     const double2 c = q.c[i];
                     co = v3(a.x, a.y, a.z); cd = v3(b.x, b.y, b.z); ray = __float_as_uint(a.w);
                     ra = ray_box(co, cd);
@@ -1503,6 +1419,98 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
         }
 #endif
         if (st == ST_MESH_DONE) { W.mBest[ray] = mBest; W.mPrim[ray] = mPrim; st = ST_IDLE; }
+    }
+}
+
+// SDFShape.Intersect (SDF.cs:32-76) / Volume.Intersect (Volume.cs:169-197) for every work item of kind KIND in `q`; the Hit's T goes
+// to W.mBest of the item's ray.  Persistent warps, one item per lane, a finished lane takes the next item of its kind: every lane of
+// a warp runs the same loop body (one SDF evaluation, or one Volume.Sign, per step) from its first step to its last, which is what
+// the per-iteration class votes of round 1's single kernel could not give (MARCH / NODE / LEAF / GLUE lanes side by side).
+// The loops are reproduced step for step - t advances by the reference's own additions - so T is bit-identical.
+template <int KIND>
+PT_D void march_items(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t n = *q.count;
+    bool have = false, exhausted = false;
+    uint32_t ray = 0, data = 0;
+    V3 co = v3(0, 0, 0), cd = v3(0, 0, 1);
+    double t = 0, tend = 0, step = 0;   // SDF: t, t2, -;  Volume: t, tmax, step
+    int it = 0;                         // SDF: iteration counter;  Volume: refinement counter
+    uint32_t flags = 0;                 // SDF: bit 0 = `jump`;  Volume: bits 0-15 sign + 1, bit 16 refining, bits 17-31 pending sign + 1
+    uint32_t taken = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !have && !exhausted);
+        const unsigned busy = __ballot_sync(full, have);
+        if (!idle && !busy) {
+            for (int o = 16; o; o >>= 1) taken += __shfl_xor_sync(full, taken, o);
+            if ((threadIdx.x & 31) == 0 && taken) atomicAdd(W.kindItems + KIND, (unsigned long long)taken);
+            break;
+        }
+        if (__popc(idle) >= PT_SPLIT_FETCH_MIN || !busy) {
+            while (!have && !exhausted) {
+                auto g = cooperative_groups::coalesced_threads();
+                uint32_t base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(cursor, g.size());
+                const uint32_t i = g.shfl(base, 0) + g.thread_rank();
+                if (i >= n) { exhausted = true; break; }
+                const float4 b = q.b[i];
+                const uint32_t tag = __float_as_uint(b.w);
+                if ((tag >> kItemKindShift) != (uint32_t)KIND) continue;  // a Mesh item or the other marcher's
+                const float4 a = q.a[i];
+                const double2 c = q.c[i];
+                co = v3(a.x, a.y, a.z); cd = v3(b.x, b.y, b.z); ray = __float_as_uint(a.w); data = tag & kItemIndexMask;
+                t = c.x; tend = c.y; it = 0;
+                if (KIND == (int)kItemSdf) flags = 1u;                                 // jump = true
+                else { flags = 0u; step = (double)(1.0f / 512.0f); }                   // sign = -1
+                have = true; taken++;
+            }
+        }
+        if (have) {
+            bool done = false;
+            double result = kHitInf;
+            if (KIND == (int)kItemSdf) {  // the loop body of SDF.cs:47-74
+                const ptgpu_sdf_shape& sh = S.sdfShapes[data];
+#pragma unroll 1
+                for (int k = 0; k < PT_SDF_BURST && !done; k++) {
+                    if (it >= 1000) { done = true; break; }
+                    it++;
+                    double dist = sdf_evaluate(S.sdfOps + sh.progFirst, sh.progCount, ray_at(co, cd, t));
+                    const bool jump = flags & 1u;
+                    if (jump && dist < 0) { t -= (double)0.001f; flags = 0u; continue; }
+                    if (dist < (double)0.00001f) { result = t; done = true; break; }
+                    if (jump && dist < (double)0.001f) dist = (double)0.001f;
+                    t += dist;
+                    if (t > tend) done = true;
+                }
+            } else {  // Volume.cs:172-196, one Sign() per step
+                const ptgpu_volume& v = S.volumes[data];
+#pragma unroll 1
+                for (int k = 0; k < PT_VOL_BURST && !done; k++) {
+                    const bool refining = (flags >> 16) & 1u;
+                    if (!refining) {
+                        if (!(t <= tend)) { done = true; break; }  // the `t <= tmax` loop test
+                        const int sign = (int)(flags & 0xFFFFu) - 1;
+                        if (sign == 1) {  // steps that can only return 1 again (vol_skip)
+                            const long long kskip = vol_skip(S, v, data, co, cd, t, step, tend);
+                            if (kskip > 0) { t = vol_advance(t, step, kskip); continue; }
+                        }
+                        const int sg = vol_sign(S, v, ray_at(co, cd, t));
+                        if (sg == 0 || (sign >= 0 && sg != sign)) {
+                            t -= step; step /= 64; t += step;
+                            flags = (flags & 0xFFFFu) | (1u << 16) | ((uint32_t)(sg + 1) << 17);
+                            it = 0;
+                        } else { flags = (uint32_t)(sg + 1); t += step; }
+                    } else if (it < 64) {
+                        if (vol_sign(S, v, ray_at(co, cd, t)) == 0) { result = t - step; done = true; break; }
+                        t += step; it++;
+                    } else {  // the refinement found nothing: `sign = s`, then the outer loop's `t += step` (step stays shrunk)
+                        flags = flags >> 17;
+                        t += step;
+                    }
+                }
+            }
+            if (done) { W.mBest[ray] = result; W.mPrim[ray] = -1; have = false; }
+        }
     }
 }
 

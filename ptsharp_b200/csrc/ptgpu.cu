@@ -3,16 +3,22 @@
 // Pipeline per batch of camera samples (replaces Renderer.RenderParallel's pixel/spp loops, Renderer.cs:287-311,
 // and DefaultSampler.sample's recursion, Sampler.cs:55-145, with an iterative throughput-weighted form):
 //
-//   k_raygen   Camera.CastRay (Camera.cs:98-119) + the fu/fv jitter of Renderer.cs:297-304      -> ray queue
+//   k_raygen        Camera.CastRay (Camera.cs:98-119) + the fu/fv jitter of Renderer.cs:297-304, pixel-major   -> ray queue
 //   for depth = 0 .. MaxBounces:
-//     k_trace  Scene.Intersect (closest hit, kd-tree short stack)                               -> hit records
-//     k_shade  Hit.Info, emission/termination, Ray.Bounce, sampleLights ray generation          -> next ray queue,
-//              (queue appends are warp-aggregated: one atomic per coalesced group)                 shadow queue, sum
-//     k_shadow sampleLight's closest-hit identity test (Sampler.cs:262-265)                      -> sum buffer
-//   k_add_sample  c /= spp; Buffer.AddSample (Welford, Buffer.cs:33-44)
+//     Scene.Intersect of every queued ray (the split tracer, pt_device.cuh):
+//       k_scene_trace<START>    Scene.tree, analytic shapes, instance set-up; a work item per Mesh / SDFShape / Volume entered
+//       rounds of  k_mesh (Mesh.tree walks) / k_march<SDF> / k_march<VOLUME> (the marching loops)  +  k_scene_trace<RESUME>
+//                                                                                                   -> hit records
+//     k_bin_count / k_bin_scan / k_bin_scatter    shade order: hit records by surface and patch
+//     k_shade         Hit.Info, emission/termination, Ray.Bounce, sampleLights ray generation           -> next ray queue,
+//                     (queue appends are warp-aggregated: one atomic per coalesced group)                 shadow queue, sum
+//     k_scene_shadow<...> + the same rounds: sampleLight's visibility test (Sampler.cs:262-265) with the exact any-hit cut-off
+//                                                                                                   -> sum buffer
+//   k_add_sample    c /= spp; Buffer.AddSample (Welford, Buffer.cs:33-44); with several devices behind the handle it also sums
+//                   their pass accumulators over NVLink peer access
 //
-// All kernels are persistent grid-stride loops sized to the SM count and read their item counts from device memory,
-// so a pass is issued without any host synchronisation.  Random numbers: Philox4x32-10 keyed on
+// Kernels read their item counts from device memory, so a pass is issued without host synchronisation (scenes whose rays
+// may enter more than four deferred shapes poll one queue count per round).  Random numbers: Philox4x32-10 keyed on
 // (seed, pass | pixel, sample, path node, sub-stream, draw) — see rng_enter().
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -177,7 +183,7 @@ struct PassD {  // ptgpu_pass plus derived values, passed by value to kernels
     ptgpu_camera cam;
 };
 
-struct DeviceCounters { unsigned long long cameraSamples, segments, shadowRays, nanSamples; };
+struct DeviceCounters { unsigned long long cameraSamples, segments, shadowRays, nanSamples; unsigned long long kindItems[3]; };  // kindItems: work items emitted for k_mesh / k_march<SDF> / k_march<VOLUME>
 
 // Ray record: 52 bytes in three float4 streams + one u32 stream (SoA so each stream coalesces).
 //   od0 = (o.x, o.y, o.z, bits(pixel))   od1 = (d.x, d.y, d.z, bits(meta))   bt = (beta.r, beta.g, beta.b, bits(pathBits))
@@ -269,19 +275,6 @@ __global__ void __launch_bounds__(256) k_raygen(PassD P, unsigned long long g0, 
         q.smp[i] = sample;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { *count = n; atomicAdd(&cnt->cameraSamples, (unsigned long long)n); }
-}
-
-// K2.  Closest hit for every queued ray (persistent warps, per-lane ray replacement; see trace_rays).
-#ifndef PT_TRACE_MINBLOCKS
-#define PT_TRACE_MINBLOCKS 8
-#endif
-__global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_trace(DScene S, RayQueue q, const uint32_t* __restrict__ count, uint32_t* __restrict__ cursor, HitQueue hq,
-                                                DeviceCounters* cnt) {
-    const uint32_t n = *count;
-    trace_rays(S, n, cursor,
-               [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
-               [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
 
 // Light geometry used by sampleLight (Sampler.cs:215-236): Sphere -> its centre/radius; Cylinder -> (0,0,(Z0+Z1)/2),
@@ -562,24 +555,8 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
     }
 }
 
-// K4.  sampleLight's visibility test: closest hit, then identity with the light (Sampler.cs:261-265).
-__global__ void __launch_bounds__(128, PT_TRACE_MINBLOCKS) k_shadow(DScene S, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t* __restrict__ cursor,
-                                                 uint32_t capShadow, float* __restrict__ sum, DeviceCounters* cnt) {
-    uint32_t n = *scount;
-    if (n > capShadow) n = capShadow;
-    trace_rays(S, n, cursor,
-               [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
-               [&](uint32_t i, const HitRec& h) {
-                   const uint32_t light = f2u(sq.sd[i].w);
-                   if (h.shape >= 0 && (uint32_t)h.shape == light) {
-                       float4 c = sq.sc[i];
-                       accumulate(sum, cnt, f2u(sq.so[i].w), c.x, c.y, c.z);
-                   }
-               });
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
-}
-
-// K2/K4, split form (see "split tracer" in pt_device.cuh): scene level as streaming kernels, mesh walks as a persistent one.
+// K2 / K4.  Scene.Intersect of the path segments and of sampleLight's visibility rays (Sampler.cs:261-265: closest hit, then identity
+// with the light) - see "split tracer" in pt_device.cuh: the scene level as streaming kernels, the deferred shapes as persistent ones.
 #ifndef PT_SCENE_MINBLOCKS
 #define PT_SCENE_MINBLOCKS 8
 #endif
@@ -594,21 +571,27 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, MeshQueue in,
-                                                       MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
+__global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, uint32_t first,
+                                                       uint32_t chunk, MeshQueue in, MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
+    // The shadow queue may hold several times the rays the tracer has per-ray state for: it is traced in chunks of `chunk` records
+    // starting at `first`; inside a chunk rays are numbered from 0 (state, work items), the queue is read at first + i.
     constexpr bool RESUME = MODE != SCENE_START;
-    uint32_t n = RESUME ? *in.count : *scount;
-    if (!RESUME && n > capShadow) n = capShadow;
+    uint32_t n;
+    if (RESUME) n = *in.count;
+    else {
+        const uint32_t total = min(*scount, capShadow);
+        n = total > first ? min(total - first, chunk) : 0u;
+    }
     scene_advance<MODE, PT_ANYHIT != 0>(S, W, n, in, out,
-                          [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[i], b = sq.sd[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
+                          [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[first + i], b = sq.sd[first + i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) {
-                              const uint32_t light = f2u(sq.sd[i].w);
+                              const uint32_t light = f2u(sq.sd[first + i].w);
                               if (h.shape >= 0 && (uint32_t)h.shape == light) {
-                                  float4 c = sq.sc[i];
-                                  accumulate(sum, cnt, f2u(sq.so[i].w), c.x, c.y, c.z);
+                                  float4 c = sq.sc[first + i];
+                                  accumulate(sum, cnt, f2u(sq.so[first + i].w), c.x, c.y, c.z);
                               }
                           },
-                          [&](uint32_t i) { return (int32_t)f2u(sq.sd[i].w); });
+                          [&](uint32_t i) { return (int32_t)f2u(sq.sd[first + i].w); });
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->shadowRays, (unsigned long long)n);
 }
 // Small blocks: the warps of a launch finish at very different times (a few grazing rays take ~1000 steps) and a block's
@@ -627,6 +610,14 @@ template <bool ANYHIT>
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
     extern __shared__ uint4 smemStack[];  // PT_SMEM_STACK rows of blockDim.x entries
     mesh_walk<ANYHIT>(S, W, q, cursor, smemStack);
+}
+
+#ifndef PT_MARCH_MINBLOCKS
+#define PT_MARCH_MINBLOCKS 6
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(64, PT_MARCH_MINBLOCKS) k_march(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
+    march_items<KIND>(S, W, q, cursor);
 }
 
 __global__ void k_clamp_count(uint32_t* count, uint32_t cap, uint32_t* overflow) {
@@ -785,36 +776,7 @@ __global__ void k_firefly_apply(float* __restrict__ sum, const uint32_t* __restr
     }
 }
 
-// K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same trace_rays as the pipeline.
-__global__ void __launch_bounds__(128) k_intersect_batch(DScene S, int n, uint32_t* __restrict__ cursor, const float* __restrict__ o3, const float* __restrict__ d3,
-                                                          int32_t* shape, int32_t* prim, double* t, float* normal3, float* position3, int32_t* inside, int32_t* material) {
-    trace_rays(S, (uint32_t)n, cursor,
-               [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
-               [&](uint32_t i, const HitRec& h) {
-                   V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
-                   shape[i] = h.shape;
-                   t[i] = h.t;
-                   int32_t localPrim = -1;
-                   V3 nn = v3(0, 0, 0), pp = v3(0, 0, 0);
-                   int32_t ins = 0, mat = -1;
-                   if (h.shape >= 0) {
-                       if (h.prim >= 0) {  // report the triangle's index inside its mesh (Mesh.Triangles[])
-                           ptgpu_shape sh = S.shapes[h.shape];
-                           if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
-                           localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
-                       }
-                       if (normal3 || position3 || inside || material) {  // Hit.Info only when asked for
-                           Surface sf = hit_info(S, o, d, h);
-                           nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
-                       }
-                   }
-                   prim[i] = localPrim;
-                   if (normal3) { normal3[3 * i] = nn.x; normal3[3 * i + 1] = nn.y; normal3[3 * i + 2] = nn.z; }
-                   if (position3) { position3[3 * i] = pp.x; position3[3 * i + 1] = pp.y; position3[3 * i + 2] = pp.z; }
-                   if (inside) inside[i] = ins;
-                   if (material) material[i] = mat;
-               });
-}
+// K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same split tracer as the pipeline.
 struct BatchOut { int32_t* shape; int32_t* prim; double* t; float* normal3; float* position3; int32_t* inside; int32_t* material; };
 template <int MODE>
 __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uint32_t nStart, MeshQueue in, MeshQueue out, const float* __restrict__ o3,
@@ -956,9 +918,12 @@ struct ptgpu_ctx {
     Lane lanes[kMaxLanes];
     int numLanes = 1;
     cudaEvent_t evFork = nullptr;
-    bool useSplit = false;
+    bool hasKind[3] = {false, false, false};  // deferred shapes in the scene: Mesh, SDFShape, Volume (directly or under a TransformedShape)
+    uint64_t roundItems = 0;                    // profiling: work items (all kinds) of the rounds in which k_mesh ran
+    double kindMs[3] = {0, 0, 0};               // profiling: device time / launches of k_mesh, k_march<SDF>, k_march<VOLUME> in the last pass
+    uint64_t kindLaunches[3] = {0, 0, 0};
     int splitStackEnt = 2;
-    int splitRounds = 0;          // > 0: every ray enters at most this many meshes (fixed rounds, no host sync); 0: loop on the queue count
+    int splitRounds = 0;          // 0: no deferred shapes; > 0: every ray enters at most this many (fixed rounds, no host sync); -1: loop on the queue count
     uint32_t* dCounts = nullptr;  // [6] batch cursor, [8],[9] firefly list counts
     DeviceCounters* dCounters = nullptr;
     // image state
@@ -970,8 +935,7 @@ struct ptgpu_ctx {
     uint8_t* dReject = nullptr;
     // stats
     uint64_t launches = 0;
-    double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0, meshMs = 0;
-    uint64_t meshItems = 0, meshLaunches = 0;
+    double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0;
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
 };
@@ -1095,6 +1059,7 @@ static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
     CK(cudaMalloc(&W.mBest, cap * 8)); CK(cudaMalloc(&W.mPrim, cap * 4));
     CK(cudaMalloc(&W.sceneStack, cap * (uint64_t)stackEnt * sizeof(uint4)));
     W.stackEnt = stackEnt;
+    W.kindItems = ctx->dCounters->kindItems;
     for (int i = 0; i < 2; i++) {
         CK(cudaMalloc(&L.mq[i].a, cap * sizeof(float4))); CK(cudaMalloc(&L.mq[i].b, cap * sizeof(float4))); CK(cudaMalloc(&L.mq[i].c, cap * sizeof(double2)));
         CK(cudaMalloc(&L.mq[i].lim, cap * sizeof(float)));
@@ -1103,20 +1068,25 @@ static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
     L.splitCap = cap;
     return PTGPU_OK;
 }
-// One Scene.Intersect wavefront in split form.  start(out) launches the scene kernel for the fresh rays; resume(in, out)
-// launches it for the rays named by `in`'s items.  Fixed number of rounds when the scene bounds it, else until empty.
+// One Scene.Intersect wavefront.  start(out) launches the scene kernel for the fresh rays; resume(in, out) launches it for the rays
+// named by `in`'s items, after the consumer kernels of the deferred shapes (k_mesh, k_march<SDF>, k_march<VOLUME>: whichever kinds
+// the scene holds) have written their Hits.  No rounds for scenes without deferred shapes, a fixed number when the scene bounds
+// what a ray can enter, else until the queue is empty.
 #ifndef PT_FINISH_MAX
-#define PT_FINISH_MAX 65536   // pending mesh walks at or below which the remaining rounds run as one SCENE_FINISH launch
+#define PT_FINISH_MAX 65536   // pending items at or below which the remaining rounds run as one SCENE_FINISH launch
 #endif
 template <bool ANYHIT = false, class StartFn, class ResumeFn, class FinishFn>
 static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, ResumeFn resume, FinishFn finish) {
-    uint32_t* cursor = L.counts + 12;
-    CK(cudaMemsetAsync(L.counts + 10, 0, 3 * sizeof(uint32_t), st));
+    uint32_t* cursor = L.counts + 12;  // [12] k_mesh, [13] k_march<SDF>, [14] k_march<VOLUME>
+    CK(cudaMemsetAsync(L.counts + 10, 0, 2 * sizeof(uint32_t), st));
     start(L.mq[0]);
     ctx->launches++;
     int cur = 0;
-    for (int round = 0; ctx->splitRounds == 0 || round < ctx->splitRounds; round++) {
-        if (ctx->splitRounds == 0) {
+    static const bool detail = std::getenv("PTGPU_TRACE_DETAIL") != nullptr;
+    const bool timed = ctx->profiling || detail;
+    const int gridMesh = grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK), gridMarch = grid_for(ctx, PT_MARCH_MINBLOCKS);
+    for (int round = 0; ctx->splitRounds < 0 || round < ctx->splitRounds; round++) {
+        if (ctx->splitRounds < 0) {
             uint32_t pending = 0;
             CK(cudaMemcpyAsync(&pending, L.mq[cur].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1124,22 +1094,27 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
             if (pending <= PT_FINISH_MAX && round > 0) { finish(L.mq[cur]); ctx->launches++; break; }
         }
         CK(cudaMemsetAsync(L.mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
-        CK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
-        static const bool detail = std::getenv("PTGPU_TRACE_DETAIL") != nullptr;
-        const int gridMesh = grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK);
-        if (ctx->profiling || detail) {  // per-launch device time of the dominant kernel (bench.py's roofline)
-            uint32_t items = 0;
-            cudaMemcpyAsync(&items, L.mq[cur].count, 4, cudaMemcpyDeviceToHost, st);
-            cudaEventRecord(ctx->evC, st);
-            k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
-            cudaEventRecord(ctx->evD, st); cudaEventSynchronize(ctx->evD);
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->evC, ctx->evD);
-            ctx->meshMs += ms; ctx->meshItems += items; ctx->meshLaunches++;
-            if (detail) fprintf(stderr, "k_mesh round %d items %u  %.3f ms  (%.1f Mitems/s)\n", round, items, ms, items / ms / 1e3);
-        } else
-            k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor);
+        CK(cudaMemsetAsync(cursor, 0, 3 * sizeof(uint32_t), st));
+        // per-launch device time of each consumer kernel when profiling (bench.py's roofline): kind 0 mesh, 1 SDF, 2 Volume
+        uint32_t items = 0;
+        if (timed) cudaMemcpyAsync(&items, L.mq[cur].count, 4, cudaMemcpyDeviceToHost, st);  // read by the time the first consumer is timed
+        auto consumer = [&](int kind, auto launch) {
+            if (timed) cudaEventRecord(ctx->evC, st);
+            launch();
+            ctx->launches++;
+            if (timed) {
+                cudaEventRecord(ctx->evD, st); cudaEventSynchronize(ctx->evD);
+                float ms = 0; cudaEventElapsedTime(&ms, ctx->evC, ctx->evD);
+                ctx->kindMs[kind] += ms; ctx->kindLaunches[kind]++;
+                if (kind == 0) ctx->roundItems += items;  // all kinds; the marchers' own counts are subtracted in ptgpu_get_counters
+                if (detail) fprintf(stderr, "%s round %d  %.3f ms\n", kind == 0 ? "k_mesh" : kind == 1 ? "k_march<SDF>" : "k_march<VOLUME>", round, ms);
+            }
+        };
+        if (ctx->hasKind[0]) consumer(0, [&] { k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor); });
+        if (ctx->hasKind[1]) consumer(1, [&] { k_march<(int)kItemSdf><<<gridMarch, 64, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor + 1); });
+        if (ctx->hasKind[2]) consumer(2, [&] { k_march<(int)kItemVolume><<<gridMarch, 64, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor + 2); });
         resume(L.mq[cur], L.mq[cur ^ 1]);
-        ctx->launches += 2;
+        ctx->launches++;
         cur ^= 1;
     }
     return PTGPU_OK;
@@ -1509,6 +1484,38 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
     UP(volumes, s->volumes, s->numVolumes);
     UP(volumeWindows, s->volumeWindows, s->numVolumeWindows);
     UP(volumeData, s->volumeData, s->numVolumeData);
+    {   // per Volume: the largest voxel of every 4x4x4 block, dilated by two voxels, never below 0 (voxels outside the grid read 0);
+        // a NaN voxel makes its blocks +inf (never skipped).  See vol_skip in pt_device.cuh.
+        std::vector<VolBlocks> vbs(s->numVolumes ? s->numVolumes : 1);
+        std::vector<double> bmax;
+        for (uint32_t i = 0; i < s->numVolumes; i++) {
+            const ptgpu_volume& v = s->volumes[i];
+            VolBlocks vb;
+            vb.first = bmax.size(); vb.pad = 0;
+            vb.nbx = (v.w + kVolBlock - 1) / kVolBlock; vb.nby = (v.h + kVolBlock - 1) / kVolBlock; vb.nbz = (v.d + kVolBlock - 1) / kVolBlock;
+            const double* data = s->volumeData + v.dataOffset;
+            for (int bz = -1; bz <= vb.nbz; bz++)
+                for (int by = -1; by <= vb.nby; by++)
+                    for (int bx = -1; bx <= vb.nbx; bx++) {
+                        double mx = 0;
+                        for (int z = std::max(0, bz * kVolBlock - 2); z <= std::min(v.d - 1, bz * kVolBlock + kVolBlock + 2); z++)
+                            for (int y = std::max(0, by * kVolBlock - 2); y <= std::min(v.h - 1, by * kVolBlock + kVolBlock + 2); y++)
+                                for (int x = std::max(0, bx * kVolBlock - 2); x <= std::min(v.w - 1, bx * kVolBlock + kVolBlock + 2); x++) {
+                                    const double q = data[(size_t)x + (size_t)y * v.w + (size_t)z * v.w * v.h];
+                                    if (!(q == q)) mx = INFINITY; else if (q > mx) mx = q;
+                                }
+                        bmax.push_back(mx);
+                    }
+            vbs[i] = vb;
+        }
+        if (bmax.empty()) bmax.push_back(0);
+        const VolBlocks* dvb = nullptr;
+        if ((rc = upload(ctx, vbs.data(), (uint64_t)vbs.size(), &dvb)) != PTGPU_OK) return rc;
+        const double* dbm = nullptr;
+        if ((rc = upload(ctx, bmax.data(), (uint64_t)bmax.size(), &dbm)) != PTGPU_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));  // the vectors are locals
+        D.volBlocks = dvb; D.volBlockMax = dbm;
+    }
     UP(materials, s->materials, s->numMaterials);
     UP(textures, s->textures, s->numTextures);
     {
@@ -1585,23 +1592,24 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         ctx->dLights = const_cast<DLight*>(dl);
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    {   // split tracer: scenes with meshes and without marched shapes; bound on the meshes a ray can enter = mesh-like
-        // items over all leaves of Scene.tree (a ray visits a leaf, and a shape of a leaf, at most once)
+    {   // bound on the deferred shapes (Mesh / SDFShape / Volume, directly or instanced) a ray can enter = such items over all
+        // leaves of Scene.tree (a ray visits a leaf, and a shape of a leaf, at most once)
         const ptgpu_tree& stree = s->trees[s->sceneTree];
         uint64_t end = s->numNodes;
         for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > stree.root && s->trees[k].root < end) end = s->trees[k].root;
-        uint64_t meshItems = 0;
+        uint64_t deferred = 0;
+        ctx->hasKind[0] = ctx->hasKind[1] = ctx->hasKind[2] = false;
         for (uint64_t i = stree.root; i < end; i++) {
             const ptgpu_node& n = s->nodes[i];
             if ((n.a & 3u) != 0) continue;
             for (uint32_t k = 0; k < n.b; k++) {
                 ptgpu_shape sh = s->shapes[s->leafItems[(n.a >> 2) + k]];
                 if (sh.type == PTGPU_TRANSFORMED) sh = s->shapes[s->instances[sh.data].shape];
-                if (sh.type == PTGPU_MESH) meshItems++;
+                const int kind = sh.type == PTGPU_MESH ? 0 : sh.type == PTGPU_SDF ? 1 : sh.type == PTGPU_VOLUME ? 2 : -1;
+                if (kind >= 0) { deferred++; ctx->hasKind[kind] = true; }
             }
         }
-        ctx->useSplit = PT_SPLIT && meshItems > 0 && s->numSdfShapes == 0 && s->numVolumes == 0;
-        ctx->splitRounds = meshItems <= 4 ? (int)meshItems : 0;
+        ctx->splitRounds = deferred <= 4 ? (int)deferred : -1;
         ctx->splitStackEnt = (int)stree.maxDepth + 2;
     }
     // The mesh nodes are re-read by every ray while hundreds of MB of queue records stream through the L2 between two
@@ -1725,11 +1733,16 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     const int nroot = (int)std::sqrt((double)P.firstHitSamples);
     const uint64_t modes0 = (P.specularMode == PTGPU_SPECULAR_NAIVE) ? 1 : 2;
     const uint64_t modesN = (P.specularMode == PTGPU_SPECULAR_ALL) ? 2 : 1;
+    const bool prof = ctx->profiling;
+    // a profiled pass, and a scene whose rounds are polled from the host (splitRounds < 0: issued lane by lane anyway), use ONE lane
+    // with the capacity of all of them
+    const bool oneLane = prof || ctx->splitRounds < 0;
+    const uint64_t laneCap = std::min<uint64_t>(oneLane ? ctx->capRays * (uint64_t)ctx->numLanes : ctx->capRays, 1ull << 30);
     uint64_t grow = 1, maxGrow = 1;
     for (int depth = 0; depth < P.maxBounces; depth++) {
         grow *= (depth == 0) ? (uint64_t)nroot * nroot * modes0 : modesN;
         if (grow > maxGrow) maxGrow = grow;
-        if (maxGrow > ctx->capRays) break;
+        if (maxGrow > laneCap) break;
     }
     // shadow rays spawned by one shade pass <= children of that pass * lights sampled per child
     const uint64_t lightsPer = (P.directLighting && ctx->scene.numLights) ? (P.lightMode == PTGPU_LIGHT_ALL ? ctx->scene.numLights : 1) : 0;
@@ -1738,10 +1751,12 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         uint64_t g = 1;
         for (int depth = 0; depth <= P.maxBounces; depth++) { g *= (depth == 0) ? (uint64_t)nroot * nroot * modes0 : modesN; if (g > childGrow) childGrow = g; if (g > (1ull << 40)) break; }
     }
-    uint64_t batch = ctx->capRays / maxGrow;
+    uint64_t batch = laneCap / maxGrow;
     if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's branching factor");
     uint64_t capShadow = batch * childGrow * (lightsPer ? lightsPer : 1);
-    const uint64_t shadowCeil = std::min<uint64_t>(ctx->capRays * 4, 0xFFFF0000ull);  // slots are 32-bit
+    // up to 4x the ray capacity (48-byte records); the tracer's per-ray state is sized for the rays and the shadow queue is traced in
+    // chunks of that size
+    const uint64_t shadowCeil = std::min<uint64_t>(laneCap * 4, 0xFFFF0000ull);  // slots are 32-bit
     if (capShadow > shadowCeil) {  // shrink the batch so the shadow queue stays bounded
         batch = shadowCeil / (childGrow * (lightsPer ? lightsPer : 1));
         if (batch == 0) return fail(ctx, PTGPU_E_LIMIT, "queue capacity too small for this sampler's light count");
@@ -1749,9 +1764,8 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     }
     if (capShadow == 0) capShadow = 1;
     if (batch > total) batch = total;
-    const bool prof = ctx->profiling;
     // spread the pass over the lanes: at least one batch per lane when the pass is large enough to be worth it
-    int lanesUsed = prof ? 1 : ctx->numLanes;
+    int lanesUsed = oneLane ? 1 : ctx->numLanes;
     {
         const uint64_t per = (total + (uint64_t)lanesUsed - 1) / (uint64_t)lanesUsed;
         const uint64_t minBatch = 1ull << 18;
@@ -1760,16 +1774,21 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         if (nBatches < (uint64_t)lanesUsed) lanesUsed = (int)nBatches;
     }
     int rc = PTGPU_OK;
+    const uint64_t shadowThisBatch = std::max<uint64_t>(1, batch * childGrow * (lightsPer ? lightsPer : 1));  // most shadow records one shade launch can append
     for (int k = 0; k < lanesUsed; k++) {
         Lane& L = ctx->lanes[k];
         // queues grow with the largest batch seen so far (powers of two), so a small pass does not allocate the full capacity
-        const uint64_t needShadow = std::max<uint64_t>(1, batch * childGrow * (lightsPer ? lightsPer : 1));
-        if ((rc = ensure_queues(ctx, L, batch * maxGrow, needShadow)) != PTGPU_OK) return rc;
-        if (ctx->useSplit && (rc = ensure_split(ctx, L, std::max<uint64_t>(L.capRays, L.capShadow), ctx->splitStackEnt)) != PTGPU_OK) return rc;
+        if ((rc = ensure_queues(ctx, L, batch * maxGrow, shadowThisBatch)) != PTGPU_OK) return rc;
+        if ((rc = ensure_split(ctx, L, L.capRays, ctx->splitStackEnt)) != PTGPU_OK) return rc;
     }
-    const int gridTrace = grid_for(ctx, PT_TRACE_MINBLOCKS), gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
+    const int gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
     float ms = 0;
-    if (prof) { ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = ctx->meshMs = 0; ctx->meshItems = ctx->meshLaunches = ctx->traceLaunches = 0; }
+    if (prof) {
+        ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; ctx->traceLaunches = 0;
+        for (int k = 0; k < 3; k++) { ctx->kindMs[k] = 0; ctx->kindLaunches[k] = 0; }
+        ctx->roundItems = 0;
+        CK(cudaMemsetAsync(&ctx->dCounters->kindItems[0], 0, 3 * sizeof(unsigned long long), callerStream));
+    }
     // fork: the lanes' streams continue from the caller's stream ...
     if (!prof) {
         CK(cudaEventRecord(ctx->evFork, callerStream));
@@ -1791,7 +1810,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             CK(cudaMemsetAsync(counts + 2, 0, sizeof(uint32_t), stream));
             CK(cudaMemsetAsync(counts + 4, 0, 2 * sizeof(uint32_t), stream));  // trace / shadow work cursors
             if (prof) cudaEventRecord(ctx->evA, stream);
-            if (ctx->useSplit) {
+            {
                 const RayQueue rqc = L.rq[cur];
                 uint32_t* cnt = counts + cur;
                 rc = run_split(ctx, L, stream,
@@ -1799,9 +1818,6 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                                [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); },
                                [&](const MeshQueue& in) { k_scene_trace<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); });
                 if (rc != PTGPU_OK) return rc;
-            } else {
-                k_trace<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.rq[cur], counts + cur, counts + 4, L.hq, ctx->dCounters);
-                ctx->launches++;
                 if (prof) ctx->traceLaunches++;
             }
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->traceMs += ms; cudaEventRecord(ctx->evA, stream); }
@@ -1820,15 +1836,15 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 2;
             if (lightsPer) {
-                if (ctx->useSplit) {
+                // in chunks of the tracer's per-ray state (the shadow queue of this launch can hold up to 4x the ray capacity)
+                const uint32_t chunk = (uint32_t)std::min<uint64_t>(L.splitCap, 0xFFFFFFFFull);
+                for (uint64_t first64 = 0; first64 < shadowThisBatch; first64 += chunk) {
+                    const uint32_t first = (uint32_t)first64;
                     rc = run_split<PT_ANYHIT != 0>(ctx, L, stream,
-                                   [&](const MeshQueue& out) { k_scene_shadow<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, out, out, d_sum, ctx->dCounters); },
-                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, out, d_sum, ctx->dCounters); },
-                                   [&](const MeshQueue& in) { k_scene_shadow<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, in, in, d_sum, ctx->dCounters); });
+                                   [&](const MeshQueue& out) { k_scene_shadow<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); },
+                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); },
+                                   [&](const MeshQueue& in) { k_scene_shadow<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); });
                     if (rc != PTGPU_OK) return rc;
-                } else {
-                    k_shadow<<<gridTrace, 128, 0, stream>>>(ctx->scene, L.sq, counts + 2, counts + 5, (uint32_t)L.capShadow, d_sum, ctx->dCounters);
-                    ctx->launches++;
                 }
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
             }
@@ -2149,7 +2165,7 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
     CKC(cudaMemcpyAsync(dO, o3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(dD, d3, N * 12, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemsetAsync(ctx->dCounts + 6, 0, sizeof(uint32_t), ctx->stream));
-    if (ctx->useSplit) {
+    {
         Lane& L = ctx->lanes[0];
         int rcs = ensure_split(ctx, L, std::max<uint64_t>(N, L.splitCap), ctx->splitStackEnt);
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
@@ -2159,9 +2175,6 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
                         [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<SCENE_RESUME><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); },
                         [&](const MeshQueue& in) { k_scene_batch<SCENE_FINISH><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); });
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
-    } else {
-    k_intersect_batch<<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, n, ctx->dCounts + 6, dO, dD, dS, dPr, dT, dN, dP, dI, dM);
-    ctx->launches++;
     }
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(shape, dS, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2262,7 +2275,10 @@ int ptgpu_get_counters(ptgpu_ctx* ctx, ptgpu_counters* out) {
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->lastPassMs = ms;
     out->lastPassMs = ctx->lastPassMs;
     out->traceMs = ctx->traceMs; out->shadeMs = ctx->shadeMs; out->shadowMs = ctx->shadowMs; out->raygenMs = ctx->raygenMs;
-    out->meshMs = ctx->meshMs; out->meshItems = ctx->meshItems; out->meshLaunches = ctx->meshLaunches;
+    out->meshMs = ctx->kindMs[0]; out->meshLaunches = ctx->kindLaunches[0];
+    out->meshItems = ctx->roundItems >= dc.kindItems[1] + dc.kindItems[2] ? ctx->roundItems - dc.kindItems[1] - dc.kindItems[2] : 0;
+    out->sdfMs = ctx->kindMs[1]; out->sdfItems = dc.kindItems[1]; out->sdfLaunches = ctx->kindLaunches[1];
+    out->volumeMs = ctx->kindMs[2]; out->volumeItems = dc.kindItems[2]; out->volumeLaunches = ctx->kindLaunches[2];
     out->traceLaunches = ctx->traceLaunches;
     take_overflow(ctx);  // an overflow of a ptgpu_accumulate_device pass is reported here
     out->queueOverflows = ctx->overflowPasses;

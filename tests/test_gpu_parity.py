@@ -970,3 +970,55 @@ def test_cull_matches_no_cull(orc, bindings, device, name):
         assert nhit > 0.2 * total
     finally:
         arbiter.close()
+
+
+def _visible_volume_scene(w, n=24):
+    """A Volume the rays actually hit.  Volume.Sample reads the grid at (x, z, z) of the point (the `y <- z` and `(z + 2) / 2` quirks of
+    Volume.cs:75-78), so voxels are only reached for object z in [-1, 0): the box sits there.  Thin windows give hits, refinements
+    (Volume.cs:181-190) and long empty stretches (vol_skip), directly and under a TransformedShape."""
+    from ptsharp_b200 import hostmath as hm
+    F = lambda x: float(np.float32(x))
+    colors = [0x004358, 0x1F8A70, 0xBEDB39, 0xFFE11A, 0xFD7400]
+    windows = [(F(0.2) + F(0.1) * i, F(0.2) + F(0.1) * i + F(0.02), w.GlossyMaterial(hm.hex_color(c), F(1.3), hm.radians(10))) for i, c in enumerate(colors)]
+    c = (np.arange(n) + 0.5) / n * 2 - 1
+    _, qy, qx = np.meshgrid(c, c, c, indexing="ij")               # index [z, y, x]; Sample() reads (x, y(z), z(z)): a blob around object z = -0.5
+    data = np.exp(-3 * (qx ** 2 + (2 * qy + 1) ** 2)) * (0.85 + 0.15 * np.sin(9 * qx) * np.sin(7 * qy))
+    w.add(w.volume((-1, -1, -1), (1, 1, F(-0.001)), data, 1.0, windows))
+    w.add(w.transformed(w.volume((-1, -1, -1), (1, 1, F(-0.001)), data, 1.0, windows[:2]),
+                        hm.mul(hm.translate(hm.vec((2.6, 0.3, 0.2))), hm.rotate((0, 0, 1), 0.4))))
+    w.add(w.plane((0, 0, F(-1.2)), (0, 0, 1), w.DiffuseMaterial((0.8, 0.8, 0.8))))
+    w.add(w.sphere((1, -3, 4), 0.7, w.LightMaterial((1, 1, 1), 60)))
+    w.look_at((1.2, -5.0, 2.2), (1.0, 0, -0.5), (0, 0, 1), 45)
+    w.sampler(1, 3)
+
+
+def test_volume_hits_refinement_and_empty_space_skipping(orc, bindings, device):
+    """Volume.Intersect (Volume.cs:169-197) on a volume that is actually hit: closest hits bit for bit against the oracle (T, the
+    window material, the gradient normal), the product library (vol_skip: steps that can only repeat `sign == 1` are skipped with t
+    advanced in closed form) against the checker build that takes every step, and a keyed replay."""
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    _visible_volume_scene(hw); _visible_volume_scene(ow)
+    device.upload(hw)
+    o, d = _ray_batch(ow, W=160, H=120, n_secondary=15000, seed=31)
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    assert ((c["shape"] == 0) | (c["shape"] == 1)).sum() > 3000          # rays that end on one of the two volumes
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["material"], c["material"])
+    arbiter = bindings.Device(0, lib=bindings.checker_lib("nocull"))
+    try:
+        arbiter.upload(hw)
+        rng = np.random.default_rng(8)
+        n = 400_000
+        oo = (rng.random((n, 3), dtype=np.float32) * 2 - 1) * np.float32([4, 4, 2.5]) + np.float32([1, 0, 0])
+        dd = rng.normal(size=(n, 3)).astype(np.float32); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+        a, b = device.intersect_batch(oo, dd, full=False), arbiter.intersect_batch(oo, dd, full=False)
+        np.testing.assert_array_equal(a["shape"], b["shape"])
+        np.testing.assert_array_equal(a["t"].view(np.int64), b["t"].view(np.int64))
+        assert (b["shape"] <= 1).sum() > 20000
+    finally:
+        arbiter.close()
+    _replay_check(orc, device, hw, ow, 128, 96, frac=2e-3)

@@ -12,8 +12,8 @@ if '--spp' in sys.argv:
     spp_override = int(sys.argv[sys.argv.index('--spp') + 1]); args = [a for a in args if a != str(spp_override)]
 names = args or ['c1', 'c2', 'c3', 'c4', 'c5']
 DEFAULT_SPP = {'c1': 16, 'c2': 32, 'c3': 8, 'c4': 2, 'c5': 2}
-print("| config | resolution | spp (this run) | triangles | build s | pass ms | Msamples/s | Gpaths·bounce/s | shadow Grays/s | trace/shade/shadow ms |")
-print("|---|---|---|---|---|---|---|---|---|---|")
+print("| config | resolution | spp (this run) | triangles | build s | pass ms | Msamples/s | Gpaths·bounce/s | shadow Grays/s | trace/shade/shadow ms | of which k_mesh / k_march<SDF> / k_march<VOLUME> ms |")
+print("|---|---|---|---|---|---|---|---|---|---|---|")
 for n in names:
     hw = HostWorld()
     t0 = time.time(); cfg = scenes.BUILDERS[n](hw); flat = hw.flatten(); build = time.time() - t0
@@ -27,5 +27,5 @@ for n in names:
     dev.render_pass(hw.make_pass(cfg.width, cfg.height, max(1, spp // 2), pass_index=2), want_mean=False)
     p = dev.counters()
     print(f"| {cfg.name} | {cfg.width}x{cfg.height} | {spp} of {cfg.spp} | {cfg.triangles} | {build:.1f} | {ms:.1f} | {c['cameraSamples']/ms/1e3:.1f} | "
-          f"{c['segments']/ms/1e6:.3f} | {c['shadowRays']/ms/1e6:.3f} | {p['traceMs']:.0f}/{p['shadeMs']:.0f}/{p['shadowMs']:.0f} |", flush=True)
+          f"{c['segments']/ms/1e6:.3f} | {c['shadowRays']/ms/1e6:.3f} | {p['traceMs']:.0f}/{p['shadeMs']:.0f}/{p['shadowMs']:.0f} | {p['meshMs']:.0f}/{p['sdfMs']:.0f}/{p['volumeMs']:.0f} |", flush=True)
     dev.close()
