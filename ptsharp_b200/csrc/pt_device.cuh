@@ -1075,11 +1075,20 @@ enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST
 // Work items of the three kinds share one queue; the kind sits in the top two bits of the item's root word and every consumer
 // kernel takes the items of its kind.
 static constexpr uint32_t kItemKindShift = 30u, kItemMesh = 0u, kItemSdf = 1u, kItemVolume = 2u, kItemIndexMask = (1u << 30) - 1u;
-struct SplitState {      // per ray of the launch, SoA
-    double* bestT; double* bestTInner; int32_t* bestShape; int32_t* bestPrim;   // running Hit of Scene.tree's traversal
-    uint32_t* scNode; int32_t* scSp; double* scTmin; double* scTmax;            // Scene.tree cursor
-    uint32_t* sPos; uint32_t* sEnd; uint32_t* curShape; int32_t* curInst;       // position in the current scene leaf
-    double* mBest; int32_t* mPrim;                                              // Hit of the pending deferred Intersect
+// Per ray of the launch: what a ray that waits for a deferred shape carries from one scene_advance round to the next.  One 96-byte
+// record (three 32-byte sectors): the rays of a RESUME round are a scattered subset of the launch, so their state is gathered, and
+// fourteen separate arrays cost fourteen sector reads per ray (ncu on the instanced scene: 250 B of DRAM traffic per resumed ray).
+struct alignas(32) RayState {
+    double bestT, bestTInner;                                   // running Hit of Scene.tree's traversal
+    int32_t bestShape, bestPrim; uint32_t scNode; int32_t scSp; // ... and the Scene.tree cursor
+    double scTmin, scTmax;
+    uint32_t sPos, sEnd, curShape; int32_t curInst;             // position in the current scene leaf
+    double mBest; int32_t mPrim; int32_t pad0;                  // Hit of the pending deferred Intersect (written by k_mesh / k_march)
+    uint32_t pad1[4];
+};
+static_assert(sizeof(RayState) == 96, "RayState is three sectors");
+struct SplitState {
+    RayState* state;                                                            // [ray]
     uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
     unsigned long long* kindItems;                                              // [3] work items consumed per kind (counters; [0] is filled in by the host)
 };
@@ -1111,6 +1120,17 @@ PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double 
             if (!mesh_pop(mc, best, stk)) break;
         }
     }
+}
+
+PT_D void save_ray_state(RayState* p, const HitRec& best, const KdCursor& sc, uint32_t sPos, uint32_t sEnd, uint32_t curShape, int32_t curInst) {
+    uint4* rs = reinterpret_cast<uint4*>(p);  // four 128-bit stores; the fifth quad (mBest, mPrim) belongs to the consumer kernel
+    rs[0] = make_uint4((uint32_t)__double2loint(best.t), (uint32_t)__double2hiint(best.t), (uint32_t)__double2loint(best.tInner), (uint32_t)__double2hiint(best.tInner));
+    rs[1] = make_uint4((uint32_t)best.shape, (uint32_t)best.prim, sc.node, (uint32_t)sc.sp);
+    rs[2] = make_uint4((uint32_t)__double2loint(sc.tmin), (uint32_t)__double2hiint(sc.tmin), (uint32_t)__double2loint(sc.tmax), (uint32_t)__double2hiint(sc.tmax));
+    rs[3] = make_uint4(sPos, sEnd, curShape, (uint32_t)curInst);
+}
+PT_D void save_hit(RayState* p, double t, int32_t prim) {  // one 128-bit store
+    reinterpret_cast<uint4*>(p)[4] = make_uint4((uint32_t)__double2loint(t), (uint32_t)__double2hiint(t), (uint32_t)prim, 0u);
 }
 
 // Advance rays through Scene.tree until each either finishes (sink) or has to enter a Mesh (work item to `out`).
@@ -1151,9 +1171,12 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             continue;
         }
         if (RESUME) {
-            best.t = W.bestT[ray]; best.tInner = W.bestTInner[ray]; best.shape = W.bestShape[ray]; best.prim = W.bestPrim[ray];
-            sc.node = W.scNode[ray]; sc.sp = W.scSp[ray]; sc.tmin = W.scTmin[ray]; sc.tmax = W.scTmax[ray];
-            sPos = W.sPos[ray]; sEnd = W.sEnd[ray]; curShape = W.curShape[ray]; curInst = W.curInst[ray];
+            const uint4* rs = reinterpret_cast<const uint4*>(W.state + ray);  // five 128-bit loads from three consecutive sectors
+            const uint4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3], r4 = rs[4];
+            best.t = __hiloint2double((int)r0.y, (int)r0.x); best.tInner = __hiloint2double((int)r0.w, (int)r0.z);
+            best.shape = (int32_t)r1.x; best.prim = (int32_t)r1.y; sc.node = r1.z; sc.sp = (int)r1.w;
+            sc.tmin = __hiloint2double((int)r2.y, (int)r2.x); sc.tmax = __hiloint2double((int)r2.w, (int)r2.z);
+            sPos = r3.x; sEnd = r3.y; curShape = r3.z; curInst = (int32_t)r3.w;
             const float4 ia = in.a[k], ib = in.b[k];  // the item holds the ray in the shape's space (TransformedShape.cs:45): no second Matrix.MulRay
             if (curInst >= 0) { co = v3(ia.x, ia.y, ia.z); cd = v3(ib.x, ib.y, ib.z); }
             if (MODE == SCENE_FINISH) {  // the pending walk / march first
@@ -1167,7 +1190,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                     mBest = primitive_intersect(S, msh, v3(ia.x, ia.y, ia.z), v3(ib.x, ib.y, ib.z));
                     mPrim = -1;
                 }
-            } else { mBest = W.mBest[ray]; mPrim = W.mPrim[ray]; }
+            } else { mBest = __hiloint2double((int)r4.y, (int)r4.x); mPrim = (int32_t)r4.z; }
             st = ST_MESH_DONE;
         } else {
             best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
@@ -1256,9 +1279,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.c[slot] = make_double2(tmin, tmax);
                             // a float at or below tL (object-space T of an instance is not comparable with tL: no cut-off there)
                             if (SHADOW) out.lim[slot] = (curInst < 0 && tL > 0) ? __double2float_rd(tL) : -1.0f;
-                            W.bestT[ray] = best.t; W.bestTInner[ray] = best.tInner; W.bestShape[ray] = best.shape; W.bestPrim[ray] = best.prim;
-                            W.scNode[ray] = sc.node; W.scSp[ray] = sc.sp; W.scTmin[ray] = sc.tmin; W.scTmax[ray] = sc.tmax;
-                            W.sPos[ray] = sPos; W.sEnd[ray] = sEnd; W.curShape[ray] = curShape; W.curInst[ray] = curInst;
+                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst);
                             break;
                         }
                     } else if (sh.type == PTGPU_SDF || sh.type == PTGPU_VOLUME) {
@@ -1291,9 +1312,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.b[slot] = make_float4(cd.x, cd.y, cd.z, __uint_as_float((kind << kItemKindShift) | sh.data));
                             out.c[slot] = make_double2(t0, t1);
                             if (SHADOW) out.lim[slot] = -1.0f;
-                            W.bestT[ray] = best.t; W.bestTInner[ray] = best.tInner; W.bestShape[ray] = best.shape; W.bestPrim[ray] = best.prim;
-                            W.scNode[ray] = sc.node; W.scSp[ray] = sc.sp; W.scTmin[ray] = sc.tmin; W.scTmax[ray] = sc.tmax;
-                            W.sPos[ray] = sPos; W.sEnd[ray] = sEnd; W.curShape[ray] = curShape; W.curInst[ray] = curInst;
+                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst);
                             break;
                         }
                     } else {
@@ -1418,7 +1437,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
             dbgSteps = dbgLeaves = 0;
         }
 #endif
-        if (st == ST_MESH_DONE) { W.mBest[ray] = mBest; W.mPrim[ray] = mPrim; st = ST_IDLE; }
+        if (st == ST_MESH_DONE) { save_hit(W.state + ray, mBest, mPrim); st = ST_IDLE; }
     }
 }
 
@@ -1509,7 +1528,7 @@ PT_D void march_items(const DScene& S, const SplitState& W, const MeshQueue& q, 
                     }
                 }
             }
-            if (done) { W.mBest[ray] = result; W.mPrim[ray] = -1; have = false; }
+            if (done) { save_hit(W.state + ray, result, -1); have = false; }
         }
     }
 }

@@ -1020,8 +1020,7 @@ static void trim_scene_pool(ptgpu_ctx* ctx) {  // after an upload: what the new 
 }
 static void free_split(Lane& L) {
     SplitState& W = L.split;
-    void* ps[] = {W.bestT, W.bestTInner, W.bestShape, W.bestPrim, W.scNode, W.scSp, W.scTmin, W.scTmax, W.sPos, W.sEnd, W.curShape, W.curInst, W.mBest, W.mPrim,
-                  W.sceneStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c, L.mq[0].lim, L.mq[1].lim};
+    void* ps[] = {W.state, W.sceneStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c, L.mq[0].lim, L.mq[1].lim};
     for (void* p : ps) cudaFree(p);
     W = SplitState{};
     L.mq[0] = L.mq[1] = MeshQueue{};
@@ -1053,10 +1052,7 @@ static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
     CK(cudaStreamSynchronize(L.stream));
     free_split(L);
     SplitState& W = L.split;
-    CK(cudaMalloc(&W.bestT, cap * 8)); CK(cudaMalloc(&W.bestTInner, cap * 8)); CK(cudaMalloc(&W.bestShape, cap * 4)); CK(cudaMalloc(&W.bestPrim, cap * 4));
-    CK(cudaMalloc(&W.scNode, cap * 4)); CK(cudaMalloc(&W.scSp, cap * 4)); CK(cudaMalloc(&W.scTmin, cap * 8)); CK(cudaMalloc(&W.scTmax, cap * 8));
-    CK(cudaMalloc(&W.sPos, cap * 4)); CK(cudaMalloc(&W.sEnd, cap * 4)); CK(cudaMalloc(&W.curShape, cap * 4)); CK(cudaMalloc(&W.curInst, cap * 4));
-    CK(cudaMalloc(&W.mBest, cap * 8)); CK(cudaMalloc(&W.mPrim, cap * 4));
+    CK(cudaMalloc(&W.state, cap * sizeof(RayState)));
     CK(cudaMalloc(&W.sceneStack, cap * (uint64_t)stackEnt * sizeof(uint4)));
     W.stackEnt = stackEnt;
     W.kindItems = ctx->dCounters->kindItems;
@@ -1091,7 +1087,8 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
             CK(cudaMemcpyAsync(&pending, L.mq[cur].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (pending == 0) break;
-            if (pending <= PT_FINISH_MAX && round > 0) { finish(L.mq[cur]); ctx->launches++; break; }
+            static const uint32_t finishMax = std::getenv("PTGPU_FINISH_MAX") ? (uint32_t)std::atoll(std::getenv("PTGPU_FINISH_MAX")) : (uint32_t)PT_FINISH_MAX;  // development override
+            if (pending <= finishMax && round > 0) { finish(L.mq[cur]); ctx->launches++; break; }
         }
         CK(cudaMemsetAsync(L.mq[cur ^ 1].count, 0, sizeof(uint32_t), st));
         CK(cudaMemsetAsync(cursor, 0, 3 * sizeof(uint32_t), st));
