@@ -44,7 +44,7 @@ enum {
 /* Shape type codes (IShape implementations on the path). */
 enum {
     PTGPU_SPHERE = 1, PTGPU_CUBE = 2, PTGPU_PLANE = 3, PTGPU_CYLINDER = 4, PTGPU_TRIANGLE = 5, PTGPU_MESH = 6,
-    PTGPU_TRANSFORMED = 7, PTGPU_SDF = 8, PTGPU_VOLUME = 9
+    PTGPU_TRANSFORMED = 7, PTGPU_SDF = 8, PTGPU_VOLUME = 9, PTGPU_SH = 10
 };
 /* LightMode.cs, SpecularMode.cs, BounceType.cs, Axis.cs — the integer codes are part of the ABI. */
 enum { PTGPU_LIGHT_RANDOM = 0, PTGPU_LIGHT_ALL = 1 };
@@ -102,6 +102,11 @@ typedef struct ptgpu_volume {
     double zscale; uint64_t dataOffset; float bmin[3]; float bmax[3];
 } ptgpu_volume;
 
+/* SphericalHarmonic (SH.cs:7-104): Intersect walks `mesh` (the marching-cubes mesh of |p| - |Y_l^m(p/|p|)|, built on the host:
+ * MC.NewSDFMesh, MC.cs:9-66) but the Hit names the SphericalHarmonic itself: NormalAt is the gradient of that function (SH.cs:74-86),
+ * MaterialAt picks by the sign of Y_l^m (SH.cs:62-72). */
+typedef struct ptgpu_sh { int32_t l, m; uint32_t mesh; int32_t positiveMaterial, negativeMaterial; int32_t pad[3]; } ptgpu_sh;
+
 /* Material.cs:11-45.  Texture ids index textures[], -1 = null. */
 typedef struct ptgpu_material {
     double color[3]; double bumpMultiplier, emittance, index, gloss, tint, reflectivity;
@@ -140,6 +145,7 @@ typedef struct ptgpu_flat_scene {
     double envColor[3];                                      /* Scene.Color (Scene.cs:11) */
     int32_t envTexture; int32_t pad0;                        /* Scene.Texture (Scene.cs:12) */
     double envTextureAngle;                                  /* Scene.TextureAngle (Scene.cs:13) */
+    uint32_t numShs;           const ptgpu_sh* shs;          /* SphericalHarmonic shapes */
 } ptgpu_flat_scene;
 
 /* Camera.cs:11-17 after LookAt/SetFocus. */
@@ -224,7 +230,7 @@ int ptgpu_abi_version(void);
  * 0 ptgpu_params, 1 ptgpu_pass, 2 ptgpu_camera, 3 ptgpu_counters, 4 ptgpu_flat_scene, 5 ptgpu_node, 6 ptgpu_tree, 7 ptgpu_shape,
  * 8 ptgpu_sphere, 9 ptgpu_cube, 10 ptgpu_plane, 11 ptgpu_cylinder, 12 ptgpu_mesh, 13 ptgpu_tri_geom, 14 ptgpu_tri_shade,
  * 15 ptgpu_instance, 16 ptgpu_sdf_op, 17 ptgpu_sdf_shape, 18 ptgpu_volume_window, 19 ptgpu_volume, 20 ptgpu_material,
- * 21 ptgpu_texture; anything else: -1. */
+ * 21 ptgpu_texture, 22 ptgpu_sh; anything else: -1. */
 int ptgpu_abi_sizeof(int which);
 int ptgpu_create(const ptgpu_params* params, ptgpu_ctx** out);
 void ptgpu_destroy(ptgpu_ctx* ctx);

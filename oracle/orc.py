@@ -27,6 +27,7 @@ _EXTRA = {
     "set_extra": (None, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
     "set_serial": (None, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "set_task_sample": (None, [C.c_void_p, C.c_int, C.c_int]),
+    "spherical_harmonic": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]),
     "last_samples": (C.c_int, [C.c_void_p, C.c_int, c_int_p]),
     "camera_get": (None, [C.c_void_p, c_float_p, c_double_p]),
     "intersect_batch": (None, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_int_p, c_int_p, c_double_p, c_float_p,
@@ -114,6 +115,12 @@ class OracleWorld(World):
     def set_serial(self, serial=True, adaptive_threshold=1.0, adaptive_exponent=1.0):
         """The extra samples follow the serial Render() (Renderer.cs:150-191)."""
         self.lib.orc_set_serial(self.h, int(serial), float(adaptive_threshold), float(adaptive_exponent))
+
+    def spherical_harmonic(self, l, m, pm, nm, V):
+        """SphericalHarmonic.NewSphericalHarmonic(l, m, pm, nm) over the given marching-cubes triangles V (ntri, 3, 3)."""
+        V = np.ascontiguousarray(V, dtype=np.float32)
+        self._keep.append(V)
+        return self.lib.orc_spherical_harmonic(self.h, l, m, pm, nm, V.shape[0], V.ctypes.data_as(c_float_p))
 
     def set_task_sample(self, stride=1, offset=0):
         """render() only renders every `stride`-th non-empty 32x32 task of the frame (a bounded, evenly spread timing sample)."""

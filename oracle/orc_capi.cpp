@@ -101,6 +101,21 @@ int orc_mesh(orc_world* w, int ntri, const float* V, const float* N, const float
     return push_shape(w, m);
 }
 
+// SphericalHarmonic.NewSphericalHarmonic(l, m, pm, nm) with its marching-cubes mesh supplied by the caller (ntri x 9 floats).
+int orc_spherical_harmonic(orc_world* w, int l, int m, int pm, int nm, int ntri, const float* V) {
+    SphericalHarmonic* sh = new SphericalHarmonic();
+    sh->L = l; sh->M = m; sh->PositiveMaterial = w->materials[(size_t)pm]; sh->NegativeMaterial = w->materials[(size_t)nm];
+    sh->mesh.Triangles.resize((size_t)ntri);
+    for (int i = 0; i < ntri; i++) {
+        Triangle& t = sh->mesh.Triangles[(size_t)i];
+        const float* v = V + (size_t)i * 9;
+        t.V1 = Vector(v[0], v[1], v[2]); t.V2 = Vector(v[3], v[4], v[5]); t.V3 = Vector(v[6], v[7], v[8]);
+        t.index = i;
+        t.FixNormals();  // MC.cs:107
+    }
+    return push_shape(w, sh);
+}
+
 int orc_transformed(orc_world* w, int shape, const double* m16) {
     return push_shape(w, new TransformedShape(w->shapes[(size_t)shape].get(), Matrix::FromRows(m16)));
 }

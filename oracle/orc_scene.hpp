@@ -178,7 +178,7 @@ struct Hit {  // Hit.cs:4-24
 static inline Hit NoHit() { return Hit(nullptr, HIT_INF); }  // Hit.cs:24
 
 // ------------------------------------------------------------------------------------------- IShape
-enum ShapeKind { K_SPHERE = 1, K_CUBE, K_PLANE, K_CYLINDER, K_TRIANGLE, K_MESH, K_TRANSFORMED, K_SDF, K_VOLUME };
+enum ShapeKind { K_SPHERE = 1, K_CUBE, K_PLANE, K_CYLINDER, K_TRIANGLE, K_MESH, K_TRANSFORMED, K_SDF, K_VOLUME, K_SH };
 
 // IShape.cs:3-11
 struct IShape {
@@ -625,6 +625,67 @@ struct Mesh : IShape {  // Mesh.cs:6-140 (a C# struct)
     Vector NormalAt(const Vector&) const override { return Vector(); }          // :137-140
 };
 
+// ------------------------------------------------------------------------------- SphericalHarmonic
+// SH.cs:7-338.  The marching-cubes mesh (SH.cs:20, MC.cs) is handed in from outside: the oracle restates what happens to a ray
+// (Intersect / NormalAt / MaterialAt), not the authoring-time mesh generation, which tests/test_mc.py checks against its own
+// numpy restatement of MC.cs.
+struct SphericalHarmonic : IShape {
+    int L, M;
+    Material PositiveMaterial, NegativeMaterial;
+    Mesh mesh;
+    int Kind() const override { return K_SH; }
+    bool IsClass() const override { return true; }
+    void Compile() override { mesh.Compile(); }                                                 // SH.cs:24-27
+    Box BoundingBox() const override { return Box(Vector(-1, -1, -1), Vector(1, 1, 1)); }         // SH.cs:29-33
+    Hit Intersect(const Ray& r) const override {                                                  // SH.cs:47-55
+        Hit hit = mesh.Intersect(r);
+        if (!hit.Ok()) return NoHit();
+        return Hit(this, hit.T);
+    }
+    Vector UVector(const Vector&) const override { return Vector(); }
+    Material MaterialAt(const Vector& p) const override { return EvaluateHarmonic(p) < 0 ? NegativeMaterial : PositiveMaterial; }  // SH.cs:62-72
+    Vector NormalAt(const Vector& p) const override {                                             // SH.cs:74-86
+        const double e = 0.0001;
+        double x = p.X(), y = p.Y(), z = p.Z();
+        Vector n(Evaluate(Vector(x - e, y, z)) - Evaluate(Vector(x + e, y, z)),
+                 Evaluate(Vector(x, y - e, z)) - Evaluate(Vector(x, y + e, z)),
+                 Evaluate(Vector(x, y, z - e)) - Evaluate(Vector(x, y, z + e)));
+        return n.Normalize();
+    }
+    double EvaluateHarmonic(const Vector& p) const { return Harmonic(p.Normalize()); }          // SH.cs:88-91
+    double Evaluate(const Vector& p) const { return (double)p.Length() - std::fabs(Harmonic(p.Normalize())); }  // SH.cs:93-101
+    // shFunc (SH.cs:213-338) and the functions it selects (SH.cs:103-211): float literals widened, products left to right
+    double Harmonic(const Vector& d) const {
+        const double X = d.X(), Y = d.Y(), Z = d.Z();
+        if (L == 0 && M == 0) return 0.282095f;
+        if (L == 1 && M == -1) return -0.488603f * Y;
+        if (L == 1 && M == 0) return 0.488603f * Z;
+        if (L == 1 && M == 1) return -0.488603f * X;
+        if (L == 2 && M == -2) return 1.092548f * X * Y;
+        if (L == 2 && M == -1) return -1.092548f * Y * Z;
+        if (L == 2 && M == 0) return 0.315392f * (-X * X - Y * Y + 2.0f * Z * Z);
+        if (L == 2 && M == 1) return -1.092548f * X * Z;
+        if (L == 2 && M == 2) return 0.546274f * (X * X - Y * Y);
+        if (L == 3 && M == -3) return -0.590044f * Y * (3.0f * X * X - Y * Y);
+        if (L == 3 && M == -2) return 2.890611f * X * Y * Z;
+        if (L == 3 && M == -1) return -0.457046f * Y * (4.0f * Z * Z - X * X - Y * Y);
+        if (L == 3 && M == 0) return 0.373176f * Z * (2.0f * Z * Z - 3.0f * X * X - 3.0f * Y * Y);
+        if (L == 3 && M == 1) return -0.457046f * X * (4.0f * Z * Z - X * X - Y * Y);
+        if (L == 3 && M == 2) return 1.445306f * Z * (X * X - Y * Y);
+        if (L == 3 && M == 3) return -0.590044f * X * (X * X - 3.0f * Y * Y);
+        if (L == 4 && M == -4) return 2.503343f * X * Y * (X * X - Y * Y);
+        if (L == 4 && M == -3) return -1.770131f * Y * Z * (3.0f * X * X - Y * Y);
+        if (L == 4 && M == -2) return 0.946175f * X * Y * (7.0f * Z * Z - 1.0f);
+        if (L == 4 && M == -1) return -0.669047f * Y * Z * (7.0f * Z * Z - 3.0f);
+        if (L == 4 && M == 0) { double z2 = Z * Z; return 0.105786f * (35.0f * z2 * z2 - 30.0f * z2 + 3.0f); }
+        if (L == 4 && M == 1) return -0.669047f * X * Z * (7.0f * Z * Z - 3.0f);
+        if (L == 4 && M == 2) return 0.473087f * (X * X - Y * Y) * (7.0f * Z * Z - 1.0f);
+        if (L == 4 && M == 3) return -1.770131f * X * Z * (X * X - 3.0f * Y * Y);
+        if (L == 4 && M == 4) { double x2 = X * X, y2 = Y * Y; return 0.625836f * (x2 * (x2 - 3.0f * y2) - y2 * (3.0f * x2 - y2)); }
+        return std::nan("");
+    }
+};
+
 // --------------------------------------------------------------------------------- TransformedShape
 struct TransformedShape : IShape {  // TransformedShape.cs:9-93 (a C# struct)
     IShape* Shape;
@@ -952,7 +1013,7 @@ inline HitInfo Hit::Info(const Ray& r) const {  // Hit.cs:26-55
         normal = normal.Negate();
         inside = true;
         int k = shape->Kind();
-        if (k == K_VOLUME || k == K_SDF) inside = false;  // Hit.cs:41-47 (SphericalHarmonic is out of scope)
+        if (k == K_VOLUME || k == K_SDF || k == K_SH) inside = false;  // Hit.cs:41-47
     }
     HitInfo hi;
     hi.Shape = shape;

@@ -138,6 +138,8 @@ _HOST_EXTRA = {
     "renderer_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "renderer_ctx": (C.c_void_p, [C.c_void_p]),
     "load_model": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
+    "mc_mesh": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_double, C.c_int]),
+    "spherical_harmonic": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mesh_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
     "mesh_get": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p]),
 }
@@ -149,6 +151,8 @@ def host_lib() -> C.CDLL:
         gpu_lib()
         lib = C.CDLL(_build.build_host())
         bind(lib, "pth_", _HOST_EXTRA)
+        lib.pth_mc_case.restype = C.c_int; lib.pth_mc_case.argtypes = [C.c_int, c_int_p]
+        lib.pth_mc_edges.restype = C.c_int; lib.pth_mc_edges.argtypes = [C.c_int]
         _host = lib
     return _host
 
@@ -208,6 +212,30 @@ class HostWorld(World):
         if s < 0:
             raise RuntimeError(self._err())
         return s
+
+    # ---- marching cubes / spherical harmonics (host/mc.cpp; MC.cs, SH.cs) ----
+    def mc_mesh(self, sdf: int, bmin, bmax, step: float, mat: int = -1) -> int:
+        """MC.NewSDFMesh(sdf, box, step): the marching-cubes Mesh of an SDF (triangles in the reference's order)."""
+        from .authoring import _d3
+        s = self.lib.pth_mc_mesh(self.h, sdf, _d3(bmin), _d3(bmax), float(step), mat)
+        if s < 0:
+            raise RuntimeError(self._err())
+        return s
+
+    def spherical_harmonic(self, l: int, m: int, pm: int, nm: int, step: float = 0.0) -> int:
+        """SphericalHarmonic.NewSphericalHarmonic(l, m, pm, nm); step = 0: the reference's 0.01F grid."""
+        s = self.lib.pth_spherical_harmonic(self.h, l, m, pm, nm, float(step))
+        if s < 0:
+            raise RuntimeError(self._err())
+        return s
+
+    @staticmethod
+    def mc_case(index: int):
+        """(triangleTable[index] as a list of cube edges, edgetable[index]) of the marching-cubes tables (MC.cs:135-429)."""
+        lib = host_lib()
+        out = (C.c_int * 15)()
+        n = lib.pth_mc_case(index, out)
+        return [out[i] for i in range(3 * n)], lib.pth_mc_edges(index)
 
     def _mesh_op(self, shape: int, op: int, args) -> None:
         a = np.ascontiguousarray(np.asarray(list(args) + [0.0], dtype=np.float64))

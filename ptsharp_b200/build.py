@@ -36,7 +36,7 @@ def build_gpu(force=False, verbose=False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libptgpu.so")
     srcs = [os.path.join(PKG, "csrc", "ptgpu.cu"), os.path.join(PKG, "csrc", "pt_device.cuh"),
-            os.path.join(PKG, "csrc", "mesh_derive.hpp"), os.path.join(ROOT, "include", "ptgpu.h")]
+            os.path.join(PKG, "csrc", "mesh_derive.hpp"), os.path.join(PKG, "csrc", "sh_funcs.hpp"), os.path.join(ROOT, "include", "ptgpu.h")]
     if force or _newer(srcs, out):
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0]]
         subprocess.check_call(cmd)
@@ -69,9 +69,11 @@ def build_variants(force=False) -> dict:
 def build_host(force=False) -> str:
     gpu = build_gpu()
     out = os.path.join(LIBDIR, "libpthost.so")
-    srcs = [os.path.join(PKG, "host", f) for f in ("host.cpp", "capi.cpp", "loaders.cpp", "ptsharp.hpp")] + [os.path.join(ROOT, "include", "ptgpu.h")]
+    cpps = [os.path.join(PKG, "host", f) for f in ("host.cpp", "capi.cpp", "loaders.cpp", "mc.cpp")]
+    srcs = cpps + [os.path.join(PKG, "host", "ptsharp.hpp"), os.path.join(PKG, "host", "mc_table.inc"), os.path.join(PKG, "csrc", "sh_funcs.hpp"),
+                   os.path.join(ROOT, "include", "ptgpu.h")]
     if force or _newer(srcs + [gpu], out):
-        cmd = ["g++"] + CXX_FLAGS + ["-o", out, srcs[0], srcs[1], srcs[2], "-L" + LIBDIR, "-lptgpu", "-Wl,-rpath,$ORIGIN"]
+        cmd = ["g++"] + CXX_FLAGS + ["-o", out] + cpps + ["-L" + LIBDIR, "-lptgpu", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return out
 

@@ -17,6 +17,7 @@
 
 #include "../../include/ptgpu.h"
 #include "mesh_derive.hpp"
+#include "sh_funcs.hpp"
 
 #define PT_D __device__ __forceinline__
 #define PT_HD __host__ __device__ __forceinline__
@@ -155,6 +156,7 @@ struct DScene {
     const ptgpu_sdf_shape* sdfShapes;
     const ptgpu_sdf_op* sdfOps;
     const ptgpu_volume* volumes;
+    const ptgpu_sh* shs;
     const ptgpu_volume_window* volumeWindows;
     const double* volumeData;
     const ptgpu_material* materials;
@@ -1209,6 +1211,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         t = (double)vlenf(vsub(position, o));
                     }
                 }
+                if (curShape >> 31) { curShape &= 0x7FFFFFFFu; mPrim = -1; }  // SphericalHarmonic: the Hit names the solid, not the triangle (SH.cs:54)
                 if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
                 st = (SHADOW && best.t < tL) ? ST_FINISH : ST_SCENE_LEAF;  // occluded: the closest hit is closer than the light
             }
@@ -1247,8 +1250,9 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
                         sh = S.shapes[inst.shape];
                     }
-                    if (sh.type == PTGPU_MESH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
-                        const ptgpu_tree mt = S.trees[S.meshes[sh.data].tree];
+                    if (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
+                        // (SphericalHarmonic.Intersect is mesh.Intersect with the Hit renamed to the solid itself, SH.cs:47-55)
+                        const ptgpu_tree mt = S.trees[S.meshes[sh.type == PTGPU_SH ? S.shs[sh.data].mesh : sh.data].tree];
                         mBest = kHitInf;
                         double tmin = 0, tmax = -1;
                         const RayAux ra = ray_aux(co, cd);
@@ -1267,6 +1271,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             else if (tmax > lim) tmax = lim;
                         }
 #endif
+                        if (sh.type == PTGPU_SH) curShape |= 0x80000000u;  // the fold drops the triangle index
                         if (tmax < tmin || tmax <= 0) st = ST_MESH_DONE;
                         else if (MODE == SCENE_FINISH) { mesh_walk_single(S, co, cd, mt.root, tmin, tmax, mBest, mPrim, (SHADOW && curInst < 0) ? tL : -1.0); st = ST_MESH_DONE; }
                         else {
@@ -1660,6 +1665,18 @@ PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
     return vnorm_c(n);
 }
 
+// SphericalHarmonic.Evaluate / NormalAt / MaterialAt (SH.cs:62-98): p.Length() - |Y(p.Normalize())| and its central differences.
+PT_D double sh_harmonic(const ptgpu_sh& h, V3 p) { const V3 d = vnorm_c(p); return sh_eval(h.l, h.m, (double)d.x, (double)d.y, (double)d.z); }
+PT_D double sh_evaluate(const ptgpu_sh& h, V3 p) { return (double)vlenf(p) - fabs(sh_harmonic(h, p)); }
+PT_D V3 sh_normal(const ptgpu_sh& h, V3 p) {
+    const double e = 0.0001;
+    const double x = p.x, y = p.y, z = p.z;
+    const double nx = sh_evaluate(h, v3d(x - e, y, z)) - sh_evaluate(h, v3d(x + e, y, z));
+    const double ny = sh_evaluate(h, v3d(x, y - e, z)) - sh_evaluate(h, v3d(x, y + e, z));
+    const double nz = sh_evaluate(h, v3d(x, y, z - e)) - sh_evaluate(h, v3d(x, y, z + e));
+    return vnorm_c(v3d(nx, ny, nz));
+}
+
 // IShape.NormalAt for a non-transformed shape entry (prim = global triangle index for meshes).
 PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p) {
     switch (sh.type) {
@@ -1691,6 +1708,7 @@ PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p)
         case PTGPU_MESH: return tri_normal(S, (uint32_t)prim, p);  // hit.Shape is the Triangle
         case PTGPU_SDF: return sdf_normal(S, S.sdfShapes[sh.data], p);
         case PTGPU_VOLUME: return volume_normal(S, S.volumes[sh.data], p);
+        case PTGPU_SH: return sh_normal(S.shs[sh.data], p);
         default: return v3(0, 0, 0);
     }
 }
@@ -1701,6 +1719,7 @@ PT_D Mat shape_material(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3
     int32_t id = sh.material;
     if (sh.type == PTGPU_MESH) id = S.triShade[prim].material;
     else if (sh.type == PTGPU_VOLUME) id = volume_material(S, S.volumes[sh.data], p);
+    else if (sh.type == PTGPU_SH) { const ptgpu_sh& h = S.shs[sh.data]; id = sh_harmonic(h, p) < 0 ? h.negativeMaterial : h.positiveMaterial; }
     Mat m = mat_load(S, id);
     if (id < 0) return m;
     const ptgpu_material& pm = S.materials[id];
@@ -1778,7 +1797,7 @@ PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
     if (vdot(normal, d) > 0) {
         normal = vneg(normal);
         sf.inside = true;
-        if (sh.type == PTGPU_VOLUME || sh.type == PTGPU_SDF) sf.inside = false;  // Hit.cs:41-47
+        if (sh.type == PTGPU_VOLUME || sh.type == PTGPU_SDF || sh.type == PTGPU_SH) sf.inside = false;  // Hit.cs:41-47
     }
     sf.position = position;
     sf.normal = normal;

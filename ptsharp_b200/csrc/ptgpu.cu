@@ -41,6 +41,7 @@
 #define PT_ANYHIT (!PT_NO_CULL)   // 0: shadow rays take the full closest-hit walk (A/B switch for the exact any-hit cut-off, see scene_advance)
 #endif
 #include "pt_device.cuh"
+#include "sh_funcs.hpp"
 
 namespace cg = cooperative_groups;
 using namespace pt;
@@ -1158,7 +1159,7 @@ int ptgpu_abi_sizeof(int which) {
         case 12: return (int)sizeof(ptgpu_mesh); case 13: return (int)sizeof(ptgpu_tri_geom); case 14: return (int)sizeof(ptgpu_tri_shade);
         case 15: return (int)sizeof(ptgpu_instance); case 16: return (int)sizeof(ptgpu_sdf_op); case 17: return (int)sizeof(ptgpu_sdf_shape);
         case 18: return (int)sizeof(ptgpu_volume_window); case 19: return (int)sizeof(ptgpu_volume); case 20: return (int)sizeof(ptgpu_material);
-        case 21: return (int)sizeof(ptgpu_texture);
+        case 21: return (int)sizeof(ptgpu_texture); case 22: return (int)sizeof(ptgpu_sh);
         default: return -1;
     }
 }
@@ -1324,6 +1325,7 @@ static std::string validate_flat_scene(const ptgpu_flat_scene* s) {
             case PTGPU_TRANSFORMED: lim = s->numInstances; break;
             case PTGPU_SDF: lim = s->numSdfShapes; break;
             case PTGPU_VOLUME: lim = s->numVolumes; break;
+            case PTGPU_SH: lim = s->numShs; break;
             default: return bad("unknown shape type", i);
         }
         if (sh.data >= lim) return bad("shape data index out of range", i);
@@ -1338,6 +1340,11 @@ static std::string validate_flat_scene(const ptgpu_flat_scene* s) {
     }
     for (uint64_t i = 0; i < s->numTriangles; i++) {
         if (!mat_ok(s->triShade[i].material)) return bad("triangle material out of range", i);
+    }
+    for (uint32_t i = 0; i < s->numShs; i++) {
+        const ptgpu_sh& h = s->shs[i];
+        if (h.mesh >= s->numMeshes || !mat_ok(h.positiveMaterial) || !mat_ok(h.negativeMaterial)) return bad("SphericalHarmonic mesh / material out of range", i);
+        if (!sh_supported(h.l, h.m)) return bad("unsupported spherical harmonic (l <= 4, |m| <= l)", i);
     }
     for (uint32_t i = 0; i < s->numTrees; i++) if (s->trees[i].root >= s->numNodes) return bad("tree root out of range", i);
     // which tree owns a node decides what its leaf items index: nodes of a tree are contiguous from its root to the next root
@@ -1453,8 +1460,8 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
             const ptgpu_shape& inner = s->shapes[in.shape];
             float* o8 = &ib[(size_t)i * 8];
             double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            if (inner.type == PTGPU_MESH) {
-                const ptgpu_tree& t = s->trees[s->meshes[inner.data].tree];
+            if (inner.type == PTGPU_MESH || inner.type == PTGPU_SH) {
+                const ptgpu_tree& t = s->trees[s->meshes[inner.type == PTGPU_SH ? s->shs[inner.data].mesh : inner.data].tree];
                 for (int c = 0; c < 8; c++) {
                     const double p[3] = {(c & 1) ? t.bmax[0] : t.bmin[0], (c & 2) ? t.bmax[1] : t.bmin[1], (c & 4) ? t.bmax[2] : t.bmin[2]};
                     for (int r = 0; r < 3; r++) {
@@ -1479,6 +1486,7 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
     UP(sdfShapes, s->sdfShapes, s->numSdfShapes);
     UP(sdfOps, s->sdfOps, s->numSdfOps);
     UP(volumes, s->volumes, s->numVolumes);
+    UP(shs, s->shs, s->numShs);
     UP(volumeWindows, s->volumeWindows, s->numVolumeWindows);
     UP(volumeData, s->volumeData, s->numVolumeData);
     {   // per Volume: the largest voxel of every 4x4x4 block, dilated by two voxels, never below 0 (voxels outside the grid read 0);
@@ -1567,6 +1575,7 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
             else if (sh.type == PTGPU_PLANE) { for (int k = 0; k < 3; k++) { mn[k] = -1e9f; mx[k] = 1e9f; } }
             else if (sh.type == PTGPU_SDF) { std::memcpy(mn, s->sdfShapes[sh.data].bmin, 12); std::memcpy(mx, s->sdfShapes[sh.data].bmax, 12); }
             else if (sh.type == PTGPU_VOLUME) { std::memcpy(mn, s->volumes[sh.data].bmin, 12); std::memcpy(mx, s->volumes[sh.data].bmax, 12); }
+            else if (sh.type == PTGPU_SH) { for (int k = 0; k < 3; k++) { mn[k] = -1.f; mx[k] = 1.f; } }  // SH.cs:29-33
             // struct-typed lights (Mesh, TransformedShape) never pass the identity test; geometry is irrelevant
             // Box.Center / OuterRadius (Box.cs:46-50): Min + (Max-Min)*0.5 ; |Min - Center|
             float c[3], dlt[3];
@@ -1602,7 +1611,7 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
             for (uint32_t k = 0; k < n.b; k++) {
                 ptgpu_shape sh = s->shapes[s->leafItems[(n.a >> 2) + k]];
                 if (sh.type == PTGPU_TRANSFORMED) sh = s->shapes[s->instances[sh.data].shape];
-                const int kind = sh.type == PTGPU_MESH ? 0 : sh.type == PTGPU_SDF ? 1 : sh.type == PTGPU_VOLUME ? 2 : -1;
+                const int kind = (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) ? 0 : sh.type == PTGPU_SDF ? 1 : sh.type == PTGPU_VOLUME ? 2 : -1;
                 if (kind >= 0) { deferred++; ctx->hasKind[kind] = true; }
             }
         }

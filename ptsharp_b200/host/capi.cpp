@@ -91,6 +91,7 @@ int pth_mesh_op(pth_world* w, int shape, int op, const double* a) {
 // Triangles of a Mesh (V, N, T: 9 floats per triangle each; null = only count them).
 int pth_mesh_get(pth_world* w, int shape, float* V, float* N, float* T) {
     Mesh* m = dynamic_cast<Mesh*>(w->shapes[(size_t)shape].get());
+    if (!m) if (auto* sh = dynamic_cast<SphericalHarmonic*>(w->shapes[(size_t)shape].get())) m = sh->mesh.get();  // its marching-cubes mesh
     if (!m) { w->error = "pth_mesh_get: shape is not a Mesh"; return -1; }
     for (size_t i = 0; i < m->Triangles.size(); i++) {
         const Triangle& t = m->Triangles[i];
@@ -114,6 +115,22 @@ int pth_sdf_combine(pth_world* w, int op, int n, const int* items) {
     for (int i = 0; i < n; i++) v.push_back(w->sdfs[(size_t)items[i]]);
     return pushSdf(w, op == 0 ? NewUnionSDF(v) : op == 1 ? NewDifferenceSDF(v) : NewIntersectionSDF(v));
 }
+// MC.NewSDFMesh (MC.cs:9-66): the marching-cubes mesh of an SDF over a box; mat >= 0: Mesh.SetMaterial afterwards (the reference leaves
+// `new Material()` on every triangle).  SphericalHarmonic.NewSphericalHarmonic (SH.cs:14-22); step <= 0: the reference's 0.01F.
+int pth_mc_mesh(pth_world* w, int sdf, const double* bmin, const double* bmax, double step, int mat) {
+    try {
+        auto m = MC::NewSDFMesh(w->sdfs[(size_t)sdf], Box(V3(bmin), V3(bmax)), step);
+        if (mat >= 0) m->SetMaterial(w->materials[(size_t)mat]);
+        return push(w, m);
+    } catch (const std::exception& e) { w->error = e.what(); return -1; }
+}
+int pth_spherical_harmonic(pth_world* w, int l, int m, int pm, int nm, double step) {
+    try {
+        return push(w, SphericalHarmonic::NewSphericalHarmonic(l, m, w->materials[(size_t)pm], w->materials[(size_t)nm], step > 0 ? step : (double)0.01f));
+    } catch (const std::exception& e) { w->error = e.what(); return -1; }
+}
+int pth_mc_case(int index, int* out15) { return MC::CaseTriangles(index, out15); }
+int pth_mc_edges(int index) { return MC::CaseEdges(index); }
 int pth_sdf_shape(pth_world* w, int sdf, int mat) { return push(w, SDFShape::NewSDFShape(w->sdfs[(size_t)sdf], w->materials[(size_t)mat])); }
 int pth_volume(pth_world* w, const double* bmin, const double* bmax, int W, int H, int D, double zscale, const double* data, int nwin,
                const double* lo, const double* hi, const int* mats) {

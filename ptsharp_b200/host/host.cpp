@@ -660,14 +660,15 @@ void FlatScene::Bind(uint32_t sceneTree, uint32_t numSceneShapes) {
     v.numMaterials = (uint32_t)materials.size(); v.materials = materials.data();
     v.numTextures = (uint32_t)textures.size(); v.textures = textures.data();
     v.numTexels = texels.size() / 4; v.texels = texels.data();
+    v.numShs = (uint32_t)shs.size(); v.shs = shs.data();
     v.envColor[0] = env[0]; v.envColor[1] = env[1]; v.envColor[2] = env[2];
     v.envTexture = envTex; v.envTextureAngle = envAngle;
 }
 
-// Flat-scene file: "PTFS", format version, ABI version, the scalar header, then the 21 arrays in header
+// Flat-scene file: "PTFS", format version, ABI version, the scalar header, then the 22 arrays in header
 // order as (u64 count, u32 element size, bytes).  Little-endian, the in-memory layout of include/ptgpu.h.
 namespace {
-constexpr uint32_t kFlatMagic = 0x53465450u, kFlatFormat = 1;
+constexpr uint32_t kFlatMagic = 0x53465450u, kFlatFormat = 2;  // 2: texels as doubles, SphericalHarmonic shapes
 template <class T> void put_vec(std::FILE* f, const std::vector<T>& v) {
     const uint64_t n = v.size(); const uint32_t es = (uint32_t)sizeof(T);
     if (std::fwrite(&n, 8, 1, f) != 1 || std::fwrite(&es, 4, 1, f) != 1 || (n && std::fwrite(v.data(), sizeof(T), n, f) != n)) throw std::runtime_error("flat scene: write failed");
@@ -682,7 +683,7 @@ template <class T> void get_vec(std::FILE* f, std::vector<T>& v) {
 template <class F> void each_array(FlatScene& s, F&& fn) {
     fn(s.shapes); fn(s.lights); fn(s.trees); fn(s.nodes); fn(s.leafItems); fn(s.spheres); fn(s.cubes); fn(s.planes); fn(s.cylinders); fn(s.meshes);
     fn(s.triGeom); fn(s.triShade); fn(s.instances); fn(s.sdfShapes); fn(s.sdfOps); fn(s.volumes); fn(s.volumeWindows); fn(s.volumeData);
-    fn(s.materials); fn(s.textures); fn(s.texels);
+    fn(s.materials); fn(s.textures); fn(s.texels); fn(s.shs);
 }
 }  // namespace
 void SaveFlatScene(const FlatScene& scene, const std::string& path) {
@@ -721,7 +722,7 @@ uint64_t FlatScene::Bytes() const {
     auto sz = [](const auto& v) { return (uint64_t)v.size() * sizeof(v[0]); };
     return sz(shapes) + sz(lights) + sz(trees) + sz(nodes) + sz(leafItems) + sz(spheres) + sz(cubes) + sz(planes) + sz(cylinders) +
            sz(meshes) + sz(triGeom) + sz(triShade) + sz(instances) + sz(sdfShapes) + sz(sdfOps) + sz(volumes) + sz(volumeWindows) +
-           sz(volumeData) + sz(materials) + sz(textures) + sz(texels);
+           sz(volumeData) + sz(materials) + sz(textures) + sz(texels) + sz(shs);
 }
 
 namespace {
@@ -781,7 +782,8 @@ struct Flattener {
         f.trees.push_back(pt);
         return (uint32_t)f.trees.size() - 1;
     }
-    uint32_t MeshId(const Mesh* m) {
+    // anonymous: the triangles' own materials are never looked at (SphericalHarmonic: the Hit names the solid, SH.cs:54) - keep them out of materials[]
+    uint32_t MeshId(const Mesh* m, bool anonymous = false) {
         auto it = meshIds.find(m);
         if (it != meshIds.end()) return it->second;
         if (!m->tree) throw std::runtime_error("Mesh not compiled: call Scene.Compile() first");
@@ -794,7 +796,7 @@ struct Flattener {
             ptgpu_tri_shade s;
             put3(s.n1, t.N1); put3(s.n2, t.N2); put3(s.n3, t.N3);
             s.t1[0] = t.T1.x; s.t1[1] = t.T1.y; s.t2[0] = t.T2.x; s.t2[1] = t.T2.y; s.t3[0] = t.T3.x; s.t3[1] = t.T3.y;
-            s.material = MaterialId(t.Mat);
+            s.material = anonymous ? -1 : MaterialId(t.Mat);
             f.triShade.push_back(s);
         }
         pm.tree = AddTree(*m->tree, pm.triFirst);
@@ -857,6 +859,13 @@ struct Flattener {
                 f.volumeData.insert(f.volumeData.end(), q->Data.begin(), q->Data.end());
                 put3(d.bmin, q->box.Min); put3(d.bmax, q->box.Max);
                 ps.data = (uint32_t)f.volumes.size(); f.volumes.push_back(d); break;
+            }
+            case PTGPU_SH: {
+                auto* q = static_cast<const SphericalHarmonic*>(s);
+                ptgpu_sh d; std::memset(&d, 0, sizeof(d));
+                d.l = q->L; d.m = q->M; d.mesh = MeshId(q->mesh.get(), true);
+                d.positiveMaterial = MaterialId(q->PositiveMaterial); d.negativeMaterial = MaterialId(q->NegativeMaterial);
+                ps.data = (uint32_t)f.shs.size(); f.shs.push_back(d); break;
             }
             default: throw std::runtime_error("unknown shape type");
         }

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -212,6 +213,27 @@ struct SDFShape : IShape {  // SDF.cs:12-110
     Material MaterialAt(const Vector&) const override { return Mat; }
 };
 
+// Marching cubes (MC.cs) - host/mc.cpp.  The triangles come out in the reference's order.
+struct MC {
+    static std::shared_ptr<Mesh> NewSDFMesh(const SDFPtr& sdf, const Box& box, double step);                                              // MC.cs:9-66
+    static std::shared_ptr<Mesh> NewFieldMesh(const std::function<double(const Vector&)>& evaluate, const Box& box, double step);        // the same loop over any field
+    static int CaseTriangles(int index, int out15[15]);  // triangleTable[index] (MC.cs:168-429): returns the triangle count
+    static int CaseEdges(int index);                     // edgetable[index] (MC.cs:135-166)
+};
+struct SphericalHarmonic : IShape {  // SH.cs:7-104
+    int L = 0, M = 0;
+    Material PositiveMaterial, NegativeMaterial;
+    std::shared_ptr<Mesh> mesh;
+    static ShapePtr NewSphericalHarmonic(int l, int m, const Material& pm, const Material& nm, double step = (double)0.01f);
+    int Type() const override { return PTGPU_SH; }
+    bool IsClass() const override { return true; }
+    void Compile() override { mesh->Compile(); }
+    Box BoundingBox() const override { return Box(Vector(-1, -1, -1), Vector(1, 1, 1)); }
+    Material MaterialAt(const Vector& p) const override;
+    double EvaluateHarmonic(const Vector& p) const;
+    double Evaluate(const Vector& p) const;
+};
+
 struct Volume : IShape {  // Volume.cs
     struct VolumeWindow { double Lo, Hi; Material VolumeWindowMaterial; };
     int W = 0, H = 0, D = 0; double ZScale = 1;
@@ -291,6 +313,7 @@ struct FlatScene {
     std::vector<ptgpu_sdf_op> sdfOps;
     std::vector<ptgpu_volume> volumes;
     std::vector<ptgpu_volume_window> volumeWindows;
+    std::vector<ptgpu_sh> shs;
     std::vector<double> volumeData;
     std::vector<ptgpu_material> materials;
     std::vector<ptgpu_texture> textures;

@@ -25,9 +25,9 @@ def test_header_symbols_are_exported(bindings):
 
 ABI_STRUCTS = ["ptgpu_params", "ptgpu_pass", "ptgpu_camera", "ptgpu_counters", "ptgpu_flat_scene", "ptgpu_node", "ptgpu_tree", "ptgpu_shape",
                "ptgpu_sphere", "ptgpu_cube", "ptgpu_plane", "ptgpu_cylinder", "ptgpu_mesh", "ptgpu_tri_geom", "ptgpu_tri_shade",
-               "ptgpu_instance", "ptgpu_sdf_op", "ptgpu_sdf_shape", "ptgpu_volume_window", "ptgpu_volume", "ptgpu_material", "ptgpu_texture"]
+               "ptgpu_instance", "ptgpu_sdf_op", "ptgpu_sdf_shape", "ptgpu_volume_window", "ptgpu_volume", "ptgpu_material", "ptgpu_texture", "ptgpu_sh"]
 # what a plain C compiler (hence a P/Invoke [StructLayout(LayoutKind.Sequential)] mirror) lays out for include/ptgpu.h
-ABI_SIZES = [56, 168, 72, 176, 376, 16, 32, 16, 32, 24, 24, 24, 16, 48, 64, 272, 136, 32, 24, 64, 96, 16]
+ABI_SIZES = [56, 168, 72, 176, 392, 16, 32, 16, 32, 24, 24, 24, 16, 48, 64, 272, 136, 32, 24, 64, 96, 16, 32]
 
 
 def test_struct_layouts_match_header(bindings, tmp_path):

@@ -1022,3 +1022,48 @@ def test_volume_hits_refinement_and_empty_space_skipping(orc, bindings, device):
     finally:
         arbiter.close()
     _replay_check(orc, device, hw, ow, 128, 96, frac=2e-3)
+
+
+def test_marching_cubes_mesh_and_spherical_harmonic_render_like_the_oracle(orc, bindings, device):
+    """SURVEY 8f rank 4, second half.  (1) MC.NewSDFMesh of a carved SDF (host/mc.cpp) on the device vs the oracle given the same
+    triangles as a plain Mesh: closest hits bit for bit.  (2) SphericalHarmonic (SH.cs): Intersect walks the marching-cubes mesh but
+    the Hit names the solid - NormalAt is the gradient of |p| - |Y(p/|p|)|, MaterialAt the sign of Y, `inside` is forced false
+    (Hit.cs:41-47): closest hits incl. normals and materials bit for bit, directly and under a TransformedShape, then a keyed replay."""
+    from ptsharp_b200 import hostmath as hm
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    sdf = hw.sdf_difference([hw.sdf_intersection([hw.sdf_sphere(0.8), hw.sdf_cube((1.2, 1.2, 1.2))]), hw.sdf_cylinder(0.3, 2.0)])
+    gm = lambda w: w.GlossyMaterial((0.7, 0.8, 0.3), 1.4, 0.1)
+    m = hw.mc_mesh(sdf, (-1, -1, -1), (1, 1, 1), 0.04, gm(hw))
+    V, N, T = hw.mesh_triangles(m)
+    assert V.shape[0] > 5000
+    om = ow.mesh(V, gm(ow), N=N, T=T)
+    sh_args = []
+    for w in (hw, ow):
+        pm, nm = w.GlossyMaterial((0.9, 0.3, 0.2), 1.4, 0.1), w.DiffuseMaterial((0.2, 0.4, 0.9))
+        if w is hw:
+            s1 = w.spherical_harmonic(3, 2, pm, nm, 0.03); s2 = w.spherical_harmonic(4, -1, pm, nm, 0.04)
+            sh_args = [w.mesh_triangles(s1)[0], w.mesh_triangles(s2)[0]]
+        else:
+            s1 = w.spherical_harmonic(3, 2, pm, nm, sh_args[0]); s2 = w.spherical_harmonic(4, -1, pm, nm, sh_args[1])
+        w.add(w.transformed(m if w is hw else om, hm.translate(hm.vec((-2.2, 0, 0)))))
+        w.add(s1)
+        w.add(w.transformed(s2, hm.mul(hm.translate(hm.vec((2.3, 0.2, 0.1))), hm.mul(hm.rotate((0, 1, 0), 0.5), hm.scale(hm.vec((1.2, 0.9, 1.1)))))))
+        w.add(w.plane((0, 0, -1.1), (0, 0, 1), w.DiffuseMaterial((0.8, 0.8, 0.8))))
+        w.add(w.sphere((1, -3, 5), 0.8, w.LightMaterial((1, 1, 1), 60)))
+        w.look_at((0.3, -6.5, 2.0), (0, 0, 0), (0, 0, 1), 42)
+        w.sampler(1, 3)
+    device.upload(hw)
+    o, d = _ray_batch(ow, W=192, H=108, n_secondary=20000, seed=41)
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    assert (c["shape"] == 0).sum() > 1000 and (c["shape"] == 1).sum() > 300 and (c["shape"] == 2).sum() > 300
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["prim"], c["prim"])      # the triangle for the mesh, -1 for the harmonic solids
+    assert (c["prim"][c["shape"] == 1] == -1).all() and (c["prim"][c["shape"] == 0] >= 0).all()
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["inside"], c["inside"])
+    np.testing.assert_array_equal(g["material"], c["material"])
+    assert len(np.unique(c["material"][c["shape"] == 1])) == 2  # both lobes' materials
+    _replay_check(orc, device, hw, ow, 160, 90, frac=2e-3)
