@@ -165,6 +165,13 @@ struct DScene {
     // Derived at upload for mesh trees (see "mesh traversal" below):
     const uint4* meshNodes;         // 4 x uint4 per node: reference kd nodes, bounds-only nodes and micro leaves (see mesh_step)
     const float4* instBounds;       // 2 x float4 per TransformedShape of a Mesh: padded WORLD-space bounds of the instance (FP32 pre-test)
+    // Scene.tree level: which of the first kMaskShapes scene shapes a ray still has to evaluate (see "candidate mask" at scene_advance)
+    const uint4* sceneLeafMask;     // 2 x uint4 per Scene.tree node (node - root): the shapes in the leaf; bit 255 = it holds shapes >= kMaskShapes
+    const float4* candBlocks;       // 2 x float4 per block of up to 16 instanced meshes: union of their instBounds; lo.w = first member, hi.w = count
+    const float4* candMembers;      // 2 x float4 per member: its instBounds; lo.w = index in Scene.Shapes
+    uint32_t numCandBlocks;
+    uint32_t maskOn;                // 0: Scene.tree repeats (almost) nothing - the mask would only cost its own upkeep
+    uint32_t maskBase[8];           // bits of the scene shapes no bounds test can drop (everything but instanced meshes) + bit 255
     const float4* leafGeom;         // 3 x float4 per leaf triangle in sorted order: (V1, triangle id) (e1, position in the leaf) (e2, -)
     const VolBlocks* volBlocks;     // per Volume: where its table of block maxima sits in volBlockMax (see vol_skip)
     const double* volBlockMax;
@@ -1077,8 +1084,8 @@ enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST
 // Work items of the three kinds share one queue; the kind sits in the top two bits of the item's root word and every consumer
 // kernel takes the items of its kind.
 static constexpr uint32_t kItemKindShift = 30u, kItemMesh = 0u, kItemSdf = 1u, kItemVolume = 2u, kItemIndexMask = (1u << 30) - 1u;
-// Per ray of the launch: what a ray that waits for a deferred shape carries from one scene_advance round to the next.  One 96-byte
-// record (three 32-byte sectors): the rays of a RESUME round are a scattered subset of the launch, so their state is gathered, and
+// Per ray of the launch: what a ray that waits for a deferred shape carries from one scene_advance round to the next.  One 128-byte
+// record (four 32-byte sectors): the rays of a RESUME round are a scattered subset of the launch, so their state is gathered, and
 // fourteen separate arrays cost fourteen sector reads per ray (ncu on the instanced scene: 250 B of DRAM traffic per resumed ray).
 struct alignas(32) RayState {
     double bestT, bestTInner;                                   // running Hit of Scene.tree's traversal
@@ -1086,9 +1093,9 @@ struct alignas(32) RayState {
     double scTmin, scTmax;
     uint32_t sPos, sEnd, curShape; int32_t curInst;             // position in the current scene leaf
     double mBest; int32_t mPrim; int32_t pad0;                  // Hit of the pending deferred Intersect (written by k_mesh / k_march)
-    uint32_t pad1[4];
+    uint32_t mask[8];                                           // candidate mask: scene shapes the ray still has to evaluate
 };
-static_assert(sizeof(RayState) == 96, "RayState is three sectors");
+static_assert(sizeof(RayState) == 128, "RayState is four sectors");
 struct SplitState {
     RayState* state;                                                            // [ray]
     uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
@@ -1124,8 +1131,19 @@ PT_D void mesh_walk_single(const DScene& S, V3 co, V3 cd, uint32_t root, double 
     }
 }
 
-PT_D void save_ray_state(RayState* p, const HitRec& best, const KdCursor& sc, uint32_t sPos, uint32_t sEnd, uint32_t curShape, int32_t curInst) {
-    uint4* rs = reinterpret_cast<uint4*>(p);  // four 128-bit stores; the fifth quad (mBest, mPrim) belongs to the consumer kernel
+#ifndef PT_SCENE_MASK
+#define PT_SCENE_MASK (!PT_NO_CULL)   // candidate mask + mailboxing at the Scene.tree level (see scene_advance)
+#endif
+static constexpr uint32_t kMaskShapes = 255u;  // scene shapes with a bit of their own; bit 255 stands for all the others
+static constexpr int kSceneBlock = 128;        // threads per block of every kernel that runs scene_advance (the mask sits in shared memory, one column per thread)
+PT_D void save_ray_state(RayState* p, const HitRec& best, const KdCursor& sc, uint32_t sPos, uint32_t sEnd, uint32_t curShape, int32_t curInst, const uint32_t* mk) {
+    uint4* rs = reinterpret_cast<uint4*>(p);  // six 128-bit stores; the fifth quad (mBest, mPrim) belongs to the consumer kernel
+#if PT_SCENE_MASK
+    if (mk) {
+    rs[5] = make_uint4(mk[0], mk[kSceneBlock], mk[2 * kSceneBlock], mk[3 * kSceneBlock]);
+    rs[6] = make_uint4(mk[4 * kSceneBlock], mk[5 * kSceneBlock], mk[6 * kSceneBlock], mk[7 * kSceneBlock]);
+    }
+#endif
     rs[0] = make_uint4((uint32_t)__double2loint(best.t), (uint32_t)__double2hiint(best.t), (uint32_t)__double2loint(best.tInner), (uint32_t)__double2hiint(best.tInner));
     rs[1] = make_uint4((uint32_t)best.shape, (uint32_t)best.prim, sc.node, (uint32_t)sc.sp);
     rs[2] = make_uint4((uint32_t)__double2loint(sc.tmin), (uint32_t)__double2hiint(sc.tmin), (uint32_t)__double2loint(sc.tmax), (uint32_t)__double2hiint(sc.tmax));
@@ -1149,6 +1167,20 @@ enum { SCENE_START = 0, SCENE_RESUME = 1, SCENE_FINISH = 2 };
 struct NoLight { PT_D int32_t operator()(uint32_t) const { return -1; } };
 template <int MODE, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
 PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink, LightOf lightOf = LightOf()) {
+    // Candidate mask (PT_SCENE_MASK).  The reference builder puts a shape into every Scene.tree leaf its box overlaps and stops splitting
+    // at 85 % overlap, so leaves are large and repeat each other (the 200-instance scene: 501 items in 45 leaves, up to 41 per leaf, the
+    // floor cube in all of them): a camera ray ran ~200 instance pre-tests and evaluated the floor in every leaf it crossed (ncu: 23 000
+    // instructions per ray at the scene level).  Two facts make most of that a no-op: (1) a ray that misses an instanced mesh's padded
+    // world bounds gets NoHit from it wherever it meets it (the pre-test below); (2) IShape.Intersect depends on the ray and the shape
+    // only, so a second evaluation returns the Hit the first one returned, and the fold `h.T < best.T` (Tree.cs:121-125) cannot take it
+    // again - best.T only decreases (also true where the first evaluation was cut short by PT_BEST_CLIP or by a shadow ray's light).
+    // So each ray carries one bit per scene shape (the first 255; bit 255 = "the others", never cleared): set at the start for every
+    // shape but the instanced meshes, whose bits come from testing the ray against their bounds, 16 instances per block with the
+    // block's union first; cleared when the shape is evaluated.  A leaf none of whose shapes has its bit set is skipped as a whole
+    // (sceneLeafMask), otherwise its items are visited in array order as before and those without a bit are passed over.  What is
+    // evaluated, in which order, and every fold that can change best are those of the reference.
+    __shared__ uint32_t maskColumns[8 * kSceneBlock];
+    uint32_t* const mk = (PT_SCENE_MASK && S.maskOn) ? maskColumns + threadIdx.x : nullptr;
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         constexpr bool RESUME = MODE != SCENE_START;
@@ -1173,8 +1205,15 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             continue;
         }
         if (RESUME) {
-            const uint4* rs = reinterpret_cast<const uint4*>(W.state + ray);  // five 128-bit loads from three consecutive sectors
+            const uint4* rs = reinterpret_cast<const uint4*>(W.state + ray);  // seven 128-bit loads from four consecutive sectors
             const uint4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3], r4 = rs[4];
+#if PT_SCENE_MASK
+            if (mk) {
+                const uint4 r5 = rs[5], r6 = rs[6];
+                mk[0] = r5.x; mk[kSceneBlock] = r5.y; mk[2 * kSceneBlock] = r5.z; mk[3 * kSceneBlock] = r5.w;
+                mk[4 * kSceneBlock] = r6.x; mk[5 * kSceneBlock] = r6.y; mk[6 * kSceneBlock] = r6.z; mk[7 * kSceneBlock] = r6.w;
+            }
+#endif
             best.t = __hiloint2double((int)r0.y, (int)r0.x); best.tInner = __hiloint2double((int)r0.w, (int)r0.z);
             best.shape = (int32_t)r1.x; best.prim = (int32_t)r1.y; sc.node = r1.z; sc.sp = (int)r1.w;
             sc.tmin = __hiloint2double((int)r2.y, (int)r2.x); sc.tmax = __hiloint2double((int)r2.w, (int)r2.z);
@@ -1198,7 +1237,25 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             best.t = kHitInf; best.tInner = 0; best.shape = -1; best.prim = -1;
             box_intersect(sceneTree.bmin, sceneTree.bmax, o, d, sc.tmin, sc.tmax);  // Tree.cs:36-41
             if (sc.tmax < sc.tmin || sc.tmax <= 0) st = ST_FINISH;
-            else { sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE; }  // sentinel: written by scene_step with the first push
+            else {
+                sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE;  // sentinel: written by scene_step with the first push
+#if PT_SCENE_MASK
+#pragma unroll
+                for (int w = 0; w < 8; w++) if (mk) mk[w * kSceneBlock] = S.maskBase[w];
+                for (uint32_t b = 0; mk && b < S.numCandBlocks; b++) {  // the instanced meshes whose padded world bounds the ray line meets
+                    const float4 blo = __ldg(S.candBlocks + 2 * b), bhi = __ldg(S.candBlocks + 2 * b + 1);
+                    if (!box_line_hit(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, o, worldAux)) continue;
+                    const uint32_t mFirst = __float_as_uint(blo.w), mEnd = mFirst + __float_as_uint(bhi.w);
+                    for (uint32_t m = mFirst; m < mEnd; m++) {
+                        const float4 lo = __ldg(S.candMembers + 2 * m), hi = __ldg(S.candMembers + 2 * m + 1);
+                        if (box_line_hit(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, worldAux)) {
+                            const uint32_t shp = __float_as_uint(lo.w);
+                            mk[(shp >> 5) * kSceneBlock] |= 1u << (shp & 31u);
+                        }
+                    }
+                }
+#endif
+            }
         }
         for (;;) {
             if (st == ST_MESH_DONE) {  // fold the shape's Hit into the leaf's running best (Tree.cs:121-125)
@@ -1218,6 +1275,14 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             if (st == ST_SCENE_NODE) {
                 uint32_t first, count;
                 while (scene_step(S.nodes, sc, o, d, sstk, W.stackEnt, first, count) != KD_LEAF) {}
+#if PT_SCENE_MASK
+                if (mk) {   // a leaf without a shape this ray still has to evaluate: nothing in it can change best
+                    const uint4 l0 = __ldg(S.sceneLeafMask + 2 * (size_t)(sc.node - sceneTree.root)), l1 = __ldg(S.sceneLeafMask + 2 * (size_t)(sc.node - sceneTree.root) + 1);
+                    const uint32_t live = (l0.x & mk[0]) | (l0.y & mk[kSceneBlock]) | (l0.z & mk[2 * kSceneBlock]) | (l0.w & mk[3 * kSceneBlock]) |
+                                          (l1.x & mk[4 * kSceneBlock]) | (l1.y & mk[5 * kSceneBlock]) | (l1.z & mk[6 * kSceneBlock]) | (l1.w & mk[7 * kSceneBlock]);
+                    if (!live) count = 0;
+                }
+#endif
                 sPos = first; sEnd = first + count; st = ST_SCENE_LEAF;
             }
             if (st == ST_SCENE_LEAF) {
@@ -1225,6 +1290,13 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                 else {  // next shape of the leaf, in array order (Tree.cs:119-126)
                     curShape = __ldg(S.leafItems + sPos);
                     sPos++;
+#if PT_SCENE_MASK
+                    if (mk && curShape < kMaskShapes) {  // not a candidate, or evaluated in an earlier leaf: its Hit cannot change best
+                        const uint32_t word = mk[(curShape >> 5) * kSceneBlock], bit = 1u << (curShape & 31u);
+                        if (!(word & bit)) continue;
+                        mk[(curShape >> 5) * kSceneBlock] = word & ~bit;
+                    }
+#endif
                     ptgpu_shape sh = S.shapes[curShape];
                     curInst = -1; co = o; cd = d;
                     mPrim = -1;
@@ -1284,7 +1356,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.c[slot] = make_double2(tmin, tmax);
                             // a float at or below tL (object-space T of an instance is not comparable with tL: no cut-off there)
                             if (SHADOW) out.lim[slot] = (curInst < 0 && tL > 0) ? __double2float_rd(tL) : -1.0f;
-                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst);
+                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst, mk);
                             break;
                         }
                     } else if (sh.type == PTGPU_SDF || sh.type == PTGPU_VOLUME) {
@@ -1317,7 +1389,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.b[slot] = make_float4(cd.x, cd.y, cd.z, __uint_as_float((kind << kItemKindShift) | sh.data));
                             out.c[slot] = make_double2(t0, t1);
                             if (SHADOW) out.lim[slot] = -1.0f;
-                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst);
+                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst, mk);
                             break;
                         }
                     } else {

@@ -1482,6 +1482,71 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         if ((rc = upload(ctx, reinterpret_cast<const float4*>(ib.data()), (uint64_t)ib.size() / 4, &dib)) != PTGPU_OK) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
         D.instBounds = dib;
+        // Candidate mask of scene_advance: the instanced meshes among the first kMaskShapes scene shapes in Morton order of their
+        // bounds' centres, 16 to a block under the union of their bounds; every other scene shape is a candidate from the start.
+        struct Cand { uint32_t shape, inst; uint64_t key; };
+        std::vector<Cand> cands;
+        uint32_t base[8] = {0, 0, 0, 0, 0, 0, 0, 0x80000000u};
+        const ptgpu_tree& stree = s->trees[s->sceneTree];
+        auto spread = [](uint64_t v) { v &= 0x1FFFFF; v = (v | v << 32) & 0x1F00000000FFFFull; v = (v | v << 16) & 0x1F0000FF0000FFull; v = (v | v << 8) & 0x100F00F00F00F00Full;
+                                       v = (v | v << 4) & 0x10C30C30C30C30C3ull; v = (v | v << 2) & 0x1249249249249249ull; return v; };
+        for (uint32_t k = 0; k < s->numSceneShapes && k < kMaskShapes; k++) {
+            const ptgpu_shape& sh = s->shapes[k];
+            const float* b8 = sh.type == PTGPU_TRANSFORMED ? &ib[(size_t)sh.data * 8] : nullptr;
+            if (!b8 || b8[0] < -1e38f) { base[k >> 5] |= 1u << (k & 31); continue; }
+            uint64_t key = 0;
+            for (int r = 0; r < 3; r++) {
+                const double ext = std::max(1e-30, (double)stree.bmax[r] - (double)stree.bmin[r]);
+                const double u = std::min(1.0, std::max(0.0, (0.5 * ((double)b8[r] + (double)b8[4 + r]) - (double)stree.bmin[r]) / ext));
+                key |= spread((uint64_t)(u * 2097151.0)) << r;
+            }
+            cands.push_back(Cand{k, sh.data, key});
+        }
+        std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.key < b.key || (a.key == b.key && a.shape < b.shape); });
+        auto u2f = [](uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; };
+        std::vector<float> blocks, members;
+        for (size_t f0 = 0; f0 < cands.size(); f0 += 16) {
+            const size_t f1 = std::min(cands.size(), f0 + 16);
+            float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+            for (size_t m = f0; m < f1; m++) {
+                const float* b8 = &ib[(size_t)cands[m].inst * 8];
+                for (int r = 0; r < 3; r++) { lo[r] = std::min(lo[r], b8[r]); hi[r] = std::max(hi[r], b8[4 + r]); }
+                const float rec[8] = {b8[0], b8[1], b8[2], u2f(cands[m].shape), b8[4], b8[5], b8[6], 0.f};
+                members.insert(members.end(), rec, rec + 8);
+            }
+            const float rec[8] = {std::nextafter(lo[0], -INFINITY), std::nextafter(lo[1], -INFINITY), std::nextafter(lo[2], -INFINITY), u2f((uint32_t)f0),
+                                  std::nextafter(hi[0], INFINITY), std::nextafter(hi[1], INFINITY), std::nextafter(hi[2], INFINITY), u2f((uint32_t)(f1 - f0))};
+            blocks.insert(blocks.end(), rec, rec + 8);
+        }
+        D.numCandBlocks = (uint32_t)(blocks.size() / 8);
+        if (blocks.empty()) { blocks.assign(8, 0.f); members.assign(8, 0.f); }
+        const float4 *dcb = nullptr, *dcm = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(blocks.data()), (uint64_t)blocks.size() / 4, &dcb)) != PTGPU_OK) return rc;
+        if ((rc = upload(ctx, reinterpret_cast<const float4*>(members.data()), (uint64_t)members.size() / 4, &dcm)) != PTGPU_OK) return rc;
+        D.candBlocks = dcb; D.candMembers = dcm;
+        std::memcpy(D.maskBase, base, sizeof(base));
+        // per Scene.tree node: the shapes of the leaf as a mask (bit 255: it holds shapes without a bit of their own)
+        uint64_t end = s->numNodes;
+        for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > stree.root && s->trees[k].root < end) end = s->trees[k].root;
+        std::vector<uint32_t> lm((size_t)(end - stree.root) * 8, 0u);
+        for (uint64_t i = stree.root; i < end; i++) {
+            const ptgpu_node& n = s->nodes[i];
+            if ((n.a & 3u) != 0) continue;
+            uint32_t* w = &lm[(size_t)(i - stree.root) * 8];
+            for (uint32_t k = 0; k < n.b; k++) {
+                const uint32_t item = s->leafItems[(n.a >> 2) + k];
+                if (item < kMaskShapes) w[item >> 5] |= 1u << (item & 31); else w[7] |= 0x80000000u;
+            }
+        }
+        // worth its upkeep (two more quads of per-ray state, a bit test per leaf item) when the leaves repeat their shapes
+        uint64_t sceneItems = 0;
+        for (uint64_t i = stree.root; i < end; i++) if ((s->nodes[i].a & 3u) == 0) sceneItems += s->nodes[i].b;
+        static const char* maskEnv = std::getenv("PTGPU_SCENE_MASK");  // development: 0 / 1 force it off / on
+        D.maskOn = maskEnv ? (uint32_t)std::atoi(maskEnv) : (sceneItems >= 16 && 2 * sceneItems >= 3 * (uint64_t)s->numSceneShapes ? 1u : 0u);
+        const uint4* dlm = nullptr;
+        if ((rc = upload(ctx, reinterpret_cast<const uint4*>(lm.data()), (uint64_t)lm.size() / 4, &dlm)) != PTGPU_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        D.sceneLeafMask = dlm;
     }
     UP(sdfShapes, s->sdfShapes, s->numSdfShapes);
     UP(sdfOps, s->sdfOps, s->numSdfOps);
@@ -1604,6 +1669,7 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         uint64_t end = s->numNodes;
         for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > stree.root && s->trees[k].root < end) end = s->trees[k].root;
         uint64_t deferred = 0;
+        bool seen[256] = {false};
         ctx->hasKind[0] = ctx->hasKind[1] = ctx->hasKind[2] = false;
         for (uint64_t i = stree.root; i < end; i++) {
             const ptgpu_node& n = s->nodes[i];
@@ -1612,7 +1678,15 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
                 ptgpu_shape sh = s->shapes[s->leafItems[(n.a >> 2) + k]];
                 if (sh.type == PTGPU_TRANSFORMED) sh = s->shapes[s->instances[sh.data].shape];
                 const int kind = (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) ? 0 : sh.type == PTGPU_SDF ? 1 : sh.type == PTGPU_VOLUME ? 2 : -1;
-                if (kind >= 0) { deferred++; ctx->hasKind[kind] = true; }
+                if (kind >= 0) {
+                    ctx->hasKind[kind] = true;
+#if PT_SCENE_MASK
+                    const uint32_t item = s->leafItems[(n.a >> 2) + k];  // a shape with a mask bit is evaluated once per ray, whatever the number of leaves it sits in
+                    if (ctx->scene.maskOn && item < kMaskShapes) { if (!seen[item]) { seen[item] = true; deferred++; } } else deferred++;
+#else
+                    deferred++;
+#endif
+                }
             }
         }
         ctx->splitRounds = deferred <= 4 ? (int)deferred : -1;
