@@ -270,10 +270,6 @@ int ptgpu_cast_rays(ptgpu_ctx* ctx, const ptgpu_pass* pass, int32_t n, const int
 /* One draw of the keyed Philox stream (for cross-checking stream addressing). */
 int ptgpu_keyed_draw(ptgpu_ctx* ctx, uint32_t seed, uint32_t pass, uint32_t pixel, uint32_t sample, uint32_t bits,
                      uint32_t first, uint32_t depth, uint32_t sub, uint32_t drawIndex, double* out);
-/* The reciprocal form of `tsplit = (split - o) / d` used by the mesh walk (Tree.cs:86-98; kd_div in csrc/pt_device.cuh)
-   compared with the IEEE division on n operand pairs (b = float bit pattern offset + i): mismatches must come back 0. */
-int ptgpu_check_kd_div(ptgpu_ctx* ctx, uint64_t seed, uint64_t offset, uint64_t n, uint64_t* mismatches, uint64_t* fastPath);
-
 int ptgpu_get_counters(ptgpu_ctx* ctx, ptgpu_counters* out);
 int ptgpu_reset_counters(ptgpu_ctx* ctx);
 int ptgpu_set_profiling(ptgpu_ctx* ctx, int32_t on);   /* per-stage CUDA-event timing (adds syncs; off by default) */

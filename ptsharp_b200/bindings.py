@@ -65,7 +65,7 @@ class Counters(C.Structure):
 PTGPU_SYMBOLS = [
     "ptgpu_abi_version", "ptgpu_abi_sizeof", "ptgpu_create", "ptgpu_destroy", "ptgpu_last_error", "ptgpu_upload_scene", "ptgpu_scene_bytes",
     "ptgpu_render_pass", "ptgpu_accumulate_device", "ptgpu_add_sample_device", "ptgpu_read_buffer", "ptgpu_reset_buffer",
-    "ptgpu_intersect_batch", "ptgpu_cast_rays", "ptgpu_keyed_draw", "ptgpu_check_kd_div", "ptgpu_get_counters", "ptgpu_reset_counters",
+    "ptgpu_intersect_batch", "ptgpu_cast_rays", "ptgpu_keyed_draw", "ptgpu_get_counters", "ptgpu_reset_counters",
     "ptgpu_set_profiling", "ptgpu_export_buffer", "ptgpu_import_buffer",
 ]
 
@@ -98,7 +98,6 @@ def _bind_gpu(lib: C.CDLL) -> C.CDLL:
     lib.ptgpu_cast_rays.argtypes = [C.c_void_p, C.POINTER(Pass), C.c_int32, c_int_p, c_int_p, c_double_p, c_double_p,
                                     c_int_p, c_float_p, c_float_p]
     lib.ptgpu_keyed_draw.argtypes = [C.c_void_p] + [C.c_uint32] * 9 + [c_double_p]
-    lib.ptgpu_check_kd_div.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.ptgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.ptgpu_reset_counters.argtypes = [C.c_void_p]
     lib.ptgpu_set_profiling.argtypes = [C.c_void_p, C.c_int32]
@@ -443,12 +442,6 @@ class Device:
         self._ck(self.lib.ptgpu_keyed_draw(self.h, seed, pass_index, pixel, sample, bits, first, depth, sub, draw_index,
                                            C.byref(out)), "ptgpu_keyed_draw")
         return out.value
-
-    def check_kd_div(self, seed: int, offset: int, n: int):
-        """(mismatches, pairs that took the reciprocal path) of kd_div vs the IEEE division on n operand pairs."""
-        bad, fast = C.c_uint64(), C.c_uint64()
-        self._ck(self.lib.ptgpu_check_kd_div(self.h, seed, offset, n, C.byref(bad), C.byref(fast)), "ptgpu_check_kd_div")
-        return bad.value, fast.value
 
     def counters(self) -> dict:
         c = Counters()

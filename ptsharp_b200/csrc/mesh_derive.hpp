@@ -33,10 +33,7 @@
 static constexpr uint32_t kNodeVirtual = 0x80000000u, kNodeRefLeaf = 0x40000000u, kNodeIndexMask = 0x3FFFFFFFu;
 static constexpr uint32_t kRefLeaf = 1u << 29, kRefLeafRoot = 1u << 28, kRefFirstMask = (1u << 26) - 1u;
 PT_LAYOUT_HD uint32_t leaf_ref(uint32_t first, uint32_t count, bool root) { return kRefLeaf | (root ? kRefLeafRoot : 0u) | ((count - 1u) << 26) | first; }
-#ifndef PT_EXPERIMENT_BVH
-#define PT_EXPERIMENT_BVH 0   // 1 + env PTGPU_EXPERIMENT_BVH: every mesh is walked through ONE bounds-only hierarchy over all its triangles
-#endif                       // (NOT the reference's visiting order: ties and self-hits differ; a speed probe for the round-2 design)
-static constexpr int kVirtualDepthMax = PT_EXPERIMENT_BVH ? 22 : 12;  // levels of bounds-only nodes below a reference leaf (4 * 2^12 triangles)
+static constexpr int kVirtualDepthMax = 12;  // levels of bounds-only nodes below a reference leaf (4 * 2^12 triangles)
 
 // ------------------------------------------------------------------------------------------------ derivation
 struct MeshDerived {
@@ -283,73 +280,5 @@ inline bool derive_mesh(const ptgpu_flat_scene* s, MeshDerived& out, std::string
     // the roots the split tracer / trace_rays start from
     out.trees.assign(s->trees, s->trees + s->numTrees);
     for (uint32_t m = 0; m < s->numMeshes; m++) out.trees[s->meshes[m].tree].root = ref[s->trees[s->meshes[m].tree].root];
-#if PT_EXPERIMENT_BVH
-    if (std::getenv("PTGPU_EXPERIMENT_BVH")) {
-        uint64_t extraTri = 0, extraRec = 0;
-        std::vector<uint8_t> seen(s->numTrees, 0);
-        for (uint32_t m = 0; m < s->numMeshes; m++) if (!seen[s->meshes[m].tree] && s->meshes[m].triCount > 4) { seen[s->meshes[m].tree] = 1; extraTri += s->meshes[m].triCount; extraRec += virt_records(s->meshes[m].triCount); }
-        uint32_t* mn2 = static_cast<uint32_t*>(alloc((out.mnRecords + extraRec) * 64));
-        ptgpu_tri_geom* lg2 = static_cast<ptgpu_tri_geom*>(alloc((out.lgCount + extraTri) * sizeof(ptgpu_tri_geom)));
-        std::memcpy(mn2, out.mn, out.mnRecords * 64); std::memset(mn2 + out.mnRecords * 16, 0, extraRec * 64);
-        std::memcpy(lg2, out.lg, out.lgCount * sizeof(ptgpu_tri_geom));
-        uint64_t nextRec = out.mnRecords, nextTri = out.lgCount;
-        std::fill(seen.begin(), seen.end(), 0);
-        int vdepth = 0;
-        for (uint32_t m = 0; m < s->numMeshes; m++) {
-            const ptgpu_mesh& me = s->meshes[m];
-            if (seen[me.tree] || me.triCount <= 4) continue;
-            seen[me.tree] = 1;
-            const ptgpu_tree& t = s->trees[me.tree];
-            std::vector<std::pair<uint32_t, uint32_t>> order(me.triCount);
-            for (uint32_t q = 0; q < me.triCount; q++) {
-                const ptgpu_tri_geom& g = s->triGeom[me.triFirst + q];
-                uint32_t qz[3];
-                for (int c = 0; c < 3; c++) {
-                    const float v = g.v1[c] + (g.e1[c] + g.e2[c]) * (1.0f / 3.0f), e = t.bmax[c] - t.bmin[c];
-                    const float f = e > 0 ? (v - t.bmin[c]) / e : 0.f;
-                    qz[c] = (uint32_t)std::min(1023.f, std::max(0.f, f * 1023.f));
-                }
-                order[q] = {spread10(qz[0]) | (spread10(qz[1]) << 1) | (spread10(qz[2]) << 2), q};
-            }
-            std::sort(order.begin(), order.end());
-            const uint32_t t0 = (uint32_t)nextTri;
-            for (uint32_t q = 0; q < me.triCount; q++) {
-                const uint32_t tri = me.triFirst + order[q].second;
-                ptgpu_tri_geom g = s->triGeom[tri];
-                g.pad0 = bits_float(tri); g.pad1 = bits_float(order[q].second); g.pad2 = 0.f;
-                lg2[t0 + q] = g;
-            }
-            nextTri += me.triCount;
-            struct Build { uint64_t idx; uint32_t t0, t1; int depth; };
-            std::vector<Build> todo;
-            const uint64_t rootRec = nextRec++;
-            mn2[rootRec * 16 + 3] = kNodeRefLeaf;
-            todo.push_back({rootRec, t0, t0 + me.triCount, 0});
-            while (!todo.empty()) {
-                const Build bld = todo.back(); todo.pop_back();
-                vdepth = std::max(vdepth, bld.depth + 1);
-                const uint32_t cnt = bld.t1 - bld.t0, mid = bld.t0 + (cnt + 1) / 2;
-                uint32_t refs[2];
-                const uint32_t lo2[2] = {bld.t0, mid}, hi2[2] = {mid, bld.t1};
-                for (int side = 0; side < 2; side++) {
-                    const uint32_t cn = hi2[side] - lo2[side];
-                    if (cn <= 4) refs[side] = leaf_ref(lo2[side], cn, false);
-                    else { refs[side] = (uint32_t)nextRec++; todo.push_back({refs[side], lo2[side], hi2[side], bld.depth + 1}); }
-                }
-                uint32_t* o = &mn2[bld.idx * 16];
-                o[2] = refs[0] << 2; o[3] = (o[3] & kNodeRefLeaf) | kNodeVirtual | refs[1];
-                float llo[3], lhi[3], rlo[3], rhi[3];
-                padded_bounds(mid - bld.t0, [&](uint32_t q) -> const ptgpu_tri_geom& { return lg2[bld.t0 + q]; }, llo, lhi);
-                padded_bounds(bld.t1 - mid, [&](uint32_t q) -> const ptgpu_tri_geom& { return lg2[mid + q]; }, rlo, rhi);
-                const float pk[12] = {llo[0], llo[1], llo[2], lhi[0], lhi[1], lhi[2], rlo[0], rlo[1], rlo[2], rhi[0], rhi[1], rhi[2]};
-                for (int q = 0; q < 12; q++) o[4 + q] = float_bits(pk[q]);
-            }
-            out.trees[me.tree].root = (uint32_t)rootRec;
-        }
-        if (vdepth > kVirtualDepthMax) { err = "experiment: hierarchy too deep"; return false; }
-        out.mn = mn2; out.lg = lg2; out.mnRecords = nextRec; out.lgCount = nextTri;
-        std::fprintf(stderr, "derive_mesh: EXPERIMENT - meshes walked through one bounds-only hierarchy (%d levels), not the reference trees\n", vdepth);
-    }
-#endif
     return true;
 }

@@ -23,20 +23,10 @@
 #define PT_HD __host__ __device__ __forceinline__
 #define PT_DN __device__ __noinline__
 // k_shade was 215 KB of SASS with every libm call, Philox refill and texture fetch inlined at each call site, and ncu showed
-// 41 % of its stall samples in `no_instructions` (instruction-cache misses of divergent warps).  PT_COMPACT = 1 keeps ONE copy of
+// 41 % of its stall samples in `no_instructions` (instruction-cache misses of divergent warps).  The build keeps ONE copy of
 // those bodies (PT_DC = noinline, scalar arguments and results only: nothing forces a value into local memory).
-#ifndef PT_COMPACT
-#define PT_COMPACT 1
-#endif
-#if PT_COMPACT
 #define PT_DC __device__ __noinline__
-#else
-#define PT_DC __device__ __forceinline__
-#endif
 
-#ifndef PT_SHORTCUT
-#define PT_SHORTCUT 1
-#endif
 // PT_NO_CULL = 1 builds the ARBITER of every shortcut this file takes (tests/test_gpu_parity.py::test_cull_matches_no_cull): no
 // padded-bounds test ever skips a subtree, a mesh or an instance (every reference leaf is tested in full), the division-free
 // triangle filter is replaced by the reference sequence, no walk is clipped to the running best and shadow rays take the full
@@ -642,43 +632,11 @@ PT_D RayAux ray_aux(V3 o, V3 d) {
 }
 // The same slab test with fewer instructions for the mesh walk: t = lo * i - o * i by FMA, and the per-ray padding applied
 // once to the interval ends as P = pad * max|i| (>= pad * |i| on every axis: only more conservative).
-#ifndef PT_MERGED_STEP
-#define PT_MERGED_STEP 0   // 1: reference and bounds-only nodes share one instruction stream in mesh_step_t
-#endif
-#ifndef PT_RCP_DIV
-#define PT_RCP_DIV 0   // 1: tsplit of a mesh-tree step by kd_div (per-ray correctly rounded reciprocals); 0: a plain FP64 division per step
-#endif
 struct RayBox {
     float ix, iy, iz, cx, cy, cz, P;
-#if PT_RCP_DIV
-    double rx, ry, rz;  // RN(1 / (double)d) per axis (IEEE division, once per ray)
-    bool rok;           // every |d| component is a normal float: the reciprocals are finite, non-zero and normal
-#endif
 };
-// `tsplit = (split - o[axis]) / d[axis]` (Tree.cs:86-98) without a division per node.  nvcc's own div.rn.f64 fast path is
-// y = Newton-refined reciprocal, q0 = RN(a y), r = RN(a - b q0) (exact), q = RN(q0 + r y); with y = RN(1/b) that last step is
-// Markstein's correction, which returns RN(a/b) — the value the reference's double division produces — whenever nothing
-// leaves the normal range.  That is guaranteed here by construction: b is a float widened to double (24-bit significand,
-// |b| in [2^-126, 2^128) when `rok`), and the fast path is only taken for |a| in [2^-127, 2^128) (a = split - o is a difference
-// of float-valued numbers, so this is every non-zero a but subnormal-float ones), hence |q| in [2^-255, 2^255] and the residual
-// is >= 2^-310.  Everything else (a = 0, NaN, infinities, zero / subnormal direction components) takes the plain division.
-// tests/test_gpu_parity.py::test_kd_div_matches_ieee_division compares it with `/` bit for bit on 2^33 operand pairs.
-PT_D double kd_div(double a, double b, double rcp, bool rok) {
-    const uint32_t ea = ((uint32_t)__double2hiint(a) & 0x7FFFFFFFu) - 0x38000000u;  // biased exponent 896 = 2^-127
-    if (rok && ea < 0x0FF00000u) {                                                  // ... up to 1151 = 2^128 (exclusive)
-        const double q0 = a * rcp;
-        const double r = fma(-b, q0, a);
-        return fma(r, rcp, q0);
-    }
-    return a / b;
-}
 PT_D RayBox ray_box(V3 o, V3 d) {
     RayBox a;
-#if PT_RCP_DIV
-    a.rx = 1.0 / (double)d.x; a.ry = 1.0 / (double)d.y; a.rz = 1.0 / (double)d.z;
-    const float tiny = 1.17549435e-38f;  // FLT_MIN; false for NaN, true for inf -> checked with the upper bound
-    a.rok = fabsf(d.x) >= tiny && fabsf(d.y) >= tiny && fabsf(d.z) >= tiny && fabsf(d.x) < INFINITY && fabsf(d.y) < INFINITY && fabsf(d.z) < INFINITY;
-#endif
     a.ix = 1.0f / d.x; a.iy = 1.0f / d.y; a.iz = 1.0f / d.z;
     a.cx = o.x * a.ix; a.cy = o.y * a.iy; a.cz = o.z * a.iz;  // NaN when o = 0 and d = 0 on an axis: the min/max below ignore NaNs
     const float pad = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
@@ -770,25 +728,6 @@ struct PtrStack {
     PT_D void reset() {}
     PT_D void shrink(int) {}
 };
-// HybridStack<N>: the top (up to) N entries in shared memory, older ones spilled to the thread's local array.  ncu on the
-// all-local version of k_mesh: the interleaved local layout turns one lane's 16-byte entry into four 4-byte sector touches, the
-// stack made 52 % of the kernel's L1 sector traffic and 40 % of its pops missed L1 (a pop is on the ray's critical path).
-// Invariant: entry j lives in shared slot j % N for lo < j <= sp (sp - lo <= N), in loc[j] for j <= lo.
-template <int N>
-struct HybridStack {
-    uint4* sh;      // this thread's slot 0; slots are `stride` uint4 apart (one row of the block per slot)
-    uint4* loc;
-    int stride;
-    int lo;
-    PT_D uint4 get(int i) const { return i > lo ? sh[(i % N) * stride] : loc[i]; }
-    PT_D void put(int i, const uint4& v) {  // i == sp + 1 (push) or 0 after reset()
-        if (i - lo > N) { loc[lo + 1] = sh[((lo + 1) % N) * stride]; lo++; }
-        sh[(i % N) * stride] = v;
-    }
-    PT_D void reset() { lo = -1; }
-    PT_D void shrink(int sp) { lo = min(lo, sp); }  // after pops: keeps sp - lo >= 0 so a later push lands above lo
-};
-
 // Resume the nearest pending far child that can still hold a closer hit.  False = traversal finished.
 template <class Stk>
 PT_D bool mesh_pop_t(KdCursor& c, double bestT, Stk& stk) {
@@ -876,39 +815,6 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
                                   __uint_as_float(q3.w), ra, tnR);
     const uint32_t left = a >> 2, right = b & kNodeIndexMask;
     bool go;
-#if PT_MERGED_STEP
-    // One instruction stream for both node kinds (the lanes of a NODE turn hold reference and bounds-only nodes side by side, and
-    // two branches would each be issued for the whole warp).  A bounds-only node is the "both children" case of Node.Intersect with
-    // near / far in place of first / second, the far child's entry bound in place of tsplit, and tmin / tmax left alone; its lanes
-    // run the reference arithmetic on whatever q0 holds and drop the result in the selects below.
-    const bool isRef = axis != 0;
-    const double split = __hiloint2double((int)q0.y, (int)q0.x);
-    const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-#if PT_RCP_DIV
-    const double tsplit = kd_div(split - oa, da, axis == 1 ? ra.rx : (axis == 2 ? ra.ry : ra.rz), ra.rok);
-#else
-    const double tsplit = (split - oa) / da;
-#endif
-    // bounds-only: a child with best.T <= tn cannot improve or tie the running best (see the comment in the other variant)
-    hitL = hitL && (isRef || !(bestT <= (double)tnL));
-    hitR = hitR && (isRef || !(bestT <= (double)tnR));
-    const bool leftFirst = isRef ? ((oa < split) || (oa == split && da <= 0)) : !(tnR < tnL);
-    const uint32_t first = leftFirst ? left : right, second = leftFirst ? right : left;
-    const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
-    const double key = isRef ? tsplit : (double)(leftFirst ? tnR : tnL);
-    const bool onlyFirst = isRef && (tsplit > c.tmax || tsplit <= 0);
-    const bool onlySecond = isRef && !onlyFirst && tsplit < c.tmin;
-    const bool both = !onlyFirst && !onlySecond;
-    const bool skipFirst = both && !hitFirst;                          // the near child returns NoHit: what the pop of (second, key) would do
-    const bool resume = skipFirst && hitSecond && !(bestT <= key);
-    if (both && hitFirst && (isRef || hitSecond)) { c.sp++; stk.put(c.sp, stk_entry(key, second, hitSecond ? 0u : 1u)); }
-    c.node = (onlySecond || skipFirst) ? second : first;
-    go = onlyFirst ? hitFirst : (onlySecond ? hitSecond : (skipFirst ? resume : true));
-    if (isRef) {
-        if (resume) { c.tmin = key; c.tmax = netmin_best(c.tmax, bestT); }
-        else if (both && hitFirst) c.tmax = key;
-    }
-#else
     if (axis == 0) {
         // bounds-only node.  tn* are strict lower bounds of the T of any triangle below the child (the padded box contains
         // the triangles with a margin far above the FP32 error of the triangle test), so a child with best.T <= tn cannot
@@ -925,17 +831,13 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
     } else {
         const double split = __hiloint2double((int)q0.y, (int)q0.x);
         const double oa = (double)vaxis(o, axis), da = (double)vaxis(d, axis);
-#if PT_RCP_DIV
-        const double tsplit = kd_div(split - oa, da, axis == 1 ? ra.rx : (axis == 2 ? ra.ry : ra.rz), ra.rok);
-#else
         const double tsplit = (split - oa) / da;
-#endif
         const bool leftFirst = (oa < split) || (oa == split && da <= 0);
         const uint32_t first = leftFirst ? left : right, second = leftFirst ? right : left;
         const bool hitFirst = leftFirst ? hitL : hitR, hitSecond = leftFirst ? hitR : hitL;
         if (tsplit > c.tmax || tsplit <= 0) { c.node = first; go = hitFirst; }
         else if (tsplit < c.tmin) { c.node = second; go = hitSecond; }
-        else if (PT_SHORTCUT && !hitFirst) {
+        else if (!hitFirst) {
             // the near child returns NoHit: what the pop of (second, tsplit) would do, without the stack round trip
             if (bestT <= tsplit || !hitSecond) go = false;
             else { c.node = second; c.tmin = tsplit; c.tmax = netmin_best(c.tmax, bestT); go = true; }
@@ -947,7 +849,6 @@ PT_D int mesh_step_t(const uint4* __restrict__ nodes, const RayBox& ra, KdCursor
             go = hitFirst;
         }
     }
-#endif
     if (go) return MESH_INTERIOR;
     return mesh_pop_t(c, bestT, stk) ? MESH_INTERIOR : MESH_DONE;
 }
@@ -971,56 +872,6 @@ PT_D void leaf_work(const DScene& S, V3 o, V3 d, uint32_t& tPos, uint32_t tEnd, 
         }
         tPos++;
     }
-}
-
-// The triangle tests of every lane that sits in a micro leaf, spread over ALL lanes of the warp.  ncu on the per-lane
-// leaf loop: 40 % of k_mesh's issued instructions were leaf / triangle code running at 8-9 of 32 lanes (a third of the warp
-// is in a leaf at a time, and a lane with 2 triangles idles while its neighbour tests 4).  Here the (lane, triangle) pairs
-// of the warp are numbered 0 .. total-1 (prefix sum of the per-lane counts, <= 4 each, from three ballots); in round r lane
-// j tests pair 32 r + j: it finds the owner lane by bisection on the inclusive prefix (5 shuffles), pulls the owner's ray
-// with 6 shuffles and runs the unchanged triangle test; the rare hits go back to their owners one by one.  The result per
-// ray is the lexicographic minimum of (T, position in the reference leaf) over its micro leaf and the running best - what
-// the in-order loop of leaf_work gives (Tree.cs:119-126: strict <, first shape in array order wins a tie).
-PT_D void coop_leaf(const DScene& S, bool inLeaf, V3 co, V3 cd, uint32_t& tPos, uint32_t tEnd, double& best, int32_t& prim, uint32_t& bestPos) {
-    const unsigned full = 0xFFFFFFFFu;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t cnt = inLeaf ? (tEnd - tPos) : 0u;  // 0..4
-    const unsigned b0 = __ballot_sync(full, cnt & 1u), b1 = __ballot_sync(full, cnt & 2u), b2 = __ballot_sync(full, cnt & 4u);
-    const unsigned lt = (1u << lane) - 1u;
-    const uint32_t excl = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
-    const uint32_t incl = excl + cnt;
-    const uint32_t total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
-#pragma unroll 1
-    for (uint32_t base = 0; base < total; base += 32u) {  // warp-uniform
-        const uint32_t u = base + lane;
-        int owner = 0;  // first lane whose inclusive prefix exceeds u
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            const uint32_t v = __shfl_sync(full, incl, owner + step - 1);
-            if (v <= u) owner += step;
-        }
-        const uint32_t oExcl = __shfl_sync(full, excl, owner), oPos = __shfl_sync(full, tPos, owner);
-        const V3 o = v3(__shfl_sync(full, co.x, owner), __shfl_sync(full, co.y, owner), __shfl_sync(full, co.z, owner));
-        const V3 d = v3(__shfl_sync(full, cd.x, owner), __shfl_sync(full, cd.y, owner), __shfl_sync(full, cd.z, owner));
-        double t = kHitInf;
-        uint32_t hitPos = 0, hitTri = 0;
-        if (u < total) {
-            const float4* g = S.leafGeom + (size_t)(oPos + (u - oExcl)) * 3;
-            DBG_ADD(4, 1);
-            t = triangle_intersect(g, o, d);
-            if (t < kHitInf) { hitTri = __float_as_uint(__ldg(g).w); hitPos = __float_as_uint(__ldg(g + 1).w); }  // rare
-        }
-        unsigned cand = __ballot_sync(full, t < kHitInf);  // a T of INF never replaces NoHit
-        while (cand) {                                     // warp-uniform: ~2 hits per 32 tests
-            const int w = __ffs(cand) - 1;
-            cand &= cand - 1u;
-            const int ow = __shfl_sync(full, owner, w);
-            const double tw = __hiloint2double(__shfl_sync(full, __double2hiint(t), w), __shfl_sync(full, __double2loint(t), w));
-            const uint32_t pw = __shfl_sync(full, hitPos, w), iw = __shfl_sync(full, hitTri, w);
-            if ((int)lane == ow && tw <= best && (tw < best || pw < bestPos)) { best = tw; prim = (int32_t)iw; bestPos = pw; }
-        }
-    }
-    if (inLeaf) tPos = tEnd;
 }
 
 // The analytic subset (the split tracer is only used for scenes without SDFShape / Volume).
@@ -1240,19 +1091,23 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             else {
                 sc.node = sceneTree.root; sc.sp = 0; st = ST_SCENE_NODE;  // sentinel: written by scene_step with the first push
 #if PT_SCENE_MASK
+                if (mk) {
 #pragma unroll
-                for (int w = 0; w < 8; w++) if (mk) mk[w * kSceneBlock] = S.maskBase[w];
-                for (uint32_t b = 0; mk && b < S.numCandBlocks; b++) {  // the instanced meshes whose padded world bounds the ray line meets
+                for (int w = 0; w < 8; w++) mk[w * kSceneBlock] = S.maskBase[w];
+                const RayBox worldBox = ray_box(o, d);
+                float tnear;
+                for (uint32_t b = 0; b < S.numCandBlocks; b++) {  // the instanced meshes whose padded world bounds the ray line meets
                     const float4 blo = __ldg(S.candBlocks + 2 * b), bhi = __ldg(S.candBlocks + 2 * b + 1);
-                    if (!box_line_hit(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, o, worldAux)) continue;
+                    if (!box_line_hit_fast(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z, worldBox, tnear)) continue;
                     const uint32_t mFirst = __float_as_uint(blo.w), mEnd = mFirst + __float_as_uint(bhi.w);
                     for (uint32_t m = mFirst; m < mEnd; m++) {
                         const float4 lo = __ldg(S.candMembers + 2 * m), hi = __ldg(S.candMembers + 2 * m + 1);
-                        if (box_line_hit(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, worldAux)) {
+                        if (box_line_hit_fast(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, worldBox, tnear)) {
                             const uint32_t shp = __float_as_uint(lo.w);
                             mk[(shp >> 5) * kSceneBlock] |= 1u << (shp & 31u);
                         }
                     }
+                }
                 }
 #endif
             }
@@ -1408,26 +1263,8 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
 }
 
 // Mesh.Intersect for every work item of `q`; the Hit goes to W.mBest / W.mPrim of the item's ray.
-#ifndef PT_COOP_LEAF
-#define PT_COOP_LEAF 0       // 1: the triangle tests of a LEAF turn are spread over all lanes of the warp (coop_leaf)
-#endif
-#ifndef PT_COOP_LEAF_MIN
-#define PT_COOP_LEAF_MIN 5   // run a LEAF turn once this many lanes sit in a micro leaf (or no lane is walking nodes)
-#endif
-#ifndef PT_TURN_RULE
-#define PT_TURN_RULE 0    // which class a warp of mesh_walk runs next: 0 the larger one; 1 LEAF once PT_LEAF_MIN lanes wait in a micro leaf; 2 NODE while PT_NODE_MIN lanes walk nodes
-#endif
-#ifndef PT_LEAF_MIN
-#define PT_LEAF_MIN 8
-#endif
-#ifndef PT_NODE_MIN
-#define PT_NODE_MIN 8
-#endif
-#ifndef PT_SMEM_STACK
-#define PT_SMEM_STACK 0   // entries of the walk's kd stack kept in shared memory per thread (0 = all in local memory)
-#endif
 template <bool ANYHIT>
-PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor, uint4* smem) {
+PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
     float anyLim = -1.0f;  // ANYHIT (shadow rays): stop at the first Hit below it
     const uint32_t n = *q.count;
     int st = ST_IDLE;
@@ -1436,11 +1273,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
     RayBox ra = ray_box(co, cd);
     KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
     uint4 mLoc[kMeshStackEnt];
-#if PT_SMEM_STACK > 0
-    HybridStack<PT_SMEM_STACK> mStk{smem + threadIdx.x, mLoc, (int)blockDim.x, -1};
-#else
     PtrStack mStk{mLoc};
-#endif
     uint32_t tPos = 0, tEnd = 0, mBestPos = 0;
     double mBest = kHitInf;
     int32_t mPrim = -1;
@@ -1478,8 +1311,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                     st = ST_MESH_NODE;
                 }
             }
-        } else if (PT_COOP_LEAF ? !(nLeaf >= PT_COOP_LEAF_MIN || nNode == 0)
-                   : (PT_TURN_RULE == 1 ? !(nLeaf >= PT_LEAF_MIN || nNode == 0) : (PT_TURN_RULE == 2 ? (nNode >= PT_NODE_MIN || nLeaf == 0) : (nNode >= nLeaf)))) {
+        } else if (nNode >= nLeaf) {  // the class more lanes wait in
             if (st == ST_MESH_NODE) {
 #pragma unroll 1
                 for (int k = 0; k < PT_NODE_BURST && st == ST_MESH_NODE; k++) {
@@ -1493,17 +1325,12 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
                 }
             }
         } else {
-#if PT_COOP_LEAF
-            coop_leaf(S, st == ST_MESH_LEAF, co, cd, tPos, tEnd, mBest, mPrim, mBestPos);
-#endif
             if (st == ST_MESH_LEAF) {
 #ifdef PT_DEBUG_STEPS
                 dbgLeaves++;
                 DBG_ADD(3, 1);
 #endif
-#if !PT_COOP_LEAF
                 leaf_work(S, co, cd, tPos, tEnd, mBest, mPrim, mBestPos, PT_LEAF_BURST);
-#endif
                 if (ANYHIT && mBest < (double)anyLim) st = ST_MESH_DONE;  // Mesh.Intersect's T can only be <= this: closer than the light
                 else if (tPos >= tEnd) st = mesh_pop_t(mc, mBest, mStk) ? ST_MESH_NODE : ST_MESH_DONE;
             }

@@ -604,13 +604,11 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
 #ifndef PT_MESH_WARPS_PER_SM
 #define PT_MESH_WARPS_PER_SM 40
 #endif
-static constexpr size_t kMeshSmemBytes = (size_t)PT_SMEM_STACK * PT_MESH_BLOCK * sizeof(uint4);
 // 40 warps x 48 registers is the register file: each of the four sub-partitions holds 16 K registers = 10 warps of 48 (42 warps would need 40 registers).
 // ANYHIT: the items are Mesh.Intersect calls of shadow rays, each with the light's own T (see scene_advance in pt_device.cuh).
 template <bool ANYHIT>
 __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) k_mesh(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
-    extern __shared__ uint4 smemStack[];  // PT_SMEM_STACK rows of blockDim.x entries
-    mesh_walk<ANYHIT>(S, W, q, cursor, smemStack);
+    mesh_walk<ANYHIT>(S, W, q, cursor);
 }
 
 #ifndef PT_MARCH_MINBLOCKS
@@ -832,42 +830,6 @@ __global__ void k_keyed_draw(uint32_t seed, uint32_t pass, uint32_t pixel, uint3
     for (uint32_t i = 0; i <= drawIndex; i++) v = rng_next(rng);
     *out = v;
 }
-// kd_div (pt_device.cuh) against the IEEE division on `n` operand pairs: b runs over float bit patterns (index + offset, so 2^32
-// consecutive pairs visit every float), a is a difference of two floats of nearby magnitude (what split - o[axis] is), a random
-// double of the float range, or b times a random 53-bit significand's worth of near-midpoint quotients.
-__global__ void k_check_kd_div(uint64_t seed, uint64_t offset, uint64_t n, unsigned long long* out) {
-    unsigned long long bad = 0, fast = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t z = seed + (i + offset) * 0x9E3779B97F4A7C15ull;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
-        const float bf = __uint_as_float((uint32_t)(i + offset));
-        const double b = (double)bf;
-        double a;
-        const uint32_t mode = (uint32_t)(z >> 62);
-        if (mode == 0) {
-            const float f1 = __uint_as_float((uint32_t)z & 0xBFFFFFFFu | 0x20000000u);      // exponents 2^-63 .. 2^64
-            const float f2 = __uint_as_float(((uint32_t)z & 0xFF800000u) | ((uint32_t)(z >> 32) & 0x007FFFFFu));
-            a = (double)f1 - (double)f2;                                                      // same sign and exponent: cancellation
-        } else if (mode == 1) {
-            a = (double)__uint_as_float((uint32_t)z) - (double)__uint_as_float((uint32_t)(z >> 32) & 0xBFFFFFFFu);
-        } else if (mode == 2) {
-            a = __longlong_as_double((long long)((z & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(896 + (z >> 52) % 255) << 52)));
-        } else {
-            // a = RN(b * m) for a random significand m: quotients that sit next to representable numbers
-            a = b * __longlong_as_double((long long)((z & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
-        }
-        const float tiny = 1.17549435e-38f;
-        const bool rok = fabsf(bf) >= tiny && fabsf(bf) < INFINITY;
-        const double q = kd_div(a, b, 1.0 / b, rok), want = a / b;
-        const uint32_t ea = ((uint32_t)__double2hiint(a) & 0x7FFFFFFFu) - 0x38000000u;
-        fast += (rok && ea < 0x0FF00000u) ? 1 : 0;
-        const bool same = __double_as_longlong(q) == __double_as_longlong(want) || (q != q && want != want);
-        bad += same ? 0 : 1;
-    }
-    if (bad) atomicAdd(out, bad);
-    if (fast) atomicAdd(out + 1, fast);
-}
-
 // ====================================================================================================== host side
 static constexpr int kMaxLanes = 8;
 #ifndef PT_LANES
@@ -1108,7 +1070,7 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
                 if (detail) fprintf(stderr, "%s round %d  %.3f ms\n", kind == 0 ? "k_mesh" : kind == 1 ? "k_march<SDF>" : "k_march<VOLUME>", round, ms);
             }
         };
-        if (ctx->hasKind[0]) consumer(0, [&] { k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, kMeshSmemBytes, st>>>(ctx->scene, L.split, L.mq[cur], cursor); });
+        if (ctx->hasKind[0]) consumer(0, [&] { k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor); });
         if (ctx->hasKind[1]) consumer(1, [&] { k_march<(int)kItemSdf><<<gridMarch, 64, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor + 1); });
         if (ctx->hasKind[2]) consumer(2, [&] { k_march<(int)kItemVolume><<<gridMarch, 64, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor + 2); });
         resume(L.mq[cur], L.mq[cur ^ 1]);
@@ -1239,12 +1201,6 @@ static int create_one(const ptgpu_params* params, int dev, ptgpu_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     ctx->numSMs = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if (kMeshSmemBytes > 0) {  // k_mesh keeps the top of every thread's kd stack in shared memory: carve out what its resident blocks need
-        const size_t perSM = (size_t)(PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) * (kMeshSmemBytes + 1024);
-        const int pct = (int)std::min<size_t>(100, (perSM * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
-        if ((e = cudaFuncSetAttribute(k_mesh<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_mesh carveout)", e);
-        if ((e = cudaFuncSetAttribute(k_mesh<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_mesh carveout)", e);
-    }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
     // queueCapacity = path records in flight over all lanes (default 2^27, allocated on demand); flags bits 0-3 = number of lanes (0 = default)
     {
@@ -1670,6 +1626,7 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > stree.root && s->trees[k].root < end) end = s->trees[k].root;
         uint64_t deferred = 0;
         bool seen[256] = {false};
+        (void)seen;
         ctx->hasKind[0] = ctx->hasKind[1] = ctx->hasKind[2] = false;
         for (uint64_t i = stree.root; i < end; i++) {
             const ptgpu_node& n = s->nodes[i];
@@ -2314,23 +2271,6 @@ int ptgpu_keyed_draw(ptgpu_ctx* ctx, uint32_t seed, uint32_t pass, uint32_t pixe
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
     CK(e);
-    return PTGPU_OK;
-}
-
-int ptgpu_check_kd_div(ptgpu_ctx* ctx, uint64_t seed, uint64_t offset, uint64_t n, uint64_t* mismatches, uint64_t* fastPath) {
-    if (!ctx || !mismatches || !fastPath) return PTGPU_E_ARG;
-    CK(cudaSetDevice(ctx->device));
-    unsigned long long* d = nullptr;
-    CK(cudaMalloc(&d, 16));
-    cudaMemsetAsync(d, 0, 16, ctx->stream);
-    k_check_kd_div<<<148 * 8, 256, 0, ctx->stream>>>(seed, offset, n, d);
-    ctx->launches++;
-    unsigned long long h[2] = {0, 0};
-    cudaError_t e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    CK(e);
-    *mismatches = h[0]; *fastPath = h[1];
     return PTGPU_OK;
 }
 

@@ -156,17 +156,6 @@ def test_cast_rays(orc, bindings, device, aperture):
         np.testing.assert_allclose(gd, cd, rtol=2e-6, atol=1e-7)
 
 
-def test_kd_div_matches_ieee_division(device):
-    """`tsplit = (split - o[axis]) / d[axis]` (Tree.cs:86-98) is computed by the mesh walk from a per-ray reciprocal plus one
-    residual correction (kd_div, csrc/pt_device.cuh).  It must equal the IEEE double division the reference performs bit for
-    bit: 2^33 operand pairs, the divisor running twice over EVERY float bit pattern (zeros, subnormals, infinities and NaNs
-    included: those take the plain division), the dividend a cancelling difference of floats, a random double of the float
-    range or a product next to a representable quotient."""
-    bad, fast = device.check_kd_div(seed=0xC0FFEE, offset=0, n=2 ** 33)
-    assert bad == 0
-    assert fast > 0.9 * 2 ** 33  # the reciprocal path is what was exercised
-
-
 def test_keyed_stream_addressing(orc, device):
     lib = orc.lib()
     rng = np.random.default_rng(9)
