@@ -76,7 +76,8 @@ typedef struct ptgpu_tri_geom { float v1[3]; float pad0; float e1[3]; float pad1
 /* ... and what NormalAt/UVector/MaterialAt need (Triangle.cs:128-189). */
 typedef struct ptgpu_tri_shade { float n1[3], n2[3], n3[3]; float t1[2], t2[2], t3[2]; int32_t material; } ptgpu_tri_shade;
 /* TransformedShape.cs:11-13: Matrix, Matrix.Inverse() (Matrix.cs:196-217, evaluated once on the host in the same
- * operation order), inner shape (index into shapes[]; must not itself be a TransformedShape).                */
+ * operation order), inner shape (index into shapes[]).  The inner shape may itself be a TransformedShape (up to four levels): pad[0]
+ * is then 1 and the device re-measures Hit.T level by level as the nested Intersect calls do.                  */
 typedef struct ptgpu_instance { double m[16]; double inv[16]; uint32_t shape; uint32_t pad[3]; } ptgpu_instance;
 
 /* SDF.cs node types compiled by the host into a linear program (pre-order, explicit point stack). */

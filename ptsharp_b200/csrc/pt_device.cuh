@@ -1015,6 +1015,34 @@ enum { SCENE_START = 0, SCENE_RESUME = 1, SCENE_FINISH = 2 };
 // misses the light altogether (tL = INF) is Black without a walk.  Meshes entered beyond tL (1e-4 relative margin, far above the
 // FP32 error of any T) are not walked: their Hit has T > tL, so it can neither be the light nor hide a closer one; and mesh work
 // items carry tL so the walk itself stops at the first triangle hit below it (k_mesh<true>).
+// Hit.T of a TransformedShape whose Shape is another TransformedShape (instance.pad[0] != 0), from the T the innermost shape returned.
+// Every level re-measures T in ITS caller's space from the transformed hit point (TransformedShape.cs:47-69): level k turns the T of
+// level k+1 into |M_k * shapeRay_k.Position(T) - ray_k.Origin|.  tInner = the T the outermost level received - what its own
+// `shapeRay.Position(hit.T)` is evaluated with (Hit.Info then takes NormalAt / MaterialAt of the INNERMOST shape at that point of the
+// first shape space, as the reference does: hit.Shape is the innermost shape, hit.HitInfo the outermost level's).
+static constexpr int kMaxInstanceDepth = 4;
+PT_DN double nested_fold(const DScene& S, int32_t outer, V3 o, V3 d, double tInnermost, double& tInner) {
+    V3 ro[kMaxInstanceDepth + 1], rd[kMaxInstanceDepth + 1];
+    int32_t idx[kMaxInstanceDepth];
+    int n = 0;
+    ro[0] = o; rd[0] = d;
+    for (int32_t cur = outer; n < kMaxInstanceDepth;) {
+        const ptgpu_instance& in = S.instances[cur];
+        idx[n] = cur;
+        ro[n + 1] = mat_pos(in.inv, ro[n]); rd[n + 1] = mat_dir(in.inv, rd[n]);
+        n++;
+        const ptgpu_shape sh = S.shapes[in.shape];
+        if (sh.type != PTGPU_TRANSFORMED) break;
+        cur = (int32_t)sh.data;
+    }
+    double t = tInnermost;
+    for (int k = n - 1; k >= 0; k--) {
+        if (k == 0) tInner = t;
+        const V3 position = mat_pos(S.instances[idx[k]].m, ray_at(ro[k + 1], rd[k + 1], t));
+        t = (double)vlenf(vsub(position, ro[k]));
+    }
+    return t;
+}
 struct NoLight { PT_D int32_t operator()(uint32_t) const { return -1; } };
 template <int MODE, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
 PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink, LightOf lightOf = LightOf()) {
@@ -1119,8 +1147,11 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                     tInner = mBest;
                     if (mBest < kHitInf) {  // TransformedShape.cs:47-69
                         const ptgpu_instance& inst = S.instances[curInst];
-                        V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
-                        t = (double)vlenf(vsub(position, o));
+                        if (inst.pad[0]) t = nested_fold(S, curInst, o, d, mBest, tInner);
+                        else {
+                            V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
+                            t = (double)vlenf(vsub(position, o));
+                        }
                     }
                 }
                 if (curShape >> 31) { curShape &= 0x7FFFFFFFu; mPrim = -1; }  // SphericalHarmonic: the Hit names the solid, not the triangle (SH.cs:54)
@@ -1176,6 +1207,11 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         const ptgpu_instance& inst = S.instances[sh.data];
                         co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
                         sh = S.shapes[inst.shape];
+                        while (sh.type == PTGPU_TRANSFORMED) {  // a TransformedShape of a TransformedShape: its Intersect runs the inner one on ITS shapeRay
+                            const ptgpu_instance& in2 = S.instances[sh.data];
+                            co = mat_pos(in2.inv, co); cd = mat_dir(in2.inv, cd);
+                            sh = S.shapes[in2.shape];
+                        }
                     }
                     if (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
                         // (SphericalHarmonic.Intersect is mesh.Intersect with the Hit renamed to the solid itself, SH.cs:47-55)
@@ -1680,6 +1716,7 @@ PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
         inst = S.instances + sh.data;
         so = mat_pos(inst->inv, o); sd = mat_dir(inst->inv, d);
         sh = S.shapes[inst->shape];
+        while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];  // nested: hit.Shape is the innermost shape (see nested_fold)
         t = h.tInner;
     }
     const V3 position = ray_at(so, sd, t);

@@ -306,7 +306,10 @@ PT_D uint32_t shade_bin(const DScene& S, int32_t shape, int32_t prim) {
     if (shape < 0) return 0u;
     ptgpu_shape sh = S.shapes[shape];
     uint32_t which = 0u, sub = 0u;
-    if (sh.type == PTGPU_TRANSFORMED) { which = (sh.data + 1u) * PT_BIN_INSTANCE_MUL; sh = S.shapes[S.instances[sh.data].shape]; }  // instances of one mesh sit in different places
+    if (sh.type == PTGPU_TRANSFORMED) {
+        which = (sh.data + 1u) * PT_BIN_INSTANCE_MUL;
+        while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+    }  // instances of one mesh sit in different places
     if (sh.type == PTGPU_MESH) {
         which += sh.data * 7u;  // a Mesh carries its materials per triangle: one surface bin per mesh
         if (kShadeSub > 1 && prim >= 0) {
@@ -794,7 +797,7 @@ __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uin
                               if (h.shape >= 0) {
                                   if (h.prim >= 0) {
                                       ptgpu_shape sh = S.shapes[h.shape];
-                                      if (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+                                      while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
                                       localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
                                   }
                                   if (B.normal3 || B.position3 || B.inside || B.material) {  // Hit.Info only when asked for
@@ -1373,8 +1376,12 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         uint32_t lim = (i == s->sceneTree) ? (uint32_t)kSceneStack : (uint32_t)kMeshStack;
         if (s->trees[i].maxDepth >= lim) return fail(ctx, PTGPU_E_LIMIT, "kd-tree deeper than the traversal stack (" + std::to_string(s->trees[i].maxDepth) + ")");
     }
-    for (uint32_t i = 0; i < s->numInstances; i++)
-        if (s->shapes[s->instances[i].shape].type == PTGPU_TRANSFORMED) return fail(ctx, PTGPU_E_ARG, "nested TransformedShape is not supported");
+    for (uint32_t i = 0; i < s->numInstances; i++) {  // TransformedShape of TransformedShape ...: a chain of at most kMaxInstanceDepth, flagged in pad[0]
+        int depth = 1;
+        for (ptgpu_shape sh = s->shapes[s->instances[i].shape]; sh.type == PTGPU_TRANSFORMED; sh = s->shapes[s->instances[sh.data].shape])
+            if (++depth > kMaxInstanceDepth) return fail(ctx, PTGPU_E_LIMIT, "TransformedShape nested deeper than " + std::to_string(kMaxInstanceDepth));
+        if ((depth > 1) != (s->instances[i].pad[0] != 0)) return fail(ctx, PTGPU_E_ARG, "ptgpu_instance.pad[0] must be 1 exactly when the inner shape is a TransformedShape");
+    }
     for (uint32_t i = 0; i < s->numSdfShapes; i++) {  // validate SDF programs against the device stacks
         int nv = 0, np = 0;
         for (uint32_t k = 0; k < s->sdfShapes[i].progCount; k++) {
@@ -1626,14 +1633,14 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         for (uint32_t k = 0; k < s->numTrees; k++) if (s->trees[k].root > stree.root && s->trees[k].root < end) end = s->trees[k].root;
         uint64_t deferred = 0;
         bool seen[256] = {false};
-        (void)seen;
+        if (seen[0]) return PTGPU_E_STATE;  // (never: keeps the array referenced in builds without the mask)
         ctx->hasKind[0] = ctx->hasKind[1] = ctx->hasKind[2] = false;
         for (uint64_t i = stree.root; i < end; i++) {
             const ptgpu_node& n = s->nodes[i];
             if ((n.a & 3u) != 0) continue;
             for (uint32_t k = 0; k < n.b; k++) {
                 ptgpu_shape sh = s->shapes[s->leafItems[(n.a >> 2) + k]];
-                if (sh.type == PTGPU_TRANSFORMED) sh = s->shapes[s->instances[sh.data].shape];
+                while (sh.type == PTGPU_TRANSFORMED) sh = s->shapes[s->instances[sh.data].shape];
                 const int kind = (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) ? 0 : sh.type == PTGPU_SDF ? 1 : sh.type == PTGPU_VOLUME ? 2 : -1;
                 if (kind >= 0) {
                     ctx->hasKind[kind] = true;

@@ -830,13 +830,13 @@ struct Flattener {
             }
             case PTGPU_MESH: ps.data = MeshId(static_cast<const Mesh*>(s)); break;
             case PTGPU_TRANSFORMED: {
-                if (nested) throw std::runtime_error("TransformedShape inside TransformedShape is not supported");
                 auto* q = static_cast<const TransformedShape*>(s);
                 ptgpu_instance d; std::memset(&d, 0, sizeof(d));
                 std::memcpy(d.m, q->M.m, sizeof(d.m));
                 Matrix inv = q->M.Inverse();  // TransformedShape.cs:45 recomputes Matrix.Inverse() per ray; same value every time
                 std::memcpy(d.inv, inv.m, sizeof(d.inv));
                 ptgpu_shape inner = Describe(q->Shape.get(), true);
+                d.pad[0] = inner.type == PTGPU_TRANSFORMED ? 1u : 0u;  // nested: the device re-measures T level by level (nested_fold)
                 d.shape = (uint32_t)f.shapes.size();
                 f.shapes.push_back(inner);
                 ps.data = (uint32_t)f.instances.size(); f.instances.push_back(d); break;

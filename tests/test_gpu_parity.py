@@ -1056,3 +1056,42 @@ def test_marching_cubes_mesh_and_spherical_harmonic_render_like_the_oracle(orc, 
     np.testing.assert_array_equal(g["material"], c["material"])
     assert len(np.unique(c["material"][c["shape"] == 1])) == 2  # both lobes' materials
     _replay_check(orc, device, hw, ow, 160, 90, frac=2e-3)
+
+
+def test_nested_transformed_shapes_match_the_oracle(orc, bindings, device):
+    """TransformedShape.NewTransformedShape accepts any IShape (TransformedShape.cs:29-32), another TransformedShape included.  The nested
+    Intersect re-measures Hit.T at every level and leaves hit.Shape = the innermost shape, hit.HitInfo = the outermost level's - so
+    NormalAt / MaterialAt of the innermost shape are evaluated at a point of the FIRST shape space (TransformedShape.cs:52-58), which the
+    device reproduces (nested_fold, hit_info).  Two and three levels, around a Mesh, a Sphere and a Cylinder; closest hits bit for bit
+    (T, position, normal, inside, material, triangle), then a keyed replay."""
+    from ptsharp_b200 import hostmath as hm, scenes
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    V = scenes.spatial_order(scenes.displaced_icosphere(8, 1.0, (0, 0, 0)), "friendly")
+    for w in (hw, ow):
+        gm = w.GlossyMaterial((0.8, 0.5, 0.3), 1.4, 0.15)
+        dm = w.DiffuseMaterial((0.3, 0.6, 0.9))
+        mesh = w.mesh(V, gm)
+        inner = w.transformed(mesh, hm.mul(hm.rotate((0, 0, 1), 0.4), hm.scale(hm.vec((1.0, 0.7, 1.2)))))
+        w.add(w.transformed(inner, hm.translate(hm.vec((-2.4, 0.3, 0.1)))))                                   # two levels around a Mesh
+        s2 = w.transformed(w.transformed(w.sphere((0, 0, 0), 0.8, dm), hm.scale(hm.vec((1.3, 0.8, 1.0)))), hm.rotate((1, 0, 0), 0.6))
+        w.add(w.transformed(s2, hm.translate(hm.vec((0.2, 0.0, 0.2)))))                                       # three levels around a Sphere
+        cyl = w.transformed(w.cylinder(0.5, -0.7, 0.7, gm), hm.rotate((0, 1, 0), 0.9))
+        w.add(w.transformed(cyl, hm.mul(hm.translate(hm.vec((2.5, -0.2, 0.0))), hm.scale(hm.vec((1.0, 1.4, 0.8))))))   # two levels around a Cylinder
+        w.add(w.plane((0, 0, -1.3), (0, 0, 1), w.DiffuseMaterial((0.8, 0.8, 0.8))))
+        w.add(w.sphere((1, -4, 6), 1.0, w.LightMaterial((1, 1, 1), 50)))
+        w.look_at((0.2, -7.0, 2.2), (0, 0, 0), (0, 0, 1), 40)
+        w.sampler(1, 4)
+    device.upload(hw)
+    o, d = _ray_batch(ow, W=160, H=90, n_secondary=20000, seed=77)
+    g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
+    hit = c["shape"] >= 0
+    for k in range(3):
+        assert (c["shape"] == k).sum() > 300, k
+    np.testing.assert_array_equal(g["shape"], c["shape"])
+    np.testing.assert_array_equal(g["prim"], c["prim"])
+    np.testing.assert_array_equal(g["t"][hit].view(np.int64), c["t"][hit].view(np.int64))
+    np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
+    np.testing.assert_array_equal(g["inside"], c["inside"])
+    np.testing.assert_array_equal(g["material"], c["material"])
+    _replay_check(orc, device, hw, ow, 160, 90, frac=2e-3)
