@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default max(5, --steps); heavy configs: 1-2)")
     ap.add_argument("--no-other-scaling", action="store_true", help="N > 1: skip the extra measurement of the other scaling mode")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -347,7 +348,7 @@ def main():
         out = np.empty((H, W, 3), np.float32)
         host_out = torch.from_numpy(out).pin_memory().numpy()
         scene_bytes = dev.scene_bytes()  # everything ptgpu_upload_scene copies host -> device: the flat scene and the records derived from it
-        n_e2e = max(5, args.steps)
+        n_e2e = args.e2e_steps if args.e2e_steps > 0 else max(5, args.steps)
         rs = split(args.scaling)
         dev.reset_buffer()
         barrier()
