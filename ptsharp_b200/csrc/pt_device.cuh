@@ -948,10 +948,13 @@ struct alignas(32) RayState {
 };
 static_assert(sizeof(RayState) == 128, "RayState is four sectors");
 struct SplitState {
-    RayState* state;                                                            // [ray]
+    RayState* state;                                                            // [ray], stateQuads x 16 bytes apart
+    uint32_t stateQuads;                                                        // 8 with the candidate mask, 6 (three sectors) without it
     uint4* sceneStack; int stackEnt;                                            // [ray][stackEnt], entry 0 = sentinel
+    uint4* meshStack;                                                           // PT_MESH_GSTACK: [k_mesh thread][kMeshStackEnt]
     unsigned long long* kindItems;                                              // [3] work items consumed per kind (counters; [0] is filled in by the host)
 };
+PT_D RayState* ray_state(const SplitState& W, uint32_t ray) { return reinterpret_cast<RayState*>(reinterpret_cast<uint4*>(W.state) + (size_t)ray * W.stateQuads); }
 #ifndef PT_BEST_CLIP
 #define PT_BEST_CLIP (!PT_NO_CULL)   // scene_advance: no mesh walk beyond the running best of the Scene.tree traversal (see there)
 #endif
@@ -1044,7 +1047,7 @@ PT_DN double nested_fold(const DScene& S, int32_t outer, V3 o, V3 d, double tInn
     return t;
 }
 struct NoLight { PT_D int32_t operator()(uint32_t) const { return -1; } };
-template <int MODE, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
+template <int MODE, bool MASK, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
 PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink, LightOf lightOf = LightOf()) {
     // Candidate mask (PT_SCENE_MASK).  The reference builder puts a shape into every Scene.tree leaf its box overlaps and stops splitting
     // at 85 % overlap, so leaves are large and repeat each other (the 200-instance scene: 501 items in 45 leaves, up to 41 per leaf, the
@@ -1058,8 +1061,8 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
     // block's union first; cleared when the shape is evaluated.  A leaf none of whose shapes has its bit set is skipped as a whole
     // (sceneLeafMask), otherwise its items are visited in array order as before and those without a bit are passed over.  What is
     // evaluated, in which order, and every fold that can change best are those of the reference.
-    __shared__ uint32_t maskColumns[8 * kSceneBlock];
-    uint32_t* const mk = (PT_SCENE_MASK && S.maskOn) ? maskColumns + threadIdx.x : nullptr;
+    __shared__ uint32_t maskColumns[MASK ? 8 * kSceneBlock : 1];
+    uint32_t* const mk = MASK ? maskColumns + threadIdx.x : nullptr;  // MASK is a template parameter: scenes without the mask run the kernel without its code
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         constexpr bool RESUME = MODE != SCENE_START;
@@ -1084,7 +1087,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
             continue;
         }
         if (RESUME) {
-            const uint4* rs = reinterpret_cast<const uint4*>(W.state + ray);  // seven 128-bit loads from four consecutive sectors
+            const uint4* rs = reinterpret_cast<const uint4*>(ray_state(W, ray));  // seven 128-bit loads from four consecutive sectors
             const uint4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3], r4 = rs[4];
 #if PT_SCENE_MASK
             if (mk) {
@@ -1247,7 +1250,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.c[slot] = make_double2(tmin, tmax);
                             // a float at or below tL (object-space T of an instance is not comparable with tL: no cut-off there)
                             if (SHADOW) out.lim[slot] = (curInst < 0 && tL > 0) ? __double2float_rd(tL) : -1.0f;
-                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst, mk);
+                            save_ray_state(ray_state(W, ray), best, sc, sPos, sEnd, curShape, curInst, mk);
                             break;
                         }
                     } else if (sh.type == PTGPU_SDF || sh.type == PTGPU_VOLUME) {
@@ -1280,7 +1283,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             out.b[slot] = make_float4(cd.x, cd.y, cd.z, __uint_as_float((kind << kItemKindShift) | sh.data));
                             out.c[slot] = make_double2(t0, t1);
                             if (SHADOW) out.lim[slot] = -1.0f;
-                            save_ray_state(W.state + ray, best, sc, sPos, sEnd, curShape, curInst, mk);
+                            save_ray_state(ray_state(W, ray), best, sc, sPos, sEnd, curShape, curInst, mk);
                             break;
                         }
                     } else {
@@ -1299,6 +1302,9 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
 }
 
 // Mesh.Intersect for every work item of `q`; the Hit goes to W.mBest / W.mPrim of the item's ray.
+#ifndef PT_MESH_GSTACK
+#define PT_MESH_GSTACK 0
+#endif
 template <bool ANYHIT>
 PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, uint32_t* __restrict__ cursor) {
     float anyLim = -1.0f;  // ANYHIT (shadow rays): stop at the first Hit below it
@@ -1308,8 +1314,14 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
     V3 co = v3(0, 0, 0), cd = v3(0, 0, 1);
     RayBox ra = ray_box(co, cd);
     KdCursor mc; mc.node = 0; mc.tmin = mc.tmax = 0; mc.sp = 0;
+#if PT_MESH_GSTACK
+    // the kd stack in GLOBAL memory, one contiguous 16-byte entry per level and thread: a push / pop is one sector, where the interleaved
+    // layout of local memory turns it into four 4-byte touches in four lines
+    PtrStack mStk{W.meshStack + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * kMeshStackEnt};
+#else
     uint4 mLoc[kMeshStackEnt];
     PtrStack mStk{mLoc};
+#endif
     uint32_t tPos = 0, tEnd = 0, mBestPos = 0;
     double mBest = kHitInf;
     int32_t mPrim = -1;
@@ -1377,7 +1389,7 @@ PT_D void mesh_walk(const DScene& S, const SplitState& W, const MeshQueue& q, ui
             dbgSteps = dbgLeaves = 0;
         }
 #endif
-        if (st == ST_MESH_DONE) { save_hit(W.state + ray, mBest, mPrim); st = ST_IDLE; }
+        if (st == ST_MESH_DONE) { save_hit(ray_state(W, ray), mBest, mPrim); st = ST_IDLE; }
     }
 }
 
@@ -1468,7 +1480,7 @@ PT_D void march_items(const DScene& S, const SplitState& W, const MeshQueue& q, 
                     }
                 }
             }
-            if (done) { save_hit(W.state + ray, result, -1); have = false; }
+            if (done) { save_hit(ray_state(W, ray), result, -1); have = false; }
         }
     }
 }

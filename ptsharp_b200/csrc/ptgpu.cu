@@ -564,17 +564,17 @@ __global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, Pas
 #ifndef PT_SCENE_MINBLOCKS
 #define PT_SCENE_MINBLOCKS 8
 #endif
-template <int MODE>
+template <int MODE, bool MASK>
 __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
                                                       DeviceCounters* cnt) {
     constexpr bool RESUME = MODE != SCENE_START;
     const uint32_t n = RESUME ? *in.count : *count;
-    scene_advance<MODE>(S, W, n, in, out,
+    scene_advance<MODE, MASK>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
-template <int MODE>
+template <int MODE, bool MASK>
 __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, uint32_t first,
                                                        uint32_t chunk, MeshQueue in, MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
     // The shadow queue may hold several times the rays the tracer has per-ray state for: it is traced in chunks of `chunk` records
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
         const uint32_t total = min(*scount, capShadow);
         n = total > first ? min(total - first, chunk) : 0u;
     }
-    scene_advance<MODE, PT_ANYHIT != 0>(S, W, n, in, out,
+    scene_advance<MODE, MASK, PT_ANYHIT != 0>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[first + i], b = sq.sd[first + i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) {
                               const uint32_t light = f2u(sq.sd[first + i].w);
@@ -780,12 +780,12 @@ __global__ void k_firefly_apply(float* __restrict__ sum, const uint32_t* __restr
 
 // K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same split tracer as the pipeline.
 struct BatchOut { int32_t* shape; int32_t* prim; double* t; float* normal3; float* position3; int32_t* inside; int32_t* material; };
-template <int MODE>
+template <int MODE, bool MASK>
 __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uint32_t nStart, MeshQueue in, MeshQueue out, const float* __restrict__ o3,
                                                       const float* __restrict__ d3, BatchOut B) {
     constexpr bool RESUME = MODE != SCENE_START;
     const uint32_t n = RESUME ? *in.count : nStart;
-    scene_advance<MODE>(S, W, n, in, out,
+    scene_advance<MODE, MASK>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
                           [&](uint32_t i, const HitRec& h) {
                               V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
@@ -986,7 +986,7 @@ static void trim_scene_pool(ptgpu_ctx* ctx) {  // after an upload: what the new 
 }
 static void free_split(Lane& L) {
     SplitState& W = L.split;
-    void* ps[] = {W.state, W.sceneStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c, L.mq[0].lim, L.mq[1].lim};
+    void* ps[] = {W.state, W.sceneStack, W.meshStack, L.mq[0].a, L.mq[0].b, L.mq[0].c, L.mq[1].a, L.mq[1].b, L.mq[1].c, L.mq[0].lim, L.mq[1].lim};
     for (void* p : ps) cudaFree(p);
     W = SplitState{};
     L.mq[0] = L.mq[1] = MeshQueue{};
@@ -1014,12 +1014,18 @@ static int grid_for(ptgpu_ctx* ctx, int blocksPerSM) { return ctx->numSMs * bloc
 
 // Per-ray state of the split tracer for launches of up to `cap` rays.
 static int ensure_split(ptgpu_ctx* ctx, Lane& L, uint64_t cap, int stackEnt) {
+    const uint32_t quads = (PT_SCENE_MASK && ctx->scene.maskOn) ? 8u : 6u;  // records are allocated at the larger size
+    L.split.stateQuads = quads;
     if (cap <= L.splitCap && stackEnt == L.split.stackEnt) return PTGPU_OK;
     CK(cudaStreamSynchronize(L.stream));
     free_split(L);
     SplitState& W = L.split;
     CK(cudaMalloc(&W.state, cap * sizeof(RayState)));
+    W.stateQuads = quads;
     CK(cudaMalloc(&W.sceneStack, cap * (uint64_t)stackEnt * sizeof(uint4)));
+#if PT_MESH_GSTACK
+    CK(cudaMalloc(&W.meshStack, (uint64_t)grid_for(ctx, PT_MESH_WARPS_PER_SM * 32 / PT_MESH_BLOCK) * PT_MESH_BLOCK * kMeshStackEnt * sizeof(uint4)));
+#endif
     W.stackEnt = stackEnt;
     W.kindItems = ctx->dCounters->kindItems;
     for (int i = 0; i < 2; i++) {
@@ -1826,6 +1832,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         if ((rc = ensure_split(ctx, L, L.capRays, ctx->splitStackEnt)) != PTGPU_OK) return rc;
     }
     const int gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
+    const bool maskOn = PT_SCENE_MASK && ctx->scene.maskOn;  // which instantiation of the scene kernels runs (see scene_advance)
     float ms = 0;
     if (prof) {
         ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; ctx->traceLaunches = 0;
@@ -1858,9 +1865,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 const RayQueue rqc = L.rq[cur];
                 uint32_t* cnt = counts + cur;
                 rc = run_split(ctx, L, stream,
-                               [&](const MeshQueue& out) { k_scene_trace<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); },
-                               [&](const MeshQueue& in, const MeshQueue& out) { k_scene_trace<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); },
-                               [&](const MeshQueue& in) { k_scene_trace<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); });
+                               [&](const MeshQueue& out) { { if (maskOn) k_scene_trace<SCENE_START, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); else k_scene_trace<SCENE_START, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); } },
+                               [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_trace<SCENE_RESUME, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); else k_scene_trace<SCENE_RESUME, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); } },
+                               [&](const MeshQueue& in) { { if (maskOn) k_scene_trace<SCENE_FINISH, true><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); else k_scene_trace<SCENE_FINISH, false><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); } });
                 if (rc != PTGPU_OK) return rc;
                 if (prof) ctx->traceLaunches++;
             }
@@ -1885,9 +1892,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 for (uint64_t first64 = 0; first64 < shadowThisBatch; first64 += chunk) {
                     const uint32_t first = (uint32_t)first64;
                     rc = run_split<PT_ANYHIT != 0>(ctx, L, stream,
-                                   [&](const MeshQueue& out) { k_scene_shadow<SCENE_START><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); },
-                                   [&](const MeshQueue& in, const MeshQueue& out) { k_scene_shadow<SCENE_RESUME><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); },
-                                   [&](const MeshQueue& in) { k_scene_shadow<SCENE_FINISH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); });
+                                   [&](const MeshQueue& out) { { if (maskOn) k_scene_shadow<SCENE_START, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_START, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); } },
+                                   [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_shadow<SCENE_RESUME, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_RESUME, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); } },
+                                   [&](const MeshQueue& in) { { if (maskOn) k_scene_shadow<SCENE_FINISH, true><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_FINISH, false><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); } });
                     if (rc != PTGPU_OK) return rc;
                 }
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
@@ -2214,10 +2221,11 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
         int rcs = ensure_split(ctx, L, std::max<uint64_t>(N, L.splitCap), ctx->splitStackEnt);
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
         const BatchOut B{dS, dPr, dT, dN, dP, dI, dM};
+        const bool maskOn = PT_SCENE_MASK && ctx->scene.maskOn;
         rcs = run_split(ctx, L, ctx->stream,
-                        [&](const MeshQueue& out) { k_scene_batch<SCENE_START><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); },
-                        [&](const MeshQueue& in, const MeshQueue& out) { k_scene_batch<SCENE_RESUME><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); },
-                        [&](const MeshQueue& in) { k_scene_batch<SCENE_FINISH><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); });
+                        [&](const MeshQueue& out) { { if (maskOn) k_scene_batch<SCENE_START, true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); else k_scene_batch<SCENE_START, false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); } },
+                        [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_batch<SCENE_RESUME, true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); else k_scene_batch<SCENE_RESUME, false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); } },
+                        [&](const MeshQueue& in) { { if (maskOn) k_scene_batch<SCENE_FINISH, true><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); else k_scene_batch<SCENE_FINISH, false><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); } });
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
     }
     CKC(cudaGetLastError());
