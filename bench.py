@@ -10,7 +10,7 @@ A step = one pass (Renderer.RenderParallel, Renderer.cs:199-338) over the whole 
   value  device-timed throughput, scene resident in HBM, CUDA events, max over ranks;
   e2e    the same pass through the C ABI with HOST buffers: every step re-uploads the flat scene (host -> device) and reads
          the image back (device -> host);
-  roofline       the dominant kernel (k_mesh / k_march, or k_scene_trace for scenes of analytic shapes only): algorithmic bytes per launch / launch
+  roofline       the dominant kernel of the profiled pass (k_mesh / k_march, k_shade for scenes of analytic shapes): algorithmic bytes per launch / launch
                  duration measured live with CUDA events on the launching stream, vs the measured HBM peak;
   cpu_baseline   the CPU restatement in oracle/ (kind "port": the C# reference cannot be built here) on all host cores, on a
                  bounded sample of the same workload: every k-th 32x32 task of the WHOLE frame (the reference's own task list,
@@ -313,7 +313,14 @@ def main():
                  ("k_march<VOLUME>", pc["volumeMs"], pc["volumeItems"], pc["volumeLaunches"])]
         kname, kms, units, klaunches = max(kinds, key=lambda k: k[1])
         unit_bytes = MESH_BYTES_PER_ITEM
-        if kms <= 0:
+        # scenes of analytic primitives (C1, C2) spend most of the pass in k_shade (Hit.Info, Ray.Bounce, sampleLight ray generation; its time
+        # here includes the three shade-order kernels): per hit record it reads the 52-byte ray record and the 24-byte hit, and writes a
+        # 52-byte record per child and a 48-byte record per shadow ray (averages of the profiled pass)
+        scene_ms = pc["traceMs"] + pc["shadowMs"] - pc["meshMs"] - pc["sdfMs"] - pc["volumeMs"]
+        if pc["shadeMs"] > kms and pc["shadeMs"] >= scene_ms and pc["segments"]:
+            kname, kms, units, klaunches = "k_shade", pc["shadeMs"], pc["segments"], pc["traceLaunches"]
+            unit_bytes = 52 + 24 + 52 * max(0, pc["segments"] - pc["cameraSamples"]) / pc["segments"] + 48 * pc["shadowRays"] / pc["segments"]
+        elif kms <= 0 or scene_ms > kms:
             kname, unit_bytes, units, kms, klaunches = "k_scene_trace<START>", TRACE_BYTES_PER_RAY, pc["segments"], pc["traceMs"], pc["traceLaunches"]
         stage.update({"sdfMs": pc["sdfMs"], "volumeMs": pc["volumeMs"]})
         achieved = units * unit_bytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0

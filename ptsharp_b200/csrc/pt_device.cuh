@@ -909,11 +909,14 @@ PT_D double shadow_clip(double tL) { return tL > 0 ? tL : 1e300; }  // the 1e-4 
 #ifndef PT_SPLIT_FETCH_MIN
 #define PT_SPLIT_FETCH_MIN 8   // mesh_walk refills idle lanes once this many wait (or nothing else is left to do)
 #endif
+#ifndef PT_MARCH_FETCH_MIN
+#define PT_MARCH_FETCH_MIN 1   // march_items refills idle lanes once this many wait: a refill costs three loads, an idle lane a whole burst (8: C5 +15 % slower)
+#endif
 #ifndef PT_SDF_BURST
-#define PT_SDF_BURST 16   // sphere-tracing steps between two refills of a warp of march_items
+#define PT_SDF_BURST 2    // sphere-tracing steps between two refills of a warp of march_items (a lane that finishes idles to the end of the burst; 16: ncu 8 of 32 lanes per instruction)
 #endif
 #ifndef PT_VOL_BURST
-#define PT_VOL_BURST 64   // Volume marching steps between two refills
+#define PT_VOL_BURST 8    // Volume marching steps between two refills
 #endif
 enum { ST_IDLE = 0, ST_SCENE_NODE, ST_SCENE_LEAF, ST_MESH_NODE, ST_MESH_LEAF, ST_MESH_DONE, ST_FINISH, ST_EXIT };
 
@@ -1417,7 +1420,7 @@ PT_D void march_items(const DScene& S, const SplitState& W, const MeshQueue& q, 
             if ((threadIdx.x & 31) == 0 && taken) atomicAdd(W.kindItems + KIND, (unsigned long long)taken);
             break;
         }
-        if (__popc(idle) >= PT_SPLIT_FETCH_MIN || !busy) {
+        if (__popc(idle) >= PT_MARCH_FETCH_MIN || !busy) {
             while (!have && !exhausted) {
                 auto g = cooperative_groups::coalesced_threads();
                 uint32_t base = 0;

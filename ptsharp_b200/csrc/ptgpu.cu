@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(PT_MESH_BLOCK, PT_MESH_WARPS_PER_SM * 32 / PT_
 }
 
 #ifndef PT_MARCH_MINBLOCKS
-#define PT_MARCH_MINBLOCKS 6
+#define PT_MARCH_MINBLOCKS 16   // 64-thread blocks: 32 warps/SM at 64 registers.  The march loops are chains of dependent FP64 operations (ncu: `wait` is the top stall), so warps in flight pay: 6 blocks (91 registers) 213 ms per 2-spp C5 pass, 10: 175, 12: 169, 16: 166, 20: 170
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(64, PT_MARCH_MINBLOCKS) k_march(DScene S, SplitState W, MeshQueue q, uint32_t* __restrict__ cursor) {
@@ -1076,7 +1076,7 @@ static int run_split(ptgpu_ctx* ctx, Lane& L, cudaStream_t st, StartFn start, Re
                 float ms = 0; cudaEventElapsedTime(&ms, ctx->evC, ctx->evD);
                 ctx->kindMs[kind] += ms; ctx->kindLaunches[kind]++;
                 if (kind == 0) ctx->roundItems += items;  // all kinds; the marchers' own counts are subtracted in ptgpu_get_counters
-                if (detail) fprintf(stderr, "%s round %d  %.3f ms\n", kind == 0 ? "k_mesh" : kind == 1 ? "k_march<SDF>" : "k_march<VOLUME>", round, ms);
+                if (detail) fprintf(stderr, "%s round %d  queue items %u  %.3f ms\n", kind == 0 ? "k_mesh" : kind == 1 ? "k_march<SDF>" : "k_march<VOLUME>", round, items, ms);
             }
         };
         if (ctx->hasKind[0]) consumer(0, [&] { k_mesh<ANYHIT><<<gridMesh, PT_MESH_BLOCK, 0, st>>>(ctx->scene, L.split, L.mq[cur], cursor); });
