@@ -404,12 +404,31 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 8   // 64 registers: 6.8 ms vs 7.0 ms (4 blocks, 128 registers) per 8-spp C3 pass with the shade order on
 #endif
-__global__ void __launch_bounds__(128, PT_SHADE_MINBLOCKS) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
+// ncu on the Cornell box (C2), where k_shade is half of the pass: `no_instruction` is its top stall (4.3 warps per issue) - a record is
+// ~1 300 straight-line warp instructions spread over a 64 KB+ kernel, and 32 warps that each sit somewhere else in it miss the
+// instruction caches for one another.  So the warps of a block start every record together (block-uniform trip count, one barrier
+// per record) and the blocks are large: 16 warps then fetch the same lines at about the same time.  Per pass (same gpurun call):
+// C2 46.1 -> 43.2 ms, C1 20.8 -> 19.7 ms, C3 57.1 -> 56.1 ms; 128 / 256 / 1024 threads with the barrier: 44.8 / 44.2 / 44.1 ms on C2,
+// 512 threads without it 43.6 ms (C3 57.5).
+#ifndef PT_SHADE_BLOCK
+#define PT_SHADE_BLOCK 512
+#endif
+#ifndef PT_SHADE_SYNC
+#define PT_SHADE_SYNC 1
+#endif
+__global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS * 128 / PT_SHADE_BLOCK) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
                                                 HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
                                                 float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow,
                                                 const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow) {
     const uint32_t n = *count;
+#if PT_SHADE_SYNC
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
+        __syncthreads();
+        const uint32_t j = j0 + threadIdx.x;
+        if (j >= n) continue;
+#else
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+#endif
         const uint32_t i = perm ? perm[j] : j;  // shade order (see k_bin_scatter)
         float4 a = q.od0[i], b = q.od1[i], c = q.bt[i];
         const V3 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z);
@@ -1880,7 +1899,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 k_bin_scatter<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, L.hq.prim, counts + cur, L.bins, L.perm);
                 ctx->launches += 3;
             }
-            k_shade<<<gridShade, 128, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
+            k_shade<<<gridShade * 128 / PT_SHADE_BLOCK, PT_SHADE_BLOCK, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
                                                    L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow,
                                                    shadeOrder ? L.perm : nullptr, counts + 3);
             k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)L.capRays, counts + 3);
