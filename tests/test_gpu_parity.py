@@ -1097,34 +1097,39 @@ def test_nested_transformed_shapes_match_the_oracle(orc, bindings, device):
     _replay_check(orc, device, hw, ow, 160, 90, frac=2e-3)
 
 
-def test_candidate_mask_with_more_than_255_scene_shapes(orc, bindings, device):
-    """The scene level keeps one bit per scene shape for the first 255 shapes (candidate mask + mailboxing, DESIGN 4.1) and one shared bit
-    for all the others, which keep the per-item path.  340 scene shapes - instanced meshes, spheres and cubes on both sides of index 255,
-    every one of them in several Scene.tree leaves - against the oracle: closest hits bit for bit, then a keyed replay."""
+def _many_shapes_world(w):
+    """340 scene shapes - instanced meshes, spheres and cubes on both sides of index 255, every one of them in several Scene.tree leaves."""
     from ptsharp_b200 import hostmath as hm, scenes
-    hw, ow = bindings.HostWorld(), orc.OracleWorld()
     V = scenes.spatial_order(scenes.displaced_icosphere(3, 1.0, (0, 0, 0)), "friendly")
     rng = np.random.default_rng(5)
     pos = rng.uniform(-9, 9, size=(338, 3)) * np.array([1, 1, 0.25])
     kind = rng.integers(0, 3, size=338)
-    for w in (hw, ow):
-        gm = w.GlossyMaterial((0.7, 0.6, 0.4), 1.4, 0.2)
-        dm = w.DiffuseMaterial((0.4, 0.7, 0.8))
-        mesh = w.mesh(V, gm)
-        for i in range(338):
-            p = tuple(float(v) for v in pos[i])
-            if kind[i] == 0:
-                m = hm.mul(hm.translate(hm.vec(p)), hm.mul(hm.rotate((0, 0, 1), 0.37 * i), hm.scale(hm.vec((0.5 + 0.001 * i, 0.45, 0.6)))))
-                w.add(w.transformed(mesh, m))
-            elif kind[i] == 1:
-                w.add(w.sphere(p, 0.45, dm))
-            else:
-                w.add(w.cube((p[0] - 0.4, p[1] - 0.4, p[2] - 0.4), (p[0] + 0.4, p[1] + 0.4, p[2] + 0.4), gm))
-        w.add(w.cube((-12, -12, -3.2), (12, 12, -3.0), w.DiffuseMaterial((0.8, 0.8, 0.8))))
-        w.add(w.sphere((2, -3, 9), 1.5, w.LightMaterial((1, 1, 1), 40)))
-        w.look_at((0.5, -22.0, 7.0), (0, 0, 0), (0, 0, 1), 45)
-        w.sampler(1, 3)
+    gm = w.GlossyMaterial((0.7, 0.6, 0.4), 1.4, 0.2)
+    dm = w.DiffuseMaterial((0.4, 0.7, 0.8))
+    mesh = w.mesh(V, gm)
+    for i in range(338):
+        p = tuple(float(v) for v in pos[i])
+        if kind[i] == 0:
+            m = hm.mul(hm.translate(hm.vec(p)), hm.mul(hm.rotate((0, 0, 1), 0.37 * i), hm.scale(hm.vec((0.5 + 0.001 * i, 0.45, 0.6)))))
+            w.add(w.transformed(mesh, m))
+        elif kind[i] == 1:
+            w.add(w.sphere(p, 0.45, dm))
+        else:
+            w.add(w.cube((p[0] - 0.4, p[1] - 0.4, p[2] - 0.4), (p[0] + 0.4, p[1] + 0.4, p[2] + 0.4), gm))
+    w.add(w.cube((-12, -12, -3.2), (12, 12, -3.0), w.DiffuseMaterial((0.8, 0.8, 0.8))))
+    w.add(w.sphere((2, -3, 9), 1.5, w.LightMaterial((1, 1, 1), 40)))
+    w.look_at((0.5, -22.0, 7.0), (0, 0, 0), (0, 0, 1), 45)
+    w.sampler(1, 3)
     assert (kind[255:] == 0).sum() > 10 and (kind[:255] == 0).sum() > 50
+
+
+def test_candidate_mask_with_more_than_255_scene_shapes(orc, bindings, device):
+    """The scene level keeps one bit per scene shape for the first 255 shapes (candidate mask + mailboxing, DESIGN 4.1) and one shared bit
+    for all the others, which keep the per-item path.  340 scene shapes against the oracle: closest hits bit for bit and a keyed replay;
+    then the product library against the no-cull arbiter build (no mask, every item of every leaf evaluated) on 2e7 fuzz rays."""
+    hw, ow = bindings.HostWorld(), orc.OracleWorld()
+    for w in (hw, ow):
+        _many_shapes_world(w)
     device.upload(hw)
     o, d = _ray_batch(ow, W=192, H=108, n_secondary=30000, seed=11)
     g, c = device.intersect_batch(o, d), ow.intersect_batch(o, d)
@@ -1136,4 +1141,21 @@ def test_candidate_mask_with_more_than_255_scene_shapes(orc, bindings, device):
     np.testing.assert_array_equal(g["position"][hit].view(np.int32), c["position"][hit].view(np.int32))
     np.testing.assert_array_equal(g["normal"][hit].view(np.int32), c["normal"][hit].view(np.int32))
     np.testing.assert_array_equal(g["inside"], c["inside"])
+    arbiter = bindings.Device(0, lib=bindings.checker_lib("nocull"))
+    try:
+        arbiter.upload(hw)
+        hits = (c["position"][hit], c["normal"][hit])
+        rng = np.random.default_rng(77)
+        total, done, nhit = int(float(os.environ.get("PTGPU_FUZZ_RAYS", "1e8"))) // 5, 0, 0
+        while done < total:
+            n = min(5_000_000, total - done)
+            fo, fd = _fuzz_rays(rng, n, hits, 12.0)
+            gg, aa = device.intersect_batch(fo, fd, full=False), arbiter.intersect_batch(fo, fd, full=False)
+            bad = (gg["shape"] != aa["shape"]) | (gg["prim"] != aa["prim"]) | ((gg["t"].view(np.int64) != aa["t"].view(np.int64)) & (aa["shape"] >= 0))
+            assert not bad.any(), (done, int(bad.sum()), fo[bad][:4], fd[bad][:4], gg["t"][bad][:4], aa["t"][bad][:4])
+            nhit += int((aa["shape"] >= 0).sum())
+            done += n
+        assert nhit > 0.2 * total
+    finally:
+        arbiter.close()
     _replay_check(orc, device, hw, ow, 160, 90, frac=2e-3)
