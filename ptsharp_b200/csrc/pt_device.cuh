@@ -160,7 +160,9 @@ struct DScene {
     const float4* candBlocks;       // 2 x float4 per block of up to 16 instanced meshes: union of their instBounds; lo.w = first member, hi.w = count
     const float4* candMembers;      // 2 x float4 per member: its instBounds; lo.w = index in Scene.Shapes
     uint32_t numCandBlocks;
+    uint32_t shadeSurfaces, shadeSub;  // split of the shade-order bins between surfaces and patches (shade_bin in ptgpu.cu)
     uint32_t maskOn;                // 0: Scene.tree repeats (almost) nothing - the mask would only cost its own upkeep
+    uint32_t hasNested;             // a TransformedShape of a TransformedShape exists (ptgpu_instance.pad[0])
     uint32_t maskBase[8];           // bits of the scene shapes no bounds test can drop (everything but instanced meshes) + bit 255
     const float4* leafGeom;         // 3 x float4 per leaf triangle in sorted order: (V1, triangle id) (e1, position in the leaf) (e2, -)
     const VolBlocks* volBlocks;     // per Volume: where its table of block maxima sits in volBlockMax (see vol_skip)
@@ -1027,25 +1029,23 @@ enum { SCENE_START = 0, SCENE_RESUME = 1, SCENE_FINISH = 2 };
 // `shapeRay.Position(hit.T)` is evaluated with (Hit.Info then takes NormalAt / MaterialAt of the INNERMOST shape at that point of the
 // first shape space, as the reference does: hit.Shape is the innermost shape, hit.HitInfo the outermost level's).
 static constexpr int kMaxInstanceDepth = 4;
-PT_DN double nested_fold(const DScene& S, int32_t outer, V3 o, V3 d, double tInnermost, double& tInner) {
-    V3 ro[kMaxInstanceDepth + 1], rd[kMaxInstanceDepth + 1];
-    int32_t idx[kMaxInstanceDepth];
-    int n = 0;
-    ro[0] = o; rd[0] = d;
-    for (int32_t cur = outer; n < kMaxInstanceDepth;) {
-        const ptgpu_instance& in = S.instances[cur];
-        idx[n] = cur;
-        ro[n + 1] = mat_pos(in.inv, ro[n]); rd[n + 1] = mat_dir(in.inv, rd[n]);
-        n++;
-        const ptgpu_shape sh = S.shapes[in.shape];
-        if (sh.type != PTGPU_TRANSFORMED) break;
-        cur = (int32_t)sh.data;
-    }
+PT_D double nested_fold(const DScene& S, int32_t outer, V3 o, V3 d, double tInnermost, double& tInner) {
+    int n = 1;
+    for (ptgpu_shape sh = S.shapes[S.instances[outer].shape]; sh.type == PTGPU_TRANSFORMED && n < kMaxInstanceDepth; sh = S.shapes[S.instances[sh.data].shape]) n++;
     double t = tInnermost;
-    for (int k = n - 1; k >= 0; k--) {
+    for (int k = n - 1; k >= 0; k--) {  // level k: its caller's ray is the world ray taken through the k levels above it (recomputed: no arrays, the path is rare)
+        V3 ro = o, rd = d;
+        int32_t cur = outer;
+        for (int j = 0; j < k; j++) {
+            const ptgpu_instance& up = S.instances[cur];
+            ro = mat_pos(up.inv, ro); rd = mat_dir(up.inv, rd);
+            cur = (int32_t)S.shapes[up.shape].data;
+        }
+        const ptgpu_instance& in = S.instances[cur];
+        const V3 so = mat_pos(in.inv, ro), sd = mat_dir(in.inv, rd);
         if (k == 0) tInner = t;
-        const V3 position = mat_pos(S.instances[idx[k]].m, ray_at(ro[k + 1], rd[k + 1], t));
-        t = (double)vlenf(vsub(position, ro[k]));
+        const V3 position = mat_pos(in.m, ray_at(so, sd, t));
+        t = (double)vlenf(vsub(position, ro));
     }
     return t;
 }
@@ -1065,7 +1065,9 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
     // (sceneLeafMask), otherwise its items are visited in array order as before and those without a bit are passed over.  What is
     // evaluated, in which order, and every fold that can change best are those of the reference.
     __shared__ uint32_t maskColumns[MASK ? 8 * kSceneBlock : 1];
-    uint32_t* const mk = MASK ? maskColumns + threadIdx.x : nullptr;  // MASK is a template parameter: scenes without the mask run the kernel without its code
+    // MASK is a template parameter: scenes that need neither the mask nor nested TransformedShapes run the kernel without that code
+    // (with it, as runtime branches, the analytic-shape scenes C1 / C2 traced 10 % slower and C3 3 %)
+    uint32_t* const mk = (MASK && PT_SCENE_MASK && S.maskOn) ? maskColumns + threadIdx.x : nullptr;
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         constexpr bool RESUME = MODE != SCENE_START;
@@ -1153,7 +1155,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                     tInner = mBest;
                     if (mBest < kHitInf) {  // TransformedShape.cs:47-69
                         const ptgpu_instance& inst = S.instances[curInst];
-                        if (inst.pad[0]) t = nested_fold(S, curInst, o, d, mBest, tInner);
+                        if (MASK && inst.pad[0]) t = nested_fold(S, curInst, o, d, mBest, tInner);
                         else {
                             V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
                             t = (double)vlenf(vsub(position, o));
@@ -1213,10 +1215,12 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         const ptgpu_instance& inst = S.instances[sh.data];
                         co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
                         sh = S.shapes[inst.shape];
-                        while (sh.type == PTGPU_TRANSFORMED) {  // a TransformedShape of a TransformedShape: its Intersect runs the inner one on ITS shapeRay
-                            const ptgpu_instance& in2 = S.instances[sh.data];
-                            co = mat_pos(in2.inv, co); cd = mat_dir(in2.inv, cd);
-                            sh = S.shapes[in2.shape];
+                        if (MASK && inst.pad[0]) {  // flagged by the flattener: a TransformedShape of a TransformedShape - its Intersect runs the inner one on ITS shapeRay
+                            while (sh.type == PTGPU_TRANSFORMED) {
+                                const ptgpu_instance& in2 = S.instances[sh.data];
+                                co = mat_pos(in2.inv, co); cd = mat_dir(in2.inv, cd);
+                                sh = S.shapes[in2.shape];
+                            }
                         }
                     }
                     if (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
@@ -1731,7 +1735,7 @@ PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
         inst = S.instances + sh.data;
         so = mat_pos(inst->inv, o); sd = mat_dir(inst->inv, d);
         sh = S.shapes[inst->shape];
-        while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];  // nested: hit.Shape is the innermost shape (see nested_fold)
+        if (inst->pad[0]) { while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape]; }  // nested: hit.Shape is the innermost shape (see nested_fold)
         t = h.tInner;
     }
     const V3 position = ray_at(so, sd, t);

@@ -308,18 +308,21 @@ PT_D uint32_t shade_bin(const DScene& S, int32_t shape, int32_t prim) {
     uint32_t which = 0u, sub = 0u;
     if (sh.type == PTGPU_TRANSFORMED) {
         which = (sh.data + 1u) * PT_BIN_INSTANCE_MUL;
-        while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape];
+        const ptgpu_instance& inst = S.instances[sh.data];
+        sh = S.shapes[inst.shape];
+        if (inst.pad[0]) { while (sh.type == PTGPU_TRANSFORMED) sh = S.shapes[S.instances[sh.data].shape]; }
     }  // instances of one mesh sit in different places
     if (sh.type == PTGPU_MESH) {
         which += sh.data * 7u;  // a Mesh carries its materials per triangle: one surface bin per mesh
-        if (kShadeSub > 1 && prim >= 0) {
+        if (S.shadeSub > 1 && prim >= 0) {
             const ptgpu_mesh m = S.meshes[sh.data];
-            sub = (uint32_t)((float)((uint32_t)prim - m.triFirst) * __fdividef((float)kShadeSub, (float)(m.triCount ? m.triCount : 1u)));  // any monotone map will do
-            if (sub >= (uint32_t)kShadeSub) sub = kShadeSub - 1;
+            sub = (uint32_t)((float)((uint32_t)prim - m.triFirst) * __fdividef((float)S.shadeSub, (float)(m.triCount ? m.triCount : 1u)));  // any monotone map will do
+            if (sub >= S.shadeSub) sub = S.shadeSub - 1;
         }
     }
-    const uint32_t surface = 1u + ((uint32_t)sh.type * 5u + (uint32_t)(sh.material + 1) + which) % (uint32_t)(kSurfaceBins - 1);
-    return surface * (uint32_t)kShadeSub + sub;
+    // the 4096 bins are split between surfaces and patches per scene (upload_one): few surfaces -> finer patches
+    const uint32_t surface = 1u + ((uint32_t)sh.type * 5u + (uint32_t)(sh.material + 1) + which) % (S.shadeSurfaces - 1u);
+    return surface * S.shadeSub + sub;
 }
 // bins[b] += records of bin b
 __global__ void __launch_bounds__(256) k_bin_count(DScene S, const int32_t* __restrict__ shape, const int32_t* __restrict__ prim, const uint32_t* __restrict__ count,
@@ -1530,7 +1533,15 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         uint64_t sceneItems = 0;
         for (uint64_t i = stree.root; i < end; i++) if ((s->nodes[i].a & 3u) == 0) sceneItems += s->nodes[i].b;
         static const char* maskEnv = std::getenv("PTGPU_SCENE_MASK");  // development: 0 / 1 force it off / on
+        D.hasNested = 0;
+        for (uint32_t i = 0; i < s->numInstances; i++) if (s->instances[i].pad[0]) D.hasNested = 1;
         D.maskOn = maskEnv ? (uint32_t)std::atoi(maskEnv) : (sceneItems >= 16 && 2 * sceneItems >= 3 * (uint64_t)s->numSceneShapes ? 1u : 0u);
+        {   // shade order (shade_bin): kShadeBins bins = surfaces x patches.  A scene with few surfaces gets finer patches (C3, two meshes:
+            // 16 x 256, +2 % over 128 x 32), a scene with hundreds of instances keeps them apart (C4: 128 x 32).
+            uint32_t surfaces = 16;
+            while (surfaces < (uint32_t)kSurfaceBins && surfaces < 2u * (s->numSceneShapes + 1u)) surfaces <<= 1;
+            D.shadeSurfaces = surfaces; D.shadeSub = (uint32_t)kShadeBins / surfaces;
+        }
         const uint4* dlm = nullptr;
         if ((rc = upload(ctx, reinterpret_cast<const uint4*>(lm.data()), (uint64_t)lm.size() / 4, &dlm)) != PTGPU_OK) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1851,7 +1862,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         if ((rc = ensure_split(ctx, L, L.capRays, ctx->splitStackEnt)) != PTGPU_OK) return rc;
     }
     const int gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
-    const bool maskOn = PT_SCENE_MASK && ctx->scene.maskOn;  // which instantiation of the scene kernels runs (see scene_advance)
+    const bool maskOn = (PT_SCENE_MASK && ctx->scene.maskOn) || ctx->scene.hasNested;  // which instantiation of the scene kernels runs (see scene_advance)
     float ms = 0;
     if (prof) {
         ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; ctx->traceLaunches = 0;
@@ -2240,7 +2251,7 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
         int rcs = ensure_split(ctx, L, std::max<uint64_t>(N, L.splitCap), ctx->splitStackEnt);
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
         const BatchOut B{dS, dPr, dT, dN, dP, dI, dM};
-        const bool maskOn = PT_SCENE_MASK && ctx->scene.maskOn;
+        const bool maskOn = (PT_SCENE_MASK && ctx->scene.maskOn) || ctx->scene.hasNested;
         rcs = run_split(ctx, L, ctx->stream,
                         [&](const MeshQueue& out) { { if (maskOn) k_scene_batch<SCENE_START, true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); else k_scene_batch<SCENE_START, false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); } },
                         [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_batch<SCENE_RESUME, true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); else k_scene_batch<SCENE_RESUME, false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); } },
