@@ -1050,7 +1050,13 @@ PT_D double nested_fold(const DScene& S, int32_t outer, V3 o, V3 d, double tInne
     return t;
 }
 struct NoLight { PT_D int32_t operator()(uint32_t) const { return -1; } };
-template <int MODE, bool MASK, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
+// TIER: what the scene holds, so that a scene runs the kernel without the code (and the registers) of shapes it does not have - with
+// everything compiled in as runtime branches the analytic-shape scenes C1 / C2 traced 10 % slower and C3 3 %:
+//   0  analytic shapes only (Sphere, Cube, Plane, Cylinder)                       1  ... and Meshes added to the Scene directly
+//   2  everything but nesting: TransformedShape, SDFShape, Volume, SphericalHarmonic, the candidate mask
+//   3  ... and TransformedShapes of TransformedShapes (nested_fold: 3-5 % of the instanced scene's pass when merely compiled in)
+enum { TIER_ANALYTIC = 0, TIER_MESH = 1, TIER_FULL = 2, TIER_NESTED = 3 };
+template <int MODE, int TIER, bool SHADOW = false, class Source, class Sink, class LightOf = NoLight>
 PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const MeshQueue& in, const MeshQueue& out, Source source, Sink sink, LightOf lightOf = LightOf()) {
     // Candidate mask (PT_SCENE_MASK).  The reference builder puts a shape into every Scene.tree leaf its box overlaps and stops splitting
     // at 85 % overlap, so leaves are large and repeat each other (the 200-instance scene: 501 items in 45 leaves, up to 41 per leaf, the
@@ -1064,9 +1070,8 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
     // block's union first; cleared when the shape is evaluated.  A leaf none of whose shapes has its bit set is skipped as a whole
     // (sceneLeafMask), otherwise its items are visited in array order as before and those without a bit are passed over.  What is
     // evaluated, in which order, and every fold that can change best are those of the reference.
+    constexpr bool MASK = TIER >= TIER_FULL;
     __shared__ uint32_t maskColumns[MASK ? 8 * kSceneBlock : 1];
-    // MASK is a template parameter: scenes that need neither the mask nor nested TransformedShapes run the kernel without that code
-    // (with it, as runtime branches, the analytic-shape scenes C1 / C2 traced 10 % slower and C3 3 %)
     uint32_t* const mk = (MASK && PT_SCENE_MASK && S.maskOn) ? maskColumns + threadIdx.x : nullptr;
     const ptgpu_tree sceneTree = S.trees[S.sceneTree];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -1151,18 +1156,18 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
         for (;;) {
             if (st == ST_MESH_DONE) {  // fold the shape's Hit into the leaf's running best (Tree.cs:121-125)
                 double t = mBest, tInner = 0;
-                if (curInst >= 0) {
+                if (TIER >= TIER_FULL && curInst >= 0) {
                     tInner = mBest;
                     if (mBest < kHitInf) {  // TransformedShape.cs:47-69
                         const ptgpu_instance& inst = S.instances[curInst];
-                        if (MASK && inst.pad[0]) t = nested_fold(S, curInst, o, d, mBest, tInner);
+                        if (TIER == TIER_NESTED && inst.pad[0]) t = nested_fold(S, curInst, o, d, mBest, tInner);
                         else {
                             V3 position = mat_pos(inst.m, ray_at(co, cd, mBest));
                             t = (double)vlenf(vsub(position, o));
                         }
                     }
                 }
-                if (curShape >> 31) { curShape &= 0x7FFFFFFFu; mPrim = -1; }  // SphericalHarmonic: the Hit names the solid, not the triangle (SH.cs:54)
+                if (TIER >= TIER_FULL && (curShape >> 31)) { curShape &= 0x7FFFFFFFu; mPrim = -1; }  // SphericalHarmonic: the Hit names the solid, not the triangle (SH.cs:54)
                 if (t < best.t) { best.t = t; best.tInner = tInner; best.shape = (int32_t)curShape; best.prim = mPrim; }
                 st = (SHADOW && best.t < tL) ? ST_FINISH : ST_SCENE_LEAF;  // occluded: the closest hit is closer than the light
             }
@@ -1194,7 +1199,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                     ptgpu_shape sh = S.shapes[curShape];
                     curInst = -1; co = o; cd = d;
                     mPrim = -1;
-                    if (sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45
+                    if (TIER >= TIER_FULL && sh.type == PTGPU_TRANSFORMED) {  // TransformedShape.cs:45
                         curInst = (int32_t)sh.data;
                         // FP32 pre-test in world space: a ray that misses the padded world bounds of the instanced mesh gives a
                         // shapeRay that misses the mesh's Box (Tree.cs:36-41) -> NoHit, without the FP64 transform
@@ -1215,7 +1220,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                         const ptgpu_instance& inst = S.instances[sh.data];
                         co = mat_pos(inst.inv, o); cd = mat_dir(inst.inv, d);
                         sh = S.shapes[inst.shape];
-                        if (MASK && inst.pad[0]) {  // flagged by the flattener: a TransformedShape of a TransformedShape - its Intersect runs the inner one on ITS shapeRay
+                        if (TIER == TIER_NESTED && inst.pad[0]) {  // flagged by the flattener: a TransformedShape of a TransformedShape - its Intersect runs the inner one on ITS shapeRay
                             while (sh.type == PTGPU_TRANSFORMED) {
                                 const ptgpu_instance& in2 = S.instances[sh.data];
                                 co = mat_pos(in2.inv, co); cd = mat_dir(in2.inv, cd);
@@ -1223,7 +1228,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             }
                         }
                     }
-                    if (sh.type == PTGPU_MESH || sh.type == PTGPU_SH) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
+                    if (TIER >= TIER_MESH && (sh.type == PTGPU_MESH || (TIER >= TIER_FULL && sh.type == PTGPU_SH))) {  // Mesh.Intersect -> its own Tree.Intersect, starting from NoHit
                         // (SphericalHarmonic.Intersect is mesh.Intersect with the Hit renamed to the solid itself, SH.cs:47-55)
                         const ptgpu_tree mt = S.trees[S.meshes[sh.type == PTGPU_SH ? S.shs[sh.data].mesh : sh.data].tree];
                         mBest = kHitInf;
@@ -1260,7 +1265,7 @@ PT_D void scene_advance(const DScene& S, const SplitState& W, uint32_t n, const 
                             save_ray_state(ray_state(W, ray), best, sc, sPos, sEnd, curShape, curInst, mk);
                             break;
                         }
-                    } else if (sh.type == PTGPU_SDF || sh.type == PTGPU_VOLUME) {
+                    } else if (TIER >= TIER_FULL && (sh.type == PTGPU_SDF || sh.type == PTGPU_VOLUME)) {
                         // SDFShape.Intersect / Volume.Intersect: the prologue here (SDF.cs:34-46, Volume.cs:171-175), the loop in march_items
                         double t0, t1;
                         bool go;
@@ -1581,6 +1586,8 @@ PT_D V3 tri_blend_uv(const ptgpu_tri_shade& s, double u, double v, double w) {  
     return vadd(vadd(vmuls(t1, u), vmuls(t2, v)), vmuls(t3, w));
 }
 // Triangle.NormalAt (Triangle.cs:142-189)
+// STIER (shade tier, like scene_advance's TIER): 0 analytic shapes without textures, 1 ... and Meshes, still without textures, 2 everything.
+template <int STIER>
 PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
     const float4* g = S.triGeom + (size_t)tri * 3;
     float4 a = __ldg(g), b4 = __ldg(g + 1), c4 = __ldg(g + 2);
@@ -1589,7 +1596,7 @@ PT_D V3 tri_normal(const DScene& S, uint32_t tri, V3 p) {
     double u, v, w;
     tri_barycentric(v1, e1, e2, p, u, v, w);
     V3 n = vadd(vadd(vmuls(ld3(s.n1), u), vmuls(ld3(s.n2), v)), vmuls(ld3(s.n3), w));
-    if (s.material < 0) return vnorm_c(n);  // `new Material()`: no textures
+    if (STIER < 2 || s.material < 0) return vnorm_c(n);  // `new Material()` / a scene without textures
     const ptgpu_material& pm = S.materials[s.material];
     if (pm.normalTexture >= 0) {
         V3 b = tri_blend_uv(s, u, v, w);
@@ -1632,7 +1639,10 @@ PT_D V3 sh_normal(const ptgpu_sh& h, V3 p) {
 }
 
 // IShape.NormalAt for a non-transformed shape entry (prim = global triangle index for meshes).
+template <int STIER>
 PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p) {
+    if (STIER < 1 && sh.type > PTGPU_CYLINDER) return v3(0, 0, 0);
+    if (STIER < 2 && sh.type > PTGPU_MESH) return v3(0, 0, 0);
     switch (sh.type) {
         case PTGPU_SPHERE: return vnorm_c(vsub(p, ld3(S.spheres[sh.data].center)));  // Sphere.cs:78-81
         case PTGPU_CUBE: {                                                          // Cube.cs:57-69
@@ -1659,7 +1669,7 @@ PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p)
             if (fabs((double)p.z - c.z1) < epsilon) return v3(0, 0, 1);
             return v3(0, 0, 0);
         }
-        case PTGPU_MESH: return tri_normal(S, (uint32_t)prim, p);  // hit.Shape is the Triangle
+        case PTGPU_MESH: return tri_normal<STIER>(S, (uint32_t)prim, p);  // hit.Shape is the Triangle
         case PTGPU_SDF: return sdf_normal(S, S.sdfShapes[sh.data], p);
         case PTGPU_VOLUME: return volume_normal(S, S.volumes[sh.data], p);
         case PTGPU_SH: return sh_normal(S.shs[sh.data], p);
@@ -1669,13 +1679,16 @@ PT_D V3 shape_normal(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p)
 
 // Material.MaterialAt(shape, point) (Material.cs:124-138).  UVector is only evaluated when a texture needs it
 // (it has no side effects in the reference).
+template <int STIER>
 PT_D Mat shape_material(const DScene& S, const ptgpu_shape& sh, int32_t prim, V3 p) {
     int32_t id = sh.material;
-    if (sh.type == PTGPU_MESH) id = S.triShade[prim].material;
+    if (STIER >= 1 && sh.type == PTGPU_MESH) id = S.triShade[prim].material;
+    else if (STIER < 2) {}
     else if (sh.type == PTGPU_VOLUME) id = volume_material(S, S.volumes[sh.data], p);
     else if (sh.type == PTGPU_SH) { const ptgpu_sh& h = S.shs[sh.data]; id = sh_harmonic(h, p) < 0 ? h.negativeMaterial : h.positiveMaterial; }
     Mat m = mat_load(S, id);
     if (id < 0) return m;
+    if (STIER < 2) return m;  // a scene without textures
     const ptgpu_material& pm = S.materials[id];
     if (pm.texture >= 0 || pm.glossTexture >= 0) {
         V3 uv = v3(0, 0, 0);
@@ -1724,10 +1737,11 @@ struct Surface {  // HitInfo (Hit.cs:58-75)
 };
 
 // Hit.Info (Hit.cs:26-55) / the HitInfo TransformedShape.Intersect pre-fills (TransformedShape.cs:52-70).
+template <int STIER>
 PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
     Surface sf;
     ptgpu_shape sh = S.shapes[h.shape];
-    const bool xf = sh.type == PTGPU_TRANSFORMED;
+    const bool xf = STIER >= 2 && sh.type == PTGPU_TRANSFORMED;
     const ptgpu_instance* inst = nullptr;
     V3 so = o, sd = d;
     double t = h.t;
@@ -1739,8 +1753,8 @@ PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
         t = h.tInner;
     }
     const V3 position = ray_at(so, sd, t);
-    V3 normal = shape_normal(S, sh, h.prim, position);
-    sf.mat = shape_material(S, sh, h.prim, position);
+    V3 normal = shape_normal<STIER>(S, sh, h.prim, position);
+    sf.mat = shape_material<STIER>(S, sh, h.prim, position);
     sf.inside = false;
     if (xf) {
         sf.position = mat_pos(inst->m, position);
@@ -1752,7 +1766,7 @@ PT_D Surface hit_info(const DScene& S, V3 o, V3 d, const HitRec& h) {
     if (vdot(normal, d) > 0) {
         normal = vneg(normal);
         sf.inside = true;
-        if (sh.type == PTGPU_VOLUME || sh.type == PTGPU_SDF || sh.type == PTGPU_SH) sf.inside = false;  // Hit.cs:41-47
+        if (STIER >= 2 && (sh.type == PTGPU_VOLUME || sh.type == PTGPU_SDF || sh.type == PTGPU_SH)) sf.inside = false;  // Hit.cs:41-47
     }
     sf.position = position;
     sf.normal = normal;

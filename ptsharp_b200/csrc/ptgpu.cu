@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DScene S, const int32_t* __
 #ifndef PT_SHADE_SYNC
 #define PT_SHADE_SYNC 1
 #endif
+template <int STIER>
 __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS * 128 / PT_SHADE_BLOCK) k_shade(DScene S, PassD P, const DLight* __restrict__ lights, RayQueue q, const uint32_t* __restrict__ count,
                                                 HitQueue hq, RayQueue nq, uint32_t* __restrict__ ncount, ShadowQueue sq, uint32_t* __restrict__ scount,
                                                 float* __restrict__ sum, DeviceCounters* cnt, uint32_t capRays, uint32_t capShadow,
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS * 128 / PT_
         h.t = hq.t[i]; h.tInner = hq.tInner[i]; h.shape = hq.shape[i]; h.prim = hq.prim[i];
         if (h.shape < 0) {  // sampleEnvironment (Sampler.cs:177-189)
             double er = S.envColor[0], eg = S.envColor[1], eb = S.envColor[2];
-            if (S.envTexture >= 0) {
+            if (STIER >= 2 && S.envTexture >= 0) {
                 double u = atan2_c((double)d.z, (double)d.x) + S.envTextureAngle;
                 double v = atan2_c((double)d.y, (double)vlenf(v3(d.x, 0.f, d.z)));
                 u = (u + kPi) / (2 * kPi);
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS * 128 / PT_
             accumulate(sum, cnt, pixel, br * (float)er, bg * (float)eg, bb * (float)eb);
             continue;
         }
-        const Surface sf = hit_info(S, o, d, h);
+        const Surface sf = hit_info<STIER>(S, o, d, h);
         const int samples = depth == 0 ? P.firstHitSamples : 1;
         const int nroot = (int)sqrt((double)samples);
         const float invnn = 1.0f / (float)(nroot * nroot);
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS * 128 / PT_
                                 coverage = netmin(coverage, 1);
                             }
                             const ptgpu_shape lsh = S.shapes[L.shape];
-                            Mat lm = shape_material(S, lsh, -1, point);  // Material.MaterialAt(light, point)
+                            Mat lm = shape_material<STIER>(S, lsh, -1, point);  // Material.MaterialAt(light, point)
                             float m = (float)(lm.emittance * diffuse * coverage) * lscale;
                             auto g3 = cg::coalesced_threads();
                             uint32_t base = 0;
@@ -586,17 +587,17 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS * 128 / PT_
 #ifndef PT_SCENE_MINBLOCKS
 #define PT_SCENE_MINBLOCKS 8
 #endif
-template <int MODE, bool MASK>
+template <int MODE, int TIER>
 __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_trace(DScene S, SplitState W, RayQueue q, const uint32_t* __restrict__ count, MeshQueue in, MeshQueue out, HitQueue hq,
                                                       DeviceCounters* cnt) {
     constexpr bool RESUME = MODE != SCENE_START;
     const uint32_t n = RESUME ? *in.count : *count;
-    scene_advance<MODE, MASK>(S, W, n, in, out,
+    scene_advance<MODE, TIER>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = q.od0[i], b = q.od1[i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) { hq.t[i] = h.t; hq.tInner[i] = h.tInner; hq.shape[i] = h.shape; hq.prim[i] = h.prim; });
     if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->segments, (unsigned long long)n);
 }
-template <int MODE, bool MASK>
+template <int MODE, int TIER>
 __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBLOCKS) k_scene_shadow(DScene S, SplitState W, ShadowQueue sq, const uint32_t* __restrict__ scount, uint32_t capShadow, uint32_t first,
                                                        uint32_t chunk, MeshQueue in, MeshQueue out, float* __restrict__ sum, DeviceCounters* cnt) {
     // The shadow queue may hold several times the rays the tracer has per-ray state for: it is traced in chunks of `chunk` records
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(128, MODE == SCENE_FINISH ? 4 : PT_SCENE_MINBL
         const uint32_t total = min(*scount, capShadow);
         n = total > first ? min(total - first, chunk) : 0u;
     }
-    scene_advance<MODE, MASK, PT_ANYHIT != 0>(S, W, n, in, out,
+    scene_advance<MODE, TIER, PT_ANYHIT != 0>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { float4 a = sq.so[first + i], b = sq.sd[first + i]; o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); },
                           [&](uint32_t i, const HitRec& h) {
                               const uint32_t light = f2u(sq.sd[first + i].w);
@@ -802,12 +803,12 @@ __global__ void k_firefly_apply(float* __restrict__ sum, const uint32_t* __restr
 
 // K6.  Test hook: Scene.Intersect + Hit.Info on caller-supplied rays, through the same split tracer as the pipeline.
 struct BatchOut { int32_t* shape; int32_t* prim; double* t; float* normal3; float* position3; int32_t* inside; int32_t* material; };
-template <int MODE, bool MASK>
+template <int MODE, int TIER>
 __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uint32_t nStart, MeshQueue in, MeshQueue out, const float* __restrict__ o3,
                                                       const float* __restrict__ d3, BatchOut B) {
     constexpr bool RESUME = MODE != SCENE_START;
     const uint32_t n = RESUME ? *in.count : nStart;
-    scene_advance<MODE, MASK>(S, W, n, in, out,
+    scene_advance<MODE, TIER>(S, W, n, in, out,
                           [&](uint32_t i, V3& o, V3& d) { o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]); d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]); },
                           [&](uint32_t i, const HitRec& h) {
                               V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(128) k_scene_batch(DScene S, SplitState W, uin
                                       localPrim = h.prim - (int32_t)S.meshes[sh.data].triFirst;
                                   }
                                   if (B.normal3 || B.position3 || B.inside || B.material) {  // Hit.Info only when asked for
-                                      Surface sf = hit_info(S, o, d, h);
+                                      Surface sf = hit_info<2>(S, o, d, h);
                                       nn = sf.normal; pp = sf.position; ins = sf.inside ? 1 : 0; mat = sf.mat.id;
                                   }
                               }
@@ -911,6 +912,8 @@ struct ptgpu_ctx {
     double kindMs[3] = {0, 0, 0};               // profiling: device time / launches of k_mesh, k_march<SDF>, k_march<VOLUME> in the last pass
     uint64_t kindLaunches[3] = {0, 0, 0};
     int splitStackEnt = 2;
+    int sceneTier = TIER_FULL;  // TIER_* of the uploaded scene (scene_advance)
+    int shadeTier = 2;          // k_shade<STIER>: 0 analytic shapes, no textures; 1 ... and Meshes; 2 everything
     int splitRounds = 0;          // 0: no deferred shapes; > 0: every ray enters at most this many (fixed rounds, no host sync); -1: loop on the queue count
     uint32_t* dCounts = nullptr;  // [6] batch cursor, [8],[9] firefly list counts
     DeviceCounters* dCounters = nullptr;
@@ -1535,7 +1538,19 @@ static int upload_one(ptgpu_ctx* ctx, const ptgpu_flat_scene* s, MeshDerived& dv
         static const char* maskEnv = std::getenv("PTGPU_SCENE_MASK");  // development: 0 / 1 force it off / on
         D.hasNested = 0;
         for (uint32_t i = 0; i < s->numInstances; i++) if (s->instances[i].pad[0]) D.hasNested = 1;
+        {   // which scene-kernel instantiation this scene needs
+            int tier = TIER_ANALYTIC;
+            for (uint32_t k = 0; k < s->numSceneShapes; k++) {
+                const uint32_t ty = s->shapes[k].type;
+                if (ty == PTGPU_MESH) tier = std::max(tier, (int)TIER_MESH);
+                else if (ty != PTGPU_SPHERE && ty != PTGPU_CUBE && ty != PTGPU_PLANE && ty != PTGPU_CYLINDER) tier = TIER_FULL;
+            }
+            ctx->sceneTier = tier;
+        }
         D.maskOn = maskEnv ? (uint32_t)std::atoi(maskEnv) : (sceneItems >= 16 && 2 * sceneItems >= 3 * (uint64_t)s->numSceneShapes ? 1u : 0u);
+        if (D.maskOn && ctx->sceneTier < TIER_FULL) ctx->sceneTier = TIER_FULL;  // the mask lives in the full instantiations
+        if (D.hasNested) ctx->sceneTier = TIER_NESTED;
+        ctx->shadeTier = (s->numTextures > 0 || s->envTexture >= 0 || ctx->sceneTier >= TIER_FULL) ? 2 : ctx->sceneTier;
         {   // shade order (shade_bin): kShadeBins bins = surfaces x patches.  A scene with few surfaces gets finer patches (C3, two meshes:
             // 16 x 256, +2 % over 128 x 32), a scene with hundreds of instances keeps them apart (C4: 128 x 32).
             uint32_t surfaces = 16;
@@ -1862,7 +1877,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         if ((rc = ensure_split(ctx, L, L.capRays, ctx->splitStackEnt)) != PTGPU_OK) return rc;
     }
     const int gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
-    const bool maskOn = (PT_SCENE_MASK && ctx->scene.maskOn) || ctx->scene.hasNested;  // which instantiation of the scene kernels runs (see scene_advance)
+    const int tier = ctx->sceneTier;  // which instantiation of the scene kernels runs (see scene_advance)
     float ms = 0;
     if (prof) {
         ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; ctx->traceLaunches = 0;
@@ -1895,9 +1910,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 const RayQueue rqc = L.rq[cur];
                 uint32_t* cnt = counts + cur;
                 rc = run_split(ctx, L, stream,
-                               [&](const MeshQueue& out) { { if (maskOn) k_scene_trace<SCENE_START, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); else k_scene_trace<SCENE_START, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); } },
-                               [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_trace<SCENE_RESUME, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); else k_scene_trace<SCENE_RESUME, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); } },
-                               [&](const MeshQueue& in) { { if (maskOn) k_scene_trace<SCENE_FINISH, true><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); else k_scene_trace<SCENE_FINISH, false><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); } });
+                               [&](const MeshQueue& out) { { if (tier == TIER_NESTED) k_scene_trace<SCENE_START, TIER_NESTED><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); else if (tier == TIER_FULL) k_scene_trace<SCENE_START, TIER_FULL><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); else if (tier == TIER_MESH) k_scene_trace<SCENE_START, TIER_MESH><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); else k_scene_trace<SCENE_START, TIER_ANALYTIC><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, out, out, L.hq, ctx->dCounters); } },
+                               [&](const MeshQueue& in, const MeshQueue& out) { { if (tier == TIER_NESTED) k_scene_trace<SCENE_RESUME, TIER_NESTED><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); else if (tier == TIER_FULL) k_scene_trace<SCENE_RESUME, TIER_FULL><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); else if (tier == TIER_MESH) k_scene_trace<SCENE_RESUME, TIER_MESH><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); else k_scene_trace<SCENE_RESUME, TIER_ANALYTIC><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, out, L.hq, ctx->dCounters); } },
+                               [&](const MeshQueue& in) { { if (tier == TIER_NESTED) k_scene_trace<SCENE_FINISH, TIER_NESTED><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); else if (tier == TIER_FULL) k_scene_trace<SCENE_FINISH, TIER_FULL><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); else if (tier == TIER_MESH) k_scene_trace<SCENE_FINISH, TIER_MESH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); else k_scene_trace<SCENE_FINISH, TIER_ANALYTIC><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, rqc, cnt, in, in, L.hq, ctx->dCounters); } });
                 if (rc != PTGPU_OK) return rc;
                 if (prof) ctx->traceLaunches++;
             }
@@ -1910,9 +1925,12 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 k_bin_scatter<<<grid_for(ctx, 4), 256, 0, stream>>>(ctx->scene, L.hq.shape, L.hq.prim, counts + cur, L.bins, L.perm);
                 ctx->launches += 3;
             }
-            k_shade<<<gridShade * 128 / PT_SHADE_BLOCK, PT_SHADE_BLOCK, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
-                                                   L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow,
-                                                   shadeOrder ? L.perm : nullptr, counts + 3);
+            {   // the instantiation for what the scene holds (shade tier, see tri_normal in pt_device.cuh)
+                auto shade = ctx->shadeTier == 0 ? k_shade<0> : ctx->shadeTier == 1 ? k_shade<1> : k_shade<2>;
+                shade<<<gridShade * 128 / PT_SHADE_BLOCK, PT_SHADE_BLOCK, 0, stream>>>(ctx->scene, P, ctx->dLights, L.rq[cur], counts + cur, L.hq, L.rq[cur ^ 1], counts + (cur ^ 1),
+                                                                                     L.sq, counts + 2, d_sum, ctx->dCounters, (uint32_t)L.capRays, (uint32_t)L.capShadow,
+                                                                                     shadeOrder ? L.perm : nullptr, counts + 3);
+            }
             k_clamp_count<<<1, 1, 0, stream>>>(counts + (cur ^ 1), (uint32_t)L.capRays, counts + 3);
             if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadeMs += ms; cudaEventRecord(ctx->evA, stream); }
             ctx->launches += 2;
@@ -1922,9 +1940,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
                 for (uint64_t first64 = 0; first64 < shadowThisBatch; first64 += chunk) {
                     const uint32_t first = (uint32_t)first64;
                     rc = run_split<PT_ANYHIT != 0>(ctx, L, stream,
-                                   [&](const MeshQueue& out) { { if (maskOn) k_scene_shadow<SCENE_START, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_START, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); } },
-                                   [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_shadow<SCENE_RESUME, true><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_RESUME, false><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); } },
-                                   [&](const MeshQueue& in) { { if (maskOn) k_scene_shadow<SCENE_FINISH, true><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_FINISH, false><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); } });
+                                   [&](const MeshQueue& out) { { if (tier == TIER_NESTED) k_scene_shadow<SCENE_START, TIER_NESTED><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); else if (tier == TIER_FULL) k_scene_shadow<SCENE_START, TIER_FULL><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); else if (tier == TIER_MESH) k_scene_shadow<SCENE_START, TIER_MESH><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_START, TIER_ANALYTIC><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, out, out, d_sum, ctx->dCounters); } },
+                                   [&](const MeshQueue& in, const MeshQueue& out) { { if (tier == TIER_NESTED) k_scene_shadow<SCENE_RESUME, TIER_NESTED><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); else if (tier == TIER_FULL) k_scene_shadow<SCENE_RESUME, TIER_FULL><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); else if (tier == TIER_MESH) k_scene_shadow<SCENE_RESUME, TIER_MESH><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_RESUME, TIER_ANALYTIC><<<gridShade, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, out, d_sum, ctx->dCounters); } },
+                                   [&](const MeshQueue& in) { { if (tier == TIER_NESTED) k_scene_shadow<SCENE_FINISH, TIER_NESTED><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); else if (tier == TIER_FULL) k_scene_shadow<SCENE_FINISH, TIER_FULL><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); else if (tier == TIER_MESH) k_scene_shadow<SCENE_FINISH, TIER_MESH><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); else k_scene_shadow<SCENE_FINISH, TIER_ANALYTIC><<<gridFinish, 128, 0, stream>>>(ctx->scene, L.split, L.sq, counts + 2, (uint32_t)L.capShadow, first, chunk, in, in, d_sum, ctx->dCounters); } });
                     if (rc != PTGPU_OK) return rc;
                 }
                 if (prof) { cudaEventRecord(ctx->evB, stream); cudaEventSynchronize(ctx->evB); cudaEventElapsedTime(&ms, ctx->evA, ctx->evB); ctx->shadowMs += ms; }
@@ -2251,11 +2269,11 @@ int ptgpu_intersect_batch(ptgpu_ctx* ctx, int32_t n, const float* o3, const floa
         int rcs = ensure_split(ctx, L, std::max<uint64_t>(N, L.splitCap), ctx->splitStackEnt);
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
         const BatchOut B{dS, dPr, dT, dN, dP, dI, dM};
-        const bool maskOn = (PT_SCENE_MASK && ctx->scene.maskOn) || ctx->scene.hasNested;
+        const int tier = ctx->sceneTier;
         rcs = run_split(ctx, L, ctx->stream,
-                        [&](const MeshQueue& out) { { if (maskOn) k_scene_batch<SCENE_START, true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); else k_scene_batch<SCENE_START, false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); } },
-                        [&](const MeshQueue& in, const MeshQueue& out) { { if (maskOn) k_scene_batch<SCENE_RESUME, true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); else k_scene_batch<SCENE_RESUME, false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); } },
-                        [&](const MeshQueue& in) { { if (maskOn) k_scene_batch<SCENE_FINISH, true><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); else k_scene_batch<SCENE_FINISH, false><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); } });
+                        [&](const MeshQueue& out) { { if (tier == TIER_NESTED) k_scene_batch<SCENE_START, TIER_NESTED><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); else if (tier == TIER_FULL) k_scene_batch<SCENE_START, TIER_FULL><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); else if (tier == TIER_MESH) k_scene_batch<SCENE_START, TIER_MESH><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); else k_scene_batch<SCENE_START, TIER_ANALYTIC><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, out, out, dO, dD, B); } },
+                        [&](const MeshQueue& in, const MeshQueue& out) { { if (tier == TIER_NESTED) k_scene_batch<SCENE_RESUME, TIER_NESTED><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); else if (tier == TIER_FULL) k_scene_batch<SCENE_RESUME, TIER_FULL><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); else if (tier == TIER_MESH) k_scene_batch<SCENE_RESUME, TIER_MESH><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); else k_scene_batch<SCENE_RESUME, TIER_ANALYTIC><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, out, dO, dD, B); } },
+                        [&](const MeshQueue& in) { { if (tier == TIER_NESTED) k_scene_batch<SCENE_FINISH, TIER_NESTED><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); else if (tier == TIER_FULL) k_scene_batch<SCENE_FINISH, TIER_FULL><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); else if (tier == TIER_MESH) k_scene_batch<SCENE_FINISH, TIER_MESH><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); else k_scene_batch<SCENE_FINISH, TIER_ANALYTIC><<<grid_for(ctx, 4), 128, 0, ctx->stream>>>(ctx->scene, L.split, (uint32_t)n, in, in, dO, dD, B); } });
         if (rcs != PTGPU_OK) { cleanup(); return rcs; }
     }
     CKC(cudaGetLastError());

@@ -15,7 +15,7 @@ for r in rows:
         n, t, s = r[ix["Instructions Executed"]], r[ix["Thread Instructions Executed"]], r[ix["# Samples"]]
         if n.isdigit():
             k = (os.path.basename(fpath), int(r[0]))
-            per[k][0] += int(n); per[k][1] += int(t); per[k][2] += int(s)
+            per[k][0] += int(n) if n.isdigit() else 0; per[k][1] += int(t) if t.isdigit() else 0; per[k][2] += int(s) if s.isdigit() else 0
 tot = sum(v[0] for v in per.values()); totT = sum(v[1] for v in per.values()); totS = sum(v[2] for v in per.values())
 print(f"warp instructions {tot / 1e6:.1f} M, active lanes per instruction {totT / max(tot, 1):.2f}, stall samples {totS}")
 funcs = {}
