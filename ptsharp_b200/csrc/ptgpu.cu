@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -925,7 +926,7 @@ struct ptgpu_ctx {
     uint32_t* dList[2] = {nullptr, nullptr};  // firefly pixel lists (ping-pong)
     uint8_t* dReject = nullptr;
     // stats
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};  // (the lanes of a polled scene are driven by one host thread each)
     double lastPassMs = 0, traceMs = 0, shadeMs = 0, shadowMs = 0, raygenMs = 0;
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
@@ -934,16 +935,18 @@ struct ptgpu_ctx {
 static std::string g_createError;
 static std::mutex g_mu;
 
+static std::mutex g_errMu;  // ctx->error may be written by the lane threads of a polled scene
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e__ = (call);                                                                        \
         if (e__ != cudaSuccess) {                                                                        \
-            ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            { std::lock_guard<std::mutex> lk__(g_errMu); ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__); } \
             return PTGPU_E_CUDA;                                                                         \
         }                                                                                                \
     } while (0)
 
 static int fail(ptgpu_ctx* ctx, int code, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g_errMu);
     ctx->error = msg;
     return code;
 }
@@ -1831,7 +1834,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     const bool prof = ctx->profiling;
     // a profiled pass, and a scene whose rounds are polled from the host (splitRounds < 0: issued lane by lane anyway), use ONE lane
     // with the capacity of all of them
-    const bool oneLane = prof || ctx->splitRounds < 0;
+    static const bool detailEnv = std::getenv("PTGPU_TRACE_DETAIL") != nullptr;
+    const bool polled = ctx->splitRounds < 0;  // the host reads a queue count per round: every lane is then driven by its own host thread
+    const bool oneLane = prof || (polled && (detailEnv || pixelList != nullptr));
     const uint64_t laneCap = std::min<uint64_t>(oneLane ? ctx->capRays * (uint64_t)ctx->numLanes : ctx->capRays, 1ull << 30);
     uint64_t grow = 1, maxGrow = 1;
     for (int depth = 0; depth < P.maxBounces; depth++) {
@@ -1878,7 +1883,7 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
     }
     const int gridShade = grid_for(ctx, 8), gridGen = grid_for(ctx, 8), gridFinish = grid_for(ctx, 4);
     const int tier = ctx->sceneTier;  // which instantiation of the scene kernels runs (see scene_advance)
-    float ms = 0;
+    // (per-batch timing locals live in run_batch)
     if (prof) {
         ctx->traceMs = ctx->shadeMs = ctx->shadowMs = ctx->raygenMs = 0; ctx->traceLaunches = 0;
         for (int k = 0; k < 3; k++) { ctx->kindMs[k] = 0; ctx->kindLaunches[k] = 0; }
@@ -1890,8 +1895,9 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
         CK(cudaEventRecord(ctx->evFork, callerStream));
         for (int k = 0; k < lanesUsed; k++) CK(cudaStreamWaitEvent(ctx->lanes[k].stream, ctx->evFork, 0));
     }
-    uint64_t batchIndex = 0;
-    for (uint64_t g0 = 0; g0 < total; g0 += batch, batchIndex++) {
+    auto run_batch = [&](uint64_t g0, uint64_t batchIndex) -> int {
+        int rc = PTGPU_OK;
+        float ms = 0;
         Lane& L = ctx->lanes[prof ? 0 : (int)(batchIndex % (uint64_t)lanesUsed)];
         cudaStream_t stream = prof ? callerStream : L.stream;
         uint32_t* counts = L.counts;
@@ -1949,6 +1955,23 @@ static int run_pass(ptgpu_ctx* ctx, const PassD& P, int nSlots, float* d_sum, cu
             }
             cur ^= 1;
         }
+        return PTGPU_OK;
+    };
+    if (polled && lanesUsed > 1) {  // one host thread per lane: a lane's count polls block only its own thread
+        std::vector<std::thread> workers;
+        std::vector<int> rcs((size_t)lanesUsed, PTGPU_OK);
+        for (int k = 0; k < lanesUsed; k++)
+            workers.emplace_back([&, k] {
+                cudaSetDevice(ctx->device);
+                uint64_t bi = (uint64_t)k;
+                for (uint64_t g0 = (uint64_t)k * batch; g0 < total && rcs[(size_t)k] == PTGPU_OK; g0 += batch * (uint64_t)lanesUsed, bi += (uint64_t)lanesUsed) rcs[(size_t)k] = run_batch(g0, bi);
+            });
+        for (auto& w : workers) w.join();
+        for (int r : rcs) if (r != PTGPU_OK) return r;
+    } else {
+        uint64_t batchIndex = 0;
+        for (uint64_t g0 = 0; g0 < total; g0 += batch, batchIndex++)
+            if ((rc = run_batch(g0, batchIndex)) != PTGPU_OK) return rc;
     }
     // ... and the caller's stream continues after all of them (join)
     if (!prof) {
@@ -2345,7 +2368,7 @@ int ptgpu_get_counters(ptgpu_ctx* ctx, ptgpu_counters* out) {
     CK(cudaMemcpy(&dc, ctx->dCounters, sizeof(dc), cudaMemcpyDeviceToHost));
     std::memset(out, 0, sizeof(*out));
     out->cameraSamples = dc.cameraSamples; out->segments = dc.segments; out->shadowRays = dc.shadowRays; out->nanSamples = dc.nanSamples;
-    out->kernelLaunches = ctx->launches;
+    out->kernelLaunches = ctx->launches.load();
 #ifdef PT_DEBUG_STEPS
     {
         unsigned long long h[8];
