@@ -320,8 +320,15 @@ def main():
         if pc["shadeMs"] > kms and pc["shadeMs"] >= scene_ms and pc["segments"]:
             kname, kms, units, klaunches = "k_shade", pc["shadeMs"], pc["segments"], pc["traceLaunches"]
             unit_bytes = 52 + 24 + 52 * max(0, pc["segments"] - pc["cameraSamples"]) / pc["segments"] + 48 * pc["shadowRays"] / pc["segments"]
-        elif kms <= 0 or scene_ms > kms:
+        elif kms <= 0:
             kname, unit_bytes, units, kms, klaunches = "k_scene_trace<START>", TRACE_BYTES_PER_RAY, pc["segments"], pc["traceMs"], pc["traceLaunches"]
+        elif scene_ms > kms:
+            # instanced scenes (C4): the scene level - every k_scene_trace / k_scene_shadow launch (START, RESUME, FINISH) - outweighs
+            # the consumer kernels.  Unit = a ray traced (path segment or shadow ray): 32-byte ray in, 24-byte hit out; its per-round
+            # state and work items are traffic of the split, not algorithmic.  Launches: one START per depth and ray kind (the RESUME
+            # rounds are folded into that launch's time).
+            kname, unit_bytes, units, kms, klaunches = ("k_scene_trace+k_scene_shadow (scene level)", TRACE_BYTES_PER_RAY,
+                                                        pc["segments"] + pc["shadowRays"], scene_ms, 2 * pc["traceLaunches"])
         stage.update({"sdfMs": pc["sdfMs"], "volumeMs": pc["volumeMs"]})
         achieved = units * unit_bytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         traffic, traffic_src = None, None
